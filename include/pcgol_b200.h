@@ -1,0 +1,218 @@
+/* pcgol_b200.h — C ABI of the B200-native pcgol hot path (libpcgol_b200.so).
+ *
+ * This is the drop-in boundary: exactly what a cgo shim inside seqsense/pcgol
+ * would bind to replace, for the data-parallel hot path only,
+ *   - pc/storage/kdtree   (kdtree.New / KDTree.Nearest / KDTree.Range behind storage.Search)
+ *   - pc/filter/voxelgrid (voxelGrid.Filter behind filter.Filter)
+ *   - pc/registration/icp (NearestPointCorresponder.Pairs, PointToPointEvaluator.Evaluate,
+ *                          gradientDescentUpdater.Update, PointToPointICPGradient.Fit)
+ * Reference paths below are relative to the pcgol repository root.
+ *
+ * Conventions
+ *   - Plain C types only.  Every call returns a pcg_status (0 == PCG_OK); the
+ *     message of the last failure on the calling thread is pcg_last_error().
+ *     Nothing aborts or throws across this boundary.
+ *   - Clouds are passed the way pc.PointCloud stores them (pc/pointcloud.go:72-78):
+ *     an interleaved little-endian record buffer, `stride` bytes per record,
+ *     float32 x/y/z at byte offsets xyz_off[0..2].  A pc.Vec3Slice
+ *     (pc/vec3slice.go:8) is stride 12, offsets {0,4,8}.
+ *   - Host entry points copy their inputs to the device during the call and keep
+ *     no host pointer after returning (cgo pointer-passing rule).  Buffers from
+ *     pcg_host_alloc are pinned and copy at full PCIe rate.
+ *   - `*_dev` entry points take device pointers that live on the index's /
+ *     call's device, enqueue on `stream` (a cudaStream_t passed as void*, NULL =
+ *     legacy default stream) and are used by pipelines that keep clouds resident
+ *     in HBM, and by bench.py.
+ *   - Every entry point selects its CUDA device explicitly, so calls may come
+ *     from any OS thread (goroutines migrate).  Concurrent queries on one index
+ *     are safe (KDTree.Nearest/Range are goroutine-safe, kdtree.go:44-50).
+ *   - There is no CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with PCG_E_NO_DEVICE / PCG_E_CUDA.
+ */
+#ifndef PCGOL_B200_H_
+#define PCGOL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGOL_B200_ABI_VERSION 1
+
+typedef int32_t pcg_status;
+enum {
+  PCG_OK = 0,
+  PCG_E_INVALID_ARG = 1,
+  /* pc/minmax.go:10-12: MinMaxVec3 on an empty cloud -> errors.New("no point") */
+  PCG_E_NO_POINT = 2,
+  /* The reference would panic here (index out of range on its dense voxel array,
+   * pc/filter/voxelgrid/voxelgrid.go:46,151, or on its chunk table, :89). */
+  PCG_E_REF_WOULD_PANIC = 3,
+  /* The reference's result is implementation-specific here (float->int conversion
+   * of a non-finite or out-of-range value). */
+  PCG_E_REF_UNDEFINED = 4,
+  /* pc/registration/icp/evaluator.go:15-17,92-106: ErrNotEnoughPairs */
+  PCG_E_NOT_ENOUGH_PAIRS = 5,
+  PCG_E_CUDA = 6,
+  PCG_E_NO_DEVICE = 7,
+  PCG_E_TOO_LARGE = 8
+};
+
+/* Mirrors Go's storage.Neighbor{ID int; DistSq float32} (pc/storage/search.go:8-11)
+ * as laid out on 64-bit targets (16 bytes), so a []storage.Neighbor can be passed
+ * as is.  A miss is {ID:-1, DistSq:maxRange*maxRange} (kdtree.go:84-86,100-103). */
+typedef struct pcg_neighbor {
+  int64_t id;
+  float dist_sq;
+  uint32_t pad_;
+} pcg_neighbor;
+
+/* ---- library ------------------------------------------------------------- */
+int32_t pcg_abi_version(void);
+const char* pcg_last_error(void);
+const char* pcg_status_string(pcg_status s);
+int32_t pcg_device_count(void);
+/* Pinned host memory (optional; any host pointer is accepted everywhere). */
+pcg_status pcg_host_alloc(void** out, int64_t bytes);
+void pcg_host_free(void* p);
+/* Device memory on `device` for callers that keep clouds resident (Go has no CUDA runtime). */
+pcg_status pcg_device_alloc(int32_t device, void** out, int64_t bytes);
+void pcg_device_free(int32_t device, void* p);
+pcg_status pcg_memcpy_h2d(int32_t device, void* dst_dev, const void* src_host, int64_t bytes);
+pcg_status pcg_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, int64_t bytes);
+pcg_status pcg_device_synchronize(int32_t device);
+/* Number of kernels this library has launched on the calling thread's behalf, process-wide. */
+int64_t pcg_kernel_launch_count(void);
+
+/* ---- storage.Search: spatial index (replaces kdtree.New, kdtree.go:33-56) --- */
+typedef struct pcg_index pcg_index;
+
+pcg_status pcg_index_build(const void* data, int64_t n, int64_t stride, const int64_t xyz_off[3], int32_t device,
+                           pcg_index** out);
+pcg_status pcg_index_build_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                               int32_t device, void* stream, pcg_index** out);
+void pcg_index_free(pcg_index* idx);
+int64_t pcg_index_len(const pcg_index* idx);    /* Vec3RandomAccessor.Len */
+int32_t pcg_index_device(const pcg_index* idx);
+int64_t pcg_index_device_bytes(const pcg_index* idx); /* HBM held by the index */
+
+/* KDTree.Nearest for a batch (kdtree.go:83-92).  Exact search (MinDistSq == 0).
+ * Result i is the (DistSq, ID)-lexicographic minimum over points with
+ * DistSq < maxRange*maxRange, i.e. the reference's own brute-force oracle
+ * (kdtree_test.go:955-968); DistSq is ((dx*dx+dy*dy)+dz*dz) in float32 with
+ * d = point - query, no FMA (mat/vec3.go:18-20,38-40). */
+pcg_status pcg_index_nearest(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                             const int64_t q_xyz_off[3], float max_range, pcg_neighbor* out);
+/* Device variant: d_ids int32[nq] (-1 = miss), d_dist_sq float[nq]. */
+pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
+                                 const int64_t q_xyz_off[3], float max_range, int32_t* d_ids, float* d_dist_sq,
+                                 void* stream);
+
+/* KDTree.Range for a batch (kdtree.go:148-161): all points with DistSq < maxRange^2
+ * (strict), each list sorted by (DistSq, ID) — the canonical order of
+ * kdtree_test.go:926-941.  CSR result owned by the library. */
+typedef struct pcg_range_result pcg_range_result;
+pcg_status pcg_index_range(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                           const int64_t q_xyz_off[3], float max_range, pcg_range_result** out);
+int64_t pcg_range_total(const pcg_range_result* r);
+const int64_t* pcg_range_offsets(const pcg_range_result* r);       /* nq+1 entries */
+const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r); /* total entries */
+void pcg_range_free(pcg_range_result* r);
+
+/* ---- filter.Filter: VoxelGrid (pc/filter/voxelgrid/voxelgrid.go:35-187) ------ */
+/* chunk = Options.ChunkSize (option.go:7-18); any zero selects the un-chunked path
+ * (voxelgrid.go:45-47).  `out` must hold n*stride bytes; *n_out receives the number of
+ * records written.  Output records, their order (ascending chunk id, then ascending
+ * voxel key x + xs*(y + ys*z)), the kept fields of each voxel's first point and the
+ * centroid sum*(1/num)+vMin reproduce the reference bit for bit. */
+pcg_status pcg_voxelgrid_filter(const void* data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                const float leaf[3], const int64_t chunk[3], int32_t device, void* out,
+                                int64_t* n_out);
+pcg_status pcg_voxelgrid_filter_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                    const float leaf[3], const int64_t chunk[3], int32_t device, void* d_out,
+                                    int64_t* n_out, void* stream);
+/* MinMaxVec3 (pc/minmax.go:9-26) — first step of the filter, exposed for sharded runs. */
+pcg_status pcg_minmax_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3], int32_t device,
+                          float mn[3], float mx[3], void* stream);
+
+/* ---- pc/registration/icp ---------------------------------------------------- */
+enum {
+  /* The nine float32 sums of Evaluate are accumulated sequentially in target order,
+   * exactly as evaluator.go:122-145 does: bit-identical trajectory. */
+  PCG_ICP_STRICT = 0,
+  /* Fixed-shape float64 tree reduction (deterministic, independent of GPU count up to
+   * float64 rounding); differs from the reference by its float32 summation error. */
+  PCG_ICP_FAST = 1
+};
+
+/* Zero means the reference default in every field. */
+typedef struct pcg_icp_params {
+  float max_dist;        /* NearestPointCorresponder.MaxDist (correspondence.go:18-20) */
+  int32_t min_pairs;     /* PointToPointEvaluator.MinPairs, 0 -> 6 (evaluator.go:92-95) */
+  float weight[6];       /* GradientDescentUpdaterFactory.Weight, all 0 -> 0.3 (updater.go:15,25-27) */
+  float threshold[6];    /* .Threshold, all 0 -> 0.01 (updater.go:16,28-30) */
+  int32_t max_iteration; /* .MaxIteration, 0 -> 20 (updater.go:31-33) */
+  int32_t mode;          /* PCG_ICP_STRICT | PCG_ICP_FAST */
+} pcg_icp_params;
+
+/* icp.Evaluated (evaluator.go:25-30).  The reference never writes Hessian
+ * (HasHessian() == false, evaluator.go:76); it is returned zeroed. */
+typedef struct pcg_evaluated {
+  float value;
+  float gradient[6];
+  float hessian[36];
+  float dist_rms;
+} pcg_evaluated;
+
+/* icp.Stat (stat.go:3-6) + the pair count of the last Evaluate. */
+typedef struct pcg_icp_stat {
+  pcg_evaluated evaluated;
+  int32_t num_iteration;
+  int32_t pad_;
+  int64_t n_pairs;
+} pcg_icp_stat;
+
+/* NearestPointCorresponder.Pairs (correspondence.go:22-37): arrays sized n_target. */
+pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                         float max_dist, int64_t* base_id, int64_t* target_id, float* dist_sq, int64_t* n_pairs);
+
+/* PointToPointEvaluator.Evaluate (evaluator.go:91-189), default weight function. */
+pcg_status pcg_icp_evaluate(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                            const int64_t xyz_off[3], float max_dist, int32_t min_pairs, int32_t mode,
+                            pcg_evaluated* out, int64_t* n_pairs);
+
+/* PointToPointICPGradient.Fit (icp.go:23-67) with the default gradient-descent updater
+ * (updater.go:44-71).  trans is column-major (mat/mat4.go:8-10).  On
+ * PCG_E_NOT_ENOUGH_PAIRS trans/stat hold the values reached so far (icp.go:51-53). */
+pcg_status pcg_icp_fit(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                       const pcg_icp_params* params, float trans[16], pcg_icp_stat* stat);
+pcg_status pcg_icp_fit_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
+                           const int64_t xyz_off[3], const pcg_icp_params* params, float trans[16],
+                           pcg_icp_stat* stat, void* stream);
+
+/* Scan-pair farm: `count` independent (base, target) pairs, device resident, all on
+ * `device`; builds one index per pair and runs the fits concurrently. status_out[i]
+ * is the per-pair status. */
+pcg_status pcg_icp_fit_pairs_dev(int32_t count, const void* const* d_base, const int64_t* n_base,
+                                 const void* const* d_target, const int64_t* n_target, int64_t stride,
+                                 const int64_t xyz_off[3], const pcg_icp_params* params, int32_t device,
+                                 float* trans_out /* count*16 */, pcg_icp_stat* stat_out, pcg_status* status_out,
+                                 void* stream);
+
+/* One large ICP sharded over GPUs (target points split across ranks, base index
+ * replicated).  Per iteration each rank calls pcg_icp_partial_dev on its slice, the
+ * 16 doubles are sum-all-reduced by the caller (NCCL), then every rank applies
+ * pcg_icp_finish identically.  d_partial16: {Value, SumW, G0..5, R, nPairs, 0...}. */
+pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
+                               const int64_t xyz_off[3], float max_dist, const float trans[16], int32_t first,
+                               double* d_partial16, void* stream);
+/* Host-side tail of Evaluate (evaluator.go:156-186) + Update (updater.go:44-71) from
+ * all-reduced sums.  *iter is the updater's i; returns converged in *converged. */
+pcg_status pcg_icp_finish(const double partial16[16], const pcg_icp_params* params, int32_t* iter, float trans[16],
+                          pcg_evaluated* ev, int32_t* converged);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGOL_B200_H_ */

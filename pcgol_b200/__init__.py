@@ -1,0 +1,19 @@
+"""pcgol_b200 — B200-native (sm_100a) drop-in for the data-parallel hot path of
+seqsense/pcgol: storage.Search (Nearest/Range), filter.VoxelGrid and the
+point-to-point ICP loop.  Host-side mirror of the reference's interfaces over the
+C ABI in include/pcgol_b200.h; all compute is in libpcgol_b200.so (hand-written CUDA).
+"""
+from . import _lib
+from ._lib import PcgError, device_count, kernel_launch_count
+from .pc import PointCloud, PointCloudHeader
+from .storage import Index, Neighbor
+from .filter import VoxelGrid, NoPointError, ReferencePanic
+from .icp import (ErrNotEnoughPairs, Evaluated, GradientDescentUpdaterFactory, NearestPointCorresponder,
+                  PointToPointEvaluator, PointToPointICPGradient, Stat, STRICT, FAST)
+
+__all__ = [
+    "PcgError", "device_count", "kernel_launch_count", "PointCloud", "PointCloudHeader", "Index", "Neighbor",
+    "VoxelGrid", "NoPointError", "ReferencePanic", "ErrNotEnoughPairs", "Evaluated",
+    "GradientDescentUpdaterFactory", "NearestPointCorresponder", "PointToPointEvaluator",
+    "PointToPointICPGradient", "Stat", "STRICT", "FAST",
+]

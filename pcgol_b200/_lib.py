@@ -1,0 +1,135 @@
+"""ctypes binding of libpcgol_b200.so (the C ABI of include/pcgol_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at
+import time, and every compute call raises PcgError when no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcgol_b200.so")
+
+OK = 0
+E_INVALID_ARG = 1
+E_NO_POINT = 2
+E_REF_WOULD_PANIC = 3
+E_REF_UNDEFINED = 4
+E_NOT_ENOUGH_PAIRS = 5
+E_CUDA = 6
+E_NO_DEVICE = 7
+E_TOO_LARGE = 8
+
+ICP_STRICT = 0
+ICP_FAST = 1
+
+
+class PcgError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"pcgol_b200 status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+class Neighbor(C.Structure):
+    """storage.Neighbor{ID int; DistSq float32} as Go lays it out (pc/storage/search.go:8-11)."""
+
+    _fields_ = [("id", C.c_int64), ("dist_sq", C.c_float), ("pad_", C.c_uint32)]
+
+
+class IcpParams(C.Structure):
+    _fields_ = [
+        ("max_dist", C.c_float),
+        ("min_pairs", C.c_int32),
+        ("weight", C.c_float * 6),
+        ("threshold", C.c_float * 6),
+        ("max_iteration", C.c_int32),
+        ("mode", C.c_int32),
+    ]
+
+
+class Evaluated(C.Structure):
+    """icp.Evaluated (pc/registration/icp/evaluator.go:25-30)."""
+
+    _fields_ = [("value", C.c_float), ("gradient", C.c_float * 6), ("hessian", C.c_float * 36),
+                ("dist_rms", C.c_float)]
+
+
+class IcpStat(C.Structure):
+    """icp.Stat (pc/registration/icp/stat.go:3-6) + pair count of the last Evaluate."""
+
+    _fields_ = [("evaluated", Evaluated), ("num_iteration", C.c_int32), ("pad_", C.c_int32), ("n_pairs", C.c_int64)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). pcgol_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+_sigs = {
+    "pcg_abi_version": (_i32, []),
+    "pcg_last_error": (C.c_char_p, []),
+    "pcg_status_string": (C.c_char_p, [_i32]),
+    "pcg_device_count": (_i32, []),
+    "pcg_host_alloc": (_i32, [C.POINTER(_vp), _i64]),
+    "pcg_host_free": (None, [_vp]),
+    "pcg_device_alloc": (_i32, [_i32, C.POINTER(_vp), _i64]),
+    "pcg_device_free": (None, [_i32, _vp]),
+    "pcg_memcpy_h2d": (_i32, [_i32, _vp, _vp, _i64]),
+    "pcg_memcpy_d2h": (_i32, [_i32, _vp, _vp, _i64]),
+    "pcg_device_synchronize": (_i32, [_i32]),
+    "pcg_kernel_launch_count": (_i64, []),
+    "pcg_index_build": (_i32, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_vp)]),
+    "pcg_index_build_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, C.POINTER(_vp)]),
+    "pcg_index_free": (None, [_vp]),
+    "pcg_index_len": (_i64, [_vp]),
+    "pcg_index_device": (_i32, [_vp]),
+    "pcg_index_device_bytes": (_i64, [_vp]),
+    "pcg_index_nearest": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp]),
+    "pcg_index_nearest_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp, _vp]),
+    "pcg_index_range": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, C.POINTER(_vp)]),
+    "pcg_range_total": (_i64, [_vp]),
+    "pcg_range_offsets": (_vp, [_vp]),
+    "pcg_range_neighbors": (_vp, [_vp]),
+    "pcg_range_free": (None, [_vp]),
+    "pcg_voxelgrid_filter": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64)]),
+    "pcg_voxelgrid_filter_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64), _vp]),
+    "pcg_minmax_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "pcg_icp_pairs": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "pcg_icp_evaluate": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, C.POINTER(Evaluated), C.POINTER(_i64)]),
+    "pcg_icp_fit": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat)]),
+    "pcg_icp_fit_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat), _vp]),
+    "pcg_icp_fit_pairs_dev": (_i32, [_i32, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(IcpParams), _i32, _vp, _vp, _vp,
+                                     _vp]),
+    "pcg_icp_partial_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _i32, _vp, _vp]),
+    "pcg_icp_finish": (_i32, [_vp, C.POINTER(IcpParams), C.POINTER(_i32), _vp, C.POINTER(Evaluated),
+                              C.POINTER(_i32)]),
+}
+for _name, (_res, _args) in _sigs.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTED_SYMBOLS = tuple(_sigs)
+
+
+def last_error() -> str:
+    return (lib.pcg_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(status: int, ok=(OK,)) -> int:
+    if status not in ok:
+        raise PcgError(status, last_error() or (lib.pcg_status_string(status) or b"").decode())
+    return status
+
+
+def device_count() -> int:
+    return int(lib.pcg_device_count())
+
+
+def kernel_launch_count() -> int:
+    return int(lib.pcg_kernel_launch_count())

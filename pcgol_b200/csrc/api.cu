@@ -1,0 +1,473 @@
+// api.cu — the extern "C" surface declared in include/pcgol_b200.h.
+// Host entry points stage caller buffers through device memory (stream-ordered pool),
+// run the device pipelines of voxelgrid.cu / index.cu / icp.cu and copy results back.
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "bvh.cuh"
+#include "icp_math.cuh"
+
+namespace pcg {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+
+void ensure_pool(int device) {
+  static std::atomic<uint64_t> done{0};
+  if (device < 0 || device >= 64) return;
+  if (done.load(std::memory_order_acquire) & (1ull << device)) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  done.fetch_or(1ull << device, std::memory_order_release);
+}
+
+// implemented in the other translation units
+pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], uint8_t* d_out,
+                                   int64_t* n_out, cudaStream_t stream);
+void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
+void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_t* d_ids, float* d_dist_sq,
+                    pcg_neighbor* d_aos, cudaStream_t stream);
+void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                  DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream);
+pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only,
+                          float trans[16], pcg_icp_stat* stat, cudaStream_t stream);
+void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_t* n_base,
+                          const void* const* d_target, const int64_t* n_target, int64_t stride,
+                          const int64_t xyz_off[3], const pcg_icp_params& prm, int device, float* trans_out,
+                          pcg_icp_stat* stat_out, pcg_status* status_out, cudaStream_t stream);
+void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist, const float trans[16], bool first,
+                        double* d_partial16, cudaStream_t stream);
+pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm, int32_t* iter, float trans[16],
+                           pcg_evaluated* ev_out, int32_t* converged);
+void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, int32_t* d_ids, float* d_dsq,
+                      cudaStream_t stream);
+
+static void check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw StatusError{PCG_E_NO_DEVICE, std::string("no usable CUDA device: ") + cudaGetErrorString(e)};
+  if (device < 0 || device >= count) throw StatusError{PCG_E_INVALID_ARG, "device ordinal out of range"};
+}
+
+template <typename F>
+static pcg_status guarded(F f) {
+  try {
+    return f();
+  } catch (const StatusError& e) {
+    set_error(e.msg);
+    return e.s;
+  } catch (const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e.e, cudaGetErrorString(e.e), e.file, e.line,
+             e.what);
+    set_error(buf);
+    cudaGetLastError();
+    return (e.e == cudaErrorNoDevice || e.e == cudaErrorInsufficientDriver) ? PCG_E_NO_DEVICE : PCG_E_CUDA;
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed");
+    return PCG_E_TOO_LARGE;
+  } catch (...) {
+    set_error("unexpected exception");
+    return PCG_E_CUDA;
+  }
+}
+
+// Copies a host cloud to the device (whole records: other fields are needed by the filter).
+struct StagedCloud {
+  DevBuf<uint8_t> buf;
+  CloudView view;
+  StagedCloud(const void* data, int64_t n, int64_t stride, const int64_t off[3], cudaStream_t s) {
+    check_view_args(data, n, stride, off);
+    buf.alloc((size_t)std::max<int64_t>(1, n * stride), s);
+    if (n) PCG_CUDA(cudaMemcpyAsync(buf.p, data, (size_t)(n * stride), cudaMemcpyHostToDevice, s));
+    view = make_view(buf.p, n, stride, off);
+  }
+};
+
+struct RangeResult {
+  std::vector<int64_t> offsets;
+  pcg_neighbor* neighbors = nullptr;  // pinned
+  int64_t total = 0;
+  ~RangeResult() {
+    if (neighbors) cudaFreeHost(neighbors);
+  }
+};
+
+}  // namespace pcg
+
+using namespace pcg;
+
+struct pcg_index {
+  Index* ix;
+};
+struct pcg_range_result {
+  RangeResult r;
+};
+
+extern "C" {
+
+int32_t pcg_abi_version(void) { return PCGOL_B200_ABI_VERSION; }
+const char* pcg_last_error(void) { return t_error.c_str(); }
+const char* pcg_status_string(pcg_status s) {
+  switch (s) {
+    case PCG_OK: return "ok";
+    case PCG_E_INVALID_ARG: return "invalid argument";
+    case PCG_E_NO_POINT: return "no point";
+    case PCG_E_REF_WOULD_PANIC: return "reference would panic (index out of range)";
+    case PCG_E_REF_UNDEFINED: return "reference behaviour is implementation-specific for this input";
+    case PCG_E_NOT_ENOUGH_PAIRS: return "not enough correspondence pairs";
+    case PCG_E_CUDA: return "CUDA error";
+    case PCG_E_NO_DEVICE: return "no usable CUDA device";
+    case PCG_E_TOO_LARGE: return "problem too large";
+  }
+  return "unknown status";
+}
+int32_t pcg_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+int64_t pcg_kernel_launch_count(void) { return g_launches.load(); }
+
+pcg_status pcg_host_alloc(void** out, int64_t bytes) {
+  return guarded([&]() -> pcg_status {
+    if (!out || bytes < 0) throw StatusError{PCG_E_INVALID_ARG, "pcg_host_alloc: bad arguments"};
+    PCG_CUDA(cudaMallocHost(out, (size_t)std::max<int64_t>(1, bytes)));
+    return PCG_OK;
+  });
+}
+void pcg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+pcg_status pcg_device_alloc(int32_t device, void** out, int64_t bytes) {
+  return guarded([&]() -> pcg_status {
+    if (!out || bytes < 0) throw StatusError{PCG_E_INVALID_ARG, "pcg_device_alloc: bad arguments"};
+    check_device(device);
+    DeviceGuard g(device);
+    PCG_CUDA(cudaMalloc(out, (size_t)std::max<int64_t>(1, bytes)));
+    return PCG_OK;
+  });
+}
+void pcg_device_free(int32_t device, void* p) {
+  if (!p) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(device);
+  cudaFree(p);
+  if (prev >= 0) cudaSetDevice(prev);
+}
+pcg_status pcg_memcpy_h2d(int32_t device, void* dst, const void* src, int64_t bytes) {
+  return guarded([&]() -> pcg_status {
+    check_device(device);
+    DeviceGuard g(device);
+    PCG_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return PCG_OK;
+  });
+}
+pcg_status pcg_memcpy_d2h(int32_t device, void* dst, const void* src, int64_t bytes) {
+  return guarded([&]() -> pcg_status {
+    check_device(device);
+    DeviceGuard g(device);
+    PCG_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return PCG_OK;
+  });
+}
+pcg_status pcg_device_synchronize(int32_t device) {
+  return guarded([&]() -> pcg_status {
+    check_device(device);
+    DeviceGuard g(device);
+    PCG_CUDA(cudaDeviceSynchronize());
+    return PCG_OK;
+  });
+}
+
+// ---- index -----------------------------------------------------------------------------
+pcg_status pcg_index_build_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                               int32_t device, void* stream, pcg_index** out) {
+  return guarded([&]() -> pcg_status {
+    if (!out) throw StatusError{PCG_E_INVALID_ARG, "pcg_index_build: null output"};
+    *out = nullptr;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    DeviceGuard g(device);
+    CloudView v = make_view(d_data, n, stride, xyz_off);
+    Index* ix = index_build_device(v, device, (cudaStream_t)stream);
+    *out = new pcg_index{ix};
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_index_build(const void* data, int64_t n, int64_t stride, const int64_t xyz_off[3], int32_t device,
+                           pcg_index** out) {
+  return guarded([&]() -> pcg_status {
+    if (!out) throw StatusError{PCG_E_INVALID_ARG, "pcg_index_build: null output"};
+    *out = nullptr;
+    check_device(device);
+    DeviceGuard g(device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(data, n, stride, xyz_off, s);
+    Index* ix = index_build_device(c.view, device, s);
+    PCG_CUDA(cudaStreamSynchronize(s));
+    *out = new pcg_index{ix};
+    return PCG_OK;
+  });
+}
+
+void pcg_index_free(pcg_index* idx) {
+  if (!idx) return;
+  index_free(idx->ix);
+  delete idx;
+}
+int64_t pcg_index_len(const pcg_index* idx) { return idx ? idx->ix->n : 0; }
+int32_t pcg_index_device(const pcg_index* idx) { return idx ? idx->ix->device : -1; }
+int64_t pcg_index_device_bytes(const pcg_index* idx) { return idx ? idx->ix->bytes : 0; }
+
+pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
+                                 const int64_t q_xyz_off[3], float max_range, int32_t* d_ids, float* d_dist_sq,
+                                 void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
+    check_view_args(d_q, nq, q_stride, q_xyz_off);
+    if (nq && (!d_ids || !d_dist_sq)) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(idx->ix->device);
+    nearest_device(*idx->ix, make_view(d_q, nq, q_stride, q_xyz_off), max_range, d_ids, d_dist_sq, nullptr,
+                   (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_index_nearest(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                             const int64_t q_xyz_off[3], float max_range, pcg_neighbor* out) {
+  return guarded([&]() -> pcg_status {
+    if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
+    if (nq && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(idx->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+    if (nq == 0) return PCG_OK;
+    DevBuf<pcg_neighbor> d_out((size_t)nq, s);
+    nearest_device(*idx->ix, c.view, max_range, nullptr, nullptr, d_out.p, s);
+    PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)nq * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_index_range(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                           const int64_t q_xyz_off[3], float max_range, pcg_range_result** out) {
+  return guarded([&]() -> pcg_status {
+    if (!idx || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *out = nullptr;
+    DeviceGuard g(idx->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+    DevBuf<long long> d_off;
+    DevBuf<pcg_neighbor> d_nb;
+    int64_t total = 0;
+    range_device(*idx->ix, c.view, max_range, d_off, d_nb, &total, s);
+    std::unique_ptr<pcg_range_result> r(new pcg_range_result());
+    r->r.offsets.resize((size_t)nq + 1);
+    r->r.total = total;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    PCG_CUDA(cudaMemcpyAsync(r->r.offsets.data(), d_off.p, ((size_t)nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                             s));
+    if (total) {
+      PCG_CUDA(cudaMallocHost((void**)&r->r.neighbors, (size_t)total * sizeof(pcg_neighbor)));
+      PCG_CUDA(cudaMemcpyAsync(r->r.neighbors, d_nb.p, (size_t)total * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost,
+                               s));
+    }
+    PCG_CUDA(cudaStreamSynchronize(s));
+    *out = r.release();
+    return PCG_OK;
+  });
+}
+int64_t pcg_range_total(const pcg_range_result* r) { return r ? r->r.total : 0; }
+const int64_t* pcg_range_offsets(const pcg_range_result* r) { return r ? r->r.offsets.data() : nullptr; }
+const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r) { return r ? r->r.neighbors : nullptr; }
+void pcg_range_free(pcg_range_result* r) { delete r; }
+
+// ---- voxel grid -------------------------------------------------------------------------
+static void check_vg_args(const float leaf[3], const int64_t chunk[3]) {
+  if (!leaf || !chunk) throw StatusError{PCG_E_INVALID_ARG, "null leaf/chunk"};
+  for (int k = 0; k < 3; k++)
+    if (chunk[k] < 0) throw StatusError{PCG_E_INVALID_ARG, "negative chunk size"};
+}
+
+pcg_status pcg_voxelgrid_filter_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                    const float leaf[3], const int64_t chunk[3], int32_t device, void* d_out,
+                                    int64_t* n_out, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!n_out) throw StatusError{PCG_E_INVALID_ARG, "null n_out"};
+    *n_out = 0;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    if (n && !d_out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(device);
+    return voxelgrid_filter_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, (uint8_t*)d_out, n_out,
+                                   (cudaStream_t)stream);
+  });
+}
+
+pcg_status pcg_voxelgrid_filter(const void* data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                const float leaf[3], const int64_t chunk[3], int32_t device, void* out,
+                                int64_t* n_out) {
+  return guarded([&]() -> pcg_status {
+    if (!n_out) throw StatusError{PCG_E_INVALID_ARG, "null n_out"};
+    *n_out = 0;
+    check_device(device);
+    check_vg_args(leaf, chunk);
+    if (n && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(data, n, stride, xyz_off, s);
+    DevBuf<uint8_t> d_out((size_t)std::max<int64_t>(1, n * stride), s);
+    pcg_status rc = voxelgrid_filter_device(c.view, leaf, chunk, d_out.p, n_out, s);
+    if (rc == PCG_OK && *n_out) {
+      PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)(*n_out * stride), cudaMemcpyDeviceToHost, s));
+      PCG_CUDA(cudaStreamSynchronize(s));
+    }
+    return rc;
+  });
+}
+
+pcg_status pcg_minmax_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3], int32_t device,
+                          float mn[3], float mx[3], void* stream) {
+  return guarded([&]() -> pcg_status {
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    if (n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
+    DeviceGuard g(device);
+    minmax_device(make_view(d_data, n, stride, xyz_off), mn, mx, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+// ---- icp ----------------------------------------------------------------------------------
+pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                         float max_dist, int64_t* base_id, int64_t* target_id, float* dist_sq, int64_t* n_pairs) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !n_pairs) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *n_pairs = 0;
+    DeviceGuard g(base->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(target, n, stride, xyz_off, s);
+    if (n == 0) return PCG_OK;
+    DevBuf<int32_t> d_ids((size_t)n, s);
+    DevBuf<float> d_dsq((size_t)n, s);
+    icp_pairs_device(*base->ix, c.view, max_dist, d_ids.p, d_dsq.p, s);
+    std::vector<int32_t> ids((size_t)n);
+    std::vector<float> dsq((size_t)n);
+    PCG_CUDA(cudaMemcpyAsync(ids.data(), d_ids.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaMemcpyAsync(dsq.data(), d_dsq.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
+    int64_t m = 0;  // correspondence.go:27-35: unmatched targets are skipped, order kept
+    for (int64_t i = 0; i < n; i++) {
+      if (ids[(size_t)i] < 0) continue;
+      base_id[m] = ids[(size_t)i];
+      target_id[m] = i;
+      dist_sq[m] = dsq[(size_t)i];
+      m++;
+    }
+    *n_pairs = m;
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_icp_evaluate(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                            const int64_t xyz_off[3], float max_dist, int32_t min_pairs, int32_t mode,
+                            pcg_evaluated* out, int64_t* n_pairs) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(base->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(target, n, stride, xyz_off, s);
+    pcg_icp_params prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.max_dist = max_dist;
+    prm.min_pairs = min_pairs;
+    prm.mode = mode;
+    pcg_icp_stat stat;
+    pcg_status rc = icp_fit_device(*base->ix, c.view, prm, true, nullptr, &stat, s);
+    *out = stat.evaluated;
+    if (n_pairs) *n_pairs = stat.n_pairs;
+    if (rc == PCG_E_NOT_ENOUGH_PAIRS) set_error("not enough correspondence pairs");
+    return rc;
+  });
+}
+
+pcg_status pcg_icp_fit_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
+                           const int64_t xyz_off[3], const pcg_icp_params* params, float trans[16],
+                           pcg_icp_stat* stat, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !params || !trans) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    check_view_args(d_target, n, stride, xyz_off);
+    DeviceGuard g(base->ix->device);
+    pcg_status rc = icp_fit_device(*base->ix, make_view(d_target, n, stride, xyz_off), *params, false, trans, stat,
+                                   (cudaStream_t)stream);
+    if (rc == PCG_E_NOT_ENOUGH_PAIRS) set_error("not enough correspondence pairs");
+    return rc;
+  });
+}
+
+pcg_status pcg_icp_fit(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                       const pcg_icp_params* params, float trans[16], pcg_icp_stat* stat) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !params || !trans) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(base->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(target, n, stride, xyz_off, s);
+    pcg_status rc = icp_fit_device(*base->ix, c.view, *params, false, trans, stat, s);
+    if (rc == PCG_E_NOT_ENOUGH_PAIRS) set_error("not enough correspondence pairs");
+    return rc;
+  });
+}
+
+pcg_status pcg_icp_fit_pairs_dev(int32_t count, const void* const* d_base, const int64_t* n_base,
+                                 const void* const* d_target, const int64_t* n_target, int64_t stride,
+                                 const int64_t xyz_off[3], const pcg_icp_params* params, int32_t device,
+                                 float* trans_out, pcg_icp_stat* stat_out, pcg_status* status_out, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (count < 0 || (count && (!d_base || !n_base || !d_target || !n_target || !params)))
+      throw StatusError{PCG_E_INVALID_ARG, "bad arguments"};
+    check_device(device);
+    DeviceGuard g(device);
+    icp_fit_pairs_device(count, d_base, n_base, d_target, n_target, stride, xyz_off, *params, device, trans_out,
+                         stat_out, status_out, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
+                               const int64_t xyz_off[3], float max_dist, const float trans[16], int32_t first,
+                               double* d_partial16, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !trans || !d_partial16) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    check_view_args(d_target, n, stride, xyz_off);
+    DeviceGuard g(base->ix->device);
+    icp_partial_device(*base->ix, make_view(d_target, n, stride, xyz_off), max_dist, trans, first != 0, d_partial16,
+                       (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_icp_finish(const double partial16[16], const pcg_icp_params* params, int32_t* iter, float trans[16],
+                          pcg_evaluated* ev, int32_t* converged) {
+  return guarded([&]() -> pcg_status {
+    if (!partial16 || !params || !iter || !trans || !converged) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    pcg_status rc = icp_finish_host(partial16, *params, iter, trans, ev, converged);
+    if (rc == PCG_E_NOT_ENOUGH_PAIRS) set_error("not enough correspondence pairs");
+    return rc;
+  });
+}
+
+}  // extern "C"

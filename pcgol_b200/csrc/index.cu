@@ -1,0 +1,466 @@
+// index.cu — GPU-built spatial index behind storage.Search (replaces kdtree.New /
+// KDTree.Nearest / KDTree.Range, pc/storage/kdtree/kdtree.go:33-222) on sm_100a.
+//
+// Build: bounding box -> 48-bit Morton keys (16 bits per axis, cubic cells) -> stable
+// radix sort of (key, index) -> gather float4 {x,y,z,index} in Morton order -> leaf
+// boxes over 8 consecutive points and an implicit, heap-indexed binary tree of boxes
+// above them (see bvh.cuh).  No pointers, no recursion, two kernels for the tree.
+#include "bvh.cuh"
+#include "radix_sort.cuh"
+
+namespace pcg {
+
+constexpr int kMortonBitsPerAxis = 16;
+
+__device__ __forceinline__ uint32_t ord_bits(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_to_float(uint32_t o) {
+  uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+
+// out6: ordered-bit min x,y,z then max x,y,z over finite coordinates
+__global__ void __launch_bounds__(256) bbox_kernel(CloudView v, uint32_t* __restrict__ out6) {
+  uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += stride) {
+    float3 p = load_xyz(v, i);
+    float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (!isfinite(c[k])) continue;
+      uint32_t o = ord_bits(c[k]);
+      mn[k] = min(mn[k], o);
+      mx[k] = max(mx[k], o);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn[k] = min(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], d));
+      mx[k] = max(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], d));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      atomicMin(&out6[k], mn[k]);
+      atomicMax(&out6[3 + k], mx[k]);
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long spread16(uint32_t x) {  // 16 bits -> every third bit
+  unsigned long long v = x & 0xffffu;
+  v = (v | (v << 16)) & 0x0000ff0000ffull;
+  v = (v | (v << 8)) & 0x00f00f00f00full;
+  v = (v | (v << 4)) & 0x0c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x249249249249ull;
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    morton_kernel(CloudView v, const uint32_t* __restrict__ bbox6, unsigned long long* __restrict__ keys) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  float lo[3], ext = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    lo[k] = ord_to_float(bbox6[k]);
+    float hi = ord_to_float(bbox6[3 + k]);
+    ext = fmaxf(ext, hi - lo[k]);
+  }
+  const float scale = (ext > 0.f && isfinite(ext)) ? (float)(1 << kMortonBitsPerAxis) / ext : 0.f;
+  float3 p = load_xyz(v, i);
+  float c[3] = {p.x, p.y, p.z};
+  unsigned long long key = 0;
+  bool finite = isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]);
+  if (finite) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float q = (c[k] - lo[k]) * scale;
+      uint32_t u = (uint32_t)fminf(fmaxf(q, 0.f), (float)((1 << kMortonBitsPerAxis) - 1));
+      key |= spread16(u) << k;
+    }
+  } else {
+    key = (1ull << (3 * kMortonBitsPerAxis)) - 1;  // non-finite points go last; they never match a query
+  }
+  keys[i] = key;
+}
+
+__global__ void __launch_bounds__(256)
+    gather_points_kernel(CloudView v, const uint32_t* __restrict__ order, float4* __restrict__ pts, uint32_t padded) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= padded) return;
+  float4 o;
+  if (i < (uint32_t)v.n) {
+    uint32_t src = order[i];
+    float3 p = load_xyz(v, src);
+    o = make_float4(p.x, p.y, p.z, __uint_as_float(src));
+  } else {
+    const float inf = __int_as_float(0x7f800000);
+    o = make_float4(inf, inf, inf, __uint_as_float(0xffffffffu));
+  }
+  pts[i] = o;
+}
+
+// Leaf boxes and the 8 levels above them, one CTA per 256 leaves.
+__global__ void __launch_bounds__(256)
+    leaf_boxes_kernel(const float4* __restrict__ pts, float4* __restrict__ boxes, uint32_t leaves, uint32_t P) {
+  __shared__ float s_lo[256][3];
+  __shared__ float s_hi[256][3];
+  const uint32_t t = threadIdx.x;
+  const uint32_t leaf = blockIdx.x * 256 + t;
+  const float inf = __int_as_float(0x7f800000);
+  float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  if (leaf < leaves) {
+    const float4* lp = pts + (size_t)leaf * kLeaf;
+#pragma unroll
+    for (int j = 0; j < kLeaf; j++) {
+      float4 p = lp[j];
+      if (__float_as_uint(p.w) == 0xffffffffu) continue;  // padding
+      // fminf/fmaxf drop NaN operands; +-inf coordinates stay out of the boxes as well
+      if (isfinite(p.x)) { lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x); }
+      if (isfinite(p.y)) { lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y); }
+      if (isfinite(p.z)) { lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z); }
+    }
+  }
+  if (leaf < P) {
+    boxes[2 * (size_t)(P + leaf)] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    boxes[2 * (size_t)(P + leaf) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    s_lo[t][k] = lo[k];
+    s_hi[t][k] = hi[k];
+  }
+  __syncthreads();
+  // heights 1..8 inside the CTA: node ids ((P + blockIdx*256) >> h) + j
+  uint32_t width = 256;
+  uint32_t first = P + blockIdx.x * 256;
+  for (int h = 1; h <= 8; h++) {
+    width >>= 1;
+    first >>= 1;
+    if (first == 0) break;  // above the root
+    const uint32_t valid = min(width, P >> h);  // a tree smaller than one CTA has fewer nodes per level
+    float l[3], u[3];
+    if (t < valid) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        l[k] = fminf(s_lo[2 * t][k], s_lo[2 * t + 1][k]);
+        u[k] = fmaxf(s_hi[2 * t][k], s_hi[2 * t + 1][k]);
+      }
+    }
+    __syncthreads();
+    if (t < valid) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        s_lo[t][k] = l[k];
+        s_hi[t][k] = u[k];
+      }
+      uint32_t node = first + t;
+      boxes[2 * (size_t)node] = make_float4(l[0], l[1], l[2], 0.f);
+      boxes[2 * (size_t)node + 1] = make_float4(u[0], u[1], u[2], 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+// Levels above height 8 (P/256 nodes and fewer), one CTA walking up level by level.
+__global__ void __launch_bounds__(1024) top_boxes_kernel(float4* __restrict__ boxes, uint32_t P) {
+  // level with `count` nodes starting at node id `count` (heap indexing), children already written
+  for (uint32_t count = P >> 9; count >= 1; count >>= 1) {
+    for (uint32_t j = threadIdx.x; j < count; j += blockDim.x) {
+      uint32_t node = count + j;
+      float4 l0 = boxes[2 * (size_t)(2 * node)], h0 = boxes[2 * (size_t)(2 * node) + 1];
+      float4 l1 = boxes[2 * (size_t)(2 * node + 1)], h1 = boxes[2 * (size_t)(2 * node + 1) + 1];
+      boxes[2 * (size_t)node] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
+      boxes[2 * (size_t)node + 1] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
+  Index* ix = new Index();
+  ix->device = device;
+  ix->n = v.n;
+  const uint32_t n = (uint32_t)v.n;
+  ix->leaves = (n + kLeaf - 1) / kLeaf;
+  uint32_t P = 1;
+  while (P < ix->leaves) P <<= 1;
+  ix->P = P;
+  if (n == 0) return ix;
+  try {
+    const size_t padded = (size_t)ix->leaves * kLeaf;
+    const size_t pts_bytes = padded * sizeof(float4);
+    const size_t box_bytes = (size_t)4 * P * sizeof(float4);
+    PCG_CUDA(cudaMallocAsync((void**)&ix->pts, pts_bytes, stream));
+    PCG_CUDA(cudaMallocAsync((void**)&ix->boxes, box_bytes, stream));
+    ix->bytes = (int64_t)(pts_bytes + box_bytes);
+
+    DevBuf<uint32_t> bbox(6, stream);
+    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    PCG_CUDA(cudaMemcpyAsync(bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 8, div_up(n, 256));
+    PCG_LAUNCH(bbox_kernel, blocks, 256, 0, stream, v, bbox.p);
+
+    DevBuf<unsigned long long> keys0(n, stream), keys1(n, stream);
+    DevBuf<uint32_t> vals0(n, stream), vals1(n, stream);
+    PCG_LAUNCH(morton_kernel, div_up(n, 256), 256, 0, stream, v, bbox.p, keys0.p);
+    unsigned long long* kk[2] = {keys0.p, keys1.p};
+    uint32_t* vv[2] = {vals0.p, vals1.p};
+    int res = 0;
+    rsort::sort_pairs<unsigned long long>(kk, vv, n, 0, 3 * kMortonBitsPerAxis, /*identity_vals=*/true,
+                                          /*keep_keys=*/false, stream, &res);
+    PCG_LAUNCH(gather_points_kernel, div_up(padded, 256), 256, 0, stream, v, vv[res], ix->pts, (uint32_t)padded);
+    PCG_LAUNCH(leaf_boxes_kernel, div_up(P, 256), 256, 0, stream, ix->pts, ix->boxes, ix->leaves, P);
+    if (P >= 512) PCG_LAUNCH(top_boxes_kernel, 1, 1024, 0, stream, ix->boxes, P);
+  } catch (...) {
+    index_free(ix);
+    throw;
+  }
+  return ix;
+}
+
+void index_free(Index* ix) {
+  if (!ix) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(ix->device);
+  if (ix->pts) cudaFree(ix->pts);
+  if (ix->boxes) cudaFree(ix->boxes);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete ix;
+}
+
+// ---- KDTree.Nearest, batched (kdtree.go:83-92) -----------------------------------------
+__global__ void __launch_bounds__(128)
+    nearest_kernel(IndexView ix, CloudView q, float max_range_sq, int32_t* __restrict__ ids,
+                   float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n) return;
+  float3 p = load_xyz(q, i);
+  uint64_t best = nn_init(max_range_sq);
+  const uint64_t init = best;
+  uint32_t pos = 0;
+  nn_traverse(ix, p.x, p.y, p.z, best, pos);
+  const bool hit = best != init;
+  const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
+  const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
+  if (ids) {
+    ids[i] = id;
+    dist_sq[i] = d;
+  }
+  if (aos) {
+    pcg_neighbor nb;
+    nb.id = (int64_t)id;
+    nb.dist_sq = d;
+    nb.pad_ = 0;
+    aos[i] = nb;
+  }
+}
+
+void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_t* d_ids, float* d_dist_sq,
+                    pcg_neighbor* d_aos, cudaStream_t stream) {
+  if (q.n == 0) return;
+  const float mrsq = max_range * max_range;  // kdtree.go:91
+  PCG_LAUNCH(nearest_kernel, div_up(q.n, 128), 128, 0, stream, ix.view(), q, mrsq, d_ids, d_dist_sq, d_aos);
+}
+
+// ---- KDTree.Range, batched (kdtree.go:148-197) -----------------------------------------
+__global__ void __launch_bounds__(128)
+    range_count_kernel(IndexView ix, CloudView q, float max_range_sq, uint32_t* __restrict__ counts) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n) return;
+  float3 p = load_xyz(q, i);
+  uint32_t c = 0;
+  range_traverse(ix, p.x, p.y, p.z, max_range_sq, [&](uint32_t, float) { c++; });
+  counts[i] = c;
+}
+
+__global__ void __launch_bounds__(128)
+    range_fill_kernel(IndexView ix, CloudView q, float max_range_sq, const long long* __restrict__ offsets,
+                      unsigned long long* __restrict__ packed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n) return;
+  float3 p = load_xyz(q, i);
+  unsigned long long* dst = packed + offsets[i];
+  range_traverse(ix, p.x, p.y, p.z, max_range_sq, [&](uint32_t id, float d) {
+    *dst++ = ((unsigned long long)__float_as_uint(d) << 32) | id;
+  });
+}
+
+// exclusive scan uint32 counts -> int64 offsets (n+1 entries), decoupled look-back
+constexpr int kScanItems = 8;
+constexpr int kScanTile = 256 * kScanItems;
+__global__ void __launch_bounds__(256)
+    scan_counts_kernel(const uint32_t* __restrict__ counts, long long* __restrict__ offsets, uint32_t n,
+                       uint32_t* __restrict__ tile_counter, unsigned long long* __restrict__ status) {
+  __shared__ uint32_t s_scan[rsort::kWarps];
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_prefix;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kScanTile + tid * kScanItems;
+  uint32_t c[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    c[j] = (base + j < n) ? counts[base + j] : 0u;
+    sum += c[j];
+  }
+  uint32_t total = 0;
+  uint32_t excl = rsort::block_excl_scan_256(sum, s_scan, &total);
+  if (tid == 0) {
+    volatile unsigned long long* st = status;
+    unsigned long long prefix = 0;
+    if (tile == 0) {
+      st[0] = (2ull << 62) | (unsigned long long)total;
+    } else {
+      st[tile] = (1ull << 62) | (unsigned long long)total;
+      int64_t prev = (int64_t)tile - 1;
+      for (;;) {
+        unsigned long long w = st[prev];
+        unsigned long long state = w >> 62;
+        if (state == 0) continue;
+        prefix += w & ((1ull << 62) - 1);
+        if (state == 2) break;
+        prev--;
+      }
+      st[tile] = (2ull << 62) | (prefix + total);
+    }
+    s_prefix = prefix;
+    if ((uint64_t)(tile + 1) * kScanTile >= n) offsets[n] = (long long)(prefix + total);
+  }
+  __syncthreads();
+  unsigned long long run = s_prefix + excl;
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    if (base + j < n) offsets[base + j] = (long long)run;
+    run += c[j];
+  }
+}
+
+// Per-query sort of packed (DistSq bits << 32 | ID): ascending == (DistSq, ID) order.
+// Lists of up to kSortSmem entries are bitonic-sorted in shared memory, longer ones in
+// place in global memory by the same CTA.
+constexpr int kSortThreads = 128;
+constexpr int kSortSmem = 2048;
+
+__device__ __forceinline__ void bitonic_sort(unsigned long long* a, uint32_t len_pow2, uint32_t tid,
+                                             uint32_t nthreads) {
+  for (uint32_t k = 2; k <= len_pow2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = tid; i < len_pow2; i += nthreads) {
+        uint32_t l = i ^ j;
+        if (l > i) {
+          unsigned long long x = a[i], y = a[l];
+          bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            a[i] = y;
+            a[l] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+    range_sort_kernel(const long long* __restrict__ offsets, unsigned long long* __restrict__ packed,
+                      unsigned long long* __restrict__ scratch, const long long* __restrict__ scratch_off) {
+  __shared__ unsigned long long s[kSortSmem];
+  const long long b = offsets[blockIdx.x], e = offsets[blockIdx.x + 1];
+  const uint32_t len = (uint32_t)(e - b);
+  if (len <= 1) return;
+  uint32_t p2 = 1;
+  while (p2 < len) p2 <<= 1;
+  unsigned long long* a;
+  if (p2 <= kSortSmem) {
+    a = s;
+  } else {
+    a = scratch + scratch_off[blockIdx.x];
+  }
+  for (uint32_t i = threadIdx.x; i < p2; i += kSortThreads) a[i] = i < len ? packed[b + i] : ~0ull;
+  __syncthreads();
+  bitonic_sort(a, p2, threadIdx.x, kSortThreads);
+  for (uint32_t i = threadIdx.x; i < len; i += kSortThreads) packed[b + i] = a[i];
+}
+
+// scratch sizes for lists longer than kSortSmem (rounded up to a power of two), else 0
+__global__ void __launch_bounds__(256)
+    range_scratch_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ need, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t len = counts[i], p2 = 1;
+  while (p2 < len) p2 <<= 1;
+  need[i] = p2 > (uint32_t)kSortSmem ? p2 : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+    range_unpack_kernel(const unsigned long long* __restrict__ packed, pcg_neighbor* __restrict__ out, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  unsigned long long w = packed[i];
+  pcg_neighbor nb;
+  nb.id = (int64_t)(uint32_t)w;
+  nb.dist_sq = __uint_as_float((uint32_t)(w >> 32));
+  nb.pad_ = 0;
+  out[i] = nb;
+}
+
+static void scan_counts(const uint32_t* counts, long long* offsets, uint32_t n, cudaStream_t stream) {
+  const int tiles = std::max(1, div_up(n, kScanTile));
+  DevBuf<unsigned long long> status((size_t)tiles + 1, stream);
+  PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
+  PCG_LAUNCH(scan_counts_kernel, tiles, 256, 0, stream, counts, offsets, n, (uint32_t*)(status.p + tiles), status.p);
+}
+
+// Returns device CSR: offsets (nq+1) and neighbours (total), sorted per query. Synchronises.
+void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                  DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream) {
+  const uint32_t nq = (uint32_t)q.n;
+  const float mrsq = max_range * max_range;  // kdtree.go:157
+  offsets.alloc((size_t)nq + 1, stream);
+  *total_out = 0;
+  if (nq == 0) {
+    PCG_CUDA(cudaMemsetAsync(offsets.p, 0, sizeof(long long), stream));
+    PCG_CUDA(cudaStreamSynchronize(stream));
+    return;
+  }
+  DevBuf<uint32_t> counts(nq, stream), need(nq, stream);
+  DevBuf<long long> scratch_off((size_t)nq + 1, stream);
+  PCG_LAUNCH(range_count_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, counts.p);
+  scan_counts(counts.p, offsets.p, nq, stream);
+  PCG_LAUNCH(range_scratch_kernel, div_up(nq, 256), 256, 0, stream, counts.p, need.p, nq);
+  scan_counts(need.p, scratch_off.p, nq, stream);
+  long long totals[2] = {0, 0};
+  PCG_CUDA(cudaMemcpyAsync(&totals[0], offsets.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaMemcpyAsync(&totals[1], scratch_off.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  const long long total = totals[0];
+  *total_out = total;
+  if (total == 0) return;
+  DevBuf<unsigned long long> packed((size_t)total, stream);
+  DevBuf<unsigned long long> scratch((size_t)std::max<long long>(1, totals[1]), stream);
+  PCG_LAUNCH(range_fill_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, offsets.p, packed.p);
+  PCG_LAUNCH(range_sort_kernel, nq, kSortThreads, 0, stream, offsets.p, packed.p, scratch.p, scratch_off.p);
+  out.alloc((size_t)total, stream);
+  PCG_LAUNCH(range_unpack_kernel, div_up(total, 256), 256, 0, stream, packed.p, out.p, total);
+  PCG_CUDA(cudaStreamSynchronize(stream));
+}
+
+}  // namespace pcg

@@ -1,0 +1,264 @@
+// radix_sort.cuh — stable LSD radix sort of (key, uint32 payload) pairs, hand-written
+// for sm_100a.  One upfront kernel histograms every digit position; each 8-bit pass is
+// then a single "onesweep" kernel: tiles are ranked in shared memory with warp
+// match-any multi-split, the per-tile digit counts are chained between CTAs by
+// decoupled look-back (one packed 64-bit status word per tile and digit, so no fence
+// is needed between flag and value), and keys are staged in shared memory so that the
+// scatter writes coalesced runs.  Stability (equal keys keep input order) is what makes
+// the VoxelGrid centroid sums reproduce the reference's accumulation order.
+#pragma once
+
+#include "common.cuh"
+
+namespace pcg {
+namespace rsort {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kThreads = 256;  // one thread per digit for the look-back
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxPasses = 8;
+
+constexpr uint64_t kValueMask = (1ull << 54) - 1;
+constexpr int kEpochShift = 54;
+constexpr int kStateShift = 62;
+constexpr uint64_t kStateAggregate = 1ull;
+constexpr uint64_t kStateInclusive = 2ull;
+
+template <typename K>
+__device__ __forceinline__ uint32_t digit_of(K k, int shift) {
+  return (uint32_t)(k >> shift) & (kRadix - 1);
+}
+
+// All digit histograms in one read of the keys (the per-position histogram of a
+// multiset does not depend on its order, so it is valid for every later pass).
+template <typename K>
+__global__ void __launch_bounds__(256) histogram_kernel(const K* __restrict__ keys, uint32_t n, int begin_bit,
+                                                        int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kMaxPasses * kRadix];
+  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    K k = keys[i];
+    for (int p = 0; p < passes; p++) atomicAdd(&sh[p * kRadix + digit_of(k, begin_bit + p * kRadixBits)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+    uint32_t c = sh[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// Exclusive scan of one value per thread across a 256-thread block.
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_warp /*[kWarps]*/, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    uint32_t c = s_warp[w];
+    if (w < (int)warp) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  if (total) *total = tot;
+  return base + incl - v;
+}
+
+template <typename K, int IPT>
+struct TileSmem {
+  static constexpr int kTile = kThreads * IPT;
+  static constexpr size_t kBytes = (size_t)kTile * (sizeof(K) + sizeof(uint32_t));
+};
+
+template <typename K, int IPT>
+__global__ void __launch_bounds__(kThreads)
+    onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
+                    uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t epoch,
+                    const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_counter,
+                    unsigned long long* __restrict__ status) {
+  constexpr int kTile = kThreads * IPT;
+  __shared__ uint32_t s_warp_hist[kWarps][kRadix];
+  __shared__ uint32_t s_digit_start[kRadix];
+  __shared__ uint32_t s_global_base[kRadix];
+  __shared__ uint32_t s_scan[kWarps];
+  __shared__ uint32_t s_tile;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  K* s_keys = reinterpret_cast<K*>(s_dyn);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_dyn + (size_t)kTile * sizeof(K));
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // dynamic tile id: predecessors are always running
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) s_warp_hist[w][tid] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_base = tile * (uint32_t)kTile;
+  const uint32_t warp_base = tile_base + warp * (32u * IPT);
+
+  K keys[IPT];
+  uint32_t vals[IPT];
+  uint32_t offs[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    uint32_t idx = warp_base + i * 32 + lane;
+    bool valid = idx < n;
+    keys[i] = valid ? keys_in[idx] : (K)~(K)0;
+    vals[i] = vals_in ? (valid ? vals_in[idx] : 0u) : idx;
+  }
+  // Rank inside the warp: items are visited in index order (i major, lane minor).
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    uint32_t idx = warp_base + i * 32 + lane;
+    bool valid = idx < n;
+    uint32_t d = valid ? digit_of(keys[i], shift) : (uint32_t)kRadix;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    int leader = __ffs(peers) - 1;
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t pre = 0;
+    if (valid && (int)lane == leader) {
+      pre = s_warp_hist[warp][d];
+      s_warp_hist[warp][d] = pre + __popc(peers);
+    }
+    pre = __shfl_sync(0xffffffffu, pre, leader);
+    offs[i] = pre + rank;
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // Thread t owns digit t: scan the warp histograms (warp order == index order).
+  uint32_t count = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    uint32_t c = s_warp_hist[w][tid];
+    s_warp_hist[w][tid] = count;
+    count += c;
+  }
+
+  // Decoupled look-back over predecessor tiles for this digit.
+  {
+    volatile unsigned long long* st = status;
+    const uint64_t tag = (uint64_t)epoch << kEpochShift;
+    uint64_t excl = 0;
+    const size_t mine = (size_t)tile * kRadix + tid;
+    if (tile == 0) {
+      st[mine] = (kStateInclusive << kStateShift) | tag | (uint64_t)count;
+    } else {
+      st[mine] = (kStateAggregate << kStateShift) | tag | (uint64_t)count;
+      int64_t prev = (int64_t)tile - 1;
+      for (;;) {
+        uint64_t w = st[(size_t)prev * kRadix + tid];
+        uint64_t state = w >> kStateShift;
+        if (state == 0 || ((w >> kEpochShift) & 0xffu) != epoch) continue;  // not published yet for this pass
+        excl += w & kValueMask;
+        if (state == kStateInclusive) break;
+        prev--;
+      }
+      st[mine] = (kStateInclusive << kStateShift) | tag | (excl + count);
+    }
+    uint32_t digit_base = block_excl_scan_256(hist[tid], s_scan, nullptr);
+    s_global_base[tid] = digit_base + (uint32_t)excl;
+  }
+  s_digit_start[tid] = block_excl_scan_256(count, s_scan, nullptr);
+  __syncthreads();
+
+  // Stage the tile in digit order, then write coalesced runs.
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    uint32_t idx = warp_base + i * 32 + lane;
+    if (idx < n) {
+      uint32_t d = digit_of(keys[i], shift);
+      uint32_t pos = s_digit_start[d] + s_warp_hist[warp][d] + offs[i];
+      s_keys[pos] = keys[i];
+      s_vals[pos] = vals[i];
+    }
+  }
+  __syncthreads();
+  const uint32_t tile_count = min((uint32_t)kTile, n - tile_base);
+  for (uint32_t s = tid; s < tile_count; s += kThreads) {
+    K k = s_keys[s];
+    uint32_t d = digit_of(k, shift);
+    uint32_t dst = s_global_base[d] + (s - s_digit_start[d]);
+    if (keys_out) keys_out[dst] = k;
+    vals_out[dst] = s_vals[s];
+  }
+}
+
+inline int num_passes(int begin_bit, int end_bit) {
+  int bits = end_bit - begin_bit;
+  return bits <= 0 ? 0 : (bits + kRadixBits - 1) / kRadixBits;
+}
+
+template <typename K, int IPT>
+inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, int shift,
+                        uint32_t epoch, const uint32_t* hist, uint32_t* counter, unsigned long long* status,
+                        cudaStream_t stream) {
+  constexpr size_t smem = TileSmem<K, IPT>::kBytes;
+  static std::atomic<uint64_t> configured{0};  // bit per device; the attribute is per device
+  int dev = 0;
+  PCG_CUDA(cudaGetDevice(&dev));
+  if (!(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
+    PCG_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured.fetch_or(1ull << dev, std::memory_order_relaxed);
+  }
+  uint32_t tiles = (n + TileSmem<K, IPT>::kTile - 1) / TileSmem<K, IPT>::kTile;
+  PCG_LAUNCH((onesweep_kernel<K, IPT>), tiles, kThreads, smem, stream, kin, kout, vin, vout, n, shift, epoch, hist,
+             counter, status);
+}
+
+// Sorts n (key, payload) pairs by key bits [begin_bit, end_bit), stable.
+// keys[0]/vals[0] hold the input; the pair of buffers is ping-ponged and *result
+// (0 or 1) tells which one holds the output.  identity_vals: the payload is the input
+// position (vals[0] is not read).  keep_keys=false skips the key write of the last pass.
+template <typename K>
+void sort_pairs(K* keys[2], uint32_t* vals[2], uint32_t n, int begin_bit, int end_bit, bool identity_vals,
+                bool keep_keys, cudaStream_t stream, int* result) {
+  int passes = num_passes(begin_bit, end_bit);
+  *result = 0;
+  if (n == 0) return;
+  if (passes == 0) passes = 1;  // degenerate range: one pass over (all-equal) digits keeps the order
+  if (passes > kMaxPasses) throw StatusError{PCG_E_INVALID_ARG, "radix sort: more than 64 key bits"};
+  const bool small = n <= (1u << 18);
+  const uint32_t tile = small ? (uint32_t)TileSmem<K, 4>::kTile : (uint32_t)TileSmem<K, 16>::kTile;
+  const uint32_t tiles = (n + tile - 1) / tile;
+  const int eff_passes = passes;
+  // workspace: hist[passes][256] | counters[passes] (padded) | status[tiles][256]
+  const size_t hist_words = (size_t)eff_passes * kRadix;
+  const size_t head_words = hist_words + 64;
+  DevBuf<uint32_t> head(head_words, stream);
+  DevBuf<unsigned long long> status((size_t)tiles * kRadix, stream);
+  PCG_CUDA(cudaMemsetAsync(head.p, 0, head.bytes(), stream));
+  PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
+  {
+    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 8, div_up(n, 256 * 4));
+    PCG_LAUNCH((histogram_kernel<K>), blocks, 256, 0, stream, keys[0], n, begin_bit, eff_passes, head.p);
+  }
+  int cur = 0;
+  for (int p = 0; p < eff_passes; p++) {
+    const int shift = begin_bit + p * kRadixBits;
+    const bool last = p == eff_passes - 1;
+    const K* kin = keys[cur];
+    K* kout = (last && !keep_keys) ? nullptr : keys[cur ^ 1];
+    const uint32_t* vin = (p == 0 && identity_vals) ? nullptr : vals[cur];
+    uint32_t* vout = vals[cur ^ 1];
+    if (small)
+      launch_pass<K, 4>(kin, kout, vin, vout, n, shift, (uint32_t)(p + 1), head.p + (size_t)p * kRadix,
+                        head.p + hist_words + p, status.p, stream);
+    else
+      launch_pass<K, 16>(kin, kout, vin, vout, n, shift, (uint32_t)(p + 1), head.p + (size_t)p * kRadix,
+                         head.p + hist_words + p, status.p, stream);
+    cur ^= 1;
+  }
+  *result = cur;
+}
+
+}  // namespace rsort
+}  // namespace pcg

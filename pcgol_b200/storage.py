@@ -1,0 +1,115 @@
+"""storage.Search on the GPU (pc/storage/search.go:13-17, replaces pc/storage/kdtree).
+
+`Index` keeps the host accessor for Vec3At/Len/RawIndexAt and owns the device index;
+Nearest/Range for one point are batch-of-one calls, NearestBatch/RangeBatch are the
+calls the hot path uses.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from .pc import as_vec3_buffer
+
+
+@dataclass
+class Neighbor:  # storage.Neighbor
+    id: int
+    dist_sq: float
+
+
+def _off(off):
+    return (C.c_int64 * 3)(*[int(o) for o in off])
+
+
+class Index:
+    """kdtree.New(ra) replacement: `Index(cloud)` where cloud is a PointCloud or (n,3) float32."""
+
+    def __init__(self, cloud, device: int = 0):
+        data, n, stride, off = as_vec3_buffer(cloud)
+        self._cloud = cloud
+        self._xyz = None
+        self.device = device
+        self._h = C.c_void_p()
+        self._keep = data
+        _lib.check(_lib.lib.pcg_index_build(data.ctypes.data, n, stride, _off(off), device, C.byref(self._h)))
+
+    @classmethod
+    def from_device(cls, d_ptr: int, n: int, stride: int = 12, off=(0, 4, 8), device: int = 0, stream: int = 0):
+        self = cls.__new__(cls)
+        self._cloud = None
+        self._xyz = None
+        self.device = device
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib.pcg_index_build_dev(d_ptr, n, stride, _off(off), device, stream, C.byref(self._h)))
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib.pcg_index_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- pc.Vec3RandomAccessor ------------------------------------------------
+    def __len__(self) -> int:  # Len
+        return int(_lib.lib.pcg_index_len(self._h))
+
+    def vec3_at(self, i: int) -> np.ndarray:  # Vec3At
+        if self._xyz is None:
+            from .pc import PointCloud
+            self._xyz = self._cloud.xyz() if isinstance(self._cloud, PointCloud) else np.asarray(
+                self._cloud, np.float32).reshape(-1, 3)
+        return self._xyz[i]
+
+    def raw_index_at(self, i: int) -> int:  # RawIndexAt
+        return i
+
+    def device_bytes(self) -> int:
+        return int(_lib.lib.pcg_index_device_bytes(self._h))
+
+    # -- storage.Search ---------------------------------------------------------
+    def nearest(self, p, max_range: float) -> Neighbor:  # Search.Nearest
+        ids, dsq = self.nearest_batch(np.asarray(p, np.float32).reshape(1, 3), max_range)
+        return Neighbor(int(ids[0]), float(dsq[0]))
+
+    def range(self, p, max_range: float) -> List[Neighbor]:  # Search.Range
+        off, ids, dsq = self.range_batch(np.asarray(p, np.float32).reshape(1, 3), max_range)
+        return [Neighbor(int(i), float(d)) for i, d in zip(ids, dsq)]
+
+    def nearest_batch(self, queries, max_range: float) -> Tuple[np.ndarray, np.ndarray]:
+        """(ids int64[nq], dist_sq float32[nq]); miss = (-1, max_range**2)."""
+        data, n, stride, off = as_vec3_buffer(queries)
+        out = np.empty(max(n, 1), dtype=np.dtype([("id", "<i8"), ("dist_sq", "<f4"), ("pad", "<u4")]))
+        _lib.check(_lib.lib.pcg_index_nearest(self._h, data.ctypes.data, n, stride, _off(off), max_range,
+                                             out.ctypes.data))
+        return out["id"][:n].copy(), out["dist_sq"][:n].copy()
+
+    def nearest_dev(self, d_q: int, nq: int, max_range: float, d_ids: int, d_dist_sq: int, stream: int = 0,
+                    stride: int = 12, off=(0, 4, 8)):
+        _lib.check(_lib.lib.pcg_index_nearest_dev(self._h, d_q, nq, stride, _off(off), max_range, d_ids, d_dist_sq,
+                                                 stream))
+
+    def range_batch(self, queries, max_range: float):
+        """CSR (offsets int64[nq+1], ids int64[total], dist_sq float32[total]), lists in (DistSq, ID) order."""
+        data, n, stride, off = as_vec3_buffer(queries)
+        r = C.c_void_p()
+        _lib.check(_lib.lib.pcg_index_range(self._h, data.ctypes.data, n, stride, _off(off), max_range, C.byref(r)))
+        try:
+            total = int(_lib.lib.pcg_range_total(r))
+            offs = np.ctypeslib.as_array(C.cast(_lib.lib.pcg_range_offsets(r), C.POINTER(C.c_int64)),
+                                         shape=(n + 1,)).copy()
+            if total:
+                nb = np.ctypeslib.as_array(C.cast(_lib.lib.pcg_range_neighbors(r), C.POINTER(C.c_uint8)),
+                                           shape=(total * 16,)).copy()
+                nb = nb.view(np.dtype([("id", "<i8"), ("dist_sq", "<f4"), ("pad", "<u4")]))
+                ids, dsq = nb["id"].copy(), nb["dist_sq"].copy()
+            else:
+                ids, dsq = np.empty(0, np.int64), np.empty(0, np.float32)
+        finally:
+            _lib.lib.pcg_range_free(r)
+        return offs, ids, dsq

@@ -1,0 +1,381 @@
+"""Parity of the CUDA path (through the C ABI / host mirror) against the CPU oracle.
+Integer / index / byte results must be bit-exact; float tolerances are stated where used."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import pcgol_b200
+
+    assert pcgol_b200.device_count() >= 1, "GPU tests need a CUDA device"
+    return pcgol_b200
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from pcgol_b200 import synth as s
+
+    return s
+
+
+def _cloud(pg, data, stride, names):
+    hdr = pg.PointCloudHeader(fields=list(names), size=[4] * len(names), type=["F"] * len(names),
+                              count=[1] * len(names), width=len(data) // stride)
+    return pg.PointCloud(hdr, data)
+
+
+# ------------------------------------------------------------- VoxelGrid ------
+def test_voxelgrid_reference_golden(pg):
+    # pc/filter/voxelgrid/voxelgrid_test.go:12-110
+    from tests.test_oracle_golden import VG_CASES, _vg_cloud
+
+    rec = _vg_cloud()
+    for name, (chunk, exp_pts, exp_labels) in VG_CASES.items():
+        pp = _cloud(pg, rec.view(np.uint8), 16, ["x", "y", "z", "label"])
+        out = pg.VoxelGrid((0.125, 0.125, 0.125), chunk).filter(pp)
+        assert out.points == len(exp_pts), name
+        assert out.header.width == len(exp_pts) and out.header.height == 1
+        xyz = out.xyz()
+        for i, e in enumerate(exp_pts):
+            assert tuple(xyz[i]) == (f32(e[0]), f32(e[1]), f32(e[2])), name  # Vec3.Equal
+        assert out.field_u32("label").tolist() == exp_labels, name
+
+
+def test_voxelgrid_errors(pg):
+    with pytest.raises(pg.NoPointError):  # pc/minmax.go:10-12
+        pg.VoxelGrid((0.1, 0.1, 0.1)).filter(pg.PointCloud.from_xyz(np.zeros((0, 3), f32)))
+    pts = np.array([[-5, -5, -5], [1, 1, 1], [0.9, 0.9, 0.9]], f32)
+    with pytest.raises(pg.ReferencePanic):  # voxelgrid.go:46: vMax passed as size
+        pg.VoxelGrid((0.1, 0.1, 0.1)).filter(pg.PointCloud.from_xyz(pts))
+    out = pg.VoxelGrid((0.1, 0.1, 0.1), (16, 16, 16)).filter(pg.PointCloud.from_xyz(pts))
+    assert out.points == 3
+
+
+@pytest.mark.parametrize("chunk", [(0, 0, 0), (4, 4, 4), (128, 128, 128), (7, 3, 5), (1, 1, 1)])
+@pytest.mark.parametrize("layout", [(12, (0, 4, 8)), (20, (4, 8, 12)), (28, (16, 0, 8)), (13, (1, 5, 9))])
+def test_voxelgrid_random_vs_oracle(pg, oracle, chunk, layout):
+    stride, off = layout
+    rng = np.random.default_rng(hash((chunk, layout)) % (2**32))
+    n = 20000
+    buf = rng.integers(0, 255, size=(n, stride), dtype=np.uint8)
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([4.0, 3.0, 1.5], f32)).astype(f32)
+    xyz -= xyz.min(axis=0)
+    for k in range(3):
+        buf[:, off[k]:off[k] + 4] = xyz[:, k:k + 1].copy().view(np.uint8)
+    leaf = (0.1, 0.07, 0.13)
+    rc, exp = oracle.voxelgrid_filter(buf, stride, off, leaf, chunk, mode="dense")
+    assert rc == oracle.OK
+    import ctypes as C
+
+    from pcgol_b200 import _lib
+    out = np.empty(n * stride, np.uint8)
+    n_out = C.c_int64(0)
+    flat = np.ascontiguousarray(buf).reshape(-1)
+    rc = _lib.lib.pcg_voxelgrid_filter(flat.ctypes.data, n, stride, (C.c_int64 * 3)(*off),
+                                       np.asarray(leaf, f32).ctypes.data, np.asarray(chunk, np.int64).ctypes.data, 0,
+                                       out.ctypes.data, C.byref(n_out))
+    assert rc == 0, _lib.last_error()
+    assert n_out.value * stride == len(exp)
+    assert out[: len(exp)].tobytes() == exp.tobytes()
+
+
+def test_voxelgrid_negative_coordinates_chunked(pg, oracle):
+    rng = np.random.default_rng(11)
+    xyz = (rng.standard_normal((30000, 3)) * np.array([5.0, 3.0, 0.5])).astype(f32)
+    buf = xyz.view(np.uint8).reshape(-1)
+    for chunk in [(32, 32, 32), (5, 9, 2)]:
+        rc, exp = oracle.voxelgrid_filter(buf, 12, (0, 4, 8), (0.2, 0.2, 0.2), chunk, mode="dense")
+        assert rc == oracle.OK
+        out = pg.VoxelGrid((0.2, 0.2, 0.2), chunk).filter(pg.PointCloud.from_xyz(xyz))
+        assert out.data.tobytes() == exp.tobytes()
+
+
+@pytest.mark.parametrize("chunk,mode", [((0, 0, 0), "sparse"), ((128, 128, 128), "dense")])
+def test_voxelgrid_config2_1m_points(pg, oracle, synth, chunk, mode):
+    # BASELINE config 2: 1M-point scan, leaf 0.05, xyz float32 (stride 12); bit-exact vs the oracle
+    scan = synth.lidar_scan(2, n_az=15625)
+    assert len(scan) == 1_000_000
+    buf = scan.view(np.uint8).reshape(-1)
+    rc, exp = oracle.voxelgrid_filter(buf, 12, (0, 4, 8), (0.05, 0.05, 0.05), chunk, mode=mode)
+    assert rc == oracle.OK
+    out = pg.VoxelGrid((0.05, 0.05, 0.05), chunk).filter(pg.PointCloud.from_xyz(scan))
+    assert out.points * 12 == len(exp)
+    assert out.data.tobytes() == exp.tobytes()
+    # size-independent properties: voxel membership recomputed with numpy float32
+    if chunk == (0, 0, 0):
+        vmin, vmax = scan.min(axis=0), scan.max(axis=0)
+        xs, ys, _ = ((vmax / f32(0.05)).astype(np.int64))
+        p = (scan - vmin).astype(f32)
+        c = (p / f32(0.05)).astype(np.int64)
+        key = c[:, 0] + xs * (c[:, 1] + ys * c[:, 2])
+        assert out.points == len(np.unique(key))
+
+
+# ------------------------------------------------------------- Nearest / Range ------
+def test_nearest_reference_golden(pg):
+    # pc/storage/kdtree/kdtree_test.go:162-246
+    from tests.test_oracle_golden import FIXTURE7, NEAREST_CASES
+
+    idx = pg.Index(FIXTURE7)
+    assert len(idx) == 7
+    for p, nid, dsq, mr in NEAREST_CASES:
+        nb = idx.nearest(p, mr)
+        assert nb.id == nid, (p, mr)
+        assert abs(nb.dist_sq - dsq) <= 1e-5
+    # miss == {ID:-1, DistSq: maxRange^2}  kdtree_test.go:223-228
+    nb = idx.nearest((4.2, 1, 0), 0.1)
+    assert nb.id == -1 and f32(nb.dist_sq) == f32(0.1) * f32(0.1)
+
+
+def test_range_reference_golden(pg):
+    # kdtree_test.go:281-386
+    from tests.test_oracle_golden import RANGE_CASES, RANGE_FIXTURE
+
+    idx = pg.Index(RANGE_FIXTURE)
+    for p, mr, exp in RANGE_CASES:
+        nbs = idx.range(p, mr)
+        assert [n.id for n in nbs] == [e[0] for e in exp]
+        for n, e in zip(nbs, exp):
+            assert abs(n.dist_sq - e[1]) <= 1e-5
+
+
+def test_empty_index(pg):
+    idx = pg.Index(np.zeros((0, 3), f32))  # kdtree.go:84-86,150-152
+    nb = idx.nearest((1, 2, 3), 0.5)
+    assert nb.id == -1 and f32(nb.dist_sq) == f32(0.25)
+    assert idx.range((1, 2, 3), 0.5) == []
+    ids, d = idx.nearest_batch(np.zeros((0, 3), f32), 1.0)
+    assert len(ids) == 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 63, 64, 65, 100, 2047, 2048, 2049, 5000])
+def test_nearest_random_vs_naive(pg, oracle, n):
+    # kdtree_test.go:794-834: ID and DistSq bit-equal to brute force
+    rng = np.random.default_rng(n)
+    pts = (rng.random((n, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((3000, 3), dtype=f32) * f32(12.0) - f32(1.0)).astype(f32)
+    idx = pg.Index(pts)
+    nv = oracle.Search(pts, "naive")
+    for mr in (0.05, 0.7, 3.0, 100.0, float("inf")):
+        ids, d = idx.nearest_batch(q, mr)
+        eids, ed = nv.nearest(q, mr)
+        assert np.array_equal(ids, eids), (n, mr)
+        assert d.tobytes() == ed.tobytes(), (n, mr)
+
+
+def test_nearest_ties_lowest_id(pg, oracle):
+    # lattice data: many exact DistSq ties; rule = lowest ID (the reference's brute-force oracle)
+    g = np.arange(12, dtype=f32)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(3)
+    pts = pts[rng.permutation(len(pts))]
+    pts = np.concatenate([pts, pts[:200]])  # exact duplicates too
+    q = (rng.integers(0, 23, size=(4000, 3)).astype(f32) * f32(0.5))
+    ids, d = pg.Index(pts).nearest_batch(q, 5.0)
+    eids, ed = oracle.Search(pts, "naive").nearest(q, 5.0)
+    assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+
+
+def test_nearest_max_range_boundary_is_strict(pg, oracle):
+    pts = np.array([[0, 0, 0], [3, 0, 0]], f32)
+    idx = pg.Index(pts)
+    assert idx.nearest((1, 0, 0), 1.0).id == -1          # DistSq == maxRange^2 is a miss (naive rule)
+    assert idx.nearest((1, 0, 0), 1.0000001).id == 0
+    assert [n.id for n in idx.range((1, 0, 0), 2.0)] == [0]  # strict '<' (kdtree.go:167,179)
+
+
+def test_nearest_nonfinite_inputs(pg, oracle):
+    pts = np.array([[0, 0, 0], [np.nan, 1, 1], [np.inf, 0, 0], [2, 2, 2]], f32)
+    q = np.array([[0.1, 0, 0], [np.nan, 0, 0], [2, 2, 2.5], [np.inf, 0, 0]], f32)
+    ids, d = pg.Index(pts).nearest_batch(q, 10.0)
+    eids, ed = oracle.Search(pts, "naive").nearest(q, 10.0)
+    assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+
+
+def test_nearest_lidar_vs_kdtree_restatement(pg, oracle, synth):
+    base = synth.lidar_scan(0)
+    q = synth.nn_queries(base, 200_000, seed=3)
+    ids, d = pg.Index(base).nearest_batch(q, 1.0)
+    eids, ed = oracle.Search(base, "kdtree").nearest(q, 1.0, threads=8)
+    diff = np.flatnonzero(ids != eids)
+    # KD-tree tie/boundary behaviour is traversal dependent (SURVEY finding 3): any mismatch must be an exact tie
+    assert d.tobytes() == ed.tobytes()
+    assert len(diff) == 0, f"{len(diff)} id mismatches (ties)"
+
+
+def test_nearest_strided_queries(pg, oracle):
+    rng = np.random.default_rng(8)
+    pts = (rng.random((3000, 3), dtype=f32) * f32(5.0)).astype(f32)
+    nq, stride, off = 1000, 24, (8, 12, 16)
+    rec = rng.integers(0, 255, size=(nq, stride), dtype=np.uint8)
+    q = (rng.random((nq, 3), dtype=f32) * f32(5.0)).astype(f32)
+    rec[:, 8:20] = q.view(np.uint8).reshape(nq, 12)
+    hdr = pg.PointCloudHeader(fields=["a", "b", "x", "y", "z", "c"], size=[4] * 6, type=["F"] * 6, count=[1] * 6)
+    ids, d = pg.Index(pts).nearest_batch(pg.PointCloud(hdr, rec.reshape(-1)), 0.5)
+    eids, ed = oracle.Search(pts, "naive").nearest(q, 0.5)
+    assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+
+
+@pytest.mark.parametrize("n", [5, 100, 4000])
+def test_range_random_vs_naive(pg, oracle, n):
+    # kdtree_test.go:887-924 with the canonical (DistSq, ID) order of :926-941
+    rng = np.random.default_rng(100 + n)
+    pts = (rng.random((n, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((500, 3), dtype=f32) * f32(10.0)).astype(f32)
+    idx = pg.Index(pts)
+    nv = oracle.Search(pts, "naive")
+    for mr in (0.3, 1.5, 4.0):
+        off, ids, d = idx.range_batch(q, mr)
+        eoff, eids, ed = nv.range(q, mr)
+        assert np.array_equal(off, eoff)
+        assert np.array_equal(ids, eids)
+        assert d.tobytes() == ed.tobytes()
+
+
+def test_range_long_lists(pg, oracle):
+    # lists longer than the shared-memory sort tile (2048) take the global-memory path
+    rng = np.random.default_rng(5)
+    pts = (rng.random((20000, 3), dtype=f32)).astype(f32)
+    q = np.array([[0.5, 0.5, 0.5], [0.1, 0.1, 0.1], [2, 2, 2]], f32)
+    off, ids, d = pg.Index(pts).range_batch(q, 0.6)
+    eoff, eids, ed = oracle.Search(pts, "naive").range(q, 0.6)
+    assert off[1] - off[0] > 2048
+    assert np.array_equal(off, eoff) and np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+
+
+# ------------------------------------------------------------------- ICP ------
+def test_corresponder_reference_golden(pg):
+    # pc/registration/icp/correspondence_test.go:12-37
+    base = np.array([[4, 1, 0], [1, 1, 0], [8, 1, 1], [-5, 0, 1], [0, 1, 0]], f32)
+    tgt = np.array([[8, 1, 1], [-8, 1, 1], [2, 1, 0]], f32)
+    b, t, d = pg.NearestPointCorresponder(3.0).pairs(pg.Index(base), tgt)
+    assert b.tolist() == [2, 1] and t.tolist() == [0, 2] and d.tolist() == [0.0, 1.0]
+
+
+@pytest.mark.parametrize("mode", ["STRICT", "FAST"])
+def test_evaluator_reference_golden(pg, oracle, mode):
+    # pc/registration/icp/evaluator_test.go:11-77
+    base = np.array([[0, 0, 0], [1, 1, 0], [2, 2, 0], [3, 1, 1], [4, 0, 0]], f32)
+    delta = np.array([0.25, 0.125, -0.125], f32)
+    target = (base[2:5] + delta).astype(f32)
+    idx = pg.Index(base)
+    e = pg.PointToPointEvaluator(pg.NearestPointCorresponder(2.0), min_pairs=3, mode=getattr(pg, mode))
+    ev = e.evaluate(idx, target)
+    assert ev.value == f32(oracle.norm_sq(delta))  # exact (evaluator_test.go:40-42)
+    rc, oev, _ = oracle.icp_evaluate(oracle.Search(base, "kdtree"), target, 2.0, 3)
+    got = np.concatenate([[ev.value], ev.gradient, [ev.dist_rms]]).astype(f32)
+    assert got.tobytes() == oev.tobytes()
+    assert not e.has_hessian() and np.all(ev.hessian == 0)
+    with pytest.raises(pg.ErrNotEnoughPairs):  # MinPairs 0 -> 6 (evaluator.go:92-106)
+        pg.PointToPointEvaluator(pg.NearestPointCorresponder(2.0)).evaluate(idx, target)
+
+
+@pytest.mark.parametrize("zoff", [0.0, 5.0])
+def test_icp_fit_reference_golden(pg, oracle, zoff):
+    # pc/registration/icp/icp_test.go:13-98 (exact NN instead of MinDistSq=0.01): residual <= 0.05,
+    # and the whole trajectory equals the oracle run with exact search
+    from tests.test_oracle_golden import _icp_deltas
+
+    base = np.array([[-2.1, 0, 0], [-1, 1, 0], [0, 2, 0], [1, 1, 1], [2, 0, 0]], f32)
+    base[:, 2] += f32(zoff)
+    indices = [3, 1, 4, 0, 2]
+    idx = pg.Index(base)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(2.0), min_pairs=3))
+    for name, delta in _icp_deltas(oracle).items():
+        target = oracle.mat4_transform(delta, base[indices])
+        trans, stat = icp.fit(idx, target)
+        rc, etrans, eev, eit = oracle.icp_fit(oracle.Search(base, "naive"), target, oracle.icp_params(2.0, 3))
+        assert rc == oracle.OK
+        assert stat.num_iteration == eit, name
+        assert trans.tobytes() == etrans.tobytes(), name
+        moved = oracle.mat4_transform(trans, target)
+        residual = np.mean([oracle.norm_sq((moved[i] - base[j]).astype(f32)) for i, j in enumerate(indices)])
+        assert 0.05 >= residual, (name, residual)
+
+
+def test_icp_fit_not_enough_pairs_returns_partial(pg):
+    base = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0]], f32)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(0.5)))
+    with pytest.raises(pg.ErrNotEnoughPairs) as ei:
+        icp.fit(pg.Index(base), base + f32(10))
+    assert ei.value.stat.num_iteration == 1  # icp.go:50-53
+    assert ei.value.trans.tolist() == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+
+
+@pytest.mark.parametrize("n", [3000, 20000])
+def test_icp_fit_strict_bit_exact_lidar(pg, oracle, synth, n):
+    base, target = synth.icp_pair(seed=1, n=n, n_az=400)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+    trans, stat = icp.fit(pg.Index(base), target)
+    rc, etrans, eev, eit = oracle.icp_fit(oracle.Search(base, "kdtree"), target, oracle.icp_params(1.0))
+    assert rc == oracle.OK
+    assert stat.num_iteration == eit
+    got_ev = np.concatenate([[stat.evaluated.value], stat.evaluated.gradient, [stat.evaluated.dist_rms]]).astype(f32)
+    assert got_ev.tobytes() == eev.tobytes()
+    assert trans.tobytes() == etrans.tobytes()
+
+
+def test_icp_benchmark_harness_config(pg, oracle):
+    # pc/registration/icp/icp_test.go:100-142 at 4096 points: 10 forced iterations (Threshold -1)
+    n = 4096
+    width = int(np.sqrt(n))
+    res = f32(10.0) / f32(width)
+    i = np.arange(n)
+    base = np.zeros((n, 3), f32)
+    base[:, 0] = res * (i // width).astype(f32) - f32(5)
+    base[:, 1] = res * (i % width).astype(f32) - f32(5)
+    inside = (np.abs(base[:, 0]) < 1) & (np.abs(base[:, 1]) < 1)
+    base[inside, 2] = 1
+    target = (base + np.array([0.5, 0.3, -0.2], f32)).astype(f32)
+    uf = pg.GradientDescentUpdaterFactory(threshold=(-1,) * 6, max_iteration=10)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(2.0), min_pairs=3), uf)
+    trans, stat = icp.fit(pg.Index(base), target)
+    assert stat.num_iteration == 10
+    # lattice data has exact distance ties: the GPU rule (lowest ID) equals the brute-force oracle
+    rc, etrans, _, eit = oracle.icp_fit(oracle.Search(base, "naive"), target,
+                                        oracle.icp_params(2.0, 3, threshold=(-1,) * 6, max_iteration=10))
+    assert eit == 10 and trans.tobytes() == etrans.tobytes()
+
+
+def test_icp_fast_mode_close_to_f64_oracle(pg, oracle, synth):
+    base, target = synth.icp_pair(seed=2, n=20000, n_az=400)
+    e = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST)
+    idx = pg.Index(base)
+    ev = e.evaluate(idx, target)
+    rc, oev, _ = oracle.icp_evaluate(oracle.Search(base, "kdtree"), target, 1.0, 0, f64_accumulate=True)
+    got = np.concatenate([[ev.value], ev.gradient, [ev.dist_rms]]).astype(np.float64)
+    # one Evaluate on identical inputs: float64 tree vs float64 sequential, rounded to float32 -> 1e-6 relative
+    np.testing.assert_allclose(got, oev.astype(np.float64), rtol=1e-6, atol=1e-7)
+    trans, stat = pg.PointToPointICPGradient(e).fit(idx, target)
+    rc, etrans, _, eit = oracle.icp_fit(oracle.Search(base, "kdtree"), target,
+                                        oracle.icp_params(1.0, f64_accumulate=True))
+    assert abs(stat.num_iteration - eit) <= 1
+    # final transform after <= 20 chaotic iterations: 1e-3 absolute (ICP modes)
+    np.testing.assert_allclose(trans, etrans, rtol=0, atol=1e-3)
+
+
+def test_icp_fit_pairs_farm_matches_single(pg, synth):
+    import torch
+
+    pairs = [synth.icp_pair(seed=20 + k, n=4000, n_az=200) for k in range(5)]
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+    singles = [icp.fit(pg.Index(b), t) for b, t in pairs]
+    db = [torch.from_numpy(b).cuda() for b, _ in pairs]
+    dt = [torch.from_numpy(t).cuda() for _, t in pairs]
+    torch.cuda.synchronize()
+    trans, iters, status, _ = icp.fit_pairs_dev([x.data_ptr() for x in db], [len(x) for x in db],
+                                                [x.data_ptr() for x in dt], [len(x) for x in dt])
+    for k, (tr, st) in enumerate(singles):
+        assert status[k] == 0 and iters[k] == st.num_iteration
+        assert trans[k].tobytes() == tr.tobytes()
+
+
+def test_launch_counter_moves(pg):
+    before = pg.kernel_launch_count()
+    pg.Index(np.random.default_rng(0).random((100, 3), dtype=f32)).nearest((0.5, 0.5, 0.5), 1.0)
+    assert pg.kernel_launch_count() > before

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol the header declares,
+fails loudly without a GPU, and the host-side mirror types behave like the reference's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pcgol_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pcg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pcgol_b200
+    from pcgol_b200 import _lib
+
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(_lib.lib, s), f"libpcgol_b200.so does not export {s}"
+    assert set(syms) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
+    assert _lib.lib.pcg_abi_version() == 1
+
+
+def test_neighbor_layout_matches_go():
+    from pcgol_b200 import _lib
+
+    # storage.Neighbor{ID int; DistSq float32} on 64-bit Go: 16 bytes, ID at 0, DistSq at 8
+    assert C.sizeof(_lib.Neighbor) == 16
+    assert _lib.Neighbor.id.offset == 0 and _lib.Neighbor.dist_sq.offset == 8
+    assert C.sizeof(_lib.Evaluated) == 4 * (1 + 6 + 36 + 1)
+
+
+def test_no_cpu_fallback():
+    import pcgol_b200 as pg
+
+    if pg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    pts = np.zeros((8, 3), np.float32)
+    with pytest.raises(pg.PcgError) as e:
+        pg.Index(pts)
+    assert e.value.status in (pg._lib.E_NO_DEVICE, pg._lib.E_CUDA)
+    with pytest.raises(pg.PcgError):
+        pg.VoxelGrid((0.1, 0.1, 0.1)).filter(pg.PointCloud.from_xyz(pts))
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pcgol_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "orc_"):
+                    assert needle not in src, f"{f} reaches into the oracle ({needle})"
+
+
+def test_pointcloud_header_mirror():
+    import pcgol_b200 as pg
+
+    hdr = pg.PointCloudHeader(fields=["x", "y", "z", "label"], size=[4, 4, 4, 4], type=["F", "F", "F", "U"],
+                              count=[1, 1, 1, 1], width=2)
+    assert hdr.stride() == 16
+    rec = np.zeros(2, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("label", "<u4")])
+    rec[0] = (1, 2, 3, 7)
+    rec[1] = (4, 5, 6, 9)
+    pp = pg.PointCloud(hdr, rec.view(np.uint8))
+    assert pp.points == 2 and pp.xyz_offsets() == (0, 4, 8)
+    assert pp.xyz().tolist() == [[1, 2, 3], [4, 5, 6]]
+    assert pp.field_u32("label").tolist() == [7, 9]
+    with pytest.raises(KeyError):
+        pp.field_offset("intensity")
+    c = hdr.clone()
+    c.fields.append("w")
+    assert hdr.fields == ["x", "y", "z", "label"]
+
+
+def test_icp_finish_host_matches_oracle(oracle):
+    """pcg_icp_finish (tail of Evaluate + Update on the host, used by the sharded ICP) needs no GPU."""
+    from pcgol_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        n = 5000
+        sums = np.zeros(16, np.float64)
+        sums[0] = rng.uniform(10, 400)          # Value
+        sums[1] = n                             # SumW
+        sums[2:8] = rng.normal(0, 200, 6)       # G
+        sums[8] = rng.uniform(1e5, 1e6)         # R
+        sums[9] = n
+        p = _lib.IcpParams()
+        p.max_dist, p.min_pairs, p.max_iteration, p.mode = 1.0, 0, 0, _lib.ICP_FAST
+        it = C.c_int32(trial % 20)
+        trans = oracle.rotate(0, 0, 1, 0.05 * trial).copy()
+        conv = C.c_int32(0)
+        ev = _lib.Evaluated()
+        rc = _lib.lib.pcg_icp_finish(sums.ctypes.data, C.byref(p), C.byref(it), trans.ctypes.data, C.byref(ev),
+                                     C.byref(conv))
+        assert rc == 0
+        # oracle: same tail on float32 sums, then Update
+        s32 = sums.astype(np.float32)
+        f = np.float32(1) / s32[1]
+        value = np.float32(s32[0] * f)
+        g = (s32[2:8] * np.float32(np.float32(2) * f)).astype(np.float32)
+        rms = np.float32(np.sqrt(np.float64(np.float32(s32[8] * f))))
+        dist = np.float32(np.sqrt(np.float64(value)))
+        rot = np.float32(1)
+        for i in range(3, 6):
+            d = abs(np.float32(g[i] * rms))
+            if dist < d:
+                rot = min(rot, np.float32(dist / d))
+        g[3:] = (g[3:] * rot).astype(np.float32)
+        ev8 = np.concatenate([[value], g, [rms]]).astype(np.float32)
+        got8 = np.array([ev.value, *ev.gradient, ev.dist_rms], np.float32)
+        assert got8.tobytes() == ev8.tobytes()
+        et, econv = oracle.icp_update(oracle.icp_params(1.0), trial % 20, oracle.rotate(0, 0, 1, 0.05 * trial), ev8)
+        assert bool(conv.value) == econv
+        assert trans.tobytes() == et.tobytes()
