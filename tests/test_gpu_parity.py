@@ -32,7 +32,7 @@ def _cloud(pg, data, stride, names):
 # ------------------------------------------------------------- VoxelGrid ------
 def test_voxelgrid_reference_golden(pg):
     # pc/filter/voxelgrid/voxelgrid_test.go:12-110
-    from tests.test_oracle_golden import VG_CASES, _vg_cloud
+    from test_oracle_golden import VG_CASES, _vg_cloud
 
     rec = _vg_cloud()
     for name, (chunk, exp_pts, exp_labels) in VG_CASES.items():
@@ -119,7 +119,7 @@ def test_voxelgrid_config2_1m_points(pg, oracle, synth, chunk, mode):
 # ------------------------------------------------------------- Nearest / Range ------
 def test_nearest_reference_golden(pg):
     # pc/storage/kdtree/kdtree_test.go:162-246
-    from tests.test_oracle_golden import FIXTURE7, NEAREST_CASES
+    from test_oracle_golden import FIXTURE7, NEAREST_CASES
 
     idx = pg.Index(FIXTURE7)
     assert len(idx) == 7
@@ -134,7 +134,7 @@ def test_nearest_reference_golden(pg):
 
 def test_range_reference_golden(pg):
     # kdtree_test.go:281-386
-    from tests.test_oracle_golden import RANGE_CASES, RANGE_FIXTURE
+    from test_oracle_golden import RANGE_CASES, RANGE_FIXTURE
 
     idx = pg.Index(RANGE_FIXTURE)
     for p, mr, exp in RANGE_CASES:
@@ -279,7 +279,7 @@ def test_evaluator_reference_golden(pg, oracle, mode):
 def test_icp_fit_reference_golden(pg, oracle, zoff):
     # pc/registration/icp/icp_test.go:13-98 (exact NN instead of MinDistSq=0.01): residual <= 0.05,
     # and the whole trajectory equals the oracle run with exact search
-    from tests.test_oracle_golden import _icp_deltas
+    from test_oracle_golden import _icp_deltas
 
     base = np.array([[-2.1, 0, 0], [-1, 1, 0], [0, 2, 0], [1, 1, 1], [2, 0, 0]], f32)
     base[:, 2] += f32(zoff)
