@@ -84,6 +84,11 @@ pcg_status pcg_memcpy_d2h(int32_t device, void* dst_host, const void* src_dev, i
 pcg_status pcg_device_synchronize(int32_t device);
 /* Number of kernels this library has launched on the calling thread's behalf, process-wide. */
 int64_t pcg_kernel_launch_count(void);
+/* Diagnostics: when enabled, every kernel launch is bracketed by CUDA events on its
+ * stream; pcg_profile_report synchronises and writes {"kernel": {"launches", "total_ms"}}
+ * as JSON into buf (returns the length needed) and clears the records. */
+void pcg_profile_enable(int32_t on);
+int64_t pcg_profile_report(char* buf, int64_t cap);
 
 /* ---- storage.Search: spatial index (replaces kdtree.New, kdtree.go:33-56) --- */
 typedef struct pcg_index pcg_index;

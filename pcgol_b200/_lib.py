@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcgol_b200.so")
+LIB_PATH = os.environ.get("PCG_LIB") or os.path.join(_HERE, "libpcgol_b200.so")  # PCG_LIB: tuning builds only
 
 OK = 0
 E_INVALID_ARG = 1
@@ -83,6 +83,8 @@ _sigs = {
     "pcg_memcpy_d2h": (_i32, [_i32, _vp, _vp, _i64]),
     "pcg_device_synchronize": (_i32, [_i32]),
     "pcg_kernel_launch_count": (_i64, []),
+    "pcg_profile_enable": (None, [_i32]),
+    "pcg_profile_report": (_i64, [C.c_char_p, _i64]),
     "pcg_index_build": (_i32, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_vp)]),
     "pcg_index_build_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, C.POINTER(_vp)]),
     "pcg_index_free": (None, [_vp]),
@@ -133,3 +135,15 @@ def device_count() -> int:
 
 def kernel_launch_count() -> int:
     return int(lib.pcg_kernel_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    lib.pcg_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """Per-kernel {"launches", "total_ms"} recorded since profile_enable(True)."""
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    lib.pcg_profile_report(buf, len(buf))
+    return json.loads(buf.value.decode() or "{}")

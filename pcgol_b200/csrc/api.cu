@@ -2,7 +2,9 @@
 // Host entry points stage caller buffers through device memory (stream-ordered pool),
 // run the device pipelines of voxelgrid.cu / index.cu / icp.cu and copy results back.
 #include <algorithm>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "bvh.cuh"
@@ -11,6 +13,35 @@
 namespace pcg {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_profile{0};
+
+namespace {
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+thread_local cudaEvent_t t_prof_start = nullptr;
+thread_local const char* t_prof_name = nullptr;
+}  // namespace
+
+void prof_begin(const char* name, cudaStream_t s) {
+  cudaEvent_t a;
+  if (cudaEventCreate(&a) != cudaSuccess) return;
+  cudaEventRecord(a, s);
+  t_prof_start = a;
+  t_prof_name = name;
+}
+void prof_end(cudaStream_t s) {
+  if (!t_prof_start) return;
+  cudaEvent_t b;
+  if (cudaEventCreate(&b) != cudaSuccess) return;
+  cudaEventRecord(b, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back(ProfRec{t_prof_name, t_prof_start, b});
+  t_prof_start = nullptr;
+}
 static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 
@@ -137,6 +168,48 @@ int32_t pcg_device_count(void) {
   return count;
 }
 int64_t pcg_kernel_launch_count(void) { return g_launches.load(); }
+
+void pcg_profile_enable(int32_t on) { g_profile.store(on ? 1 : 0); }
+
+// Synchronises the device(s), folds the recorded events into per-kernel totals and writes
+// a JSON object {"kernel": {"launches": n, "total_ms": t}, ...}; clears the records.
+int64_t pcg_profile_report(char* buf, int64_t cap) {
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof_recs);
+  }
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first++;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[512];
+    std::string name = kv.first;
+    for (auto& c : name)
+      if (c == '"' || c == '\\') c = '_';
+    snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"total_ms\": %.6f}", first ? "" : ", ", name.c_str(),
+             (long long)kv.second.first, kv.second.second);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  if (buf && cap > 0) {
+    size_t ncopy = std::min<size_t>((size_t)cap - 1, out.size());
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return (int64_t)out.size();
+}
 
 pcg_status pcg_host_alloc(void** out, int64_t bytes) {
   return guarded([&]() -> pcg_status {

@@ -30,10 +30,19 @@ struct CudaError {
     if (e__ != cudaSuccess) throw ::pcg::CudaError{e__, #expr, __FILE__, __LINE__}; \
   } while (0)
 
+// Optional per-kernel timing (pcg_profile_enable): CUDA events on the launching stream
+// around every launch, aggregated by kernel name. Off by default; costs one relaxed load.
+extern std::atomic<int> g_profile;
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+
 // Kernel launch with launch counting + immediate launch-error check.
 #define PCG_LAUNCH(kernel, grid, block, smem, stream, ...)                    \
   do {                                                                        \
+    const bool prof__ = ::pcg::g_profile.load(std::memory_order_relaxed) != 0; \
+    if (prof__) ::pcg::prof_begin(#kernel, (stream));                         \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+    if (prof__) ::pcg::prof_end((stream));                                    \
     ::pcg::g_launches.fetch_add(1, std::memory_order_relaxed);                \
     PCG_CUDA(cudaGetLastError());                                             \
   } while (0)

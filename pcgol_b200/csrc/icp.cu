@@ -41,8 +41,9 @@ constexpr int kTerms = 9;  // Value, SumW, G0..G5, R
 
 template <int MODE>
 __global__ void __launch_bounds__(kTermThreads)
-    icp_terms_kernel(IndexView base, CloudView tgt, float max_dist_sq, IcpState* __restrict__ st,
-                     float* __restrict__ terms, int64_t n_pad, double* __restrict__ partials) {
+    icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, float max_dist_sq,
+                     IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
+                     double* __restrict__ partials) {
   if (st->done) return;
   __shared__ float s_m[16];
   __shared__ int s_first;
@@ -51,12 +52,15 @@ __global__ void __launch_bounds__(kTermThreads)
   if (tid < 16) s_m[tid] = st->trans.m[tid];
   if (tid == 0) s_first = st->num_iteration == 0;
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * kTermThreads + tid;
+  const int64_t slot = (int64_t)blockIdx.x * kTermThreads + tid;
   float t[kTerms];
 #pragma unroll
   for (int k = 0; k < kTerms; k++) t[k] = 0.f;
   int matched = 0;
-  if (i < tgt.n) {
+  if (slot < tgt.n) {
+    // Morton-ordered visit (coherent warps); the terms still land at the target's own index,
+    // so the sequential replay below adds them in target order
+    const int64_t i = perm ? (int64_t)perm[slot] : slot;
     float3 p = load_xyz(tgt, i);
     float x0 = p.x, y0 = p.y, z0 = p.z;
     // icp.go:27-30: the first Evaluate sees the raw target; later ones the ORIGINAL target
@@ -228,6 +232,7 @@ struct IcpWork {
   DevBuf<IcpState> st;
   DevBuf<float> terms;
   DevBuf<double> partials;
+  DevBuf<uint32_t> perm;
   int nblocks = 0;
   int64_t n_pad = 0;
 };
@@ -251,22 +256,27 @@ static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, floa
   const float mdsq = max_dist * max_dist;  // kdtree.go:91
   for (int it = 0; it < iterations; it++) {
     if (mode == PCG_ICP_STRICT) {
-      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_STRICT>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, mdsq, w.st.p,
-                 w.terms.p, w.n_pad, w.partials.p);
+      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_STRICT>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
+                 w.st.p, w.terms.p, w.n_pad, w.partials.p);
       PCG_LAUNCH((icp_finish_kernel<PCG_ICP_STRICT>), 1, kFinishThreads, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad,
                  w.partials.p, w.nblocks);
     } else {
-      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, mdsq, w.st.p,
-                 w.terms.p, w.n_pad, w.partials.p);
+      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
+                 w.st.p, w.terms.p, w.n_pad, w.partials.p);
       PCG_LAUNCH((icp_finish_kernel<PCG_ICP_FAST>), 1, kFinishThreads, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad,
                  w.partials.p, w.nblocks);
     }
   }
 }
 
-static void icp_prepare(const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only, IcpWork& w,
-                        cudaStream_t stream) {
+static void icp_prepare(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only,
+                        IcpWork& w, cudaStream_t stream) {
   w.nblocks = std::max(1, div_up(tgt.n, kTermThreads));
+  if (tgt.n >= kMinQueriesToReorder && base.n > 0) {
+    // the target moves by a small rigid transform per iteration: the order of the raw target stays coherent
+    w.perm.alloc((size_t)tgt.n, stream);
+    query_order_device(base, tgt, w.perm.p, stream);
+  }
   w.n_pad = (tgt.n + 3) & ~(int64_t)3;
   w.st.alloc(1, stream);
   if (prm.mode == PCG_ICP_STRICT)
@@ -295,7 +305,7 @@ pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp
   if (prm.mode != PCG_ICP_STRICT && prm.mode != PCG_ICP_FAST)
     throw StatusError{PCG_E_INVALID_ARG, "unknown ICP mode"};
   IcpWork w;
-  icp_prepare(tgt, prm, evaluate_only, w, stream);
+  icp_prepare(base, tgt, prm, evaluate_only, w, stream);
   const int total = evaluate_only ? 1 : im::make_updater(prm).max_iteration;
   IcpState h;
   int enq = 0;
@@ -346,7 +356,7 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
         CloudView bv = make_view(d_base[i], n_base[i], stride, xyz_off);
         CloudView tv = make_view(d_target[i], n_target[i], stride, xyz_off);
         indices[i] = index_build_device(bv, device, s);
-        icp_prepare(tv, prm, false, works[i], s);
+        icp_prepare(*indices[i], tv, prm, false, works[i], s);
         icp_enqueue_iterations(*indices[i], tv, prm.max_dist, prm.mode, works[i], total, s);
         PCG_CUDA(cudaMemcpyAsync(&h[i], works[i].st.p, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
       }
@@ -383,14 +393,14 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
   pcg_icp_params prm;
   std::memset(&prm, 0, sizeof(prm));
   prm.mode = PCG_ICP_FAST;
-  icp_prepare(tgt, prm, true, w, stream);
+  icp_prepare(base, tgt, prm, true, w, stream);
   IcpState h = make_state(prm, true);
   std::memcpy(h.trans.m, trans, sizeof(float) * 16);
   h.num_iteration = first ? 0 : 1;  // only "is this the first Evaluate" matters to the terms kernel
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   const float mdsq = max_dist * max_dist;
-  PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, mdsq, w.st.p,
-             w.terms.p, w.n_pad, w.partials.p);
+  PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
+             w.st.p, w.terms.p, w.n_pad, w.partials.p);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
 }
 

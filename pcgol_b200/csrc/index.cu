@@ -27,8 +27,13 @@ __host__ __device__ __forceinline__ float ord_to_float(uint32_t o) {
 #endif
 }
 
+__global__ void bbox_init_kernel(uint32_t* out6) {
+  if (threadIdx.x < 6) out6[threadIdx.x] = threadIdx.x < 3 ? 0xffffffffu : 0u;
+}
+
 // out6: ordered-bit min x,y,z then max x,y,z over finite coordinates
 __global__ void __launch_bounds__(256) bbox_kernel(CloudView v, uint32_t* __restrict__ out6) {
+  __shared__ uint32_t s_red[8][6];
   uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += stride) {
@@ -53,9 +58,19 @@ __global__ void __launch_bounds__(256) bbox_kernel(CloudView v, uint32_t* __rest
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      atomicMin(&out6[k], mn[k]);
-      atomicMax(&out6[3 + k], mx[k]);
+      s_red[threadIdx.x >> 5][k] = mn[k];
+      s_red[threadIdx.x >> 5][3 + k] = mx[k];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int k = threadIdx.x;
+    uint32_t r = s_red[0][k];
+    for (int w = 1; w < 8; w++) r = k < 3 ? min(r, s_red[w][k]) : max(r, s_red[w][k]);
+    if (k < 3)
+      atomicMin(&out6[k], r);
+    else
+      atomicMax(&out6[k], r);
   }
 }
 
@@ -208,15 +223,14 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
     PCG_CUDA(cudaMallocAsync((void**)&ix->boxes, box_bytes, stream));
     ix->bytes = (int64_t)(pts_bytes + box_bytes);
 
-    DevBuf<uint32_t> bbox(6, stream);
-    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-    PCG_CUDA(cudaMemcpyAsync(bbox.p, init, sizeof(init), cudaMemcpyHostToDevice, stream));
-    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 8, div_up(n, 256));
-    PCG_LAUNCH(bbox_kernel, blocks, 256, 0, stream, v, bbox.p);
+    PCG_CUDA(cudaMallocAsync((void**)&ix->bbox, 8 * sizeof(uint32_t), stream));
+    PCG_LAUNCH(bbox_init_kernel, 1, 32, 0, stream, ix->bbox);
+    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
+    PCG_LAUNCH(bbox_kernel, blocks, 256, 0, stream, v, ix->bbox);
 
     DevBuf<unsigned long long> keys0(n, stream), keys1(n, stream);
     DevBuf<uint32_t> vals0(n, stream), vals1(n, stream);
-    PCG_LAUNCH(morton_kernel, div_up(n, 256), 256, 0, stream, v, bbox.p, keys0.p);
+    PCG_LAUNCH(morton_kernel, div_up(n, 256), 256, 0, stream, v, ix->bbox, keys0.p);
     unsigned long long* kk[2] = {keys0.p, keys1.p};
     uint32_t* vv[2] = {vals0.p, vals1.p};
     int res = 0;
@@ -239,16 +253,112 @@ void index_free(Index* ix) {
   cudaSetDevice(ix->device);
   if (ix->pts) cudaFree(ix->pts);
   if (ix->boxes) cudaFree(ix->boxes);
+  if (ix->bbox) cudaFree(ix->bbox);
   if (prev >= 0) cudaSetDevice(prev);
   delete ix;
 }
 
+// ---- query ordering -----------------------------------------------------------------------
+#ifndef PCG_QBITS
+#define PCG_QBITS 10
+#endif
+constexpr int kQueryBitsPerAxis = PCG_QBITS;  // 10 -> 30-bit Morton key, four radix passes
+
+__global__ void __launch_bounds__(256)
+    query_key_kernel(CloudView q, const uint32_t* __restrict__ bbox6, uint32_t* __restrict__ keys,
+                     uint32_t* __restrict__ hist, int passes) {
+  __shared__ uint32_t s_hist[rsort::kMaxPasses * rsort::kRadix];
+  rsort::hist_zero(s_hist, passes);
+  __syncthreads();
+  float lo[3], ext = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    lo[k] = ord_to_float(bbox6[k]);
+    ext = fmaxf(ext, ord_to_float(bbox6[3 + k]) - lo[k]);
+  }
+  const float cells = (float)(1 << kQueryBitsPerAxis);
+  const float scale = (ext > 0.f && isfinite(ext)) ? cells / ext : 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (q.n + stride - 1) / stride;
+  for (int64_t r = 0; r < rounds; r++) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < q.n;
+    uint32_t key = 0;
+    if (valid) {
+      float3 p = load_xyz(q, i);
+      float c[3] = {p.x, p.y, p.z};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float t = (c[k] - lo[k]) * scale;  // queries outside the box clamp to its faces; NaN -> 0
+        uint32_t u = (uint32_t)fminf(fmaxf(t, 0.f), cells - 1.f);
+        key |= (uint32_t)spread16(u) << k;
+      }
+      keys[i] = key;
+    }
+    rsort::hist_add_key(s_hist, key, valid, 0, passes);
+  }
+  __syncthreads();
+  rsort::hist_flush(s_hist, hist, passes);
+}
+
+void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, cudaStream_t stream) {
+  const uint32_t n = (uint32_t)q.n;
+  if (n == 0) return;
+  DevBuf<uint32_t> keys0(n, stream), keys1(n, stream), vals1(n, stream);
+  rsort::Sorter<uint32_t> sorter;
+  sorter.prepare(n, 0, 3 * kQueryBitsPerAxis, stream);
+  const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
+  PCG_LAUNCH(query_key_kernel, blocks, 256, 0, stream, q, ix.bbox, keys0.p, sorter.hist(), sorter.passes);
+  // the payload ends on side (passes & 1): make d_perm that side so no copy is needed
+  uint32_t* kk[2] = {keys0.p, keys1.p};
+  uint32_t* vv[2] = {vals1.p, d_perm};
+  if ((sorter.passes & 1) == 0) std::swap(vv[0], vv[1]);
+  int res = 0;
+  sorter.run(kk, vv, /*identity_vals=*/true, /*keep_keys=*/false, stream, &res);
+  if (vv[res] != d_perm)
+    PCG_CUDA(cudaMemcpyAsync(d_perm, vv[res], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+}
+
 // ---- KDTree.Nearest, batched (kdtree.go:83-92) -----------------------------------------
 __global__ void __launch_bounds__(128)
-    nearest_kernel(IndexView ix, CloudView q, float max_range_sq, int32_t* __restrict__ ids,
-                   float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos) {
+    nearest_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
+                   int32_t* __restrict__ ids, float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos,
+                   unsigned int* __restrict__ counter, int leaf_votes) {
+  nn_persistent(
+      ix, (uint32_t)q.n, max_range_sq, counter, leaf_votes,
+      [&](uint32_t slot, float& x, float& y, float& z) {
+        // Morton-ordered visit; results still land at the query's own index
+        const float3 p = load_xyz(q, perm ? perm[slot] : slot);
+        x = p.x;
+        y = p.y;
+        z = p.z;
+        return true;
+      },
+      [&](uint32_t slot, float, float, float, uint64_t best, uint32_t, bool hit) {
+        const uint32_t i = perm ? perm[slot] : slot;
+        const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
+        const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
+        if (ids) {
+          ids[i] = id;
+          dist_sq[i] = d;
+        }
+        if (aos) {
+          pcg_neighbor nb;
+          nb.id = (int64_t)id;
+          nb.dist_sq = d;
+          nb.pad_ = 0;
+          aos[i] = nb;
+        }
+      });
+}
+
+// One query per thread (no work fetching): kept for comparison runs (PCG_NN_KERNEL=simple).
+__global__ void __launch_bounds__(128)
+    nearest_simple_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
+                          int32_t* __restrict__ ids, float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q.n) return;
+  if (perm) i = perm[i];
   float3 p = load_xyz(q, i);
   uint64_t best = nn_init(max_range_sq);
   const uint64_t init = best;
@@ -270,11 +380,41 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Persistent launch: enough CTAs to fill the machine, capped by the amount of work.
+static int persistent_blocks(int64_t n_queries, int threads) {
+  const int64_t by_work = (n_queries + kQueryChunk - 1) / kQueryChunk * 32 / threads + 1;
+  return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)kNumSMs * (2048 / threads), by_work));
+}
+
 void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_t* d_ids, float* d_dist_sq,
                     pcg_neighbor* d_aos, cudaStream_t stream) {
   if (q.n == 0) return;
   const float mrsq = max_range * max_range;  // kdtree.go:91
-  PCG_LAUNCH(nearest_kernel, div_up(q.n, 128), 128, 0, stream, ix.view(), q, mrsq, d_ids, d_dist_sq, d_aos);
+  DevBuf<uint32_t> perm;
+  if (q.n >= kMinQueriesToReorder && ix.n > 0) {
+    perm.alloc((size_t)q.n, stream);
+    query_order_device(ix, q, perm.p, stream);
+  }
+  DevBuf<unsigned int> counter(1, stream);
+  PCG_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), stream));
+  static const int leaf_votes = [] {
+    const char* e = getenv("PCG_NN_LEAF_VOTES");
+    return e ? atoi(e) : 16;
+  }();
+  // Measured on B200 (10M LiDAR-shaped queries vs 1M points): the one-query-per-thread kernel
+  // wins over the work-fetching one (14.3 vs 16.4 ms) — divergent sub-warps overlap each
+  // other's L2 latency, the converged rounds of the persistent kernel expose it.
+  static const bool simple = [] {
+    const char* e = getenv("PCG_NN_KERNEL");
+    return !(e && strcmp(e, "persistent") == 0);
+  }();
+  if (simple) {
+    PCG_LAUNCH(nearest_simple_kernel, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, d_ids, d_dist_sq,
+               d_aos);
+    return;
+  }
+  PCG_LAUNCH(nearest_kernel, persistent_blocks(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, d_ids,
+             d_dist_sq, d_aos, counter.p, leaf_votes);
 }
 
 // ---- KDTree.Range, batched (kdtree.go:148-197) -----------------------------------------

@@ -8,6 +8,8 @@
 // the VoxelGrid centroid sums reproduce the reference's accumulation order.
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pcg {
@@ -30,24 +32,48 @@ __device__ __forceinline__ uint32_t digit_of(K k, int shift) {
   return (uint32_t)(k >> shift) & (kRadix - 1);
 }
 
-// All digit histograms in one read of the keys (the per-position histogram of a
-// multiset does not depend on its order, so it is valid for every later pass).
+// Warp-aggregated accumulation of one key into a CTA-shared histogram [passes][256]:
+// lanes holding the same digit elect one leader that adds their count (clustered keys
+// would otherwise serialise on one shared-memory address).  All 32 lanes must call.
 template <typename K>
-__global__ void __launch_bounds__(256) histogram_kernel(const K* __restrict__ keys, uint32_t n, int begin_bit,
-                                                        int passes, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t sh[kMaxPasses * kRadix];
-  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    K k = keys[i];
-    for (int p = 0; p < passes; p++) atomicAdd(&sh[p * kRadix + digit_of(k, begin_bit + p * kRadixBits)], 1u);
+__device__ __forceinline__ void hist_add_key(uint32_t* __restrict__ sh, K key, bool valid, int begin_bit,
+                                             int passes) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (int p = 0; p < passes; p++) {
+    const uint32_t d = valid ? digit_of(key, begin_bit + p * kRadixBits) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (int)lane == __ffs(peers) - 1) atomicAdd(&sh[p * kRadix + d], (uint32_t)__popc(peers));
   }
-  __syncthreads();
+}
+__device__ __forceinline__ void hist_zero(uint32_t* sh, int passes) {
+  for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) sh[i] = 0;
+}
+__device__ __forceinline__ void hist_flush(const uint32_t* sh, uint32_t* __restrict__ hist, int passes) {
   for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
     uint32_t c = sh[i];
     if (c) atomicAdd(&hist[i], c);
   }
+}
+
+// All digit histograms in one read of the keys (the per-position histogram of a
+// multiset does not depend on its order, so it is valid for every later pass).
+// Producers of keys can fold this into their own kernel with hist_add_key instead.
+template <typename K>
+__global__ void __launch_bounds__(256) histogram_kernel(const K* __restrict__ keys, uint32_t n, int begin_bit,
+                                                        int passes, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t sh[kMaxPasses * kRadix];
+  hist_zero(sh, passes);
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (n + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; r++) {
+    uint32_t i = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    K k = valid ? keys[i] : (K)0;
+    hist_add_key(sh, k, valid, begin_bit, passes);
+  }
+  __syncthreads();
+  hist_flush(sh, hist, passes);
 }
 
 // Exclusive scan of one value per thread across a 256-thread block.
@@ -214,50 +240,95 @@ inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vo
              counter, status);
 }
 
-// Sorts n (key, payload) pairs by key bits [begin_bit, end_bit), stable.
-// keys[0]/vals[0] hold the input; the pair of buffers is ping-ponged and *result
-// (0 or 1) tells which one holds the output.  identity_vals: the payload is the input
-// position (vals[0] is not read).  keep_keys=false skips the key write of the last pass.
+inline int pick_ipt(uint32_t n) {
+  static const int forced = [] {
+    const char* e = getenv("PCG_SORT_IPT");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 4 || forced == 8 || forced == 16) return forced;
+  // largest tile that still gives every SM about four CTAs
+  for (int ipt : {16, 8}) {
+    if ((uint64_t)n >= (uint64_t)kNumSMs * 4 * kThreads * ipt) return ipt;
+  }
+  return 4;
+}
+
+// Stable LSD sort of n (key, payload) pairs by key bits [begin_bit, end_bit).
+//   prepare()    allocates and clears the workspace (histograms, tile counters, look-back status)
+//   hist()       device histogram [passes][256]; either call histogram() or let the kernel that
+//                produces the keys accumulate into it (hist_add_key / hist_flush)
+//   run()        one onesweep kernel per 8-bit digit; keys[0]/vals[0] hold the input, the buffers
+//                ping-pong and *result (0 or 1) tells which side holds the output.
+//                identity_vals: payload = input position (vals[0] is not read);
+//                keep_keys=false skips the key write of the last pass.
+template <typename K>
+struct Sorter {
+  uint32_t n = 0;
+  int begin_bit = 0, passes = 0, ipt = 16;
+  uint32_t tiles = 0;
+  size_t hist_words = 0;
+  DevBuf<uint32_t> head;
+  DevBuf<unsigned long long> status;
+
+  void prepare(uint32_t n_, int begin_bit_, int end_bit_, cudaStream_t stream) {
+    n = n_;
+    begin_bit = begin_bit_;
+    passes = num_passes(begin_bit_, end_bit_);
+    if (passes == 0) passes = 1;  // degenerate range: one pass over (all-equal) digits keeps the order
+    if (passes > kMaxPasses) throw StatusError{PCG_E_INVALID_ARG, "radix sort: more than 64 key bits"};
+    if (n == 0) return;
+    ipt = pick_ipt(n);
+    const uint32_t tile = (uint32_t)kThreads * ipt;
+    tiles = (n + tile - 1) / tile;
+    hist_words = (size_t)passes * kRadix;
+    head.alloc(hist_words + 64, stream);
+    status.alloc((size_t)tiles * kRadix, stream);
+    PCG_CUDA(cudaMemsetAsync(head.p, 0, head.bytes(), stream));
+    PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
+  }
+  uint32_t* hist() { return head.p; }
+
+  void histogram(const K* keys, cudaStream_t stream) {
+    if (n == 0) return;
+    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
+    PCG_LAUNCH((histogram_kernel<K>), blocks, 256, 0, stream, keys, n, begin_bit, passes, head.p);
+  }
+
+  void run(K* keys[2], uint32_t* vals[2], bool identity_vals, bool keep_keys, cudaStream_t stream, int* result) {
+    *result = 0;
+    if (n == 0) return;
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+      const int shift = begin_bit + p * kRadixBits;
+      const bool last = p == passes - 1;
+      const K* kin = keys[cur];
+      K* kout = (last && !keep_keys) ? nullptr : keys[cur ^ 1];
+      const uint32_t* vin = (p == 0 && identity_vals) ? nullptr : vals[cur];
+      uint32_t* vout = vals[cur ^ 1];
+      const uint32_t* h = head.p + (size_t)p * kRadix;
+      uint32_t* counter = head.p + hist_words + p;
+      const uint32_t epoch = (uint32_t)(p + 1);
+      if (ipt == 4)
+        launch_pass<K, 4>(kin, kout, vin, vout, n, shift, epoch, h, counter, status.p, stream);
+      else if (ipt == 8)
+        launch_pass<K, 8>(kin, kout, vin, vout, n, shift, epoch, h, counter, status.p, stream);
+      else
+        launch_pass<K, 16>(kin, kout, vin, vout, n, shift, epoch, h, counter, status.p, stream);
+      cur ^= 1;
+    }
+    *result = cur;
+  }
+};
+
 template <typename K>
 void sort_pairs(K* keys[2], uint32_t* vals[2], uint32_t n, int begin_bit, int end_bit, bool identity_vals,
                 bool keep_keys, cudaStream_t stream, int* result) {
-  int passes = num_passes(begin_bit, end_bit);
   *result = 0;
   if (n == 0) return;
-  if (passes == 0) passes = 1;  // degenerate range: one pass over (all-equal) digits keeps the order
-  if (passes > kMaxPasses) throw StatusError{PCG_E_INVALID_ARG, "radix sort: more than 64 key bits"};
-  const bool small = n <= (1u << 18);
-  const uint32_t tile = small ? (uint32_t)TileSmem<K, 4>::kTile : (uint32_t)TileSmem<K, 16>::kTile;
-  const uint32_t tiles = (n + tile - 1) / tile;
-  const int eff_passes = passes;
-  // workspace: hist[passes][256] | counters[passes] (padded) | status[tiles][256]
-  const size_t hist_words = (size_t)eff_passes * kRadix;
-  const size_t head_words = hist_words + 64;
-  DevBuf<uint32_t> head(head_words, stream);
-  DevBuf<unsigned long long> status((size_t)tiles * kRadix, stream);
-  PCG_CUDA(cudaMemsetAsync(head.p, 0, head.bytes(), stream));
-  PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
-  {
-    int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 8, div_up(n, 256 * 4));
-    PCG_LAUNCH((histogram_kernel<K>), blocks, 256, 0, stream, keys[0], n, begin_bit, eff_passes, head.p);
-  }
-  int cur = 0;
-  for (int p = 0; p < eff_passes; p++) {
-    const int shift = begin_bit + p * kRadixBits;
-    const bool last = p == eff_passes - 1;
-    const K* kin = keys[cur];
-    K* kout = (last && !keep_keys) ? nullptr : keys[cur ^ 1];
-    const uint32_t* vin = (p == 0 && identity_vals) ? nullptr : vals[cur];
-    uint32_t* vout = vals[cur ^ 1];
-    if (small)
-      launch_pass<K, 4>(kin, kout, vin, vout, n, shift, (uint32_t)(p + 1), head.p + (size_t)p * kRadix,
-                        head.p + hist_words + p, status.p, stream);
-    else
-      launch_pass<K, 16>(kin, kout, vin, vout, n, shift, (uint32_t)(p + 1), head.p + (size_t)p * kRadix,
-                         head.p + hist_words + p, status.p, stream);
-    cur ^= 1;
-  }
-  *result = cur;
+  Sorter<K> s;
+  s.prepare(n, begin_bit, end_bit, stream);
+  s.histogram(keys[0], stream);
+  s.run(keys, vals, identity_vals, keep_keys, stream, result);
 }
 
 }  // namespace rsort
