@@ -152,10 +152,15 @@ inline void check_view_args(const void* data, int64_t n, int64_t stride, const i
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ float load_f32_any(const uint8_t* p, int aligned) {
-  if (aligned) return __ldg((const float*)p);
+// binaryFloat32Iterator path (unaligned records): out of line so that the aligned fast path is
+// three plain loads and not an if-converted mix of both.
+static __device__ __noinline__ float load_f32_bytes(const uint8_t* p) {
   uint32_t b = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
   return __uint_as_float(b);
+}
+__device__ __forceinline__ float load_f32_any(const uint8_t* p, int aligned) {
+  if (aligned) return __ldg((const float*)p);
+  return load_f32_bytes(p);
 }
 __device__ __forceinline__ void store_f32_any(uint8_t* p, float f, int aligned) {
   if (aligned) {
@@ -170,8 +175,11 @@ __device__ __forceinline__ void store_f32_any(uint8_t* p, float f, int aligned) 
 }
 __device__ __forceinline__ float3 load_xyz(const CloudView& v, int64_t i) {
   const uint8_t* r = v.data + i * v.stride;
-  return make_float3(load_f32_any(r + v.off[0], v.aligned), load_f32_any(r + v.off[1], v.aligned),
-                     load_f32_any(r + v.off[2], v.aligned));
+  if (v.aligned) {
+    return make_float3(__ldg((const float*)(r + v.off[0])), __ldg((const float*)(r + v.off[1])),
+                       __ldg((const float*)(r + v.off[2])));
+  }
+  return make_float3(load_f32_bytes(r + v.off[0]), load_f32_bytes(r + v.off[1]), load_f32_bytes(r + v.off[2]));
 }
 
 // mat/vec3.go:18-20,38-40 : ((dx*dx + dy*dy) + dz*dz), d = a - b, every op rounded, no FMA

@@ -1,3 +1,2 @@
-PCG_NN_LEAF_VOTES=24 ncu --set full --clock-control none --import-source on -k regex:nearest_kernel -s 1 -c 1 -o gpurun_out/prof_nearest_persist -f python bench.py --only nn --steps 3 --warmup 3 > gpurun_out/ncu_nn2.log 2>&1
-PCG_NN_KERNEL=simple ncu --set full --clock-control none --import-source on -k regex:nearest_simple -s 1 -c 1 -o gpurun_out/prof_nearest_simple_perm -f python bench.py --only nn --steps 3 --warmup 3 > gpurun_out/ncu_nn3.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-extra --steps 20 --warmup 5 > gpurun_out/b_fused2.json 2>gpurun_out/b_fused2.err; tail -2 gpurun_out/b_fused2.err; python tools/show_bench.py gpurun_out/b_fused2.json
