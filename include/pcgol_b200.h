@@ -211,7 +211,12 @@ pcg_status pcg_icp_fit_pairs_dev(int32_t count, const void* const* d_base, const
  * pcg_icp_finish identically.  d_partial16: {Value, SumW, G0..5, R, nPairs, 0...}. */
 pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
                                const int64_t xyz_off[3], float max_dist, const float trans[16], int32_t first,
+                               const uint32_t* d_visit_order /* optional, from pcg_query_order_dev */,
                                double* d_partial16, void* stream);
+/* Morton visit order of a query / target cloud relative to the index (a permutation of
+ * 0..n-1 in d_order): coherent warps for repeated searches over the same cloud. */
+pcg_status pcg_query_order_dev(pcg_index* idx, const void* d_q, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                               uint32_t* d_order, void* stream);
 /* Host-side tail of Evaluate (evaluator.go:156-186) + Update (updater.go:44-71) from
  * all-reduced sums.  *iter is the updater's i; returns converged in *converged. */
 pcg_status pcg_icp_finish(const double partial16[16], const pcg_icp_params* params, int32_t* iter, float trans[16],

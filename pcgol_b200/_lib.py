@@ -107,7 +107,8 @@ _sigs = {
     "pcg_icp_fit_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat), _vp]),
     "pcg_icp_fit_pairs_dev": (_i32, [_i32, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(IcpParams), _i32, _vp, _vp, _vp,
                                      _vp]),
-    "pcg_icp_partial_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _i32, _vp, _vp]),
+    "pcg_icp_partial_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _i32, _vp, _vp, _vp]),
+    "pcg_query_order_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pcg_icp_finish": (_i32, [_vp, C.POINTER(IcpParams), C.POINTER(_i32), _vp, C.POINTER(Evaluated),
                               C.POINTER(_i32)]),
 }

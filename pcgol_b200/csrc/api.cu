@@ -72,7 +72,7 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
                           const int64_t xyz_off[3], const pcg_icp_params& prm, int device, float* trans_out,
                           pcg_icp_stat* stat_out, pcg_status* status_out, cudaStream_t stream);
 void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist, const float trans[16], bool first,
-                        double* d_partial16, cudaStream_t stream);
+                        const uint32_t* d_order, double* d_partial16, cudaStream_t stream);
 pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm, int32_t* iter, float trans[16],
                            pcg_evaluated* ev_out, int32_t* converged);
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, int32_t* d_ids, float* d_dsq,
@@ -520,15 +520,27 @@ pcg_status pcg_icp_fit_pairs_dev(int32_t count, const void* const* d_base, const
   });
 }
 
+pcg_status pcg_query_order_dev(pcg_index* idx, const void* d_q, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                               uint32_t* d_order, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!idx || (n && !d_order)) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    check_view_args(d_q, n, stride, xyz_off);
+    if (idx->ix->n == 0) throw StatusError{PCG_E_INVALID_ARG, "empty index has no bounding box to order by"};
+    DeviceGuard g(idx->ix->device);
+    query_order_device(*idx->ix, make_view(d_q, n, stride, xyz_off), d_order, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
 pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
                                const int64_t xyz_off[3], float max_dist, const float trans[16], int32_t first,
-                               double* d_partial16, void* stream) {
+                               const uint32_t* d_visit_order, double* d_partial16, void* stream) {
   return guarded([&]() -> pcg_status {
     if (!base || !trans || !d_partial16) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
     check_view_args(d_target, n, stride, xyz_off);
     DeviceGuard g(base->ix->device);
-    icp_partial_device(*base->ix, make_view(d_target, n, stride, xyz_off), max_dist, trans, first != 0, d_partial16,
-                       (cudaStream_t)stream);
+    icp_partial_device(*base->ix, make_view(d_target, n, stride, xyz_off), max_dist, trans, first != 0, d_visit_order,
+                       d_partial16, (cudaStream_t)stream);
     return PCG_OK;
   });
 }

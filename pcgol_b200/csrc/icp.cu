@@ -388,18 +388,21 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
 
 // One shard's contribution to a single large ICP (see pcg_icp_partial_dev).
 void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist, const float trans[16], bool first,
-                        double* d_partial16, cudaStream_t stream) {
+                        const uint32_t* d_order, double* d_partial16, cudaStream_t stream) {
   IcpWork w;
   pcg_icp_params prm;
   std::memset(&prm, 0, sizeof(prm));
   prm.mode = PCG_ICP_FAST;
-  icp_prepare(base, tgt, prm, true, w, stream);
+  w.nblocks = std::max(1, div_up(tgt.n, kTermThreads));
+  w.n_pad = (tgt.n + 3) & ~(int64_t)3;
+  w.st.alloc(1, stream);
+  w.partials.alloc((size_t)w.nblocks * kTerms, stream);
   IcpState h = make_state(prm, true);
   std::memcpy(h.trans.m, trans, sizeof(float) * 16);
   h.num_iteration = first ? 0 : 1;  // only "is this the first Evaluate" matters to the terms kernel
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   const float mdsq = max_dist * max_dist;
-  PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
+  PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, d_order, mdsq,
              w.st.p, w.terms.p, w.n_pad, w.partials.p);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
 }

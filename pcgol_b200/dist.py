@@ -1,0 +1,87 @@
+"""Multi-GPU sharding of the hot path (one process per GPU, torch.distributed for plumbing).
+
+The path shards only where it splits naturally:
+  * batched Nearest/Range: queries split contiguously across ranks, index replicated on every
+    GPU (each rank builds it from the same cloud); results land in disjoint slices — no
+    data-path collective.
+  * scan-pair ICP farm: pairs dealt round-robin to ranks — no collective.
+  * one large ICP: the target is split across ranks, the base index is replicated; per
+    iteration every rank reduces its slice to 16 float64 sums on the device
+    (pcg_icp_partial_dev), the sums are all-reduced (NCCL over NVLink; gloo in the CPU tests)
+    and every rank applies the identical tail of Evaluate + Update (pcg_icp_finish), so all
+    ranks hold the same transform without a broadcast.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced split of range(n): the first n % world ranks get one extra item."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def round_robin(count: int, rank: int, world: int) -> List[int]:
+    """Indices of the independent units (scan pairs, clouds) this rank owns."""
+    return list(range(rank, count, world))
+
+
+def sharded_icp_fit(partial_fn: Callable[[np.ndarray, bool], "object"], params: _lib.IcpParams,
+                    group=None, all_reduce: Optional[Callable] = None):
+    """PointToPointICPGradient.Fit (icp.go:23-67) over a target split across ranks.
+
+    partial_fn(trans16, first) returns this rank's 16 float64 sums for the current transform as a
+    torch tensor (on the GPU for NCCL, on the CPU for gloo): {Value, SumW, G0..G5, R, nPairs, 0...}.
+    Returns (status, trans16, Evaluated, num_iteration); identical on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    trans = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1], np.float32)  # icp.go:47
+    it = C.c_int32(0)
+    conv = C.c_int32(0)
+    ev = _lib.Evaluated()
+    num_iteration = 0
+    status = _lib.OK
+    while True:
+        sums = partial_fn(trans, num_iteration == 0)
+        if all_reduce is not None:
+            sums = all_reduce(sums)
+        elif dist.is_available() and dist.is_initialized():
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        host = sums.detach().to("cpu", torch.float64).numpy() if hasattr(sums, "detach") else np.asarray(sums)
+        host = np.ascontiguousarray(host, np.float64)
+        num_iteration += 1  # icp.go:50
+        status = _lib.lib.pcg_icp_finish(host.ctypes.data, C.byref(params), C.byref(it), trans.ctypes.data,
+                                         C.byref(ev), C.byref(conv))
+        if status != _lib.OK or conv.value:
+            break
+    return status, trans, ev, num_iteration
+
+
+def make_gpu_partial(index, d_target_ptr: int, n: int, max_dist: float, stream: int = 0, stride: int = 12,
+                     off=(0, 4, 8)):
+    """partial_fn for sharded_icp_fit backed by pcg_icp_partial_dev (the rank's target slice is device resident)."""
+    import torch
+
+    out = torch.zeros(16, dtype=torch.float64, device="cuda")
+    offs = (C.c_int64 * 3)(*off)
+    order = None
+    if n >= (1 << 14) and len(index) > 0:  # Morton visit order, computed once: the target only moves rigidly
+        order = torch.empty(n, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib.pcg_query_order_dev(index._h, d_target_ptr, n, stride, offs, order.data_ptr(), stream))
+
+    def partial(trans: np.ndarray, first: bool):
+        _lib.check(_lib.lib.pcg_icp_partial_dev(index._h, d_target_ptr, n, stride, offs, max_dist, trans.ctypes.data,
+                                                1 if first else 0, order.data_ptr() if order is not None else None,
+                                                out.data_ptr(), stream))
+        return out
+
+    return partial

@@ -1,0 +1,98 @@
+"""Multi-GPU paths on real devices: sharded ICP with the NCCL all-reduce (needs >= 2 GPUs; on
+one GPU the single-rank loop is still checked against the fused single-GPU Fit)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_icp_single_rank_matches_fast_fit():
+    import torch
+
+    import pcgol_b200 as pg
+    from pcgol_b200 import dist as pdist, synth
+
+    base, target = synth.icp_pair(seed=3, n=30000, n_az=500)
+    idx = pg.Index(base)
+    d_t = torch.from_numpy(target).cuda()
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    p = icp.params()
+    status, trans, ev, iters = pdist.sharded_icp_fit(pdist.make_gpu_partial(idx, d_t.data_ptr(), len(target), 1.0), p)
+    ftrans, fstat = icp.fit(idx, target)
+    assert status == 0 and iters == fstat.num_iteration
+    # same float64 partial sums folded in a different order -> identical after rounding to float32,
+    # up to rare 1-ulp flips amplified over the iterations
+    np.testing.assert_allclose(trans, ftrans, rtol=0, atol=1e-5)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    import pcgol_b200 as pg
+    from pcgol_b200 import dist as pdist, synth
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        base, target = synth.icp_pair(seed=3, n=30000, n_az=500)
+        idx = pg.Index(base, device=rank)  # replicated index
+        lo, hi = pdist.shard_bounds(len(target), rank, world)
+        d_t = torch.from_numpy(target[lo:hi].copy()).cuda()
+        icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+        status, trans, ev, iters = pdist.sharded_icp_fit(
+            pdist.make_gpu_partial(idx, d_t.data_ptr(), hi - lo, 1.0), icp.params())
+        # query sharding: disjoint slices of the same queries, index replicated, no collective
+        q_all = synth.nn_queries(base, 50000, seed=5)
+        qlo, qhi = pdist.shard_bounds(len(q_all), rank, world)
+        ids, dsq = idx.nearest_batch(q_all[qlo:qhi], 1.0)
+        q.put((rank, status, trans.tobytes(), iters, qlo, ids.tobytes(), dsq.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_icp_and_queries_world2_nccl():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import pcgol_b200 as pg
+    from pcgol_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=500) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert res[0][1] == res[1][1] == 0
+    assert res[0][2] == res[1][2] and res[0][3] == res[1][3]  # identical transform on both ranks
+    base, target = synth.icp_pair(seed=3, n=30000, n_az=500)
+    idx = pg.Index(base)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    ftrans, fstat = icp.fit(idx, target)
+    assert fstat.num_iteration == res[0][3]
+    np.testing.assert_allclose(np.frombuffer(res[0][2], np.float32), ftrans, rtol=0, atol=1e-5)
+    q_all = synth.nn_queries(base, 50000, seed=5)
+    ids, dsq = idx.nearest_batch(q_all, 1.0)
+    got_ids = np.concatenate([np.frombuffer(r[5], np.int64) for r in res])
+    got_dsq = np.concatenate([np.frombuffer(r[6], np.float32) for r in res])
+    assert np.array_equal(got_ids, ids) and got_dsq.tobytes() == dsq.tobytes()
