@@ -1,0 +1,302 @@
+package pcgolgpu
+
+/*
+#cgo LDFLAGS: -lpcgol_b200
+#include <stdlib.h>
+#include "pcgol_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"runtime"
+	"unsafe"
+
+	"github.com/seqsense/pcgol/mat"
+	"github.com/seqsense/pcgol/pc"
+	"github.com/seqsense/pcgol/pc/filter"
+	"github.com/seqsense/pcgol/pc/filter/voxelgrid"
+	"github.com/seqsense/pcgol/pc/registration/icp"
+	"github.com/seqsense/pcgol/pc/storage"
+)
+
+// Status errors that have no counterpart in the reference (it would panic there).
+var ErrReferenceWouldPanic = errors.New("pcgolgpu: reference would panic (voxel/chunk index out of range)")
+
+func statusError(s C.pcg_status) error {
+	switch s {
+	case C.PCG_OK:
+		return nil
+	case C.PCG_E_NO_POINT:
+		return errors.New("no point") // pc/minmax.go:10-12
+	case C.PCG_E_NOT_ENOUGH_PAIRS:
+		return icp.ErrNotEnoughPairs // pc/registration/icp/evaluator.go:15-17
+	case C.PCG_E_REF_WOULD_PANIC:
+		return ErrReferenceWouldPanic
+	}
+	return fmt.Errorf("pcgolgpu: status %d: %s", int(s), C.GoString(C.pcg_last_error()))
+}
+
+// flatten turns any Vec3RandomAccessor into (pointer, n, stride, xyz offsets).
+// Fast paths pass the caller's memory as is (no Go pointer is retained by C after the call):
+// pc.Vec3Slice is []mat.Vec3 = contiguous [3]float32 records.
+func flatten(ra pc.Vec3RandomAccessor) (unsafe.Pointer, C.int64_t, C.int64_t, [3]C.int64_t, []float32) {
+	off := [3]C.int64_t{0, 4, 8}
+	if v, ok := ra.(pc.Vec3Slice); ok {
+		if len(v) == 0 {
+			return nil, 0, 12, off, nil
+		}
+		return unsafe.Pointer(&v[0]), C.int64_t(len(v)), 12, off, nil
+	}
+	buf := make([]float32, 3*ra.Len()) // generic path: copy through Vec3At
+	for i := 0; i < ra.Len(); i++ {
+		p := ra.Vec3At(i)
+		copy(buf[3*i:], p[:])
+	}
+	if len(buf) == 0 {
+		return nil, 0, 12, off, buf
+	}
+	return unsafe.Pointer(&buf[0]), C.int64_t(ra.Len()), 12, off, buf
+}
+
+// Index implements storage.Search on the GPU (pc/storage/search.go:13-17).
+type Index struct {
+	pc.Vec3RandomAccessor // Vec3At / Len / RawIndexAt stay on the host accessor
+	h                     *C.pcg_index
+}
+
+var _ storage.Search = (*Index)(nil)
+
+// NewIndex is the drop-in for kdtree.New (pc/storage/kdtree/kdtree.go:33).
+func NewIndex(ra pc.Vec3RandomAccessor, device int) (*Index, error) {
+	p, n, stride, off, keep := flatten(ra)
+	idx := &Index{Vec3RandomAccessor: ra}
+	s := C.pcg_index_build(p, n, stride, &off[0], C.int32_t(device), &idx.h)
+	runtime.KeepAlive(keep)
+	runtime.KeepAlive(ra)
+	if err := statusError(s); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(idx, (*Index).Close)
+	return idx, nil
+}
+
+func (k *Index) Close() {
+	if k.h != nil {
+		C.pcg_index_free(k.h)
+		k.h = nil
+	}
+}
+
+// Nearest is KDTree.Nearest (kdtree.go:83-92) as a batch of one.
+func (k *Index) Nearest(p mat.Vec3, maxRange float32) storage.Neighbor {
+	var out [1]storage.Neighbor
+	k.NearestBatch(pc.Vec3Slice{p}, maxRange, out[:])
+	return out[0]
+}
+
+// Range is KDTree.Range (kdtree.go:148-161), sorted by (DistSq, ID).
+func (k *Index) Range(p mat.Vec3, maxRange float32) []storage.Neighbor {
+	_, nb := k.RangeBatch(pc.Vec3Slice{p}, maxRange)
+	return nb
+}
+
+// NearestBatch answers every query in one call. storage.Neighbor{ID int; DistSq float32} has
+// the layout of C.pcg_neighbor on 64-bit targets, so `out` is written in place.
+func (k *Index) NearestBatch(q pc.Vec3RandomAccessor, maxRange float32, out []storage.Neighbor) {
+	p, n, stride, off, keep := flatten(q)
+	if n == 0 {
+		return
+	}
+	s := C.pcg_index_nearest(k.h, p, n, stride, &off[0], C.float(maxRange), (*C.pcg_neighbor)(unsafe.Pointer(&out[0])))
+	runtime.KeepAlive(keep)
+	runtime.KeepAlive(q)
+	if s != C.PCG_OK {
+		panic(statusError(s)) // Nearest has no error return in the reference
+	}
+}
+
+// RangeBatch returns CSR offsets (len(q)+1) and the concatenated neighbour lists.
+func (k *Index) RangeBatch(q pc.Vec3RandomAccessor, maxRange float32) ([]int64, []storage.Neighbor) {
+	p, n, stride, off, keep := flatten(q)
+	var r *C.pcg_range_result
+	s := C.pcg_index_range(k.h, p, n, stride, &off[0], C.float(maxRange), &r)
+	runtime.KeepAlive(keep)
+	runtime.KeepAlive(q)
+	if s != C.PCG_OK {
+		panic(statusError(s))
+	}
+	defer C.pcg_range_free(r)
+	total := int(C.pcg_range_total(r))
+	offs := make([]int64, int(n)+1)
+	copy(offs, unsafe.Slice((*int64)(unsafe.Pointer(C.pcg_range_offsets(r))), int(n)+1))
+	nb := make([]storage.Neighbor, total)
+	if total > 0 {
+		copy(nb, unsafe.Slice((*storage.Neighbor)(unsafe.Pointer(C.pcg_range_neighbors(r))), total))
+	}
+	return offs, nb
+}
+
+// voxelGrid implements filter.Filter (pc/filter/filter.go:7-9).
+type voxelGrid struct {
+	voxelgrid.Options
+	device int
+}
+
+// NewVoxelGrid is the drop-in for voxelgrid.New (pc/filter/voxelgrid/voxelgrid.go:23-33).
+func NewVoxelGrid(leafSize mat.Vec3, opts ...voxelgrid.Option) filter.Filter {
+	vg := &voxelGrid{Options: voxelgrid.Options{LeafSize: leafSize}}
+	for _, o := range opts {
+		o(&vg.Options)
+	}
+	return vg
+}
+
+func xyzOffsets(pp *pc.PointCloud) ([3]C.int64_t, error) {
+	var off [3]C.int64_t
+	found := 0
+	o := 0
+	for i, name := range pp.Fields {
+		switch name {
+		case "xyz":
+			return [3]C.int64_t{C.int64_t(o), C.int64_t(o + 4), C.int64_t(o + 8)}, nil
+		case "x":
+			off[0] = C.int64_t(o)
+			found |= 1
+		case "y":
+			off[1] = C.int64_t(o)
+			found |= 2
+		case "z":
+			off[2] = C.int64_t(o)
+			found |= 4
+		}
+		o += pp.Size[i] * pp.Count[i]
+	}
+	if found != 7 {
+		return off, errors.New("invalid field name") // pc/pointcloud.go:115
+	}
+	return off, nil
+}
+
+// Filter is voxelGrid.Filter (voxelgrid.go:35-134): same records, same order, same bits.
+func (f *voxelGrid) Filter(pp *pc.PointCloud) (*pc.PointCloud, error) {
+	off, err := xyzOffsets(pp)
+	if err != nil {
+		return nil, err
+	}
+	stride := pp.Stride()
+	out := make([]byte, stride*pp.Points)
+	leaf := [3]C.float{C.float(f.LeafSize[0]), C.float(f.LeafSize[1]), C.float(f.LeafSize[2])}
+	chunk := [3]C.int64_t{C.int64_t(f.ChunkSize[0]), C.int64_t(f.ChunkSize[1]), C.int64_t(f.ChunkSize[2])}
+	var in, outp unsafe.Pointer
+	if pp.Points > 0 {
+		in, outp = unsafe.Pointer(&pp.Data[0]), unsafe.Pointer(&out[0])
+	}
+	var n C.int64_t
+	s := C.pcg_voxelgrid_filter(in, C.int64_t(pp.Points), C.int64_t(stride), &off[0], &leaf[0], &chunk[0],
+		C.int32_t(f.device), outp, &n)
+	runtime.KeepAlive(pp)
+	if err := statusError(s); err != nil {
+		return nil, err
+	}
+	newPc := &pc.PointCloud{PointCloudHeader: pp.Clone(), Points: int(n), Data: out[:int(n)*stride]}
+	newPc.Width, newPc.Height = int(n), 1
+	return newPc, nil
+}
+
+// NearestPointCorresponder implements icp.PointToPointCorresponder (correspondence.go:14-37).
+type NearestPointCorresponder struct{ MaxDist float32 }
+
+func (c *NearestPointCorresponder) Pairs(base storage.Search, target pc.Vec3RandomAccessor) []icp.PointToPointCorrespondence {
+	idx := base.(*Index)
+	p, n, stride, off, keep := flatten(target)
+	baseID := make([]int64, int(n)+1)
+	targetID := make([]int64, int(n)+1)
+	dsq := make([]float32, int(n)+1)
+	var m C.int64_t
+	s := C.pcg_icp_pairs(idx.h, p, n, stride, &off[0], C.float(c.MaxDist),
+		(*C.int64_t)(unsafe.Pointer(&baseID[0])), (*C.int64_t)(unsafe.Pointer(&targetID[0])), (*C.float)(unsafe.Pointer(&dsq[0])), &m)
+	runtime.KeepAlive(keep)
+	if s != C.PCG_OK {
+		panic(statusError(s))
+	}
+	out := make([]icp.PointToPointCorrespondence, int(m))
+	for i := range out {
+		out[i] = icp.PointToPointCorrespondence{BaseID: int(baseID[i]), TargetID: int(targetID[i]), SquaredDistance: dsq[i]}
+	}
+	return out
+}
+
+// Mode selects the accumulation order of Evaluate: Strict reproduces the reference's
+// sequential float32 sums bit for bit, Fast uses a fixed float64 tree.
+type Mode int32
+
+const (
+	Strict Mode = C.PCG_ICP_STRICT
+	Fast   Mode = C.PCG_ICP_FAST
+)
+
+// PointToPointEvaluator implements icp.Evaluator (evaluator.go:32-36,69-189) with the default weight function.
+type PointToPointEvaluator struct {
+	Corresponder *NearestPointCorresponder
+	MinPairs     int
+	Mode         Mode
+}
+
+func (PointToPointEvaluator) HasGradient() bool { return true }
+func (PointToPointEvaluator) HasHessian() bool  { return false }
+
+func evaluatedFromC(e *C.pcg_evaluated) icp.Evaluated {
+	var out icp.Evaluated
+	out.Value = float32(e.value)
+	for i := 0; i < 6; i++ {
+		out.Gradient[i] = float32(e.gradient[i])
+	}
+	out.DistRMS = float32(e.dist_rms)
+	return out
+}
+
+func (e *PointToPointEvaluator) Evaluate(base storage.Search, target pc.Vec3RandomAccessor) (*icp.Evaluated, error) {
+	idx := base.(*Index)
+	p, n, stride, off, keep := flatten(target)
+	var ev C.pcg_evaluated
+	var np C.int64_t
+	s := C.pcg_icp_evaluate(idx.h, p, n, stride, &off[0], C.float(e.Corresponder.MaxDist), C.int32_t(e.MinPairs),
+		C.int32_t(e.Mode), &ev, &np)
+	runtime.KeepAlive(keep)
+	if err := statusError(s); err != nil {
+		return nil, err
+	}
+	out := evaluatedFromC(&ev)
+	return &out, nil
+}
+
+// PointToPointICPGradient.Fit has the signature of icp.PointToPointICPGradient.Fit (icp.go:23);
+// the whole loop (correspondence, Evaluate, Update, re-transform) runs on the device.
+type PointToPointICPGradient struct {
+	Evaluator      *PointToPointEvaluator
+	UpdaterFactory *icp.GradientDescentUpdaterFactory
+}
+
+func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomAccessor) (mat.Mat4, icp.Stat, error) {
+	idx := base.(*Index)
+	p, n, stride, off, keep := flatten(target)
+	var prm C.pcg_icp_params
+	prm.max_dist = C.float(r.Evaluator.Corresponder.MaxDist)
+	prm.min_pairs = C.int32_t(r.Evaluator.MinPairs)
+	prm.mode = C.int32_t(r.Evaluator.Mode)
+	if f := r.UpdaterFactory; f != nil { // zero values select the reference defaults (updater.go:24-33)
+		for i := 0; i < 6; i++ {
+			prm.weight[i] = C.float(f.Weight[i])
+			prm.threshold[i] = C.float(f.Threshold[i])
+		}
+		prm.max_iteration = C.int32_t(f.MaxIteration)
+	}
+	var trans mat.Mat4
+	var st C.pcg_icp_stat
+	s := C.pcg_icp_fit(idx.h, p, n, stride, &off[0], &prm, (*C.float)(unsafe.Pointer(&trans[0])), &st)
+	runtime.KeepAlive(keep)
+	stat := icp.Stat{Evaluated: evaluatedFromC(&st.evaluated), NumIteration: int(st.num_iteration)}
+	return trans, stat, statusError(s) // on ErrNotEnoughPairs: (trans so far, stat, err) like icp.go:51-53
+}

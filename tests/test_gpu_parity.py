@@ -379,3 +379,19 @@ def test_launch_counter_moves(pg):
     before = pg.kernel_launch_count()
     pg.Index(np.random.default_rng(0).random((100, 3), dtype=f32)).nearest((0.5, 0.5, 0.5), 1.0)
     assert pg.kernel_launch_count() > before
+
+
+def test_cpp_host_mirror_replays_reference_tables(pg):
+    """include/pcgol_b200.hpp (C++ mirror of storage.Search / filter.Filter / icp types) against the
+    reference's own table tests (tests/cpp/reference_tests.cpp)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "reference_tests")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok (0 failures)" in r.stdout
