@@ -1,6 +1,3 @@
-nvidia-smi -L
-python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -5
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -5 gpurun_out/bench_n2.err; python tools/show_bench.py gpurun_out/bench_n2.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_n2.json')); print(d['extra']['icp_sharded'])"
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1c.json 2> gpurun_out/bench_n1c.err;  python tools/show_bench.py gpurun_out/bench_n1c.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_n1c.json')); print(d['extra']['icp_sharded'])"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1_c.json 2> gpurun_out/bench_r1_c.err; tail -3 gpurun_out/bench_r1_c.err; python tools/show_bench.py gpurun_out/bench_r1_c.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_c.json 2>/dev/null; cat gpurun_out/bench_ref_c.json | cut -c1-400
