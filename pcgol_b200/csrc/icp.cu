@@ -1,18 +1,20 @@
 // icp.cu — point-to-point ICP by gradient descent (pc/registration/icp) on sm_100a.
 //
-// One iteration of PointToPointICPGradient.Fit (icp.go:48-65) is two kernels:
+// One iteration of PointToPointICPGradient.Fit (icp.go:48-65):
 //   icp_terms_kernel   per target point: Mat4.Transform with the accumulated transform
 //                      (icp.go:62-64), exact nearest neighbour in the base index
 //                      (correspondence.go:22-37) and the nine per-pair terms of
 //                      Evaluate (evaluator.go:130-144), fused — the pair list never exists.
-//   icp_finish_kernel  one CTA: reduces the nine sums, applies the tail of Evaluate
-//                      (evaluator.go:156-186) and gradientDescentUpdater.Update
-//                      (updater.go:44-71) on the device, so the loop never returns to
-//                      the host; once `done` is set the remaining launches fall through.
-// STRICT mode replays the reference's sequential float32 accumulation (nine warps, one
-// per accumulator, streaming the terms through shared memory): the trajectory is
-// bit-identical to the reference.  FAST mode reduces float64 partial sums in a fixed
-// tree (deterministic, GPU-count independent up to float64 rounding).
+//   FAST mode          every CTA folds its terms into float64 partials; the CTA that finishes
+//                      last (ticket counter) adds the partials in a fixed order (deterministic,
+//                      GPU-count independent up to float64 rounding) and runs the tail — one
+//                      kernel per iteration.
+//   STRICT mode        the terms are stored at the target's index and icp_replay_kernel (nine
+//                      single-warp CTAs, one accumulator each, on nine SMs) replays the
+//                      reference's sequential float32 accumulation: bit-identical trajectory.
+//   tail               evaluator.go:156-186 + gradientDescentUpdater.Update (updater.go:44-71)
+//                      run on the device, so the loop never returns to the host; once `done`
+//                      is set the remaining launches fall through.
 #include <algorithm>
 #include <vector>
 
@@ -33,20 +35,26 @@ struct IcpState {
   im::Eval ev;
   long long n_pairs;
   unsigned int pair_counter;
-  unsigned int pad_;
+  unsigned int ticket;   // CTAs that have published their part of the current reduction
+  float sums[12];        // the nine accumulators of the current Evaluate (strict replay, one CTA each)
 };
 
 constexpr int kTermThreads = 128;
 constexpr int kTerms = 9;  // Value, SumW, G0..G5, R
 
+__device__ __forceinline__ void icp_fast_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+                                                    int nblocks, float* s_sum, int* s_last);
+
 template <int MODE>
 __global__ void __launch_bounds__(kTermThreads)
     icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, float max_dist_sq,
                      IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
-                     double* __restrict__ partials) {
+                     double* __restrict__ partials, int finalize) {
   if (st->done) return;
   __shared__ float s_m[16];
   __shared__ int s_first;
+  __shared__ int s_last;
+  __shared__ float s_sum[kTerms];
   __shared__ double s_red[kTermThreads / 32][kTerms];
   const int tid = threadIdx.x;
   if (tid < 16) s_m[tid] = st->trans.m[tid];
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(kTermThreads)
     uint64_t best = nn_init(max_dist_sq);
     const uint64_t init = best;
     uint32_t pos = 0;
-    nn_traverse(base, x0, y0, z0, best, pos);
+    PCG_NN_TRAVERSE(base, x0, y0, z0, best, pos);
     if (best != init) {  // correspondence.go:27-29
       matched = 1;
       const float4 pb = __ldg(base.pts + pos);
@@ -113,11 +121,12 @@ __global__ void __launch_bounds__(kTermThreads)
       for (int w = 0; w < kTermThreads / 32; w++) s += s_red[w][tid];
       partials[(int64_t)blockIdx.x * kTerms + tid] = s;
     }
+    if (finalize) icp_fast_last_block(st, partials, (int)gridDim.x, s_sum, &s_last);
   }
 }
 
 constexpr int kFinishThreads = 32 * kTerms;
-constexpr int kChunk = 512;  // floats per staged chunk and accumulator
+constexpr int kChunk = 512;  // floats per staged chunk
 
 __device__ __forceinline__ float4 load_terms4(const float* __restrict__ s, int64_t idx, int64_t n) {
   if (idx + 3 < n) return *reinterpret_cast<const float4*>(s + idx);
@@ -128,78 +137,24 @@ __device__ __forceinline__ float4 load_terms4(const float* __restrict__ s, int64
   return v;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kFinishThreads)
-    icp_finish_kernel(IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad,
-                      const double* __restrict__ partials, int nblocks) {
-  if (st->done) return;
-  __shared__ __align__(16) float s_buf[kTerms][2][kChunk];
-  __shared__ float s_sum[kTerms];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (MODE == PCG_ICP_STRICT) {
-    // Warp `warp` owns accumulator `warp`. All lanes stream the next chunk from global
-    // memory while lane 0 adds the current one in order: the float32 sum is the reference's.
-    const float* __restrict__ src = terms + (int64_t)warp * n_pad;
-    const int64_t nchunks = (n + kChunk - 1) / kChunk;
-    float acc = 0.f;
-    float4 r[kChunk / 128];
-#pragma unroll
-    for (int j = 0; j < kChunk / 128; j++) r[j] = load_terms4(src, (int64_t)j * 128 + lane * 4, n);
-#pragma unroll
-    for (int j = 0; j < kChunk / 128; j++) *reinterpret_cast<float4*>(&s_buf[warp][0][j * 128 + lane * 4]) = r[j];
-    __syncwarp();
-    for (int64_t c = 0; c < nchunks; c++) {
-      const bool more = c + 1 < nchunks;
-      if (more) {
-#pragma unroll
-        for (int j = 0; j < kChunk / 128; j++)
-          r[j] = load_terms4(src, (c + 1) * kChunk + (int64_t)j * 128 + lane * 4, n);
-      }
-      if (lane == 0) {
-        const float4* b4 = reinterpret_cast<const float4*>(&s_buf[warp][c & 1][0]);
-#pragma unroll 8
-        for (int j = 0; j < kChunk / 4; j++) {
-          const float4 v = b4[j];
-          acc = __fadd_rn(acc, v.x);
-          acc = __fadd_rn(acc, v.y);
-          acc = __fadd_rn(acc, v.z);
-          acc = __fadd_rn(acc, v.w);
-        }
-      }
-      __syncwarp();
-      if (more) {
-#pragma unroll
-        for (int j = 0; j < kChunk / 128; j++)
-          *reinterpret_cast<float4*>(&s_buf[warp][(c + 1) & 1][j * 128 + lane * 4]) = r[j];
-      }
-      __syncwarp();
-    }
-    if (lane == 0) s_sum[warp] = acc;
-  } else {
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kTerms + warp];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) s_sum[warp] = (float)s;
-  }
-  __syncthreads();
-  if (tid != 0) return;
+// Tail of Evaluate + Update from the nine sums (one thread).
+__device__ __forceinline__ void icp_finalize(IcpState* __restrict__ st, const float* sum9) {
   const long long n_pairs = (long long)st->pair_counter;
   st->pair_counter = 0;
   st->n_pairs = n_pairs;
-  st->num_iteration++;                    // icp.go:50
-  if (n_pairs < (long long)st->min_pairs) {  // evaluator.go:97-106
+  st->num_iteration++;                        // icp.go:50
+  if (n_pairs < (long long)st->min_pairs) {   // evaluator.go:97-106
     st->status = PCG_E_NOT_ENOUGH_PAIRS;
     st->done = 1;
     return;
   }
   im::Sums sums;
-  sums.value = s_sum[0];
-  sums.sum_weight = s_sum[1];
-  for (int k = 0; k < 6; k++) sums.g[k] = s_sum[2 + k];
-  sums.rms = s_sum[8];
+  sums.value = sum9[0];
+  sums.sum_weight = sum9[1];
+  for (int k = 0; k < 6; k++) sums.g[k] = sum9[2 + k];
+  sums.rms = sum9[8];
   const im::Eval ev = im::evaluate_tail(sums);
-  st->ev = ev;                            // icp.go:54
+  st->ev = ev;                                // icp.go:54
   if (st->evaluate_only) {
     st->done = 1;
     return;
@@ -210,6 +165,90 @@ __global__ void __launch_bounds__(kFinishThreads)
   st->trans = trans;
   st->iter = iter;
   if (converged) st->done = 1;
+}
+
+// FAST mode: called by every CTA of icp_terms_kernel after it wrote its partials; the last one
+// to arrive reduces all of them (fixed order: lane-strided columns, then a shuffle tree).
+__device__ __forceinline__ void icp_fast_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+                                                    int nblocks, float* s_sum, int* s_last) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __threadfence();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    *s_last = (t == (unsigned int)nblocks - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  for (int k = warp; k < kTerms; k += kTermThreads / 32) {
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += __ldcg(&partials[(int64_t)b * kTerms + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) s_sum[k] = (float)s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    st->ticket = 0;
+    icp_finalize(st, s_sum);
+  }
+}
+
+// STRICT mode: CTA k (one warp) owns accumulator k.  All lanes stream the next chunk from
+// global memory while lane 0 adds the current one in order out of shared memory: the float32
+// sum is the reference's (evaluator.go:130-144).  Nine CTAs land on nine SMs, so each
+// dependent FADD chain has an issue port to itself; the last CTA to finish runs the tail.
+__global__ void __launch_bounds__(32)
+    icp_replay_kernel(IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad) {
+  if (st->done) return;
+  __shared__ __align__(16) float s_buf[2][kChunk];
+  const int lane = threadIdx.x, k = blockIdx.x;
+  const float* __restrict__ src = terms + (int64_t)k * n_pad;
+  const int64_t nchunks = (n + kChunk - 1) / kChunk;
+  float acc = 0.f;
+  float4 r[kChunk / 128];
+#pragma unroll
+  for (int j = 0; j < kChunk / 128; j++) r[j] = load_terms4(src, (int64_t)j * 128 + lane * 4, n);
+#pragma unroll
+  for (int j = 0; j < kChunk / 128; j++) *reinterpret_cast<float4*>(&s_buf[0][j * 128 + lane * 4]) = r[j];
+  __syncwarp();
+  for (int64_t c = 0; c < nchunks; c++) {
+    const bool more = c + 1 < nchunks;
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < kChunk / 128; j++) r[j] = load_terms4(src, (c + 1) * kChunk + (int64_t)j * 128 + lane * 4, n);
+    }
+    if (lane == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(&s_buf[c & 1][0]);
+#pragma unroll 16
+      for (int j = 0; j < kChunk / 4; j++) {
+        const float4 v = b4[j];
+        acc = __fadd_rn(acc, v.x);
+        acc = __fadd_rn(acc, v.y);
+        acc = __fadd_rn(acc, v.z);
+        acc = __fadd_rn(acc, v.w);
+      }
+    }
+    __syncwarp();
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < kChunk / 128; j++)
+        *reinterpret_cast<float4*>(&s_buf[(c + 1) & 1][j * 128 + lane * 4]) = r[j];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    st->sums[k] = acc;
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    if (t == (unsigned int)kTerms - 1u) {
+      __threadfence();
+      float sum9[kTerms];
+      for (int j = 0; j < kTerms; j++) sum9[j] = __ldcg(&st->sums[j]);
+      st->ticket = 0;
+      icp_finalize(st, sum9);
+    }
+  }
 }
 
 // Sharded ICP: fold the per-CTA float64 partials into 16 doubles for the all-reduce.
@@ -257,14 +296,11 @@ static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, floa
   for (int it = 0; it < iterations; it++) {
     if (mode == PCG_ICP_STRICT) {
       PCG_LAUNCH((icp_terms_kernel<PCG_ICP_STRICT>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
-                 w.st.p, w.terms.p, w.n_pad, w.partials.p);
-      PCG_LAUNCH((icp_finish_kernel<PCG_ICP_STRICT>), 1, kFinishThreads, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad,
-                 w.partials.p, w.nblocks);
+                 w.st.p, w.terms.p, w.n_pad, w.partials.p, 0);
+      PCG_LAUNCH(icp_replay_kernel, kTerms, 32, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad);
     } else {
       PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
-                 w.st.p, w.terms.p, w.n_pad, w.partials.p);
-      PCG_LAUNCH((icp_finish_kernel<PCG_ICP_FAST>), 1, kFinishThreads, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad,
-                 w.partials.p, w.nblocks);
+                 w.st.p, w.terms.p, w.n_pad, w.partials.p, 1);
     }
   }
 }
@@ -403,7 +439,7 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   const float mdsq = max_dist * max_dist;
   PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, d_order, mdsq,
-             w.st.p, w.terms.p, w.n_pad, w.partials.p);
+             w.st.p, w.terms.p, w.n_pad, w.partials.p, 0);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
 }
 
@@ -446,7 +482,7 @@ __global__ void __launch_bounds__(128)
   uint64_t best = nn_init(max_dist_sq);
   const uint64_t init = best;
   uint32_t pos = 0;
-  nn_traverse(base, p.x, p.y, p.z, best, pos);
+  PCG_NN_TRAVERSE(base, p.x, p.y, p.z, best, pos);
   const bool hit = best != init;
   ids[i] = hit ? (int32_t)(uint32_t)best : -1;
   dsq[i] = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_dist_sq;

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128)
   uint64_t best = nn_init(max_range_sq);
   const uint64_t init = best;
   uint32_t pos = 0;
-  nn_traverse(ix, p.x, p.y, p.z, best, pos);
+  PCG_NN_TRAVERSE(ix, p.x, p.y, p.z, best, pos);
   const bool hit = best != init;
   const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
   const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;

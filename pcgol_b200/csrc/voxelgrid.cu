@@ -688,11 +688,16 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
   // ---- phase 3: segmented centroid (same arithmetic as voxel_reduce_kernel)
   K* s_key = reinterpret_cast<K*>(dyn);
   float* s_p = reinterpret_cast<float*>(dyn + (size_t)kTile * sizeof(K));  // [3][kTile]
+  long long vc_cid = -1;  // sorted positions change chunk rarely: keep vcMin of the last chunk id
+  float vc[3] = {0.f, 0.f, 0.f};
   for (uint32_t l = tid; l < tile_count; l += kThreads) {
     const K key = __ldcg(&skeys[tile_base + l]);
     const float3 pt = load_xyz(v, __ldcg(&svals[tile_base + l]));
-    float vc[3];
-    chunk_min(P, (long long)((unsigned long long)key >> P.key_bits), vc);
+    const long long cid = (long long)((unsigned long long)key >> P.key_bits);
+    if (cid != vc_cid) {
+      chunk_min(P, cid, vc);
+      vc_cid = cid;
+    }
     s_key[l] = key;
     s_p[l] = __fsub_rn(pt.x, vc[0]);
     s_p[kTile + l] = __fsub_rn(pt.y, vc[1]);
@@ -749,8 +754,13 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       num++;
       ll++;
     } while (ll < tile_count && s_key[ll] == key);
-    float vc[3];
-    chunk_min(P, (long long)((unsigned long long)key >> P.key_bits), vc);
+    {
+      const long long cid = (long long)((unsigned long long)key >> P.key_bits);
+      if (cid != vc_cid) {
+        chunk_min(P, cid, vc);
+        vc_cid = cid;
+      }
+    }
     if (ll == tile_count) {  // the voxel continues in the next tile(s)
       uint32_t g = tile_base + tile_count;
       while (g < n && __ldcg(&skeys[g]) == key) {

@@ -26,3 +26,8 @@ if icp:
         for k, kv in (v.get("kernels") or {}).items():
             print(f"    {k:44s} {kv['launches']:4d} x {kv['avg_us']:9.2f} us  share {kv['share']:.3f}")
     print("  cpu", icp.get("cpu_baseline", {}).get("value"), "parity", icp.get("parity"))
+
+for k in ("icp_sharded", "icp_farm"):
+    if ex.get(k):
+        v = dict(ex[k]); v.pop("trans", None); v.pop("config", None)
+        print(k, v)
