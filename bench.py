@@ -506,6 +506,65 @@ def bench_icp_farm(pg, torch, dist, rank, args, peak, pairs_per_gpu=64, distinct
             "modes": out}
 
 
+def bench_config5(pg, torch, dist, rank, args, peak):
+    """BASELINE config 5 on one GPU (opt-in, --config5): 50M-point map, VoxelGrid (multi-kernel path, HBM-sized
+    working set) and batched Range (1M queries, r = 0.2 m) against the 50M-point index."""
+    from pcgol_b200 import synth
+
+    big = synth.tiled_map(10, 5)
+    n = len(big)
+    dev = torch.device("cuda")
+    device = torch.cuda.current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+    d_in = torch.from_numpy(big).to(dev)
+    d_out = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+    vg = pg.VoxelGrid(LEAF, CHUNK, device=device)
+    m_box = [0]
+
+    def step(i):
+        m_box[0] = vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr(), stream)
+
+    step(0)
+    step(1)
+    ms = timed_region(dist, torch, step, 5)
+    report = profile_kernels(pg, torch, step, 3)
+    m = m_box[0]
+    kb = 8
+    algo = {"minmax_kernel": 12 * n, "(voxel_key_kernel<K>)": 12 * n + kb * n, "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n,
+            "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m}
+    roof, shares = dominant(report, algo, peak)
+    step_s = ms / 5 / 1e3
+    out = {"voxelgrid": {"points": n, "voxels_out": int(m), "value_mpts": n / step_s / 1e6, "ms_per_step": ms / 5,
+                         "roofline": roof, "kernels": shares,
+                         "pipeline_roofline": {"algorithmic_bytes_per_step": 12 * n + 12 * m,
+                                               "achieved": (12 * n + 12 * m) / step_s / 1e9, "peak": peak[0],
+                                               "frac": (12 * n + 12 * m) / step_s / 1e9 / peak[0]}}}
+    t0 = time.perf_counter()
+    idx = pg.Index.from_device(d_in.data_ptr(), n, device=device, stream=stream)
+    torch.cuda.synchronize()
+    out["index_build_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["index_bytes"] = idx.device_bytes()
+    rng = np.random.default_rng(5)
+    sel = rng.choice(n, 1_000_000, replace=False)
+    q = (big[sel] + rng.normal(0, 0.05, (len(sel), 3))).astype(np.float32)
+    t0 = time.perf_counter()
+    off, ids, dsq = idx.range_batch(q, 0.2)
+    dt = time.perf_counter() - t0
+    out["range"] = {"queries": len(q), "neighbours": int(off[-1]), "queries_per_s_e2e": len(q) / dt,
+                    "neighbours_per_s_e2e": int(off[-1]) / dt, "radius": 0.2}
+    d_q = torch.from_numpy(q).to(dev)
+    d_ids = torch.empty(len(q), dtype=torch.int32, device=dev)
+    d_d = torch.empty(len(q), dtype=torch.float32, device=dev)
+
+    def nstep(i):
+        idx.nearest_dev(d_q.data_ptr(), len(q), 1.0, d_ids.data_ptr(), d_d.data_ptr(), stream)
+
+    nstep(0)
+    ms = timed_region(dist, torch, nstep, 5)
+    out["nearest"] = {"queries": len(q), "value": len(q) * 5 / (ms / 1e3), "ms_per_step": ms / 5}
+    return out
+
+
 def bench_icp_sharded(pg, torch, dist, rank, args, peak):
     """BASELINE config 5 (ICP part): ONE alignment of a 1M-pt scan against a 1M-pt base, target sharded over the
     ranks, base index replicated, 16 float64 sums all-reduced over NCCL each iteration."""
@@ -618,6 +677,7 @@ def run_ours(args):
         icp = bench_icp(pg, torch, dist, rank, args, peak)
         icp_sh = bench_icp_sharded(pg, torch, dist, rank, args, peak)
         icp_farm = bench_icp_farm(pg, torch, dist, rank, args, peak)
+    cfg5 = bench_config5(pg, torch, dist, rank, args, peak) if args.config5 else None
     line = None
     if rank == 0:
         cores = os.cpu_count() or 1
@@ -630,6 +690,8 @@ def run_ours(args):
         if not args.no_extra:
             cpu_extras(nn, icp, cores)
             extra = {"nn": nn, "icp": icp, "icp_sharded": icp_sh, "icp_farm": icp_farm}
+        if cfg5 is not None:
+            extra["config5_50m"] = cfg5
         line = {
             "metric": "VoxelGrid Mpts/s", "value": vg["value"], "unit": "Mpts/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": vg["ms_per_step"], "higher_is_better": True,
@@ -666,6 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="primary VoxelGrid line only")
+    ap.add_argument("--config5", action="store_true", help="add the 50M-point map workload (slow; not in the default run)")
     ap.add_argument("--only", default=None, choices=["nn", "icp"],
                     help="profiling aid: run just this extra workload and print its object (not a bench line)")
     args = ap.parse_args()

@@ -171,6 +171,7 @@ int64_t pcg_kernel_launch_count(void) { return g_launches.load(); }
 
 void pcg_profile_enable(int32_t on) { g_profile.store(on ? 1 : 0); }
 
+
 // Synchronises the device(s), folds the recorded events into per-kernel totals and writes
 // a JSON object {"kernel": {"launches": n, "total_ms": t}, ...}; clears the records.
 int64_t pcg_profile_report(char* buf, int64_t cap) {

@@ -119,9 +119,19 @@ __device__ __forceinline__ void nn_traverse(const IndexView& ix, float qx, float
 // boxes are one aligned 128-byte line), so the chain of dependent loads per descent is half as
 // long.  Children are ordered by their box distance with the child slot packed into the two
 // low mantissa bits; clearing those bits again only lowers the bound, so pruning stays exact.
+#ifdef PCG_NN_STATS
+__device__ unsigned long long g_nn_stats[4];  // node steps, leaf scans, pushes, queries (tuning builds only)
+#define PCG_STAT(i) atomicAdd(&g_nn_stats[i], 1ull)
+#else
+#define PCG_STAT(i) \
+  do {              \
+  } while (0)
+#endif
+
 __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, float qy, float qz, uint64_t& best,
                                              uint32_t& best_pos) {
   if (ix.n == 0) return;
+  PCG_STAT(3);
   if (qx != qx || qy != qy || qz != qz) return;
   uint32_t stack_node[kMaxStack + 8];
   float stack_d[kMaxStack + 8];
@@ -151,6 +161,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
   for (;;) {
     while (node < P) {
       const float4* cb = ix.boxes + 8 * (size_t)node;  // boxes of nodes 4*node .. 4*node+3
+      PCG_STAT(0);
       uint32_t key[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -179,6 +190,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
       for (int j = 3; j >= 1; j--) {  // farthest first: the nearest of them is popped first
         const float dj = __uint_as_float(key[j] & ~3u);
         if (dj <= bestd) {
+          PCG_STAT(2);
           stack_node[sp] = 4 * node + (key[j] & 3u);
           stack_d[sp] = dj;
           sp++;
@@ -187,6 +199,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
       node = 4 * node + (key[0] & 3u);
     }
     if (node) {
+      PCG_STAT(1);
       const uint32_t base = (node - P) * kLeaf;
       const float4* lp = ix.pts + base;
 #pragma unroll

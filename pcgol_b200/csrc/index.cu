@@ -83,6 +83,38 @@ __device__ __forceinline__ unsigned long long spread16(uint32_t x) {  // 16 bits
   return v;
 }
 
+// 3-D Hilbert index (Skilling's transpose algorithm) of BITS-bit coordinates.  Unlike the Morton
+// curve the Hilbert curve never jumps: runs of consecutive points - the leaves and every implicit
+// node above them - stay compact, which is what makes the packed tree prune well
+// (measured: 12 -> see DESIGN.md leaf scans per query with Morton order).
+template <int BITS>
+__device__ __forceinline__ unsigned long long hilbert_key(uint32_t x0, uint32_t x1, uint32_t x2) {
+  uint32_t X[3] = {x0, x1, x2};
+  const uint32_t M = 1u << (BITS - 1);
+  for (uint32_t Q = M; Q > 1; Q >>= 1) {
+    const uint32_t Pm = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (X[i] & Q) {
+        X[0] ^= Pm;
+      } else {
+        const uint32_t t = (X[0] ^ X[i]) & Pm;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  uint32_t t = 0;
+  for (uint32_t Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t;
+  X[1] ^= t;
+  X[2] ^= t;
+  return (spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2]);
+}
+
 __global__ void __launch_bounds__(256)
     morton_kernel(CloudView v, const uint32_t* __restrict__ bbox6, unsigned long long* __restrict__ keys) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,12 +132,17 @@ __global__ void __launch_bounds__(256)
   unsigned long long key = 0;
   bool finite = isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]);
   if (finite) {
+    uint32_t u[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       float q = (c[k] - lo[k]) * scale;
-      uint32_t u = (uint32_t)fminf(fmaxf(q, 0.f), (float)((1 << kMortonBitsPerAxis) - 1));
-      key |= spread16(u) << k;
+      u[k] = (uint32_t)fminf(fmaxf(q, 0.f), (float)((1 << kMortonBitsPerAxis) - 1));
     }
+#ifdef PCG_MORTON
+    key = spread16(u[0]) | (spread16(u[1]) << 1) | (spread16(u[2]) << 2);
+#else
+    key = hilbert_key<kMortonBitsPerAxis>(u[0], u[1], u[2]);
+#endif
   } else {
     key = (1ull << (3 * kMortonBitsPerAxis)) - 1;  // non-finite points go last; they never match a query
   }
@@ -258,6 +295,18 @@ void index_free(Index* ix) {
   delete ix;
 }
 
+#ifdef PCG_NN_STATS
+}  // namespace pcg
+extern "C" void pcg_debug_nn_stats(unsigned long long out[4]) {
+  using namespace pcg;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_nn_stats, sizeof(unsigned long long) * 4);
+  unsigned long long z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_nn_stats, z, sizeof(z));
+}
+namespace pcg {
+#endif
+
 // ---- query ordering -----------------------------------------------------------------------
 #ifndef PCG_QBITS
 #define PCG_QBITS 10
@@ -287,12 +336,17 @@ __global__ void __launch_bounds__(256)
     if (valid) {
       float3 p = load_xyz(q, i);
       float c[3] = {p.x, p.y, p.z};
+      uint32_t u[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         float t = (c[k] - lo[k]) * scale;  // queries outside the box clamp to its faces; NaN -> 0
-        uint32_t u = (uint32_t)fminf(fmaxf(t, 0.f), cells - 1.f);
-        key |= (uint32_t)spread16(u) << k;
+        u[k] = (uint32_t)fminf(fmaxf(t, 0.f), cells - 1.f);
       }
+#ifdef PCG_MORTON
+      key = (uint32_t)(spread16(u[0]) | (spread16(u[1]) << 1) | (spread16(u[2]) << 2));
+#else
+      key = (uint32_t)hilbert_key<kQueryBitsPerAxis>(u[0], u[1], u[2]);
+#endif
       keys[i] = key;
     }
     rsort::hist_add_key(s_hist, key, valid, 0, passes);

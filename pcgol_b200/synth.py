@@ -123,3 +123,21 @@ def with_fields(xyz: np.ndarray, extra_u32: int = 1, seed: int = 9) -> tuple:
     rec[:, :3] = xyz.view(np.uint32)
     rec[:, 3:] = rng.integers(0, 2**32 - 1, size=(n, extra_u32), dtype=np.uint32)
     return rec.view(np.uint8).reshape(-1), 4 * (3 + extra_u32), (0, 4, 8)
+
+
+def tiled_map(n_tiles_x: int, n_tiles_y: int, seed: int = 2, n_az: int = 15625, spacing=(78.0, 48.0)) -> np.ndarray:
+    """BASELINE config 5 stand-in: a large map made of shifted copies of 1M-point scans (ray casting
+    50M rays on the host would take minutes).  Copies get a small per-tile jitter so that no two points
+    coincide; min(x, y, z) stays 0."""
+    scan = lidar_scan(seed, n_az=n_az)
+    rng = np.random.default_rng(seed + 12345)
+    out = np.empty((n_tiles_x * n_tiles_y * len(scan), 3), np.float32)
+    k = 0
+    for ix in range(n_tiles_x):
+        for iy in range(n_tiles_y):
+            sh = np.array([ix * spacing[0], iy * spacing[1], 0.0], np.float32)
+            jit = rng.normal(0.0, 0.003, scan.shape).astype(np.float32) if (ix or iy) else 0.0
+            out[k:k + len(scan)] = scan + sh + jit
+            k += len(scan)
+    out -= out.min(axis=0)
+    return out
