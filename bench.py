@@ -237,6 +237,20 @@ def profile_kernels(pg, torch, fn, steps):
     return pg._lib.profile_report()
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/ncu_summary.py traffic); None if that kernel was not captured."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    for key, val in table.items():
+        if key in kernel_name:
+            return val.get("dram_bytes_per_launch")
+    return None
+
+
 def dominant(report, algo_bytes, peak):
     """Roofline object for the kernel with the largest share of the step."""
     if not report:
@@ -250,7 +264,8 @@ def dominant(report, algo_bytes, peak):
     roof = {"bound": "hbm", "kernel": name, "avg_launch_us": avg_s * 1e6, "share_of_step": shares[name]["share"],
             "algorithmic_bytes_per_launch": b, "achieved": (b / avg_s / 1e9) if b else None, "peak": peak[0],
             "peak_source": peak[1], "unit": "GB/s", "frac": (b / avg_s / 1e9 / peak[0]) if b else None,
-            "traffic": None}
+            "traffic": ncu_traffic(name),
+            "timing": "CUDA events around every launch of this kernel over K steps (separate pass, same command)"}
     return roof, shares
 
 
@@ -309,6 +324,7 @@ def bench_voxelgrid(pg, torch, dist, rank, args, peak):
     # algorithmic bytes per launch of each kernel of the pipeline
     kb = 4  # (chunk id, voxel key) needs 29 bits for this config -> 32-bit sort keys
     algo = {
+        "voxelgrid_fused_kernel<IPT>": 12 * n + 12 * m,  # the whole Filter is this one kernel: N*stride in, M*stride out
         "minmax_kernel": 12 * n,
         "(voxel_key_kernel<K>)": 12 * n + kb * n,
         "(histogram_kernel<K>)": kb * n,

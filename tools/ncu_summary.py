@@ -64,5 +64,34 @@ def rep(path, out):
     print(open(out).read())
 
 
+def traffic(out, *reps):
+    """profiles/traffic.json: {kernel short name: {dram_bytes_per_launch, source}} from --set full captures."""
+    import json
+    import os
+
+    table = json.load(open(out)) if os.path.exists(out) else {}
+    for path in reps:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per = {}
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = hdr.index(m)
+                tot += float(r[i].replace(",", "")) * scale[units[i]]
+            per.setdefault(name, []).append(tot)
+        for name, vals in per.items():
+            table[name] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals),
+                           "source": os.path.basename(path)}
+    json.dump(table, open(out, "w"), indent=1, sort_keys=True)
+    print(json.dumps(table, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], *sys.argv[3:])
+    else:
+        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
