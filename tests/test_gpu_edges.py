@@ -1,0 +1,144 @@
+"""Edge cases of the hot path on the GPU, each checked against the oracle: ragged and degenerate
+sizes, duplicates, zero ranges, non-finite parameters, tile-boundary sizes of the fused kernel."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import pcgol_b200
+
+    return pcgol_b200
+
+
+def _vg_both(pg, oracle, xyz, leaf, chunk):
+    rc, exp = oracle.voxelgrid_filter(xyz.view(np.uint8).reshape(-1), 12, (0, 4, 8), leaf, chunk, mode="sparse")
+    from pcgol_b200 import _lib
+    out = np.empty(max(1, xyz.size * 4), np.uint8)
+    n_out = C.c_int64(0)
+    flat = np.ascontiguousarray(xyz).view(np.uint8).reshape(-1)
+    grc = _lib.lib.pcg_voxelgrid_filter(flat.ctypes.data if len(flat) else None, len(xyz), 12, (C.c_int64 * 3)(0, 4, 8),
+                                        np.asarray(leaf, f32).ctypes.data, np.asarray(chunk, np.int64).ctypes.data, 0,
+                                        out.ctypes.data, C.byref(n_out))
+    return rc, exp, grc, out[: n_out.value * 12]
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 511, 512, 513, 2047, 2048, 2049, 8191, 8192, 8193, 303103, 303104,
+                               303105])
+def test_voxelgrid_sizes_around_tile_boundaries(pg, oracle, n):
+    rng = np.random.default_rng(n)
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([6.0, 5.0, 2.0], f32)).astype(f32)
+    xyz -= xyz.min(axis=0)
+    for chunk in ((0, 0, 0), (16, 16, 16)):
+        rc, exp, grc, got = _vg_both(pg, oracle, xyz, (0.25, 0.25, 0.25), chunk)
+        assert rc == oracle.OK and grc == 0
+        assert got.tobytes() == exp.tobytes(), (n, chunk)
+
+
+def test_voxelgrid_all_points_identical_and_duplicates(pg, oracle):
+    xyz = np.tile(np.array([[1.5, 2.5, 0.5]], f32), (5000, 1))
+    for chunk in ((0, 0, 0), (8, 8, 8)):
+        rc, exp, grc, got = _vg_both(pg, oracle, xyz, (0.1, 0.1, 0.1), chunk)
+        assert rc == oracle.OK and grc == 0 and got.tobytes() == exp.tobytes()
+        assert len(got) == 12
+    rng = np.random.default_rng(1)
+    base = (rng.random((300, 3), dtype=f32) * f32(3)).astype(f32)
+    xyz = base[rng.integers(0, 300, 20000)]  # heavy duplication: long voxels crossing tiles
+    xyz = (xyz - xyz.min(axis=0)).astype(f32)
+    rc, exp, grc, got = _vg_both(pg, oracle, xyz, (0.5, 0.5, 0.5), (0, 0, 0))
+    assert rc == oracle.OK and grc == 0 and got.tobytes() == exp.tobytes()
+
+
+def test_voxelgrid_one_giant_voxel_spans_many_tiles(pg, oracle):
+    rng = np.random.default_rng(2)
+    xyz = (rng.random((100000, 3), dtype=f32) * f32(0.9)).astype(f32)
+    xyz[0] = 0
+    rc, exp, grc, got = _vg_both(pg, oracle, xyz, (1.0, 1.0, 1.0), (0, 0, 0))
+    assert rc == oracle.OK and grc == 0
+    assert len(exp) == 12 and got.tobytes() == exp.tobytes()  # 100k-term sequential float32 sum, bit-exact
+
+
+def test_voxelgrid_signed_zero_minimum(pg, oracle):
+    # MinMaxVec3 keeps the first occurrence among equal values (-0 == +0): the sign of vMin survives
+    xyz = np.array([[0.0, -0.0, 0.0], [-0.0, 0.0, -0.0], [1.0, 1.0, 1.0], [1.01, 1.0, 1.0], [-0.0, -0.0, 0.0]], f32)
+    for order in (slice(None), slice(None, None, -1)):
+        pts = np.ascontiguousarray(xyz[order])
+        rc, exp, grc, got = _vg_both(pg, oracle, pts, (0.5, 0.5, 0.5), (4, 4, 4))
+        assert rc == oracle.OK and grc == 0 and got.tobytes() == exp.tobytes()
+
+
+def test_voxelgrid_bad_leaf_is_reported_not_crashed(pg, oracle):
+    from pcgol_b200 import _lib
+    xyz = np.array([[0, 0, 0], [1, 1, 1]], f32)
+    rc, exp, grc, got = _vg_both(pg, oracle, xyz, (0.0, 0.1, 0.1), (0, 0, 0))  # division by zero -> int(+Inf)
+    assert rc == oracle.E_REF_UNDEFINED and grc == _lib.E_REF_UNDEFINED
+    rc, exp, grc, got = _vg_both(pg, oracle, xyz, (0.1, 0.1, 0.1), (0, 0, 0))
+    assert rc == oracle.OK and grc == 0 and got.tobytes() == exp.tobytes()
+
+
+def test_nearest_duplicates_zero_range_and_self_queries(pg, oracle):
+    rng = np.random.default_rng(3)
+    pts = (rng.random((4000, 3), dtype=f32) * f32(4)).astype(f32)
+    pts = np.concatenate([pts, pts[:1000], pts[:10]])  # duplicates: lowest index must win
+    idx = pg.Index(pts)
+    nv = oracle.Search(pts, "naive")
+    for mr in (0.0, 1e-30, 0.2, 50.0):
+        ids, d = idx.nearest_batch(pts, mr)
+        eids, ed = nv.nearest(pts, mr)
+        assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes(), mr
+    off, rids, rd = idx.range_batch(pts[:300], 0.0)
+    assert off[-1] == 0
+    off, rids, rd = idx.range_batch(pts[:300], 0.3)
+    eoff, erids, erd = nv.range(pts[:300], 0.3)
+    assert np.array_equal(off, eoff) and np.array_equal(rids, erids) and rd.tobytes() == erd.tobytes()
+
+
+def test_nearest_collinear_and_coplanar_clouds(pg, oracle):
+    t = np.linspace(0, 10, 3000, dtype=f32)
+    line = np.stack([t, np.zeros_like(t), np.zeros_like(t)], 1)
+    g = np.linspace(0, 5, 60, dtype=f32)
+    plane = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    plane = np.concatenate([plane, np.full((len(plane), 1), 2.0, f32)], 1).astype(f32)
+    rng = np.random.default_rng(4)
+    for pts in (line, plane):
+        q = (pts[rng.integers(0, len(pts), 2000)] + rng.normal(0, 0.2, (2000, 3))).astype(f32)
+        ids, d = pg.Index(pts).nearest_batch(q, 1.0)
+        eids, ed = oracle.Search(pts, "naive").nearest(q, 1.0)
+        assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+
+
+def test_icp_single_iteration_budget_and_custom_updater(pg, oracle):
+    from pcgol_b200 import synth
+    base, target = synth.icp_pair(seed=9, n=5000, n_az=200)
+    idx = pg.Index(base)
+    for kw in (dict(max_iteration=1), dict(max_iteration=7, weight=(0.1, 0.2, 0.3, 0.05, 0.05, 0.4)),
+               dict(threshold=(1e-4,) * 6, max_iteration=35), dict(threshold=(10.0,) * 6)):
+        uf = pg.GradientDescentUpdaterFactory(weight=kw.get("weight", (0,) * 6), threshold=kw.get("threshold", (0,) * 6),
+                                              max_iteration=kw.get("max_iteration", 0))
+        icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)), uf)
+        trans, stat = icp.fit(idx, target)
+        rc, etrans, eev, eit = oracle.icp_fit(oracle.Search(base, "kdtree"), target,
+                                              oracle.icp_params(1.0, 0, kw.get("weight"), kw.get("threshold"),
+                                                                kw.get("max_iteration", 0)))
+        assert rc == oracle.OK and stat.num_iteration == eit, kw
+        assert trans.tobytes() == etrans.tobytes(), kw
+
+
+def test_icp_large_rotation_step_uses_trig_branch(pg, oracle):
+    # |delta omega| >= 0.1 rad reaches the sin/cos branch of rodriguesToRotation (rodrigues.go:26-31)
+    from pcgol_b200 import synth
+    base, _ = synth.icp_pair(seed=4, n=4000, n_az=200)
+    target = synth.rigid(base, 25.0, (0.0, 0.0, 0.0), base.mean(axis=0))
+    uf = pg.GradientDescentUpdaterFactory(weight=(0.3, 0.3, 0.3, 3.0, 3.0, 3.0), max_iteration=6)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(3.0)), uf)
+    trans, stat = icp.fit(pg.Index(base), target)
+    rc, etrans, _, eit = oracle.icp_fit(oracle.Search(base, "kdtree"), target,
+                                        oracle.icp_params(3.0, 0, (0.3, 0.3, 0.3, 3.0, 3.0, 3.0), None, 6))
+    assert rc == oracle.OK and stat.num_iteration == eit
+    # float64 sin/cos of the device vs glibc: equal after rounding to float32 except on rare last-ulp flips
+    np.testing.assert_allclose(trans, etrans, rtol=0, atol=2e-6)

@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -3 gpurun_out/bench_n2.err | cut -c1-300; python tools/show_bench.py gpurun_out/bench_n2.json | grep -E "VoxelGrid|^NN|^ICP|icp_"
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.json 2>/dev/null; python tools/show_bench.py gpurun_out/bench_n1.json | grep -E "VoxelGrid|^NN|^ICP|icp_"
+python -m pytest tests/test_gpu_edges.py -x -q 2>&1 | tail -15
