@@ -117,24 +117,25 @@ func (k *Index) NearestBatch(q pc.Vec3RandomAccessor, maxRange float32, out []st
 	}
 }
 
-// RangeBatch returns CSR offsets (len(q)+1) and the concatenated neighbour lists.
+// RangeBatch returns CSR offsets (len(q)+1) and the concatenated neighbour lists, using the
+// two-call protocol so that the result lives in Go-allocated memory (count, then fill).
 func (k *Index) RangeBatch(q pc.Vec3RandomAccessor, maxRange float32) ([]int64, []storage.Neighbor) {
 	p, n, stride, off, keep := flatten(q)
-	var r *C.pcg_range_result
-	s := C.pcg_index_range(k.h, p, n, stride, &off[0], C.float(maxRange), &r)
-	runtime.KeepAlive(keep)
-	runtime.KeepAlive(q)
+	offs := make([]int64, int(n)+1)
+	s := C.pcg_index_range_count(k.h, p, n, stride, &off[0], C.float(maxRange), (*C.int64_t)(unsafe.Pointer(&offs[0])))
 	if s != C.PCG_OK {
 		panic(statusError(s))
 	}
-	defer C.pcg_range_free(r)
-	total := int(C.pcg_range_total(r))
-	offs := make([]int64, int(n)+1)
-	copy(offs, unsafe.Slice((*int64)(unsafe.Pointer(C.pcg_range_offsets(r))), int(n)+1))
-	nb := make([]storage.Neighbor, total)
-	if total > 0 {
-		copy(nb, unsafe.Slice((*storage.Neighbor)(unsafe.Pointer(C.pcg_range_neighbors(r))), total))
+	nb := make([]storage.Neighbor, offs[n])
+	if len(nb) > 0 {
+		s = C.pcg_index_range_fill(k.h, p, n, stride, &off[0], C.float(maxRange),
+			(*C.int64_t)(unsafe.Pointer(&offs[0])), (*C.pcg_neighbor)(unsafe.Pointer(&nb[0])))
+		if s != C.PCG_OK {
+			panic(statusError(s))
+		}
 	}
+	runtime.KeepAlive(keep)
+	runtime.KeepAlive(q)
 	return offs, nb
 }
 

@@ -120,6 +120,14 @@ pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, in
 typedef struct pcg_range_result pcg_range_result;
 pcg_status pcg_index_range(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
                            const int64_t q_xyz_off[3], float max_range, pcg_range_result** out);
+/* Two-call form with caller-owned buffers (lets a Go caller allocate / reuse / pin the result):
+ * count fills offsets[nq+1]; fill writes offsets[nq] neighbours, list i at [offsets[i], offsets[i+1]).
+ * The offsets passed to fill must come from count with the same queries and range. */
+pcg_status pcg_index_range_count(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                 const int64_t q_xyz_off[3], float max_range, int64_t* offsets);
+pcg_status pcg_index_range_fill(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                const int64_t q_xyz_off[3], float max_range, const int64_t* offsets,
+                                pcg_neighbor* out);
 int64_t pcg_range_total(const pcg_range_result* r);
 const int64_t* pcg_range_offsets(const pcg_range_result* r);       /* nq+1 entries */
 const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r); /* total entries */

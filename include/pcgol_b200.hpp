@@ -129,15 +129,13 @@ class Index : public Search {
     return out;
   }
   std::vector<Neighbor> RangeBatch(const pc::View& q, float maxRange, std::vector<int64_t>* offsets) const {
-    pcg_range_result* r = nullptr;
-    check(pcg_index_range(h_, q.data, q.n, q.stride, q.off.data(), maxRange, &r));
-    const int64_t total = pcg_range_total(r);
-    const int64_t* off = pcg_range_offsets(r);
-    const pcg_neighbor* nb = pcg_range_neighbors(r);
-    offsets->assign(off, off + q.n + 1);
+    offsets->assign((size_t)q.n + 1, 0);  // two-call protocol: count, then fill into caller-owned memory
+    check(pcg_index_range_count(h_, q.data, q.n, q.stride, q.off.data(), maxRange, offsets->data()));
+    const int64_t total = offsets->back();
+    std::vector<pcg_neighbor> raw((size_t)total);
+    check(pcg_index_range_fill(h_, q.data, q.n, q.stride, q.off.data(), maxRange, offsets->data(), raw.data()));
     std::vector<Neighbor> out((size_t)total);
-    for (int64_t i = 0; i < total; i++) out[(size_t)i] = Neighbor{nb[i].id, nb[i].dist_sq};
-    pcg_range_free(r);
+    for (int64_t i = 0; i < total; i++) out[(size_t)i] = Neighbor{raw[(size_t)i].id, raw[(size_t)i].dist_sq};
     return out;
   }
   pcg_index* handle() const { return h_; }

@@ -94,6 +94,8 @@ _sigs = {
     "pcg_index_nearest": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp]),
     "pcg_index_nearest_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp, _vp]),
     "pcg_index_range": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, C.POINTER(_vp)]),
+    "pcg_index_range_count": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp]),
+    "pcg_index_range_fill": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp]),
     "pcg_range_total": (_i64, [_vp]),
     "pcg_range_offsets": (_vp, [_vp]),
     "pcg_range_neighbors": (_vp, [_vp]),

@@ -2,6 +2,7 @@
 // Host entry points stage caller buffers through device memory (stream-ordered pool),
 // run the device pipelines of voxelgrid.cu / index.cu / icp.cu and copy results back.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -65,6 +66,10 @@ void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_
                     pcg_neighbor* d_aos, cudaStream_t stream);
 void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
                   DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream);
+void range_count_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                        int64_t* total_out, cudaStream_t stream);
+void range_fill_device(const Index& ix, const CloudView& q, float max_range, const long long* d_offsets,
+                       int64_t total, pcg_neighbor* d_out, cudaStream_t stream);
 pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only,
                           float trans[16], pcg_icp_stat* stat, cudaStream_t stream);
 void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_t* n_base,
@@ -123,11 +128,10 @@ struct StagedCloud {
 
 struct RangeResult {
   std::vector<int64_t> offsets;
-  pcg_neighbor* neighbors = nullptr;  // pinned
+  // plain heap memory: page-locking a result of hundreds of MB costs far more than the copy it would speed up
+  pcg_neighbor* neighbors = nullptr;
   int64_t total = 0;
-  ~RangeResult() {
-    if (neighbors) cudaFreeHost(neighbors);
-  }
+  ~RangeResult() { free(neighbors); }
 };
 
 }  // namespace pcg
@@ -355,7 +359,8 @@ pcg_status pcg_index_range(pcg_index* idx, const void* q, int64_t nq, int64_t q_
     PCG_CUDA(cudaMemcpyAsync(r->r.offsets.data(), d_off.p, ((size_t)nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
                              s));
     if (total) {
-      PCG_CUDA(cudaMallocHost((void**)&r->r.neighbors, (size_t)total * sizeof(pcg_neighbor)));
+      r->r.neighbors = (pcg_neighbor*)malloc((size_t)total * sizeof(pcg_neighbor));
+      if (!r->r.neighbors) throw std::bad_alloc();
       PCG_CUDA(cudaMemcpyAsync(r->r.neighbors, d_nb.p, (size_t)total * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost,
                                s));
     }
@@ -364,6 +369,44 @@ pcg_status pcg_index_range(pcg_index* idx, const void* q, int64_t nq, int64_t q_
     return PCG_OK;
   });
 }
+// Two-call protocol with caller-owned (reusable, possibly pinned) buffers.
+pcg_status pcg_index_range_count(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                 const int64_t q_xyz_off[3], float max_range, int64_t* offsets) {
+  return guarded([&]() -> pcg_status {
+    if (!idx || !offsets) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(idx->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+    DevBuf<long long> d_off;
+    int64_t total = 0;
+    range_count_device(*idx->ix, c.view, max_range, d_off, &total, s);
+    PCG_CUDA(cudaMemcpyAsync(offsets, d_off.p, ((size_t)nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_index_range_fill(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                const int64_t q_xyz_off[3], float max_range, const int64_t* offsets,
+                                pcg_neighbor* out) {
+  return guarded([&]() -> pcg_status {
+    if (!idx || !offsets) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    const int64_t total = offsets[nq];
+    if (total < 0 || (total && !out)) throw StatusError{PCG_E_INVALID_ARG, "bad offsets / null output"};
+    if (nq == 0 || total == 0) return PCG_OK;
+    DeviceGuard g(idx->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+    DevBuf<long long> d_off((size_t)nq + 1, s);
+    PCG_CUDA(cudaMemcpyAsync(d_off.p, offsets, ((size_t)nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    DevBuf<pcg_neighbor> d_out((size_t)total, s);
+    range_fill_device(*idx->ix, c.view, max_range, d_off.p, total, d_out.p, s);
+    PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)total * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
+    return PCG_OK;
+  });
+}
+
 int64_t pcg_range_total(const pcg_range_result* r) { return r ? r->r.total : 0; }
 const int64_t* pcg_range_offsets(const pcg_range_result* r) { return r ? r->r.offsets.data() : nullptr; }
 const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r) { return r ? r->r.neighbors : nullptr; }

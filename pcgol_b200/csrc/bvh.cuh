@@ -133,8 +133,9 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
   if (ix.n == 0) return;
   PCG_STAT(3);
   if (qx != qx || qy != qy || qz != qz) return;
-  uint32_t stack_node[kMaxStack + 8];
-  float stack_d[kMaxStack + 8];
+  // one 64-bit word per deferred child: (box-distance bits << 32 | node id) -> one local-memory access per
+  // push and per pop
+  unsigned long long stack[kMaxStack + 8];
   int sp = 0;
   float bestd = __uint_as_float((uint32_t)(best >> 32));
   {
@@ -151,11 +152,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
     const bool first0 = d0 <= d1;
     const float dn = first0 ? d0 : d1, df = first0 ? d1 : d0;
     if (!(dn <= bestd)) return;
-    if (df <= bestd) {
-      stack_node[sp] = first0 ? 3u : 2u;
-      stack_d[sp] = df;
-      sp++;
-    }
+    if (df <= bestd) stack[sp++] = ((unsigned long long)__float_as_uint(df) << 32) | (first0 ? 3u : 2u);
     node = first0 ? 2u : 3u;
   }
   for (;;) {
@@ -191,9 +188,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
         const float dj = __uint_as_float(key[j] & ~3u);
         if (dj <= bestd) {
           PCG_STAT(2);
-          stack_node[sp] = 4 * node + (key[j] & 3u);
-          stack_d[sp] = dj;
-          sp++;
+          stack[sp++] = ((unsigned long long)(key[j] & ~3u) << 32) | (4 * node + (key[j] & 3u));
         }
       }
       node = 4 * node + (key[0] & 3u);
@@ -216,9 +211,9 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
     }
     node = 0;
     while (sp > 0) {
-      --sp;
-      if (stack_d[sp] <= bestd) {
-        node = stack_node[sp];
+      const unsigned long long e = stack[--sp];
+      if (__uint_as_float((uint32_t)(e >> 32)) <= bestd) {
+        node = (uint32_t)e;
         break;
       }
     }

@@ -624,8 +624,9 @@ static void scan_counts(const uint32_t* counts, long long* offsets, uint32_t n, 
 }
 
 // Returns device CSR: offsets (nq+1) and neighbours (total), sorted per query. Synchronises.
-void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
-                  DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream) {
+// Count pass: offsets[nq+1] (exclusive scan of the per-query neighbour counts). Synchronises.
+void range_count_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                        int64_t* total_out, cudaStream_t stream) {
   const uint32_t nq = (uint32_t)q.n;
   const float mrsq = max_range * max_range;  // kdtree.go:157
   offsets.alloc((size_t)nq + 1, stream);
@@ -635,26 +636,52 @@ void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<l
     PCG_CUDA(cudaStreamSynchronize(stream));
     return;
   }
-  DevBuf<uint32_t> counts(nq, stream), need(nq, stream);
-  DevBuf<long long> scratch_off((size_t)nq + 1, stream);
+  DevBuf<uint32_t> counts(nq, stream);
   PCG_LAUNCH(range_count_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, counts.p);
   scan_counts(counts.p, offsets.p, nq, stream);
-  PCG_LAUNCH(range_scratch_kernel, div_up(nq, 256), 256, 0, stream, counts.p, need.p, nq);
-  scan_counts(need.p, scratch_off.p, nq, stream);
-  long long totals[2] = {0, 0};
-  PCG_CUDA(cudaMemcpyAsync(&totals[0], offsets.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
-  PCG_CUDA(cudaMemcpyAsync(&totals[1], scratch_off.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  long long total = 0;
+  PCG_CUDA(cudaMemcpyAsync(&total, offsets.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
   PCG_CUDA(cudaStreamSynchronize(stream));
-  const long long total = totals[0];
   *total_out = total;
-  if (total == 0) return;
-  DevBuf<unsigned long long> packed((size_t)total, stream);
-  DevBuf<unsigned long long> scratch((size_t)std::max<long long>(1, totals[1]), stream);
-  PCG_LAUNCH(range_fill_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, offsets.p, packed.p);
-  PCG_LAUNCH(range_sort_kernel, nq, kSortThreads, 0, stream, offsets.p, packed.p, scratch.p, scratch_off.p);
-  out.alloc((size_t)total, stream);
-  PCG_LAUNCH(range_unpack_kernel, div_up(total, 256), 256, 0, stream, packed.p, out.p, total);
+}
+
+__global__ void __launch_bounds__(256)
+    range_scratch_from_offsets_kernel(const long long* __restrict__ offsets, uint32_t* __restrict__ need, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t len = (uint32_t)(offsets[i + 1] - offsets[i]), p2 = 1;
+  while (p2 < len) p2 <<= 1;
+  need[i] = p2 > (uint32_t)kSortSmem ? p2 : 0u;
+}
+
+// Fill pass for known offsets: neighbours of every query, each list sorted by (DistSq, ID). Synchronises.
+void range_fill_device(const Index& ix, const CloudView& q, float max_range, const long long* d_offsets,
+                       int64_t total, pcg_neighbor* d_out, cudaStream_t stream) {
+  const uint32_t nq = (uint32_t)q.n;
+  if (nq == 0 || total == 0) return;
+  const float mrsq = max_range * max_range;
+  DevBuf<uint32_t> need(nq, stream);
+  DevBuf<long long> scratch_off((size_t)nq + 1, stream);
+  PCG_LAUNCH(range_scratch_from_offsets_kernel, div_up(nq, 256), 256, 0, stream, d_offsets, need.p, nq);
+  scan_counts(need.p, scratch_off.p, nq, stream);
+  long long scratch_total = 0;
+  PCG_CUDA(cudaMemcpyAsync(&scratch_total, scratch_off.p + nq, sizeof(long long), cudaMemcpyDeviceToHost, stream));
   PCG_CUDA(cudaStreamSynchronize(stream));
+  DevBuf<unsigned long long> packed((size_t)total, stream);
+  DevBuf<unsigned long long> scratch((size_t)std::max<long long>(1, scratch_total), stream);
+  PCG_LAUNCH(range_fill_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, d_offsets, packed.p);
+  PCG_LAUNCH(range_sort_kernel, nq, kSortThreads, 0, stream, d_offsets, packed.p, scratch.p, scratch_off.p);
+  PCG_LAUNCH(range_unpack_kernel, div_up(total, 256), 256, 0, stream, packed.p, d_out, (long long)total);
+  PCG_CUDA(cudaStreamSynchronize(stream));
+}
+
+// Returns device CSR: offsets (nq+1) and neighbours (total), sorted per query. Synchronises.
+void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                  DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream) {
+  range_count_device(ix, q, max_range, offsets, total_out, stream);
+  if (*total_out == 0) return;
+  out.alloc((size_t)*total_out, stream);
+  range_fill_device(ix, q, max_range, offsets.p, *total_out, out.p, stream);
 }
 
 }  // namespace pcg

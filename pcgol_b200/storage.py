@@ -95,7 +95,20 @@ class Index:
                                                  stream))
 
     def range_batch(self, queries, max_range: float):
-        """CSR (offsets int64[nq+1], ids int64[total], dist_sq float32[total]), lists in (DistSq, ID) order."""
+        """CSR (offsets int64[nq+1], ids int64[total], dist_sq float32[total]), lists in (DistSq, ID) order.
+        Uses the two-call protocol (count, then fill into a caller-owned buffer)."""
+        data, n, stride, off = as_vec3_buffer(queries)
+        offs = np.zeros(n + 1, np.int64)
+        _lib.check(_lib.lib.pcg_index_range_count(self._h, data.ctypes.data, n, stride, _off(off), max_range,
+                                                 offs.ctypes.data))
+        total = int(offs[-1])
+        nb = np.empty(max(total, 1), dtype=np.dtype([("id", "<i8"), ("dist_sq", "<f4"), ("pad", "<u4")]))
+        _lib.check(_lib.lib.pcg_index_range_fill(self._h, data.ctypes.data, n, stride, _off(off), max_range,
+                                                offs.ctypes.data, nb.ctypes.data))
+        return offs, nb["id"][:total].copy(), nb["dist_sq"][:total].copy()
+
+    def range_batch_owned(self, queries, max_range: float):
+        """Same result through the one-call form (library-owned CSR, pcg_index_range)."""
         data, n, stride, off = as_vec3_buffer(queries)
         r = C.c_void_p()
         _lib.check(_lib.lib.pcg_index_range(self._h, data.ctypes.data, n, stride, _off(off), max_range, C.byref(r)))

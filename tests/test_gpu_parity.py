@@ -237,6 +237,16 @@ def test_range_random_vs_naive(pg, oracle, n):
         assert d.tobytes() == ed.tobytes()
 
 
+def test_range_one_call_form_equals_two_call_form(pg):
+    rng = np.random.default_rng(6)
+    pts = (rng.random((5000, 3), dtype=f32) * f32(3.0)).astype(f32)
+    q = (rng.random((400, 3), dtype=f32) * f32(3.0)).astype(f32)
+    idx = pg.Index(pts)
+    a = idx.range_batch(q, 0.4)
+    b = idx.range_batch_owned(q, 0.4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+
+
 def test_range_long_lists(pg, oracle):
     # lists longer than the shared-memory sort tile (2048) take the global-memory path
     rng = np.random.default_rng(5)

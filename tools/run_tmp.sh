@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_edges.py -x -q 2>&1 | tail -15
+python tools/range_bench.py
