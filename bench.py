@@ -490,7 +490,8 @@ def bench_icp(pg, torch, dist, rank, args, peak):
         iters = res["stat"].num_iteration
         algo = {"(icp_terms_kernel<PCG_ICP_STRICT>)": 12 * len(target) + 36 * len(target),
                 "(icp_terms_kernel<PCG_ICP_FAST>)": 12 * len(target),
-                "icp_replay_kernel": 36 * len(target)}
+                "icp_replay_kernel": 36 * len(target), "icp_replay_sums_kernel": 36 * len(target),
+                "icp_replay_summaries_kernel": 36 * len(target), "icp_replay_walk_kernel": 36 * len(target) // 16}
         roof, shares = dominant(report, algo, peak)
         h_t = torch.from_numpy(target).pin_memory()
         p = icp.params()

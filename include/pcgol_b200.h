@@ -87,6 +87,12 @@ int64_t pcg_kernel_launch_count(void);
 /* Diagnostics: when enabled, every kernel launch is bracketed by CUDA events on its
  * stream; pcg_profile_report synchronises and writes {"kernel": {"launches", "total_ms"}}
  * as JSON into buf (returns the length needed) and clears the records. */
+/* Test hook: the float32 sum of x[0..n) accumulated one element at a time in index order (the
+ * order of PointToPointEvaluator.Evaluate, evaluator.go:122-145), computed on the device by the
+ * strict-mode replay: exact_path 1 = binade-parallel exact replay, 0 = plain sequential chain.
+ * out is float[4]: the sum, then (exact path only) chunks taken as one integer add, chunks replayed
+ * element by element, and SM cycles of the in-order walk. */
+pcg_status pcg_debug_sequential_sum_f32(const float* x, int64_t n, int32_t device, int32_t exact_path, float* out);
 void pcg_profile_enable(int32_t on);
 int64_t pcg_profile_report(char* buf, int64_t cap);
 

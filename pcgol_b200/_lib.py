@@ -83,6 +83,7 @@ _sigs = {
     "pcg_memcpy_d2h": (_i32, [_i32, _vp, _vp, _i64]),
     "pcg_device_synchronize": (_i32, [_i32]),
     "pcg_kernel_launch_count": (_i64, []),
+    "pcg_debug_sequential_sum_f32": (_i32, [_vp, _i64, _i32, _i32, _vp]),
     "pcg_profile_enable": (None, [_i32]),
     "pcg_profile_report": (_i64, [C.c_char_p, _i64]),
     "pcg_index_build": (_i32, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_vp)]),

@@ -82,6 +82,7 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
                            pcg_evaluated* ev_out, int32_t* converged);
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, int32_t* d_ids, float* d_dsq,
                       cudaStream_t stream);
+float debug_sequential_sum(const float* d_x, int64_t n, bool exact_path, cudaStream_t stream, float* stats3);
 
 static void check_device(int device) {
   int count = 0;
@@ -174,6 +175,25 @@ int32_t pcg_device_count(void) {
 int64_t pcg_kernel_launch_count(void) { return g_launches.load(); }
 
 void pcg_profile_enable(int32_t on) { g_profile.store(on ? 1 : 0); }
+
+pcg_status pcg_debug_sequential_sum_f32(const float* x, int64_t n, int32_t device, int32_t exact_path, float* out) {
+  return guarded([&]() -> pcg_status {
+    if (!out || n < 0 || (n && !x)) throw StatusError{PCG_E_INVALID_ARG, "bad arguments"};
+    check_device(device);
+    DeviceGuard g(device);
+    cudaStream_t s = cudaStreamPerThread;
+    const int64_t n_pad = (n + 3) & ~(int64_t)3;
+    DevBuf<float> d((size_t)std::max<int64_t>(4, n_pad), s);
+    PCG_CUDA(cudaMemsetAsync(d.p, 0, d.bytes(), s));
+    if (n) PCG_CUDA(cudaMemcpyAsync(d.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+    float stats[3] = {0, 0, 0};
+    *out = debug_sequential_sum(d.p, n, exact_path != 0, s, stats);
+    out[1] = stats[0];  // out is float[4]: sum, chunks on the integer path, chunks replayed, cycles of the walk
+    out[2] = stats[1];
+    out[3] = stats[2];
+    return PCG_OK;
+  });
+}
 
 
 // Synchronises the device(s), folds the recorded events into per-kernel totals and writes

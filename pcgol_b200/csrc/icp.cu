@@ -9,13 +9,15 @@
 //                      last (ticket counter) adds the partials in a fixed order (deterministic,
 //                      GPU-count independent up to float64 rounding) and runs the tail — one
 //                      kernel per iteration.
-//   STRICT mode        the terms are stored at the target's index and icp_replay_kernel (nine
-//                      single-warp CTAs, one accumulator each, on nine SMs) replays the
-//                      reference's sequential float32 accumulation: bit-identical trajectory.
+//   STRICT mode        the terms are stored at the target's index and the exact replay (see "fast exact
+//                      replay" below: binade-parallel integer sums, element-wise only around binade
+//                      crossings) reproduces the reference's sequential float32 accumulation:
+//                      bit-identical trajectory.  icp_replay_kernel is the plain sequential chain.
 //   tail               evaluator.go:156-186 + gradientDescentUpdater.Update (updater.go:44-71)
 //                      run on the device, so the loop never returns to the host; once `done`
 //                      is set the remaining launches fall through.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "bvh.cuh"
@@ -251,6 +253,271 @@ __global__ void __launch_bounds__(32)
   }
 }
 
+// ---- STRICT mode, fast exact replay -------------------------------------------------------------
+// The reference adds the terms one by one in float32.  While the accumulator s stays inside one
+// binade [2^e, 2^(e+1)) (either sign), s is an integer multiple M of ulp = 2^(e-23) and every step
+// is fl(s + x) = (M + RN(x / ulp)) * ulp: the rounding only sees x - except for an exact tie
+// (x / ulp = q + 1/2), where round-to-even looks at the parity of M + q and always leaves an even
+// result.  So inside a binade the sequential float32 sum is an INTEGER sum driven by a two-state
+// automaton (the parity of the running integer).  Elements are maps parity -> (increment, parity),
+// their composition is associative, hence the sum is parallel:
+//   1. a float64 prefix sum guesses the accumulator (only its binade matters) at every chunk start;
+//   2. every chunk is folded in parallel (one warp, ordered tree composition) into, for both start
+//      parities: the total increment and the min / max of the running prefix, in units of ulp;
+//   3. one warp walks the chunks in order with the TRUE accumulator: if it lies in the guessed
+//      binade and every prefix keeps it strictly inside (one unit of margin at both ends, because
+//      the pre-rounded terms are off by at most half a unit), the chunk is ONE exact integer add;
+//      otherwise the chunk is replayed element by element like the reference (from shared memory).
+// The result is the reference's float32 sum, bit for bit, for any input; LiDAR residuals take the
+// element-wise path only around the few binade crossings of each accumulator.
+constexpr int kReplayChunk = 256;
+constexpr int kReplayThreads = 512;
+constexpr int kReplayBatch = 256;  // chunk summaries staged in shared memory per round of the walk
+
+// Summary of one chunk as the walk consumes it.  Variant v = (accumulator negative ? 2 : 0) | parity
+// of its integer mantissa M (signed, 2^23 <= |M| < 2^24): the chunk is one exact integer add iff the
+// accumulator's exponent is `exp` and lo[v] <= M <= hi[v]; then M += tot[v].
+struct __align__(16) ReplayChunk {
+  int lo[4], hi[4], tot[4];
+  int exp;    // binade of the guessed accumulator (999 when the summary is unusable)
+  float ulp;  // 2^(exp-23)
+  int pad_[2];
+};
+
+// Parity automaton of a run of elements: for start parity p, the integer increment, the parity
+// afterwards and the extremes of the running increment.
+struct ParityMap {
+  long long off[2], mn[2], mx[2];
+  int np;  // bit p = parity after the run when started with parity p
+};
+__device__ __forceinline__ ParityMap compose(const ParityMap& a, const ParityMap& b) {  // a first, then b
+  ParityMap r;
+  r.np = 0;
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    const int mid = (a.np >> p) & 1;
+    r.off[p] = a.off[p] + b.off[mid];
+    r.mn[p] = min(a.mn[p], a.off[p] + b.mn[mid]);
+    r.mx[p] = max(a.mx[p], a.off[p] + b.mx[mid]);
+    r.np |= ((b.np >> mid) & 1) << p;
+  }
+  return r;
+}
+__device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
+  return (long long)shfl_down_u64((uint64_t)v, d);
+}
+
+__device__ __forceinline__ int float_exponent(float f) { return (int)((__float_as_uint(f) >> 23) & 0xff) - 127; }
+
+// Phase A (whole GPU): float64 sum of every chunk of every stream; one warp per chunk.
+__global__ void __launch_bounds__(256)
+    icp_replay_sums_kernel(const IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad,
+                           int64_t nchunks, int streams, double* __restrict__ chunk_sums) {
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nchunks * streams) return;
+  const int64_t k = w / nchunks, c = w - k * nchunks;
+  const float* __restrict__ x = terms + k * n_pad;
+  const int64_t base = c * kReplayChunk + lane * 8;
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += (base + j < n) ? (double)x[base + j] : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) chunk_sums[w] = s;
+}
+
+// Phase B (whole GPU): parity-automaton summary of every chunk in units of the guessed binade's ulp.
+__global__ void __launch_bounds__(256)
+    icp_replay_summaries_kernel(const IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n,
+                                int64_t n_pad, int64_t nchunks, int streams, const double* __restrict__ chunk_sums,
+                                ReplayChunk* __restrict__ chunks) {
+  if (st->done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nchunks * streams) return;
+  const int64_t k = w / nchunks, c = w - k * nchunks;
+  const float* __restrict__ x = terms + k * n_pad;
+  // guess of the accumulator at the chunk start: float64 sum of the preceding chunks (only its binade matters)
+  double g = 0.0;
+  for (int64_t j = lane; j < c; j += 32) g += __ldg(&chunk_sums[k * nchunks + j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+  const float guess = (float)g;
+  const int e = float_exponent(guess);
+  bool regular = guess != 0.f && e > -100 && e < 128;  // not zero / (near) denormal / inf / nan
+  const double scale = regular ? __longlong_as_double((long long)(1023 + 23 - e) << 52) : 0.0;  // 2^(23-e), exact
+  const int64_t base = c * kReplayChunk + lane * 8;
+  ParityMap m;
+  m.off[0] = m.off[1] = 0;
+  m.mn[0] = m.mn[1] = 0x7fffffffffffffffll;
+  m.mx[0] = m.mx[1] = -0x7fffffffffffffffll;
+  m.np = 2;  // identity: parity p stays p
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float xv = (base + j < n) ? x[base + j] : 0.f;
+    const double y = (double)xv * scale;  // exact: power-of-two scaling inside double's range
+    double q = floor(y);
+    const bool sane = fabs(y) < 1.0e12;    // else: far beyond the accumulator, inf or nan -> not this binade
+    if (!sane) {
+      regular = false;
+      q = 0.0;
+    }
+    const double frac = sane ? y - q : 0.0;
+    const long long qi = (long long)q;
+    ParityMap el;
+    if (frac == 0.5) {
+      // tie: round to even -> the result M + off is even whatever the start parity
+      el.off[0] = qi + (qi & 1);        // M even: M + qi even iff qi even
+      el.off[1] = qi + ((qi + 1) & 1);  // M odd:  M + qi even iff qi odd
+      el.np = 0;
+    } else {
+      const long long r = qi + (frac > 0.5 ? 1 : 0);
+      el.off[0] = el.off[1] = r;
+      el.np = (r & 1) ? 1 : 2;  // odd increment flips the parity (bit p = p ^ 1), even keeps it
+    }
+    el.mn[0] = el.mx[0] = el.off[0];
+    el.mn[1] = el.mx[1] = el.off[1];
+    m = compose(m, el);
+  }
+  // ordered tree composition across the warp: lane l <- (lanes l .. l+o-1) then (lanes l+o .. l+2o-1)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    ParityMap right;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      right.off[p] = shfl_down_ll(m.off[p], o);
+      right.mn[p] = shfl_down_ll(m.mn[p], o);
+      right.mx[p] = shfl_down_ll(m.mx[p], o);
+    }
+    right.np = __shfl_down_sync(0xffffffffu, m.np, o);
+    if ((lane & (2 * o - 1)) == 0) m = compose(m, right);
+  }
+  const bool all_regular = __all_sync(0xffffffffu, regular);
+  if (lane == 0) {
+    ReplayChunk rc;
+    const long long kLo = 1ll << 23, kHi = 1ll << 24, kClamp = 1ll << 30;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      // every running value M + prefix must stay strictly inside the binade, with one unit of margin
+      // (the pre-rounded terms are off by at most half a unit): positive M in [2^23+1, 2^24-1] - prefix, ...
+      long long lo_pos = kLo + 1 - m.mn[p], hi_pos = kHi - 1 - m.mx[p];
+      long long lo_neg = -kHi + 1 - m.mn[p], hi_neg = -kLo - 1 - m.mx[p];
+      lo_pos = max(-kClamp, min(kClamp, lo_pos));
+      hi_pos = max(-kClamp, min(kClamp, hi_pos));
+      lo_neg = max(-kClamp, min(kClamp, lo_neg));
+      hi_neg = max(-kClamp, min(kClamp, hi_neg));
+      const long long t = max(-kClamp, min(kClamp, m.off[p]));
+      rc.lo[p] = (int)lo_pos;
+      rc.hi[p] = (int)hi_pos;
+      rc.lo[2 + p] = (int)lo_neg;
+      rc.hi[2 + p] = (int)hi_neg;
+      rc.tot[p] = rc.tot[2 + p] = (int)t;
+    }
+    rc.exp = all_regular ? e : 999;
+    rc.ulp = all_regular ? __uint_as_float((uint32_t)(e - 23 + 127) << 23) : 0.f;
+    rc.pad_[0] = rc.pad_[1] = 0;
+    chunks[w] = rc;
+  }
+}
+
+// Phase C (one CTA per stream): in-order walk with the true accumulator.  The chunk summaries are
+// staged in shared memory by the whole CTA; warp 0 walks (every lane carries the same accumulator).
+__global__ void __launch_bounds__(kReplayThreads)
+    icp_replay_walk_kernel(IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad,
+                           int64_t nchunks, const ReplayChunk* __restrict__ chunks_all) {
+  if (st->done) return;
+  __shared__ __align__(16) float s_x[kReplayChunk];
+  __shared__ ReplayChunk s_chunks[kReplayBatch];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.x;
+  const float* __restrict__ x = terms + (int64_t)k * n_pad;
+  const ReplayChunk* __restrict__ chunks = chunks_all + (int64_t)k * nchunks;
+  float acc = 0.f;
+  unsigned int n_fast = 0, n_slow = 0;
+  const long long t_walk0 = clock64();
+  for (int64_t c0 = 0; c0 < nchunks; c0 += kReplayBatch) {
+    const int batch = (int)min((int64_t)kReplayBatch, nchunks - c0);
+    __syncthreads();
+    {
+      const int4* src = reinterpret_cast<const int4*>(chunks + c0);
+      int4* dst = reinterpret_cast<int4*>(s_chunks);
+      const int words = batch * (int)(sizeof(ReplayChunk) / sizeof(int4));
+      for (int i = tid; i < words; i += kReplayThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      ReplayChunk nxt = s_chunks[0];
+      for (int ci = 0; ci < batch; ci++) {
+        // the next summary is fetched before the (accumulator-dependent) work on this one: the walk's
+        // critical path is then a dozen dependent ALU operations per chunk, no shared-memory latency
+        const ReplayChunk rc = nxt;
+        nxt = s_chunks[min(ci + 1, batch - 1)];
+        const uint32_t bits = __float_as_uint(acc);
+        const int mag = (int)((bits & 0x7fffffu) | 0x800000u);  // acc = M * ulp, |M| = 2^23 | mantissa (exact)
+        const bool neg = (bits >> 31) != 0;
+        const int M = neg ? -mag : mag;
+        const bool odd = (mag & 1) != 0;
+        const int lo = neg ? (odd ? rc.lo[3] : rc.lo[2]) : (odd ? rc.lo[1] : rc.lo[0]);
+        const int hi = neg ? (odd ? rc.hi[3] : rc.hi[2]) : (odd ? rc.hi[1] : rc.hi[0]);
+        const int tot = odd ? rc.tot[1] : rc.tot[0];
+        const bool fast = ((int)((bits >> 23) & 0xff) - 127 == rc.exp) && M >= lo && M <= hi;
+        // |M + tot| < 2^24 -> exact in float; scaling by ulp (a normal power of two) is exact
+        if (fast) acc = __fmul_rn(__int2float_rn(M + tot), rc.ulp);
+        n_fast += fast ? 1u : 0u;
+        n_slow += fast ? 0u : 1u;
+        if (!fast) {  // replay the chunk like the reference
+          const int64_t base = (c0 + ci) * kReplayChunk;
+#pragma unroll
+          for (int j = 0; j < kReplayChunk / 32; j++) {
+            const int64_t i = base + j * 32 + lane;
+            s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
+          }
+          __syncwarp();
+          const float4* b4 = reinterpret_cast<const float4*>(s_x);
+#pragma unroll 8
+          for (int j = 0; j < kReplayChunk / 4; j++) {
+            const float4 v = b4[j];
+            acc = __fadd_rn(acc, v.x);
+            acc = __fadd_rn(acc, v.y);
+            acc = __fadd_rn(acc, v.z);
+            acc = __fadd_rn(acc, v.w);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    st->sums[k] = acc;
+    if (gridDim.x == 1) {  // test hook launch: expose the walk statistics
+      st->sums[9] = (float)n_fast;
+      st->sums[10] = (float)n_slow;
+      st->sums[11] = (float)(clock64() - t_walk0);
+    }
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    if (t == (unsigned int)kTerms - 1u) {
+      __threadfence();
+      float sum9[kTerms];
+      for (int j = 0; j < kTerms; j++) sum9[j] = __ldcg(&st->sums[j]);
+      st->ticket = 0;
+      icp_finalize(st, sum9);
+    }
+  }
+}
+
+// Launches the three phases for `streams` accumulators (9 in a Fit, 1 from the test hook).
+static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int64_t n_pad, int streams,
+                                ReplayChunk* chunks, double* sums, cudaStream_t stream) {
+  const int64_t nchunks = std::max<int64_t>(1, (n + kReplayChunk - 1) / kReplayChunk);
+  const int blocks = div_up(nchunks * streams, 256 / 32);
+  PCG_LAUNCH(icp_replay_sums_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums);
+  PCG_LAUNCH(icp_replay_summaries_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums, chunks);
+  PCG_LAUNCH(icp_replay_walk_kernel, streams, kReplayThreads, 0, stream, st, terms, n, n_pad, nchunks, chunks);
+}
+
 // Sharded ICP: fold the per-CTA float64 partials into 16 doubles for the all-reduce.
 __global__ void __launch_bounds__(kFinishThreads)
     icp_partial_reduce_kernel(IcpState* __restrict__ st, const double* __restrict__ partials, int nblocks,
@@ -272,6 +539,8 @@ struct IcpWork {
   DevBuf<float> terms;
   DevBuf<double> partials;
   DevBuf<uint32_t> perm;
+  DevBuf<ReplayChunk> replay_chunks;  // strict replay: [9][chunks]
+  DevBuf<double> replay_sums;         // strict replay: [9][chunks]
   int nblocks = 0;
   int64_t n_pad = 0;
 };
@@ -297,7 +566,11 @@ static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, floa
     if (mode == PCG_ICP_STRICT) {
       PCG_LAUNCH((icp_terms_kernel<PCG_ICP_STRICT>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
                  w.st.p, w.terms.p, w.n_pad, w.partials.p, 0);
-      PCG_LAUNCH(icp_replay_kernel, kTerms, 32, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad);
+      static const bool sequential_replay = getenv("PCG_ICP_REPLAY_SEQ") != nullptr;  // comparison runs only
+      if (sequential_replay)
+        PCG_LAUNCH(icp_replay_kernel, kTerms, 32, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad);
+      else
+        launch_exact_replay(w.st.p, w.terms.p, tgt.n, w.n_pad, kTerms, w.replay_chunks.p, w.replay_sums.p, stream);
     } else {
       PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
                  w.st.p, w.terms.p, w.n_pad, w.partials.p, 1);
@@ -315,9 +588,12 @@ static void icp_prepare(const Index& base, const CloudView& tgt, const pcg_icp_p
   }
   w.n_pad = (tgt.n + 3) & ~(int64_t)3;
   w.st.alloc(1, stream);
-  if (prm.mode == PCG_ICP_STRICT)
+  if (prm.mode == PCG_ICP_STRICT) {
     w.terms.alloc((size_t)std::max<int64_t>(4, w.n_pad) * kTerms, stream);
-  else
+    const size_t nchunks = (size_t)std::max<int64_t>(1, (tgt.n + kReplayChunk - 1) / kReplayChunk);
+    w.replay_chunks.alloc(nchunks * kTerms, stream);
+    w.replay_sums.alloc(nchunks * kTerms, stream);
+  } else
     w.partials.alloc((size_t)w.nblocks * kTerms, stream);
   IcpState h = make_state(prm, evaluate_only);
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
@@ -470,6 +746,29 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
   *iter = i;
   *converged = c ? 1 : 0;
   return PCG_OK;
+}
+
+// Test hook: the reference-order (sequential) float32 sum of a device array through either replay kernel.
+float debug_sequential_sum(const float* d_x, int64_t n, bool exact_path, cudaStream_t stream, float* stats3) {
+  const int64_t n_pad = (n + 3) & ~(int64_t)3;
+  DevBuf<IcpState> st(1, stream);
+  PCG_CUDA(cudaMemsetAsync(st.p, 0, sizeof(IcpState), stream));
+  const size_t nchunks = (size_t)std::max<int64_t>(1, (n + kReplayChunk - 1) / kReplayChunk);
+  DevBuf<ReplayChunk> chunks(nchunks, stream);
+  DevBuf<double> sums(nchunks, stream);
+  if (exact_path)
+    launch_exact_replay(st.p, d_x, n, n_pad, 1, chunks.p, sums.p, stream);
+  else
+    PCG_LAUNCH(icp_replay_kernel, 1, 32, 0, stream, st.p, d_x, n, n_pad);
+  IcpState h;
+  PCG_CUDA(cudaMemcpyAsync(&h, st.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  if (stats3) {
+    stats3[0] = h.sums[9];
+    stats3[1] = h.sums[10];
+    stats3[2] = h.sums[11];
+  }
+  return h.sums[0];
 }
 
 // NearestPointCorresponder.Pairs building block: nearest neighbour of every target point.

@@ -142,3 +142,44 @@ def test_icp_large_rotation_step_uses_trig_branch(pg, oracle):
     assert rc == oracle.OK and stat.num_iteration == eit
     # float64 sin/cos of the device vs glibc: equal after rounding to float32 except on rare last-ulp flips
     np.testing.assert_allclose(trans, etrans, rtol=0, atol=2e-6)
+
+
+def _seq_sum(pg, x, exact):
+    x = np.ascontiguousarray(x, f32)
+    out = (C.c_float * 4)()
+    pg._lib.check(pg._lib.lib.pcg_debug_sequential_sum_f32(x.ctypes.data if len(x) else None, len(x), 0, 1 if exact else 0,
+                                                          out))
+    return f32(out[0])
+
+
+def test_strict_replay_is_the_sequential_float32_sum(pg):
+    """The binade-parallel replay must equal the one-by-one float32 accumulation for ANY stream
+    (np.cumsum in float32 is that accumulation), not just for well-behaved residuals."""
+    rng = np.random.default_rng(7)
+    streams = {
+        "normal": rng.normal(0, 1, 100_003).astype(f32),
+        "positive": (rng.random(200_000, dtype=f32) * f32(0.3)),
+        "tiny_then_huge": np.concatenate([rng.random(5000, dtype=f32) * f32(1e-6), rng.random(5000, dtype=f32) * f32(1e6),
+                                          rng.normal(0, 1e-3, 5000).astype(f32)]),
+        "cancel": np.concatenate([np.full(3000, 0.1, f32), np.full(3000, -0.1, f32), rng.normal(0, 1, 3000).astype(f32)]),
+        "ties_quarters": (rng.integers(-8, 9, 50_000).astype(f32) * f32(0.25)),   # exact ties everywhere
+        "ties_halfulp": np.concatenate([[f32(1.0)], np.full(20_000, f32(2.0 ** -24), f32)]),
+        "zeros": np.zeros(10_000, f32),
+        "sparse": np.where(rng.random(100_000) < 0.01, rng.normal(0, 5, 100_000), 0).astype(f32),
+        "wide": (rng.normal(0, 1, 60_000) * np.exp(rng.normal(0, 12, 60_000))).astype(f32),
+        "denormal": (rng.random(4000, dtype=f32) * f32(1e-41)),
+        "with_inf": np.concatenate([rng.normal(0, 1, 1000).astype(f32), [f32(np.inf)], rng.normal(0, 1, 1000).astype(f32)]),
+        "with_nan": np.concatenate([rng.normal(0, 1, 700).astype(f32), [f32(np.nan)], rng.normal(0, 1, 300).astype(f32)]),
+        "overflow": np.full(5000, f32(3e38), f32),
+        "ramp": np.arange(1, 70_000, dtype=f32),
+        "alternating": (np.where(np.arange(90_000) % 2 == 0, 1.0, -1.0) * rng.random(90_000)).astype(f32) * f32(100),
+    }
+    for n in (0, 1, 2, 255, 256, 257, 511, 512, 513, 1023, 1025):
+        streams[f"len{n}"] = rng.normal(0, 3, n).astype(f32)
+    for name, x in streams.items():
+        with np.errstate(all="ignore"):
+            exp = np.cumsum(x, dtype=f32)[-1] if len(x) else f32(0)
+        got_seq = _seq_sum(pg, x, exact=False)
+        got = _seq_sum(pg, x, exact=True)
+        assert got_seq.tobytes() == f32(exp).tobytes() or (np.isnan(exp) and np.isnan(got_seq)), name
+        assert got.tobytes() == got_seq.tobytes() or (np.isnan(got) and np.isnan(got_seq)), (name, got, got_seq)

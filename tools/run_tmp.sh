@@ -1,3 +1,2 @@
-nvidia-smi -L | wc -l
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; tail -3 gpurun_out/bench_n8.err | cut -c1-300; wc -l gpurun_out/bench_n8.json; python tools/show_bench.py gpurun_out/bench_n8.json | grep -E "VoxelGrid|clocks|^NN|^ICP|icp_"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 20 --warmup 5 --no-extra > gpurun_out/bench_n4.json 2> gpurun_out/bench_n4.err; python tools/show_bench.py gpurun_out/bench_n4.json | grep -E "VoxelGrid"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1_f.json 2> gpurun_out/bench_r1_f.err; tail -2 gpurun_out/bench_r1_f.err; python tools/show_bench.py gpurun_out/bench_r1_f.json | grep -E "VoxelGrid|^NN|^ICP|icp_|replay|terms"
