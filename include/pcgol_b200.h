@@ -38,7 +38,9 @@
 extern "C" {
 #endif
 
-#define PCGOL_B200_ABI_VERSION 1
+/* 2: pcg_icp_params gained min_dist_sq + updater (appended); DeletePoint, MinDistSq search, Hessian,
+ *    region growing and PCD entry points added. */
+#define PCGOL_B200_ABI_VERSION 2
 
 typedef int32_t pcg_status;
 enum {
@@ -120,6 +122,28 @@ pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, in
                                  const int64_t q_xyz_off[3], float max_range, int32_t* d_ids, float* d_dist_sq,
                                  void* stream);
 
+/* KDTree.MinDistSq > 0 (kdtree.go:19-22,104,120,140): approximate search that may stop at the
+ * first candidate with DistSq < min_dist_sq.  Every answer is the exact nearest neighbour or a real
+ * point of the cloud with DistSq < min_dist_sq (and < maxRange^2), DistSq always belonging to the
+ * returned ID — the contract the reference's answers satisfy; WHICH close point is returned depends
+ * on the traversal there as here, so IDs are not comparable between implementations.  One
+ * reference quirk is not reproduced: with maxRange^2 < MinDistSq the reference can report a miss
+ * after looking at a single leaf (kdtree.go:100-106); this library still returns the exact answer.
+ * min_dist_sq == 0 is the exact search. */
+pcg_status pcg_index_nearest_approx(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                    const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
+                                    pcg_neighbor* out);
+pcg_status pcg_index_nearest_approx_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
+                                        const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
+                                        int32_t* d_ids, float* d_dist_sq, void* stream);
+
+/* KDTree.DeletePoint (kdtree.go:322-332) for a batch of ids: afterwards no search returns them
+ * (naiveSearch.deletePoint, kdtree_test.go:1003-1005, is the oracle).  Len() is unchanged, deleting
+ * an id twice is a no-op, and an id outside [0, Len()-1] fails with PCG_E_INVALID_ARG ("%d does not
+ * correspond to any point in the tree") without deleting anything.  Like the reference, a delete
+ * must not run concurrently with searches on the same index. */
+pcg_status pcg_index_delete_points(pcg_index* idx, const int64_t* ids, int64_t n);
+
 /* KDTree.Range for a batch (kdtree.go:148-161): all points with DistSq < maxRange^2
  * (strict), each list sorted by (DistSq, ID) — the canonical order of
  * kdtree_test.go:926-941.  CSR result owned by the library. */
@@ -162,7 +186,20 @@ enum {
   PCG_ICP_STRICT = 0,
   /* Fixed-shape float64 tree reduction (deterministic, independent of GPU count up to
    * float64 rounding); differs from the reference by its float32 summation error. */
-  PCG_ICP_FAST = 1
+  PCG_ICP_FAST = 1,
+  /* OR-ed into the mode of pcg_icp_evaluate: also fill Evaluated.Hessian (see pcg_evaluated). */
+  PCG_ICP_WITH_HESSIAN = 0x100
+};
+
+enum {
+  /* gradientDescentUpdater (updater.go:39-71): the reference's only updater. */
+  PCG_UPDATER_GRADIENT_DESCENT = 0,
+  /* Solves the 6x6 normal equations H d = -g accumulated by Evaluate (float64 Cholesky) and applies
+   * the increment the way the reference applies its own (Translate * Rodrigues * trans,
+   * updater.go:65-68); same convergence test on the gradient (updater.go:45-54) and the same
+   * MaxIteration cap.  Weight is ignored.  Not in the reference: a consumer of the
+   * Evaluated.Hessian / HasHessian() hooks it declares (evaluator.go:25-36,76). */
+  PCG_UPDATER_GAUSS_NEWTON = 1
 };
 
 /* Zero means the reference default in every field. */
@@ -173,10 +210,17 @@ typedef struct pcg_icp_params {
   float threshold[6];    /* .Threshold, all 0 -> 0.01 (updater.go:16,28-30) */
   int32_t max_iteration; /* .MaxIteration, 0 -> 20 (updater.go:31-33) */
   int32_t mode;          /* PCG_ICP_STRICT | PCG_ICP_FAST */
+  /* ABI 2 */
+  float min_dist_sq;     /* KDTree.MinDistSq of the base search (kdtree.go:19-22); 0 = exact.  The reference's own
+                          * ICP test and benchmark set 0.01 (icp_test.go:58,118-120). */
+  int32_t updater;       /* PCG_UPDATER_GRADIENT_DESCENT | PCG_UPDATER_GAUSS_NEWTON */
 } pcg_icp_params;
 
-/* icp.Evaluated (evaluator.go:25-30).  The reference never writes Hessian
- * (HasHessian() == false, evaluator.go:76); it is returned zeroed. */
+/* icp.Evaluated (evaluator.go:25-30).  The reference never writes Hessian (HasHessian() == false,
+ * evaluator.go:76): it is zero unless PCG_ICP_WITH_HESSIAN / PCG_UPDATER_GAUSS_NEWTON is selected.
+ * Then it is the Gauss-Newton Hessian of Value, 2f * sum J^T J with J = [I | -[pt]x] per pair (pt =
+ * transformed target point, f = 1/sum w as in evaluator.go:156-159), accumulated in float64;
+ * 6x6 symmetric, index = col*6 + row, parameter order (tx,ty,tz,rx,ry,rz) like Gradient. */
 typedef struct pcg_evaluated {
   float value;
   float gradient[6];
@@ -196,10 +240,21 @@ typedef struct pcg_icp_stat {
 pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
                          float max_dist, int64_t* base_id, int64_t* target_id, float* dist_sq, int64_t* n_pairs);
 
+/* Pairs over a base search with KDTree.MinDistSq = min_dist_sq (see pcg_index_nearest_approx). */
+pcg_status pcg_icp_pairs_approx(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                                const int64_t xyz_off[3], float max_dist, float min_dist_sq, int64_t* base_id,
+                                int64_t* target_id, float* dist_sq, int64_t* n_pairs);
+
 /* PointToPointEvaluator.Evaluate (evaluator.go:91-189), default weight function. */
 pcg_status pcg_icp_evaluate(pcg_index* base, const void* target, int64_t n, int64_t stride,
                             const int64_t xyz_off[3], float max_dist, int32_t min_pairs, int32_t mode,
                             pcg_evaluated* out, int64_t* n_pairs);
+
+/* Evaluate with the full parameter block: max_dist, min_pairs, mode (| PCG_ICP_WITH_HESSIAN) and
+ * min_dist_sq are used, the updater fields are not. */
+pcg_status pcg_icp_evaluate_params(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                                   const int64_t xyz_off[3], const pcg_icp_params* params, pcg_evaluated* out,
+                                   int64_t* n_pairs);
 
 /* PointToPointICPGradient.Fit (icp.go:23-67) with the default gradient-descent updater
  * (updater.go:44-71).  trans is column-major (mat/mat4.go:8-10).  On

@@ -46,6 +46,10 @@ def lib():
         _lib.orc_search_new.argtypes = [C.c_void_p, C.c_int64, C.c_int32]
         _lib.orc_search_free.argtypes = [C.c_void_p]
         _lib.orc_search_set_min_dist_sq.argtypes = [C.c_void_p, C.c_float]
+        _lib.orc_search_delete_point.restype = C.c_int32
+        _lib.orc_search_delete_point.argtypes = [C.c_void_p, C.c_int64]
+        _lib.orc_search_find_minimum.restype = C.c_int64
+        _lib.orc_search_find_minimum.argtypes = [C.c_void_p, C.c_int32]
         _lib.orc_kdtree_num_nodes.restype = C.c_int64
         _lib.orc_kdtree_num_nodes.argtypes = [C.c_void_p]
         _lib.orc_kdtree_max_depth.restype = C.c_int32
@@ -69,6 +73,11 @@ def lib():
         _lib.orc_icp_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib.orc_icp_fit.restype = C.c_int32
         _lib.orc_icp_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_icp_normal_equations.restype = C.c_int32
+        _lib.orc_icp_normal_equations.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]
+        _lib.orc_icp_fit_gn.restype = C.c_int32
+        _lib.orc_icp_fit_gn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_mat4_mul.argtypes = [C.c_void_p] * 3
         _lib.orc_mat4_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib.orc_translate.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
@@ -133,6 +142,14 @@ class Search:
 
     def set_min_dist_sq(self, v: float):
         lib().orc_search_set_min_dist_sq(self._h, v)
+
+    def delete_point(self, pid: int) -> bool:
+        """KDTree.DeletePoint (kdtree.go:322-332); False == the reference's error (id out of range)."""
+        return lib().orc_search_delete_point(self._h, int(pid)) == 0
+
+    def find_minimum(self, dim: int) -> int:
+        """findMinimumImpl from the root (kdtree.go:224-266); -2 == the reference's error (dim > 2)."""
+        return int(lib().orc_search_find_minimum(self._h, dim))
 
     def nearest(self, q, max_range: float, threads: int = 1):
         q = _f32(q).reshape(-1, 3)
@@ -230,6 +247,26 @@ def icp_fit(base: Search, target, params: IcpParams):
     ev = np.zeros(8, np.float32)
     it = C.c_int32(0)
     rc = lib().orc_icp_fit(base._h, _p(t), len(t), C.byref(params), _p(trans), _p(ev), C.byref(it))
+    return rc, trans, ev, it.value
+
+
+def icp_normal_equations(base: Search, target, max_dist: float, min_pairs: int = 0):
+    """Extension check (not in the reference): (status, hessian36 = 2f*sum J^T J, b6 = sum J^T r, n_pairs)."""
+    t = _f32(target).reshape(-1, 3)
+    h = np.zeros(36, np.float32)
+    b = np.zeros(6, np.float64)
+    npairs = C.c_int64(0)
+    rc = lib().orc_icp_normal_equations(base._h, _p(t), len(t), max_dist, min_pairs, _p(h), _p(b), C.byref(npairs))
+    return rc, h, b, npairs.value
+
+
+def icp_fit_gn(base: Search, target, params: IcpParams):
+    """Extension check: Fit with the Gauss-Newton step. Returns (status, trans16, ev8, num_iteration)."""
+    t = _f32(target).reshape(-1, 3)
+    trans = np.zeros(16, np.float32)
+    ev = np.zeros(8, np.float32)
+    it = C.c_int32(0)
+    rc = lib().orc_icp_fit_gn(base._h, _p(t), len(t), C.byref(params), _p(trans), _p(ev), C.byref(it))
     return rc, trans, ev, it.value
 
 

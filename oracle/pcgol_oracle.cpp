@@ -156,6 +156,9 @@ struct Search {
   int64_t n = 0;
   virtual ~Search() {}
   inline Vec3 at(int64_t i) const { return {{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}}; }
+  // KDTree.DeletePoint (kdtree.go:322-332) / naiveSearch.deletePoint (kdtree_test.go:1003-1005).
+  // Returns false for an id outside [0, Len()-1] (the reference returns an error and changes nothing).
+  virtual bool delete_point(int64_t id) = 0;
   virtual Neighbor nearest(const Vec3& p, float max_range) const = 0;
   virtual void range(const Vec3& p, float max_range, std::vector<Neighbor>& out) const = 0;
 };
@@ -168,10 +171,33 @@ inline bool neighbor_id_less(const Neighbor& a, const Neighbor& b) {
 
 // Brute force: pc/storage/kdtree/kdtree_test.go:943-985 (naiveSearch)
 struct Naive : Search {
+  std::vector<uint8_t> deleted;  // kdtree_test.go:945-948 (deletedPoints)
+  bool delete_point(int64_t id) override {
+    if (id < 0 || id > n - 1) return false;
+    if (deleted.empty()) deleted.assign((size_t)n, 0);
+    deleted[(size_t)id] = 1;
+    return true;
+  }
+  inline bool gone(int64_t i) const { return !deleted.empty() && deleted[(size_t)i]; }
+  // kdtree_test.go:987-1001 (findMinimum): first live point with the smallest coordinate
+  int64_t find_minimum(int dim) const {
+    int64_t id = -1;
+    float mn = 0.f;
+    for (int64_t i = 0; i < n; i++) {
+      if (gone(i)) continue;
+      float v = xyz[3 * i + dim];
+      if (id == -1 || v < mn) {
+        mn = v;
+        id = i;
+      }
+    }
+    return id;
+  }
   Neighbor nearest(const Vec3& p, float max_range) const override {
     float dsq = max_range * max_range;
     int64_t id = -1;
     for (int64_t i = 0; i < n; i++) {
+      if (gone(i)) continue;
       float d1 = vnormsq(vsub(at(i), p));
       if (d1 < dsq) {
         id = i;
@@ -184,6 +210,7 @@ struct Naive : Search {
     float th = max_range * max_range;
     out.clear();
     for (int64_t i = 0; i < n; i++) {
+      if (gone(i)) continue;
       float d = vnormsq(vsub(at(i), p));
       if (d < th) out.push_back({i, d});
     }
@@ -230,6 +257,61 @@ struct KDTree : Search {
     nodes.reserve(n);
     if (n > 0) root = new_node(ids.data(), n, 0);
     max_depth = depth_of(root, 0);
+  }
+
+  // kdtree.go:224-264 (findMinimumImpl): id of the point with the smallest coordinate `dim` below nd
+  // (-1 for nil).  dim > 2 is an error in the reference (-2 here).
+  int64_t find_minimum(int32_t nd, int dim) const {
+    if (dim > 2) return -2;
+    if (nd < 0) return -1;
+    const KDNode& nn = nodes[nd];
+    auto min_node = [&](int d, int64_t a, int64_t b, int64_t c) {
+      int64_t mn = a;
+      if (b != -1 && xyz[3 * b + d] < xyz[3 * mn + d]) mn = b;
+      if (c != -1 && xyz[3 * c + d] < xyz[3 * mn + d]) mn = c;
+      return mn;
+    };
+    if (nn.dim == dim) {
+      if (nn.child[0] < 0) return nn.id;
+      return find_minimum(nn.child[0], dim);
+    }
+    const int64_t m0 = find_minimum(nn.child[0], dim);
+    const int64_t m1 = find_minimum(nn.child[1], dim);
+    return min_node(dim, nn.id, m0, m1);
+  }
+
+  // kdtree.go:266-320 (deleteNodeImpl): returns the node that replaces nd (-1 == nil)
+  int32_t delete_node(int32_t nd, int64_t pid) {
+    if (nd < 0) return -1;
+    if (pid == nodes[nd].id) {
+      if (nodes[nd].child[1] >= 0) {
+        const int64_t mn = find_minimum(nodes[nd].child[1], nodes[nd].dim);
+        const int32_t child = delete_node(nodes[nd].child[1], mn);
+        nodes[nd].id = mn;
+        nodes[nd].child[1] = child;
+      } else if (nodes[nd].child[0] >= 0) {
+        const int64_t mn = find_minimum(nodes[nd].child[0], nodes[nd].dim);
+        const int32_t child = delete_node(nodes[nd].child[0], mn);
+        nodes[nd].id = mn;
+        nodes[nd].child[0] = -1;
+        nodes[nd].child[1] = child;
+      } else {
+        return -1;
+      }
+      return nd;
+    }
+    const float pivot = xyz[3 * nodes[nd].id + nodes[nd].dim];
+    const float v = xyz[3 * pid + nodes[nd].dim];
+    if (v <= pivot) nodes[nd].child[0] = delete_node(nodes[nd].child[0], pid);
+    if (v >= pivot) nodes[nd].child[1] = delete_node(nodes[nd].child[1], pid);
+    return nd;
+  }
+
+  // kdtree.go:322-332 (DeletePoint)
+  bool delete_point(int64_t pid) override {
+    if (pid < 0 || pid > n - 1) return false;
+    root = delete_node(root, pid);
+    return true;
   }
 
   // kdtree.go:199-222 (searchLeafNode); the node stack is the tail of `st`
@@ -787,6 +869,117 @@ int icp_fit(const Search& base, const float* target, int64_t n, const IcpParams&
   return ORC_OK;
 }
 
+// ----------------------------------------------------------------------------
+// Extension check (NOT a restatement: the reference declares Evaluated.Hessian and
+// HasHessian(), evaluator.go:25-36,76, but never fills / consumes them).  Literal
+// definition of what the product's PCG_ICP_WITH_HESSIAN / PCG_UPDATER_GAUSS_NEWTON compute:
+// per pair the 3x6 Jacobian J = [I | -[pt]x] of the residual r = pt - pb under the increment
+// Translate(dt) * Rodrigues(dw) applied on the left (updater.go:65-68); A = sum J^T J,
+// b = sum J^T r in float64, pair by pair.  Evaluated.Hessian = 2f * A (f of evaluator.go:156-159).
+// ----------------------------------------------------------------------------
+int icp_normal_equations(const Search& base, const float* target, int64_t n, float max_dist, int min_pairs,
+                         double A[36], double b[6], int64_t* n_pairs) {
+  if (min_pairs == 0) min_pairs = 6;
+  std::vector<Pair> pairs;
+  icp_pairs(base, target, n, max_dist, pairs);
+  if (n_pairs) *n_pairs = (int64_t)pairs.size();
+  for (int i = 0; i < 36; i++) A[i] = 0;
+  for (int i = 0; i < 6; i++) b[i] = 0;
+  if ((int64_t)pairs.size() < (int64_t)min_pairs) return ORC_E_NOT_ENOUGH_PAIRS;
+  for (const Pair& pr : pairs) {
+    Vec3 pb = base.at(pr.base_id);
+    const double x = target[3 * pr.target_id], y = target[3 * pr.target_id + 1], z = target[3 * pr.target_id + 2];
+    const double r[3] = {x - (double)pb[0], y - (double)pb[1], z - (double)pb[2]};
+    // J[row][col]: d r / d (tx,ty,tz,wx,wy,wz);  d(w x p) = -[p]x dw
+    const double J[3][6] = {{1, 0, 0, 0, z, -y}, {0, 1, 0, -z, 0, x}, {0, 0, 1, y, -x, 0}};
+    for (int c = 0; c < 6; c++) {
+      for (int rr = 0; rr < 6; rr++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += J[k][rr] * J[k][c];
+        A[c * 6 + rr] += s;  // index = col*6 + row
+      }
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += J[k][c] * r[k];
+      b[c] += s;
+    }
+  }
+  return ORC_OK;
+}
+
+// Solves A d = -b (6x6) by Gaussian elimination with partial pivoting, float64.
+bool solve6(const double A_in[36], const double b[6], double d[6]) {
+  double M[6][7];
+  for (int r = 0; r < 6; r++) {
+    for (int c = 0; c < 6; c++) M[r][c] = A_in[c * 6 + r];
+    M[r][6] = -b[r];
+  }
+  for (int c = 0; c < 6; c++) {
+    int piv = c;
+    for (int r = c + 1; r < 6; r++)
+      if (std::fabs(M[r][c]) > std::fabs(M[piv][c])) piv = r;
+    if (!(std::fabs(M[piv][c]) > 0)) return false;
+    if (piv != c)
+      for (int k = 0; k < 7; k++) std::swap(M[piv][k], M[c][k]);
+    for (int r = c + 1; r < 6; r++) {
+      const double f = M[r][c] / M[c][c];
+      for (int k = c; k < 7; k++) M[r][k] -= f * M[c][k];
+    }
+  }
+  for (int r = 5; r >= 0; r--) {
+    double v = M[r][6];
+    for (int k = r + 1; k < 6; k++) v -= M[r][k] * d[k];
+    d[r] = v / M[r][r];
+  }
+  return true;
+}
+
+// Fit with the Gauss-Newton step in place of the damped gradient: same loop (icp.go:23-67),
+// same convergence test and increment composition (updater.go:45-54,65-70).
+int icp_fit_gn(const Search& base, const float* target, int64_t n, const IcpParams& prm, Mat4* trans_out,
+               IcpStat* stat) {
+  std::vector<float> tt(target, target + 3 * n);
+  Updater up(prm);
+  std::memset(stat, 0, sizeof(*stat));
+  Mat4 trans = m4translate(0, 0, 0);
+  for (;;) {
+    Evaluated ev;
+    int rc = prm.f64_accumulate
+                 ? icp_evaluate_t<double>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr)
+                 : icp_evaluate_t<float>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr);
+    stat->num_iteration++;
+    if (rc != ORC_OK) {
+      *trans_out = trans;
+      return rc;
+    }
+    stat->ev = ev;
+    bool flat = true;
+    for (int j = 0; j < 6; j++) {
+      float g = ev.gradient[j];
+      if (g < -up.threshold[j] || up.threshold[j] < g) {
+        flat = false;
+        break;
+      }
+    }
+    if (flat) break;
+    double A[36], b[6], d[6];
+    icp_normal_equations(base, tt.data(), n, prm.max_dist, prm.min_pairs, A, b, nullptr);
+    if (!solve6(A, b, d)) break;
+    Mat4 delta_trans = m4translate((float)d[0], (float)d[1], (float)d[2]);
+    Mat4 delta_rot = rodrigues_to_rotation(Vec3{{(float)d[3], (float)d[4], (float)d[5]}});
+    trans = m4mul(delta_trans, m4mul(delta_rot, trans));
+    up.i++;
+    if (up.i >= up.max_iteration) break;
+    for (int64_t i = 0; i < n; i++) {
+      Vec3 t = m4transform(trans, Vec3{{target[3 * i], target[3 * i + 1], target[3 * i + 2]}});
+      tt[3 * i] = t[0];
+      tt[3 * i + 1] = t[1];
+      tt[3 * i + 2] = t[2];
+    }
+  }
+  *trans_out = trans;
+  return ORC_OK;
+}
+
 template <typename F>
 void parallel_for(int64_t n, int threads, F f) {
   if (threads <= 1 || n < 2) {
@@ -827,6 +1020,16 @@ void orc_search_free(void* h) { delete static_cast<Search*>(h); }
 // KDTree.MinDistSq (kdtree.go:20-22); ignored for brute force
 void orc_search_set_min_dist_sq(void* h, float v) {
   if (auto* k = dynamic_cast<KDTree*>(static_cast<Search*>(h))) k->min_dist_sq = v;
+}
+
+// DeletePoint: 0 = ok, 1 = "does not correspond to any point in the tree" (kdtree.go:323-325)
+int32_t orc_search_delete_point(void* h, int64_t id) { return static_cast<Search*>(h)->delete_point(id) ? 0 : 1; }
+// findMinimumImpl from the root (kdtree_test.go:388-411) / naiveSearch.findMinimum; -2 = error (dim > 2)
+int64_t orc_search_find_minimum(void* h, int32_t dim) {
+  Search* s = static_cast<Search*>(h);
+  if (auto* k = dynamic_cast<KDTree*>(s)) return k->find_minimum(k->root, dim);
+  if (auto* nv = dynamic_cast<Naive*>(s)) return dim > 2 ? -2 : nv->find_minimum(dim);
+  return -2;
 }
 
 int64_t orc_kdtree_num_nodes(void* h) {
@@ -969,6 +1172,34 @@ int32_t orc_icp_fit(void* base, const float* target, int64_t n, const IcpParams*
   Mat4 t;
   IcpStat st;
   int rc = icp_fit(*static_cast<Search*>(base), target, n, *prm, &t, &st);
+  std::memcpy(trans16, t.m, sizeof(t.m));
+  stat_ev8[0] = st.ev.value;
+  for (int i = 0; i < 6; i++) stat_ev8[1 + i] = st.ev.gradient[i];
+  stat_ev8[7] = st.ev.dist_rms;
+  *num_iteration = st.num_iteration;
+  return rc;
+}
+
+// Extension check: normal equations of one Evaluate. hess36 = 2f * sum J^T J (float32, index col*6+row),
+// b6 = sum J^T r (float64).
+int32_t orc_icp_normal_equations(void* base, const float* target, int64_t n, float max_dist, int32_t min_pairs,
+                                 float* hess36, double* b6, int64_t* n_pairs) {
+  double A[36];
+  int64_t np = 0;
+  int rc = icp_normal_equations(*static_cast<Search*>(base), target, n, max_dist, min_pairs, A, b6, &np);
+  if (n_pairs) *n_pairs = np;
+  float sw = (float)np, f = 1;
+  if (sw > 1) f = 1 / sw;
+  for (int i = 0; i < 36; i++) hess36[i] = (float)(A[i] * 2.0 * (double)f);
+  return rc;
+}
+
+// Extension check: Fit with the Gauss-Newton updater.
+int32_t orc_icp_fit_gn(void* base, const float* target, int64_t n, const IcpParams* prm, float* trans16,
+                       float* stat_ev8, int32_t* num_iteration) {
+  Mat4 t;
+  IcpStat st;
+  int rc = icp_fit_gn(*static_cast<Search*>(base), target, n, *prm, &t, &st);
   std::memcpy(trans16, t.m, sizeof(t.m));
   stat_ev8[0] = st.ev.value;
   for (int i = 0; i < 6; i++) stat_ev8[1 + i] = st.ev.gradient[i];

@@ -23,6 +23,9 @@ E_TOO_LARGE = 8
 
 ICP_STRICT = 0
 ICP_FAST = 1
+ICP_WITH_HESSIAN = 0x100
+UPDATER_GRADIENT_DESCENT = 0
+UPDATER_GAUSS_NEWTON = 1
 
 
 class PcgError(RuntimeError):
@@ -46,6 +49,8 @@ class IcpParams(C.Structure):
         ("threshold", C.c_float * 6),
         ("max_iteration", C.c_int32),
         ("mode", C.c_int32),
+        ("min_dist_sq", C.c_float),  # ABI 2: KDTree.MinDistSq of the base search (kdtree.go:19-22)
+        ("updater", C.c_int32),      # ABI 2: UPDATER_GRADIENT_DESCENT | UPDATER_GAUSS_NEWTON
     ]
 
 
@@ -94,6 +99,9 @@ _sigs = {
     "pcg_index_device_bytes": (_i64, [_vp]),
     "pcg_index_nearest": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp]),
     "pcg_index_nearest_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp, _vp]),
+    "pcg_index_nearest_approx": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _f, _vp]),
+    "pcg_index_nearest_approx_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _f, _vp, _vp, _vp]),
+    "pcg_index_delete_points": (_i32, [_vp, _vp, _i64]),
     "pcg_index_range": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, C.POINTER(_vp)]),
     "pcg_index_range_count": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp]),
     "pcg_index_range_fill": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp]),
@@ -105,6 +113,9 @@ _sigs = {
     "pcg_voxelgrid_filter_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64), _vp]),
     "pcg_minmax_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),
     "pcg_icp_pairs": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "pcg_icp_pairs_approx": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _f, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "pcg_icp_evaluate_params": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), C.POINTER(Evaluated),
+                                       C.POINTER(_i64)]),
     "pcg_icp_evaluate": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, C.POINTER(Evaluated), C.POINTER(_i64)]),
     "pcg_icp_fit": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat)]),
     "pcg_icp_fit_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat), _vp]),

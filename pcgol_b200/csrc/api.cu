@@ -62,8 +62,8 @@ void ensure_pool(int device) {
 pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], uint8_t* d_out,
                                    int64_t* n_out, cudaStream_t stream);
 void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
-void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_t* d_ids, float* d_dist_sq,
-                    pcg_neighbor* d_aos, cudaStream_t stream);
+void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
+                    float* d_dist_sq, pcg_neighbor* d_aos, cudaStream_t stream);
 void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
                   DevBuf<pcg_neighbor>& out, int64_t* total_out, cudaStream_t stream);
 void range_count_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
@@ -80,8 +80,8 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
                         const uint32_t* d_order, double* d_partial16, cudaStream_t stream);
 pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm, int32_t* iter, float trans[16],
                            pcg_evaluated* ev_out, int32_t* converged);
-void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, int32_t* d_ids, float* d_dsq,
-                      cudaStream_t stream);
+void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
+                      float* d_dsq, cudaStream_t stream);
 float debug_sequential_sum(const float* d_x, int64_t n, bool exact_path, cudaStream_t stream, float* stats3);
 
 static void check_device(int device) {
@@ -329,32 +329,68 @@ int64_t pcg_index_len(const pcg_index* idx) { return idx ? idx->ix->n : 0; }
 int32_t pcg_index_device(const pcg_index* idx) { return idx ? idx->ix->device : -1; }
 int64_t pcg_index_device_bytes(const pcg_index* idx) { return idx ? idx->ix->bytes : 0; }
 
-pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
-                                 const int64_t q_xyz_off[3], float max_range, int32_t* d_ids, float* d_dist_sq,
-                                 void* stream) {
+pcg_status pcg_index_nearest_approx_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
+                                        const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
+                                        int32_t* d_ids, float* d_dist_sq, void* stream) {
   return guarded([&]() -> pcg_status {
     if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
     check_view_args(d_q, nq, q_stride, q_xyz_off);
     if (nq && (!d_ids || !d_dist_sq)) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    if (!(min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
     DeviceGuard g(idx->ix->device);
-    nearest_device(*idx->ix, make_view(d_q, nq, q_stride, q_xyz_off), max_range, d_ids, d_dist_sq, nullptr,
-                   (cudaStream_t)stream);
+    nearest_device(*idx->ix, make_view(d_q, nq, q_stride, q_xyz_off), max_range, min_dist_sq, d_ids, d_dist_sq,
+                   nullptr, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
+                                 const int64_t q_xyz_off[3], float max_range, int32_t* d_ids, float* d_dist_sq,
+                                 void* stream) {
+  return pcg_index_nearest_approx_dev(idx, d_q, nq, q_stride, q_xyz_off, max_range, 0.f, d_ids, d_dist_sq, stream);
+}
+
+pcg_status pcg_index_nearest_approx(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
+                                    const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
+                                    pcg_neighbor* out) {
+  return guarded([&]() -> pcg_status {
+    if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
+    if (nq && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    if (!(min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
+    DeviceGuard g(idx->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+    if (nq == 0) return PCG_OK;
+    DevBuf<pcg_neighbor> d_out((size_t)nq, s);
+    nearest_device(*idx->ix, c.view, max_range, min_dist_sq, nullptr, nullptr, d_out.p, s);
+    PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)nq * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
     return PCG_OK;
   });
 }
 
 pcg_status pcg_index_nearest(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
                              const int64_t q_xyz_off[3], float max_range, pcg_neighbor* out) {
+  return pcg_index_nearest_approx(idx, q, nq, q_stride, q_xyz_off, max_range, 0.f, out);
+}
+
+pcg_status pcg_index_delete_points(pcg_index* idx, const int64_t* ids, int64_t n) {
   return guarded([&]() -> pcg_status {
-    if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
-    if (nq && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    if (!idx || n < 0 || (n && !ids)) throw StatusError{PCG_E_INVALID_ARG, "bad arguments"};
+    const int64_t len = idx->ix->n;
+    for (int64_t i = 0; i < n; i++) {
+      if (ids[i] < 0 || ids[i] > len - 1) {  // kdtree.go:323-325
+        char buf[96];
+        snprintf(buf, sizeof(buf), "%lld does not correspond to any point in the tree", (long long)ids[i]);
+        throw StatusError{PCG_E_INVALID_ARG, buf};
+      }
+    }
+    if (n == 0) return PCG_OK;
     DeviceGuard g(idx->ix->device);
     cudaStream_t s = cudaStreamPerThread;
-    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
-    if (nq == 0) return PCG_OK;
-    DevBuf<pcg_neighbor> d_out((size_t)nq, s);
-    nearest_device(*idx->ix, c.view, max_range, nullptr, nullptr, d_out.p, s);
-    PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)nq * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+    DevBuf<int64_t> d_ids((size_t)n, s);
+    PCG_CUDA(cudaMemcpyAsync(d_ids.p, ids, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    index_delete_points_device(*idx->ix, d_ids.p, n, s);
     PCG_CUDA(cudaStreamSynchronize(s));
     return PCG_OK;
   });
@@ -492,8 +528,15 @@ pcg_status pcg_minmax_dev(const void* d_data, int64_t n, int64_t stride, const i
 // ---- icp ----------------------------------------------------------------------------------
 pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t stride, const int64_t xyz_off[3],
                          float max_dist, int64_t* base_id, int64_t* target_id, float* dist_sq, int64_t* n_pairs) {
+  return pcg_icp_pairs_approx(base, target, n, stride, xyz_off, max_dist, 0.f, base_id, target_id, dist_sq, n_pairs);
+}
+
+pcg_status pcg_icp_pairs_approx(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                                const int64_t xyz_off[3], float max_dist, float min_dist_sq, int64_t* base_id,
+                                int64_t* target_id, float* dist_sq, int64_t* n_pairs) {
   return guarded([&]() -> pcg_status {
     if (!base || !n_pairs) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (!(min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
     *n_pairs = 0;
     DeviceGuard g(base->ix->device);
     cudaStream_t s = cudaStreamPerThread;
@@ -501,7 +544,7 @@ pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t
     if (n == 0) return PCG_OK;
     DevBuf<int32_t> d_ids((size_t)n, s);
     DevBuf<float> d_dsq((size_t)n, s);
-    icp_pairs_device(*base->ix, c.view, max_dist, d_ids.p, d_dsq.p, s);
+    icp_pairs_device(*base->ix, c.view, max_dist, min_dist_sq, d_ids.p, d_dsq.p, s);
     std::vector<int32_t> ids((size_t)n);
     std::vector<float> dsq((size_t)n);
     PCG_CUDA(cudaMemcpyAsync(ids.data(), d_ids.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
@@ -523,16 +566,23 @@ pcg_status pcg_icp_pairs(pcg_index* base, const void* target, int64_t n, int64_t
 pcg_status pcg_icp_evaluate(pcg_index* base, const void* target, int64_t n, int64_t stride,
                             const int64_t xyz_off[3], float max_dist, int32_t min_pairs, int32_t mode,
                             pcg_evaluated* out, int64_t* n_pairs) {
+  pcg_icp_params prm;
+  std::memset(&prm, 0, sizeof(prm));
+  prm.max_dist = max_dist;
+  prm.min_pairs = min_pairs;
+  prm.mode = mode;
+  return pcg_icp_evaluate_params(base, target, n, stride, xyz_off, &prm, out, n_pairs);
+}
+
+pcg_status pcg_icp_evaluate_params(pcg_index* base, const void* target, int64_t n, int64_t stride,
+                                   const int64_t xyz_off[3], const pcg_icp_params* params, pcg_evaluated* out,
+                                   int64_t* n_pairs) {
   return guarded([&]() -> pcg_status {
-    if (!base || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (!base || !out || !params) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
     DeviceGuard g(base->ix->device);
     cudaStream_t s = cudaStreamPerThread;
     StagedCloud c(target, n, stride, xyz_off, s);
-    pcg_icp_params prm;
-    std::memset(&prm, 0, sizeof(prm));
-    prm.max_dist = max_dist;
-    prm.min_pairs = min_pairs;
-    prm.mode = mode;
+    const pcg_icp_params& prm = *params;
     pcg_icp_stat stat;
     pcg_status rc = icp_fit_device(*base->ix, c.view, prm, true, nullptr, &stat, s);
     *out = stat.evaluated;

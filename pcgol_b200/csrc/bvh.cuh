@@ -21,6 +21,8 @@
 // arg-min — the reference's own brute-force oracle (kdtree_test.go:955-968).
 #pragma once
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pcg {
@@ -128,8 +130,13 @@ __device__ unsigned long long g_nn_stats[4];  // node steps, leaf scans, pushes,
   } while (0)
 #endif
 
+// APPROX mirrors KDTree.MinDistSq (kdtree.go:19-22,104,120,140): the search stops at the first
+// candidate with DistSq < min_dist_sq.  The answer is then either the exact nearest neighbour or a
+// real point closer than sqrt(MinDistSq) - the contract every MinDistSq answer of the reference
+// satisfies (which point is traversal-dependent there too).
+template <bool APPROX = false>
 __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, float qy, float qz, uint64_t& best,
-                                             uint32_t& best_pos) {
+                                             uint32_t& best_pos, float min_dist_sq = 0.f) {
   if (ix.n == 0) return;
   PCG_STAT(3);
   if (qx != qx || qy != qy || qz != qz) return;
@@ -208,6 +215,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
         }
       }
       bestd = __uint_as_float((uint32_t)(best >> 32));
+      if (APPROX && bestd < min_dist_sq) return;
     }
     node = 0;
     while (sp > 0) {
@@ -226,7 +234,7 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
 #ifdef PCG_BVH2
 #define PCG_NN_TRAVERSE nn_traverse
 #else
-#define PCG_NN_TRAVERSE nn_traverse4
+#define PCG_NN_TRAVERSE nn_traverse4<false>
 #endif
 
 // Persistent, work-fetching form of nn_traverse for batches.  Per-query work varies by an
@@ -421,11 +429,18 @@ struct Index {
   float4* pts = nullptr;
   float4* boxes = nullptr;
   uint32_t* bbox = nullptr;  // order-preserving bits of min x,y,z / max x,y,z over finite coordinates
+  // KDTree.DeletePoint (kdtree.go:322-332): tombstones.  inv maps an original id to its slot in pts
+  // (built on the first delete); a deleted slot keeps its id but its coordinates become +inf, so no
+  // search can ever accept it (the boxes stay valid: they only get conservative).
+  uint32_t* inv = nullptr;
+  std::mutex mu;  // serialises DeletePoint calls (queries racing a delete are undefined, as in the reference)
   int64_t bytes = 0;
   IndexView view() const { return IndexView{pts, boxes, P, (uint32_t)n}; }
 };
 
 Index* index_build_device(const CloudView& v, int device, cudaStream_t stream);
+// d_ids: n point ids, already validated against [0, ix.n). Enqueues on `stream`.
+void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream);
 void index_free(Index* ix);
 // Queries visited in Morton order make the threads of a warp walk the same part of the tree.
 // Writes a permutation (sorted position -> query index) into d_perm[q.n].

@@ -37,15 +37,17 @@ void prof_begin(const char* name, cudaStream_t s);
 void prof_end(cudaStream_t s);
 
 // Kernel launch with launch counting + immediate launch-error check.
-#define PCG_LAUNCH(kernel, grid, block, smem, stream, ...)                    \
+#define PCG_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)        \
   do {                                                                        \
     const bool prof__ = ::pcg::g_profile.load(std::memory_order_relaxed) != 0; \
-    if (prof__) ::pcg::prof_begin(#kernel, (stream));                         \
+    if (prof__) ::pcg::prof_begin((name), (stream));                          \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
     if (prof__) ::pcg::prof_end((stream));                                    \
     ::pcg::g_launches.fetch_add(1, std::memory_order_relaxed);                \
     PCG_CUDA(cudaGetLastError());                                             \
   } while (0)
+#define PCG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  PCG_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 struct StatusError {
   pcg_status s;

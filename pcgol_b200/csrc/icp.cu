@@ -39,19 +39,53 @@ struct IcpState {
   unsigned int pair_counter;
   unsigned int ticket;   // CTAs that have published their part of the current reduction
   float sums[12];        // the nine accumulators of the current Evaluate (strict replay, one CTA each)
+  // normal equations (never read unless want_hessian / Gauss-Newton)
+  int32_t want_hessian;
+  int32_t pad_;
+  double hsum[9];        // sum x,y,z,xx,xy,xz,yy,yz,zz of the matched, transformed target points
+  float hess[36];        // Evaluated.Hessian of the last Evaluate
 };
 
 constexpr int kTermThreads = 128;
 constexpr int kTerms = 9;  // Value, SumW, G0..G5, R
+constexpr int kHTerms = 9; // sum p (3) + second moments of p (6): the Gauss-Newton Hessian
 
-__device__ __forceinline__ void icp_fast_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
-                                                    int nblocks, float* s_sum, int* s_last);
+__device__ __noinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+                                               const double* __restrict__ hpartials, int nblocks, bool do_main,
+                                               bool do_hess, float* s_sum, int* s_last);
 
-template <int MODE>
-__global__ void __launch_bounds__(kTermThreads)
+// Block-wide float64 sum of K per-thread values -> out[blockIdx.x * K + k] (fixed order).
+template <int K>
+__device__ __forceinline__ void block_sum_f64(const float* t, double (*s_red)[K], double* __restrict__ out) {
+  const int tid = threadIdx.x;
+  double d[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    d[k] = (double)t[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[k] += __shfl_down_sync(0xffffffffu, d[k], o);
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) s_red[tid >> 5][k] = d[k];
+  }
+  __syncthreads();
+  if (tid < K) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTermThreads / 32; w++) s += s_red[w][tid];
+    out[(int64_t)blockIdx.x * K + tid] = s;
+  }
+  __syncthreads();
+}
+
+// APPROX: KDTree.MinDistSq > 0 on the base search (kdtree.go:19-22).  HESS: also accumulate the
+// nine moments of the normal equations (icp_math.cuh).
+template <int MODE, bool APPROX, bool HESS>
+__global__ void __launch_bounds__(kTermThreads, 16)
     icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, float max_dist_sq,
-                     IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
-                     double* __restrict__ partials, int finalize) {
+                     float min_dist_sq, IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
+                     double* __restrict__ partials, double* __restrict__ hpartials, int finalize) {
   if (st->done) return;
   __shared__ float s_m[16];
   __shared__ int s_first;
@@ -64,8 +98,11 @@ __global__ void __launch_bounds__(kTermThreads)
   __syncthreads();
   const int64_t slot = (int64_t)blockIdx.x * kTermThreads + tid;
   float t[kTerms];
+  float ht[kHTerms];
 #pragma unroll
   for (int k = 0; k < kTerms; k++) t[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kHTerms; k++) ht[k] = 0.f;
   int matched = 0;
   if (slot < tgt.n) {
     // Morton-ordered visit (coherent warps); the terms still land at the target's own index,
@@ -79,7 +116,11 @@ __global__ void __launch_bounds__(kTermThreads)
     uint64_t best = nn_init(max_dist_sq);
     const uint64_t init = best;
     uint32_t pos = 0;
+#ifdef PCG_BVH2
     PCG_NN_TRAVERSE(base, x0, y0, z0, best, pos);
+#else
+    nn_traverse4<APPROX>(base, x0, y0, z0, best, pos, min_dist_sq);
+#endif
     if (best != init) {  // correspondence.go:27-29
       matched = 1;
       const float4 pb = __ldg(base.pts + pos);
@@ -95,6 +136,17 @@ __global__ void __launch_bounds__(kTermThreads)
       t[6] = im::sub(im::mul(x0, z1), im::mul(z0, x1));
       t[7] = im::sub(im::mul(y0, x1), im::mul(x0, y1));
       t[8] = im::add(im::add(im::mul(x0, x0), im::mul(y0, y0)), im::mul(z0, z0));
+      if (HESS) {
+        ht[0] = x0;
+        ht[1] = y0;
+        ht[2] = z0;
+        ht[3] = im::mul(x0, x0);
+        ht[4] = im::mul(x0, y0);
+        ht[5] = im::mul(x0, z0);
+        ht[6] = im::mul(y0, y0);
+        ht[7] = im::mul(y0, z0);
+        ht[8] = im::mul(z0, z0);
+      }
     }
     if (MODE == PCG_ICP_STRICT) {
       // unmatched targets contribute +0: x + (+0) == x for every partial sum the reference can hold
@@ -104,27 +156,10 @@ __global__ void __launch_bounds__(kTermThreads)
   }
   const int block_pairs = __syncthreads_count(matched);
   if (tid == 0 && block_pairs) atomicAdd(&st->pair_counter, (unsigned int)block_pairs);
-  if (MODE == PCG_ICP_FAST) {
-    double d[kTerms];
-#pragma unroll
-    for (int k = 0; k < kTerms; k++) {
-      d[k] = (double)t[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) d[k] += __shfl_down_sync(0xffffffffu, d[k], o);
-    }
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int k = 0; k < kTerms; k++) s_red[tid >> 5][k] = d[k];
-    }
-    __syncthreads();
-    if (tid < kTerms) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < kTermThreads / 32; w++) s += s_red[w][tid];
-      partials[(int64_t)blockIdx.x * kTerms + tid] = s;
-    }
-    if (finalize) icp_fast_last_block(st, partials, (int)gridDim.x, s_sum, &s_last);
-  }
+  if (HESS) block_sum_f64<kHTerms>(ht, s_red, hpartials);
+  if (MODE == PCG_ICP_FAST) block_sum_f64<kTerms>(t, s_red, partials);
+  if (finalize && (MODE == PCG_ICP_FAST || HESS))
+    icp_last_block(st, partials, hpartials, (int)gridDim.x, MODE == PCG_ICP_FAST, HESS, s_sum, &s_last);
 }
 
 constexpr int kFinishThreads = 32 * kTerms;
@@ -157,22 +192,33 @@ __device__ __forceinline__ void icp_finalize(IcpState* __restrict__ st, const fl
   sums.rms = sum9[8];
   const im::Eval ev = im::evaluate_tail(sums);
   st->ev = ev;                                // icp.go:54
+  im::HSums hs = {};
+  if (st->want_hessian) {
+    hs.n = (double)n_pairs;
+    for (int k = 0; k < 3; k++) hs.p[k] = st->hsum[k];
+    for (int k = 0; k < 6; k++) hs.pp[k] = st->hsum[3 + k];
+    im::hessian_from_sums(hs, sums.sum_weight, st->hess);
+  }
   if (st->evaluate_only) {
     st->done = 1;
     return;
   }
   im::M4 trans = st->trans;
   int iter = st->iter;
-  const bool converged = im::updater_update(st->cfg, &iter, &trans, ev);  // icp.go:57
+  const bool converged = st->cfg.kind == PCG_UPDATER_GAUSS_NEWTON
+                             ? im::updater_update_gn(st->cfg, &iter, &trans, ev, sums, hs)
+                             : im::updater_update(st->cfg, &iter, &trans, ev);  // icp.go:57
   st->trans = trans;
   st->iter = iter;
   if (converged) st->done = 1;
 }
 
-// FAST mode: called by every CTA of icp_terms_kernel after it wrote its partials; the last one
-// to arrive reduces all of them (fixed order: lane-strided columns, then a shuffle tree).
-__device__ __forceinline__ void icp_fast_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
-                                                    int nblocks, float* s_sum, int* s_last) {
+// Called by every CTA of icp_terms_kernel after it wrote its partials; the last one to arrive
+// reduces all of them (fixed order: lane-strided columns, then a shuffle tree).  do_main: the nine
+// Evaluate sums (FAST mode) followed by the tail; do_hess: the nine moments of the normal equations.
+__device__ __noinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+                                               const double* __restrict__ hpartials, int nblocks, bool do_main,
+                                               bool do_hess, float* s_sum, int* s_last) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __threadfence();
   if (tid == 0) {
@@ -182,17 +228,28 @@ __device__ __forceinline__ void icp_fast_last_block(IcpState* __restrict__ st, c
   __syncthreads();
   if (!*s_last) return;
   __threadfence();
-  for (int k = warp; k < kTerms; k += kTermThreads / 32) {
-    double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += __ldcg(&partials[(int64_t)b * kTerms + k]);
+  if (do_hess) {
+    for (int k = warp; k < kHTerms; k += kTermThreads / 32) {
+      double s = 0.0;
+      for (int b = lane; b < nblocks; b += 32) s += __ldcg(&hpartials[(int64_t)b * kHTerms + k]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) s_sum[k] = (float)s;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) st->hsum[k] = s;
+    }
+  }
+  if (do_main) {
+    for (int k = warp; k < kTerms; k += kTermThreads / 32) {
+      double s = 0.0;
+      for (int b = lane; b < nblocks; b += 32) s += __ldcg(&partials[(int64_t)b * kTerms + k]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) s_sum[k] = (float)s;
+    }
   }
   __syncthreads();
   if (tid == 0) {
     st->ticket = 0;
-    icp_finalize(st, s_sum);
+    if (do_main) icp_finalize(st, s_sum);
   }
 }
 
@@ -538,6 +595,7 @@ struct IcpWork {
   DevBuf<IcpState> st;
   DevBuf<float> terms;
   DevBuf<double> partials;
+  DevBuf<double> hpartials;  // [nblocks][9] when the normal equations are accumulated
   DevBuf<uint32_t> perm;
   DevBuf<ReplayChunk> replay_chunks;  // strict replay: [9][chunks]
   DevBuf<double> replay_sums;         // strict replay: [9][chunks]
@@ -552,28 +610,60 @@ static IcpState make_state(const pcg_icp_params& prm, bool evaluate_only) {
   h.cfg = im::make_updater(prm);
   h.min_pairs = prm.min_pairs == 0 ? 6 : prm.min_pairs;  // evaluator.go:92-95
   h.evaluate_only = evaluate_only ? 1 : 0;
+  h.want_hessian = ((prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON) ? 1 : 0;
   return h;
+}
+
+static void check_icp_params(const pcg_icp_params& prm) {
+  const int mode = prm.mode & ~PCG_ICP_WITH_HESSIAN;
+  if (mode != PCG_ICP_STRICT && mode != PCG_ICP_FAST) throw StatusError{PCG_E_INVALID_ARG, "unknown ICP mode"};
+  if (prm.updater != PCG_UPDATER_GRADIENT_DESCENT && prm.updater != PCG_UPDATER_GAUSS_NEWTON)
+    throw StatusError{PCG_E_INVALID_ARG, "unknown ICP updater"};
+  if (!(prm.min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
+}
+
+// One launch of the fused correspondence + terms kernel for the (mode, MinDistSq, Hessian) combination.
+template <int MODE>
+static void launch_terms(const Index& base, const CloudView& tgt, const uint32_t* perm, float mdsq, float min_dist_sq,
+                         bool hess, IcpState* st, float* terms, int64_t n_pad, double* partials, double* hpartials,
+                         int nblocks, int finalize, cudaStream_t stream) {
+  const char* name = MODE == PCG_ICP_STRICT ? "(icp_terms_kernel<PCG_ICP_STRICT>)" : "(icp_terms_kernel<PCG_ICP_FAST>)";
+  const bool approx = min_dist_sq > 0.f;
+#define PCG_TERMS(A, H)                                                                                              \
+  PCG_LAUNCH_NAMED(name, (icp_terms_kernel<MODE, A, H>), nblocks, kTermThreads, 0, stream, base.view(), tgt, perm, mdsq, \
+                   min_dist_sq, st, terms, n_pad, partials, hpartials, finalize)
+  if (approx && hess)
+    PCG_TERMS(true, true);
+  else if (approx)
+    PCG_TERMS(true, false);
+  else if (hess)
+    PCG_TERMS(false, true);
+  else
+    PCG_TERMS(false, false);
+#undef PCG_TERMS
 }
 
 // Enqueues a whole Fit (or a single Evaluate) on `stream` without synchronising.
 // Returns false if max_iteration exceeds what is enqueued at once (caller then polls).
 constexpr int kMaxEnqueuedIterations = 64;
 
-static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, float max_dist, int mode, IcpWork& w,
+static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, IcpWork& w,
                                    int iterations, cudaStream_t stream) {
-  const float mdsq = max_dist * max_dist;  // kdtree.go:91
+  const float mdsq = prm.max_dist * prm.max_dist;  // kdtree.go:91
+  const int mode = prm.mode & ~PCG_ICP_WITH_HESSIAN;
+  const bool hess = (prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON;
   for (int it = 0; it < iterations; it++) {
     if (mode == PCG_ICP_STRICT) {
-      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_STRICT>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
-                 w.st.p, w.terms.p, w.n_pad, w.partials.p, 0);
+      launch_terms<PCG_ICP_STRICT>(base, tgt, w.perm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
+                                   w.partials.p, w.hpartials.p, w.nblocks, 1, stream);
       static const bool sequential_replay = getenv("PCG_ICP_REPLAY_SEQ") != nullptr;  // comparison runs only
       if (sequential_replay)
         PCG_LAUNCH(icp_replay_kernel, kTerms, 32, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad);
       else
         launch_exact_replay(w.st.p, w.terms.p, tgt.n, w.n_pad, kTerms, w.replay_chunks.p, w.replay_sums.p, stream);
     } else {
-      PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, w.perm.p, mdsq,
-                 w.st.p, w.terms.p, w.n_pad, w.partials.p, 1);
+      launch_terms<PCG_ICP_FAST>(base, tgt, w.perm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
+                                 w.partials.p, w.hpartials.p, w.nblocks, 1, stream);
     }
   }
 }
@@ -588,7 +678,9 @@ static void icp_prepare(const Index& base, const CloudView& tgt, const pcg_icp_p
   }
   w.n_pad = (tgt.n + 3) & ~(int64_t)3;
   w.st.alloc(1, stream);
-  if (prm.mode == PCG_ICP_STRICT) {
+  if ((prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON)
+    w.hpartials.alloc((size_t)w.nblocks * kHTerms, stream);
+  if ((prm.mode & ~PCG_ICP_WITH_HESSIAN) == PCG_ICP_STRICT) {
     w.terms.alloc((size_t)std::max<int64_t>(4, w.n_pad) * kTerms, stream);
     const size_t nchunks = (size_t)std::max<int64_t>(1, (tgt.n + kReplayChunk - 1) / kReplayChunk);
     w.replay_chunks.alloc(nchunks * kTerms, stream);
@@ -606,6 +698,7 @@ static void state_to_outputs(const IcpState& h, float trans[16], pcg_icp_stat* s
     stat->evaluated.value = h.ev.value;
     for (int k = 0; k < 6; k++) stat->evaluated.gradient[k] = h.ev.g[k];
     stat->evaluated.dist_rms = h.ev.dist_rms;
+    if (h.want_hessian) std::memcpy(stat->evaluated.hessian, h.hess, sizeof(h.hess));
     stat->num_iteration = h.num_iteration;
     stat->n_pairs = h.n_pairs;
   }
@@ -614,8 +707,7 @@ static void state_to_outputs(const IcpState& h, float trans[16], pcg_icp_stat* s
 // PointToPointICPGradient.Fit (icp.go:23-67) / Evaluate only. Synchronises `stream`.
 pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only,
                           float trans[16], pcg_icp_stat* stat, cudaStream_t stream) {
-  if (prm.mode != PCG_ICP_STRICT && prm.mode != PCG_ICP_FAST)
-    throw StatusError{PCG_E_INVALID_ARG, "unknown ICP mode"};
+  check_icp_params(prm);
   IcpWork w;
   icp_prepare(base, tgt, prm, evaluate_only, w, stream);
   const int total = evaluate_only ? 1 : im::make_updater(prm).max_iteration;
@@ -624,7 +716,7 @@ pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp
   for (;;) {
     // every Update that does not converge increments i, so `total` Evaluate calls always suffice
     const int batch = std::min(kMaxEnqueuedIterations, std::max(1, total - enq));
-    icp_enqueue_iterations(base, tgt, prm.max_dist, prm.mode, w, batch, stream);
+    icp_enqueue_iterations(base, tgt, prm, w, batch, stream);
     enq += batch;
     PCG_CUDA(cudaMemcpyAsync(&h, w.st.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
     PCG_CUDA(cudaStreamSynchronize(stream));
@@ -641,8 +733,7 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
                           const int64_t xyz_off[3], const pcg_icp_params& prm, int device, float* trans_out,
                           pcg_icp_stat* stat_out, pcg_status* status_out, cudaStream_t stream) {
   if (count <= 0) return;
-  if (prm.mode != PCG_ICP_STRICT && prm.mode != PCG_ICP_FAST)
-    throw StatusError{PCG_E_INVALID_ARG, "unknown ICP mode"};
+  check_icp_params(prm);
   const int total = im::make_updater(prm).max_iteration;
   if (total > kMaxEnqueuedIterations)
     throw StatusError{PCG_E_INVALID_ARG, "pcg_icp_fit_pairs_dev supports MaxIteration <= 64"};
@@ -669,7 +760,7 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
         CloudView tv = make_view(d_target[i], n_target[i], stride, xyz_off);
         indices[i] = index_build_device(bv, device, s);
         icp_prepare(*indices[i], tv, prm, false, works[i], s);
-        icp_enqueue_iterations(*indices[i], tv, prm.max_dist, prm.mode, works[i], total, s);
+        icp_enqueue_iterations(*indices[i], tv, prm, works[i], total, s);
         PCG_CUDA(cudaMemcpyAsync(&h[i], works[i].st.p, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
       }
       for (int s = 0; s < ns; s++) {
@@ -714,8 +805,8 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
   h.num_iteration = first ? 0 : 1;  // only "is this the first Evaluate" matters to the terms kernel
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   const float mdsq = max_dist * max_dist;
-  PCG_LAUNCH((icp_terms_kernel<PCG_ICP_FAST>), w.nblocks, kTermThreads, 0, stream, base.view(), tgt, d_order, mdsq,
-             w.st.p, w.terms.p, w.n_pad, w.partials.p, 0);
+  launch_terms<PCG_ICP_FAST>(base, tgt, d_order, mdsq, 0.f, false, w.st.p, w.terms.p, w.n_pad, w.partials.p, nullptr,
+                             w.nblocks, 0, stream);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
 }
 
@@ -772,8 +863,9 @@ float debug_sequential_sum(const float* d_x, int64_t n, bool exact_path, cudaStr
 }
 
 // NearestPointCorresponder.Pairs building block: nearest neighbour of every target point.
+template <bool APPROX>
 __global__ void __launch_bounds__(128)
-    icp_pairs_kernel(IndexView base, CloudView tgt, float max_dist_sq, int32_t* __restrict__ ids,
+    icp_pairs_kernel(IndexView base, CloudView tgt, float max_dist_sq, float min_dist_sq, int32_t* __restrict__ ids,
                      float* __restrict__ dsq) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tgt.n) return;
@@ -781,17 +873,25 @@ __global__ void __launch_bounds__(128)
   uint64_t best = nn_init(max_dist_sq);
   const uint64_t init = best;
   uint32_t pos = 0;
+#ifdef PCG_BVH2
   PCG_NN_TRAVERSE(base, p.x, p.y, p.z, best, pos);
+#else
+  nn_traverse4<APPROX>(base, p.x, p.y, p.z, best, pos, min_dist_sq);
+#endif
   const bool hit = best != init;
   ids[i] = hit ? (int32_t)(uint32_t)best : -1;
   dsq[i] = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_dist_sq;
 }
 
-void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, int32_t* d_ids, float* d_dsq,
-                      cudaStream_t stream) {
+void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
+                      float* d_dsq, cudaStream_t stream) {
   if (tgt.n == 0) return;
-  PCG_LAUNCH(icp_pairs_kernel, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist, d_ids,
-             d_dsq);
+  if (min_dist_sq > 0.f)
+    PCG_LAUNCH(icp_pairs_kernel<true>, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist,
+               min_dist_sq, d_ids, d_dsq);
+  else
+    PCG_LAUNCH(icp_pairs_kernel<false>, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist, 0.f,
+               d_ids, d_dsq);
 }
 
 }  // namespace pcg

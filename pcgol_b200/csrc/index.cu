@@ -291,8 +291,44 @@ void index_free(Index* ix) {
   if (ix->pts) cudaFree(ix->pts);
   if (ix->boxes) cudaFree(ix->boxes);
   if (ix->bbox) cudaFree(ix->bbox);
+  if (ix->inv) cudaFree(ix->inv);
   if (prev >= 0) cudaSetDevice(prev);
   delete ix;
+}
+
+// ---- KDTree.DeletePoint (kdtree.go:322-332) as tombstones ------------------------------------
+__global__ void __launch_bounds__(256)
+    inverse_slots_kernel(const float4* __restrict__ pts, uint32_t padded, uint32_t* __restrict__ inv) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= padded) return;
+  const uint32_t id = __float_as_uint(pts[i].w);
+  if (id != 0xffffffffu) inv[id] = i;
+}
+
+__global__ void __launch_bounds__(256)
+    delete_points_kernel(float4* __restrict__ pts, const uint32_t* __restrict__ inv, const int64_t* __restrict__ ids,
+                         int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = inv[ids[i]];
+  const float inf = __int_as_float(0x7f800000);
+  // x,y,z only: the id in .w stays (deleting twice is a no-op, like the reference's second walk)
+  float* p = reinterpret_cast<float*>(pts + slot);
+  p[0] = inf;
+  p[1] = inf;
+  p[2] = inf;
+}
+
+void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream) {
+  if (n == 0 || ix.n == 0) return;
+  std::lock_guard<std::mutex> lk(ix.mu);
+  if (!ix.inv) {
+    PCG_CUDA(cudaMallocAsync((void**)&ix.inv, (size_t)ix.n * sizeof(uint32_t), stream));
+    ix.bytes += ix.n * (int64_t)sizeof(uint32_t);
+    const uint32_t padded = ix.leaves * kLeaf;
+    PCG_LAUNCH(inverse_slots_kernel, div_up(padded, 256), 256, 0, stream, ix.pts, padded, ix.inv);
+  }
+  PCG_LAUNCH(delete_points_kernel, div_up(n, 256), 256, 0, stream, ix.pts, ix.inv, d_ids, n);
 }
 
 #ifdef PCG_NN_STATS
@@ -407,9 +443,11 @@ __global__ void __launch_bounds__(128)
 }
 
 // One query per thread (no work fetching): kept for comparison runs (PCG_NN_KERNEL=simple).
+template <bool APPROX>
 __global__ void __launch_bounds__(128)
     nearest_simple_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
-                          int32_t* __restrict__ ids, float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos) {
+                          float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
+                          pcg_neighbor* __restrict__ aos) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q.n) return;
   if (perm) i = perm[i];
@@ -417,7 +455,11 @@ __global__ void __launch_bounds__(128)
   uint64_t best = nn_init(max_range_sq);
   const uint64_t init = best;
   uint32_t pos = 0;
+#ifdef PCG_BVH2
   PCG_NN_TRAVERSE(ix, p.x, p.y, p.z, best, pos);
+#else
+  nn_traverse4<APPROX>(ix, p.x, p.y, p.z, best, pos, min_dist_sq);
+#endif
   const bool hit = best != init;
   const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
   const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
@@ -440,8 +482,8 @@ static int persistent_blocks(int64_t n_queries, int threads) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)kNumSMs * (2048 / threads), by_work));
 }
 
-void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_t* d_ids, float* d_dist_sq,
-                    pcg_neighbor* d_aos, cudaStream_t stream) {
+void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
+                    float* d_dist_sq, pcg_neighbor* d_aos, cudaStream_t stream) {
   if (q.n == 0) return;
   const float mrsq = max_range * max_range;  // kdtree.go:91
   DevBuf<uint32_t> perm;
@@ -462,9 +504,14 @@ void nearest_device(const Index& ix, const CloudView& q, float max_range, int32_
     const char* e = getenv("PCG_NN_KERNEL");
     return !(e && strcmp(e, "persistent") == 0);
   }();
+  if (min_dist_sq > 0.f) {  // KDTree.MinDistSq > 0: approximate search (kdtree.go:19-22)
+    PCG_LAUNCH(nearest_simple_kernel<true>, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, min_dist_sq,
+               d_ids, d_dist_sq, d_aos);
+    return;
+  }
   if (simple) {
-    PCG_LAUNCH(nearest_simple_kernel, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, d_ids, d_dist_sq,
-               d_aos);
+    PCG_LAUNCH(nearest_simple_kernel<false>, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, 0.f, d_ids,
+               d_dist_sq, d_aos);
     return;
   }
   PCG_LAUNCH(nearest_kernel, persistent_blocks(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, d_ids,

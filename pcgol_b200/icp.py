@@ -19,6 +19,7 @@ from .storage import Index
 
 STRICT = _lib.ICP_STRICT
 FAST = _lib.ICP_FAST
+WITH_HESSIAN = _lib.ICP_WITH_HESSIAN
 
 
 class ErrNotEnoughPairs(RuntimeError):  # evaluator.go:15-17
@@ -63,8 +64,9 @@ class NearestPointCorresponder:
         t = np.empty(max(n, 1), np.int64)
         d = np.empty(max(n, 1), np.float32)
         m = C.c_int64(0)
-        _lib.check(_lib.lib.pcg_icp_pairs(base._h, data.ctypes.data, n, stride, _off(off), self.max_dist,
-                                         b.ctypes.data, t.ctypes.data, d.ctypes.data, C.byref(m)))
+        _lib.check(_lib.lib.pcg_icp_pairs_approx(base._h, data.ctypes.data, n, stride, _off(off), self.max_dist,
+                                                getattr(base, "min_dist_sq", 0.0), b.ctypes.data, t.ctypes.data,
+                                                d.ctypes.data, C.byref(m)))
         return b[: m.value].copy(), t[: m.value].copy(), d[: m.value].copy()
 
 
@@ -78,14 +80,16 @@ class PointToPointEvaluator:
         return True
 
     def has_hessian(self) -> bool:
-        return False
+        """False like the reference (evaluator.go:76) unless the mode carries WITH_HESSIAN."""
+        return bool(self.mode & WITH_HESSIAN)
 
     def evaluate(self, base: Index, target) -> Evaluated:
         data, n, stride, off = as_vec3_buffer(target)
         ev = _lib.Evaluated()
         npairs = C.c_int64(0)
-        rc = _lib.lib.pcg_icp_evaluate(base._h, data.ctypes.data, n, stride, _off(off), self.corresponder.max_dist,
-                                       self.min_pairs, self.mode, C.byref(ev), C.byref(npairs))
+        p = _params(self, None, base)
+        rc = _lib.lib.pcg_icp_evaluate_params(base._h, data.ctypes.data, n, stride, _off(off), C.byref(p),
+                                              C.byref(ev), C.byref(npairs))
         if rc == _lib.E_NOT_ENOUGH_PAIRS:
             raise ErrNotEnoughPairs()
         _lib.check(rc)
@@ -97,9 +101,20 @@ class GradientDescentUpdaterFactory:
     weight: Sequence[float] = (0,) * 6
     threshold: Sequence[float] = (0,) * 6
     max_iteration: int = 0
+    kind = _lib.UPDATER_GRADIENT_DESCENT
 
 
-def _params(evaluator: PointToPointEvaluator, uf: Optional[GradientDescentUpdaterFactory]) -> _lib.IcpParams:
+@dataclass
+class GaussNewtonUpdaterFactory:
+    """Not in the reference: consumes Evaluated.Hessian (the hook evaluator.go:25-36 declares) and
+    solves the 6x6 normal equations per iteration; same convergence test and MaxIteration cap."""
+    threshold: Sequence[float] = (0,) * 6
+    max_iteration: int = 0
+    weight: Sequence[float] = (0,) * 6  # ignored
+    kind = _lib.UPDATER_GAUSS_NEWTON
+
+
+def _params(evaluator: PointToPointEvaluator, uf, base: Optional[Index] = None) -> _lib.IcpParams:
     uf = uf or GradientDescentUpdaterFactory()
     p = _lib.IcpParams()
     p.max_dist = evaluator.corresponder.max_dist
@@ -109,16 +124,19 @@ def _params(evaluator: PointToPointEvaluator, uf: Optional[GradientDescentUpdate
         p.threshold[k] = uf.threshold[k]
     p.max_iteration = uf.max_iteration
     p.mode = evaluator.mode
+    p.updater = uf.kind
+    # the base search's own MinDistSq applies to the correspondences, as with a *kdtree.KDTree in the reference
+    p.min_dist_sq = getattr(base, "min_dist_sq", 0.0) if base is not None else 0.0
     return p
 
 
 @dataclass
 class PointToPointICPGradient:
     evaluator: PointToPointEvaluator
-    updater_factory: Optional[GradientDescentUpdaterFactory] = None
+    updater_factory: Optional[object] = None  # GradientDescentUpdaterFactory | GaussNewtonUpdaterFactory
 
-    def params(self) -> _lib.IcpParams:
-        return _params(self.evaluator, self.updater_factory)
+    def params(self, base: Optional[Index] = None) -> _lib.IcpParams:
+        return _params(self.evaluator, self.updater_factory, base)
 
     def _finish(self, rc, trans, stat):
         st = Stat(Evaluated._from_c(stat.evaluated), int(stat.num_iteration), int(stat.n_pairs))
@@ -130,7 +148,7 @@ class PointToPointICPGradient:
     def fit(self, base: Index, target) -> Tuple[np.ndarray, Stat]:
         """Returns (trans float32[16] column-major, Stat); raises ErrNotEnoughPairs like the reference."""
         data, n, stride, off = as_vec3_buffer(target)
-        p = self.params()
+        p = self.params(base)
         trans = np.zeros(16, np.float32)
         stat = _lib.IcpStat()
         rc = _lib.lib.pcg_icp_fit(base._h, data.ctypes.data, n, stride, _off(off), C.byref(p), trans.ctypes.data,
@@ -138,7 +156,7 @@ class PointToPointICPGradient:
         return self._finish(rc, trans, stat)
 
     def fit_dev(self, base: Index, d_target: int, n: int, stream: int = 0, stride: int = 12, off=(0, 4, 8)):
-        p = self.params()
+        p = self.params(base)
         trans = np.zeros(16, np.float32)
         stat = _lib.IcpStat()
         rc = _lib.lib.pcg_icp_fit_dev(base._h, d_target, n, stride, _off(off), C.byref(p), trans.ctypes.data,

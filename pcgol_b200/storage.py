@@ -29,11 +29,13 @@ def _off(off):
 class Index:
     """kdtree.New(ra) replacement: `Index(cloud)` where cloud is a PointCloud or (n,3) float32."""
 
-    def __init__(self, cloud, device: int = 0):
+    def __init__(self, cloud, device: int = 0, min_dist_sq: float = 0.0):
         data, n, stride, off = as_vec3_buffer(cloud)
         self._cloud = cloud
         self._xyz = None
         self.device = device
+        #: KDTree.MinDistSq (kdtree.go:19-22): > 0 makes nearest / nearest_batch an approximate search
+        self.min_dist_sq = float(min_dist_sq)
         self._h = C.c_void_p()
         self._keep = data
         _lib.check(_lib.lib.pcg_index_build(data.ctypes.data, n, stride, _off(off), device, C.byref(self._h)))
@@ -44,6 +46,7 @@ class Index:
         self._cloud = None
         self._xyz = None
         self.device = device
+        self.min_dist_sq = 0.0
         self._h = C.c_void_p()
         _lib.check(_lib.lib.pcg_index_build_dev(d_ptr, n, stride, _off(off), device, stream, C.byref(self._h)))
         return self
@@ -82,12 +85,31 @@ class Index:
         return [Neighbor(int(i), float(d)) for i, d in zip(ids, dsq)]
 
     def nearest_batch(self, queries, max_range: float) -> Tuple[np.ndarray, np.ndarray]:
-        """(ids int64[nq], dist_sq float32[nq]); miss = (-1, max_range**2)."""
+        """(ids int64[nq], dist_sq float32[nq]); miss = (-1, max_range**2).  Exact unless min_dist_sq > 0."""
         data, n, stride, off = as_vec3_buffer(queries)
         out = np.empty(max(n, 1), dtype=np.dtype([("id", "<i8"), ("dist_sq", "<f4"), ("pad", "<u4")]))
-        _lib.check(_lib.lib.pcg_index_nearest(self._h, data.ctypes.data, n, stride, _off(off), max_range,
-                                             out.ctypes.data))
+        _lib.check(_lib.lib.pcg_index_nearest_approx(self._h, data.ctypes.data, n, stride, _off(off), max_range,
+                                                    self.min_dist_sq, out.ctypes.data))
         return out["id"][:n].copy(), out["dist_sq"][:n].copy()
+
+    def with_min_dist_sq(self, min_dist_sq: float) -> "Index":
+        """KDTree.With(opts) (kdtree.go:58-65): a shallow copy sharing the device index."""
+        import copy
+        other = copy.copy(self)
+        other.min_dist_sq = float(min_dist_sq)
+        other._shared = self  # keeps the owner alive; only the owner frees the handle
+        other.close = lambda: None
+        return other
+
+    # -- KDTree.DeletePoint (kdtree.go:322-332) ---------------------------------
+    def delete_point(self, pid: int) -> None:
+        self.delete_points([pid])
+
+    def delete_points(self, ids) -> None:
+        """Tombstones: the points stop matching any search; len() is unchanged. An id outside
+        [0, len-1] raises (status INVALID_ARG, the reference's error text) and deletes nothing."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        _lib.check(_lib.lib.pcg_index_delete_points(self._h, ids.ctypes.data, len(ids)))
 
     def nearest_dev(self, d_q: int, nq: int, max_range: float, d_ids: int, d_dist_sq: int, stream: int = 0,
                     stride: int = 12, off=(0, 4, 8)):

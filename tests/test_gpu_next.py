@@ -1,0 +1,246 @@
+"""GPU parity for the SURVEY §8(f) "next" rows: KDTree.DeletePoint and MinDistSq (N3), the normal
+equations / Gauss-Newton updater (N4).  Everything goes through the C ABI via the host mirror."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import pcgol_b200
+
+    assert pcgol_b200.device_count() >= 1, "GPU tests need a CUDA device"
+    return pcgol_b200
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from pcgol_b200 import synth as s
+
+    return s
+
+
+# --------------------------------------------------------------- DeletePoint ------
+def test_delete_point_reference_cases(pg, oracle):
+    # kdtree_test.go:413-751 : after DeletePoint the searches behave like naiveSearch with the point gone
+    from test_oracle_golden import DELETE_CASES, FIXTURE7
+
+    rng = np.random.default_rng(0)
+    q = np.concatenate([FIXTURE7, (rng.random((200, 3), dtype=f32) * f32(7.0)).astype(f32)])
+    for name, steps in DELETE_CASES.items():
+        idx = pg.Index(FIXTURE7)
+        nv = oracle.Search(FIXTURE7, "naive")
+        for pid, has_error, _tree in steps:
+            if has_error:
+                with pytest.raises(pg.PcgError) as ei:
+                    idx.delete_point(pid)
+                assert ei.value.status == pg.E_INVALID_ARG
+                assert f"{pid} does not correspond to any point in the tree" in str(ei.value)
+            else:
+                idx.delete_point(pid)
+                assert nv.delete_point(pid)
+            assert len(idx) == len(FIXTURE7)  # Len() is the accessor's, unchanged
+            for mr in (0.5, 1.5, 10.0):
+                ids, d = idx.nearest_batch(q, mr)
+                eids, ed = nv.nearest(q, mr)
+                assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes(), (name, pid, mr)
+                off, rid, rd = idx.range_batch(q, mr)
+                eoff, erid, erd = nv.range(q, mr)
+                assert np.array_equal(off, eoff) and np.array_equal(rid, erid) and rd.tobytes() == erd.tobytes()
+
+
+def test_delete_all_points_on_a_line(pg):
+    # kdtree_test.go:731-751
+    pts = np.array([[4, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], f32)
+    idx = pg.Index(pts)
+    for i in range(len(pts)):
+        idx.delete_point(i)
+        nb = idx.nearest(pts[i], 0.001)
+        assert nb.id < 0
+    ids, d = idx.nearest_batch(pts, 100.0)
+    assert np.all(ids == -1) and np.all(d == f32(100.0) * f32(100.0))
+    assert idx.range(pts[0], 100.0) == []
+
+
+@pytest.mark.parametrize("n,seed", [(100, 1), (5000, 2), (40000, 3)])
+def test_delete_point_random_cloud(pg, oracle, n, seed):
+    # kdtree_test.go:864-885 scaled up; a batch delete, then single deletes, duplicates included
+    rng = np.random.default_rng(seed)
+    pts = (rng.random((n, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((2000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    idx = pg.Index(pts)
+    nv = oracle.Search(pts, "naive")
+    dead = rng.permutation(n)[: n // 3]
+    idx.delete_points(dead[: len(dead) // 2])
+    for i in dead[len(dead) // 2:][:50]:
+        idx.delete_point(int(i))
+    idx.delete_points(dead)  # deleting again is a no-op (kdtree_test.go "TwiceTheSamePoint")
+    for i in dead:
+        assert nv.delete_point(int(i))
+    # queries placed exactly on deleted points must not find them
+    qq = np.concatenate([q, pts[dead[:500]]])
+    for mr in (0.05, 0.7, 20.0):
+        ids, d = idx.nearest_batch(qq, mr)
+        eids, ed = nv.nearest(qq, mr)
+        assert np.array_equal(ids, eids) and d.tobytes() == ed.tobytes()
+        assert not np.isin(ids, dead).any()
+    off, rid, rd = idx.range_batch(qq[:300], 0.9)
+    eoff, erid, erd = nv.range(qq[:300], 0.9)
+    assert np.array_equal(off, eoff) and np.array_equal(rid, erid) and rd.tobytes() == erd.tobytes()
+    with pytest.raises(pg.PcgError):
+        idx.delete_points([0, n])  # one bad id: nothing is deleted
+    with pytest.raises(pg.PcgError):
+        idx.delete_point(-1)
+
+
+def test_delete_then_icp_pairs(pg, oracle):
+    # the tombstones are honoured by the fused ICP correspondence search as well
+    rng = np.random.default_rng(11)
+    base = (rng.random((3000, 3), dtype=f32) * f32(5.0)).astype(f32)
+    target = (base[:1500] + rng.normal(0, 0.02, (1500, 3)).astype(f32)).astype(f32)
+    idx = pg.Index(base)
+    nv = oracle.Search(base, "naive")
+    dead = np.arange(0, 1500, 3)
+    idx.delete_points(dead)
+    for i in dead:
+        nv.delete_point(int(i))
+    b, t, d = pg.NearestPointCorresponder(0.5).pairs(idx, target)
+    eb, et, ed = oracle.icp_pairs(nv, target, 0.5)
+    assert np.array_equal(b, eb) and np.array_equal(t, et) and d.tobytes() == ed.tobytes()
+    ev = pg.PointToPointEvaluator(pg.NearestPointCorresponder(0.5)).evaluate(idx, target)
+    rc, eev, _ = oracle.icp_evaluate(nv, target, 0.5)
+    assert rc == oracle.OK
+    assert np.array([ev.value, *ev.gradient, ev.dist_rms], f32).tobytes() == eev.tobytes()
+
+
+# ----------------------------------------------------------------- MinDistSq ------
+def test_min_dist_sq_zero_is_exact(pg, oracle):
+    rng = np.random.default_rng(4)
+    pts = (rng.random((20000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((30000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    idx = pg.Index(pts)
+    a = idx.nearest_batch(q, 0.8)
+    b = idx.with_min_dist_sq(0.0).nearest_batch(q, 0.8)
+    assert np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes()
+
+
+@pytest.mark.parametrize("mds", [0.01, 0.05, 0.5])
+def test_min_dist_sq_contract(pg, oracle, mds):
+    # KDTree.MinDistSq (kdtree.go:19-22): exact NN, or a real point closer than sqrt(MinDistSq)
+    from test_oracle_golden import check_min_dist_contract
+
+    rng = np.random.default_rng(5)
+    pts = (rng.random((5000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((20000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    nv = oracle.Search(pts, "kdtree")  # exact (== naive, pinned by test_oracle_golden)
+    idx = pg.Index(pts, min_dist_sq=mds)
+    for mr in (0.1, 1.0, 20.0):
+        ids, d = idx.nearest_batch(q, mr)
+        eids, ed = nv.nearest(q, mr, threads=8)
+        check_min_dist_contract(pts, q, mr, mds, ids, d, eids, ed, allow_early_miss=False)
+    if mds >= 0.05:
+        assert np.any(idx.nearest_batch(q, 20.0)[0] != nv.nearest(q, 20.0, threads=8)[0])  # really approximate
+
+
+def test_min_dist_sq_invalid(pg):
+    idx = pg.Index(np.zeros((4, 3), f32), min_dist_sq=-1.0)
+    with pytest.raises(pg.PcgError):
+        idx.nearest_batch(np.zeros((1, 3), f32), 1.0)
+    idx.min_dist_sq = float("nan")
+    with pytest.raises(pg.PcgError):
+        idx.nearest_batch(np.zeros((1, 3), f32), 1.0)
+
+
+@pytest.mark.parametrize("zoff", [0.0, 5.0])
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_icp_reference_table_with_min_dist_sq(pg, oracle, zoff, mode):
+    # pc/registration/icp/icp_test.go:13-98 as the reference runs it: kdtree MinDistSq=0.01, MaxDist=2,
+    # MinPairs=3, residual <= 0.05.  (The approximate search is traversal-dependent, so the reference's own
+    # acceptance bound is the parity criterion here.)
+    from test_oracle_golden import _icp_deltas
+
+    base = np.array([[-2.1, 0, 0], [-1, 1, 0], [0, 2, 0], [1, 1, 1], [2, 0, 0]], f32)
+    base[:, 2] += f32(zoff)
+    indices = [3, 1, 4, 0, 2]
+    idx = pg.Index(base, min_dist_sq=0.01)
+    ev = pg.PointToPointEvaluator(pg.NearestPointCorresponder(2.0), min_pairs=3,
+                                  mode=pg.STRICT if mode == "strict" else pg.FAST)
+    icp = pg.PointToPointICPGradient(ev)
+    for name, delta in _icp_deltas(oracle).items():
+        target = oracle.mat4_transform(delta, base[indices])
+        trans, stat = icp.fit(idx, target)
+        assert 1 <= stat.num_iteration <= 20
+        moved = oracle.mat4_transform(trans, target)
+        residual = f32(0)
+        for i, j in enumerate(indices):
+            residual = f32(residual + f32(oracle.norm_sq((moved[i] - base[j]).astype(f32))))
+        residual = f32(residual / f32(len(indices)))
+        assert 0.05 >= residual, (name, residual)
+
+
+# ------------------------------------------------- Hessian / Gauss-Newton (N4) ------
+def _hessian_case(synth, n):
+    base, target = synth.icp_pair(seed=1, n=n)
+    return base, target
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_hessian_matches_definition(pg, oracle, synth, mode):
+    # Evaluated.Hessian = 2f * sum J^T J, J = [I | -[pt]x]: the oracle accumulates J^T J pair by pair in
+    # float64 from the definition, the kernel reduces nine moments; tolerance 1e-5 relative to |H|max
+    base, target = _hessian_case(synth, 20000)
+    idx = pg.Index(base)
+    nv = oracle.Search(base, "kdtree")
+    m = (pg.STRICT if mode == "strict" else pg.FAST) | pg.WITH_HESSIAN
+    e = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=m)
+    assert e.has_hessian()
+    ev = e.evaluate(idx, target)
+    rc, h, b, npairs = oracle.icp_normal_equations(nv, target, 1.0)
+    assert rc == oracle.OK
+    H = ev.hessian.reshape(6, 6)
+    assert np.array_equal(H, H.T)
+    scale = np.abs(h).max()
+    assert np.abs(ev.hessian - h).max() <= 1e-5 * scale
+    # gradient (before the rotation limit) is 2f * b: cross-check the translation part, which the limit leaves alone
+    g = (2.0 / npairs) * b
+    assert np.allclose(ev.gradient[:3], g[:3], rtol=1e-4, atol=1e-6)
+    # without the flag the reference behaviour is kept: Hessian stays zero
+    ev0 = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=m & ~pg.WITH_HESSIAN).evaluate(idx, target)
+    assert np.all(ev0.hessian == 0)
+    assert np.array([ev0.value, *ev0.gradient, ev0.dist_rms], f32).tobytes() == np.array(
+        [ev.value, *ev.gradient, ev.dist_rms], f32).tobytes()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_gauss_newton_fit_matches_oracle(pg, oracle, synth, mode):
+    base, target = _hessian_case(synth, 20000)
+    idx = pg.Index(base)
+    nv = oracle.Search(base, "kdtree")
+    ev = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.STRICT if mode == "strict" else pg.FAST)
+    trans, stat = pg.PointToPointICPGradient(ev, pg.GaussNewtonUpdaterFactory()).fit(idx, target)
+    rc, etrans, eev, eit = oracle.icp_fit_gn(nv, target, oracle.icp_params(1.0, f64_accumulate=(mode == "fast")))
+    assert rc == oracle.OK
+    assert stat.num_iteration == eit
+    # the float64 solves agree to rounding; the float32 trajectory then differs by a few ulp at most
+    assert np.abs(trans - etrans).max() <= 1e-5 * max(1.0, np.abs(etrans).max())
+    assert abs(stat.evaluated.value - eev[0]) <= 1e-5 * eev[0]
+    # and it beats the reference's damped gradient on the same budget of Evaluate calls
+    gd_trans, gd_stat = pg.PointToPointICPGradient(ev).fit(idx, target)
+    assert stat.evaluated.value < gd_stat.evaluated.value
+
+
+def test_gauss_newton_recovers_known_motion(pg, oracle):
+    # a rigid motion of an asymmetric cloud with exact correspondences inside MaxDist: one or two steps
+    rng = np.random.default_rng(3)
+    base = (rng.random((4000, 3), dtype=f32) * np.array([8, 5, 3], f32)).astype(f32)
+    delta = oracle.mat4_mul(oracle.translate(0.02, -0.015, 0.01), oracle.rotate(0, 0, 1, 0.004))
+    target = oracle.mat4_transform(delta, base)
+    idx = pg.Index(base)
+    ev = pg.PointToPointEvaluator(pg.NearestPointCorresponder(0.5), mode=pg.FAST)
+    trans, stat = pg.PointToPointICPGradient(ev, pg.GaussNewtonUpdaterFactory(threshold=(1e-4,) * 6)).fit(idx, target)
+    moved = oracle.mat4_transform(trans, target)
+    assert np.abs(moved - base).max() < 2e-4
+    assert stat.num_iteration <= 4

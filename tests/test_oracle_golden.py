@@ -175,6 +175,127 @@ def test_empty_tree(oracle):
         assert off.tolist() == [0, 0]
 
 
+# ------------------------------------------- kdtree: DeletePoint, MinDistSq ------
+def _tree(k):
+    root, ids, dim, left, right = k.dump()
+
+    def node(i):
+        if i < 0:
+            return None
+        return (int(ids[i]), int(dim[i]), node(left[i]), node(right[i]))
+
+    return node(root)
+
+
+def _leaf(i, d):
+    return (i, d, None, None)
+
+
+FULL_TREE = (3, 0, (4, 1, _leaf(5, 2), _leaf(1, 2)), (0, 1, _leaf(2, 2), _leaf(6, 2)))
+AFTER_DEL_3 = (0, 0, (4, 1, _leaf(5, 2), _leaf(1, 2)), (6, 1, _leaf(2, 2), None))
+DELETE_CASES = {  # kdtree_test.go:413-716: (pID, hasError, expected tree) applied in sequence
+    "LeafThenNodeWithRightSubTree": [
+        (5, False, (3, 0, (4, 1, None, _leaf(1, 2)), (0, 1, _leaf(2, 2), _leaf(6, 2)))),
+        (4, False, (3, 0, _leaf(1, 1), (0, 1, _leaf(2, 2), _leaf(6, 2)))),
+    ],
+    "RootThenNodeWithLeftSubTree": [
+        (3, False, AFTER_DEL_3),
+        (6, False, (0, 0, (4, 1, _leaf(5, 2), _leaf(1, 2)), _leaf(2, 1))),
+    ],
+    "NodeWithBothLeftAndRightSubTrees": [
+        (0, False, (3, 0, (4, 1, _leaf(5, 2), _leaf(1, 2)), (6, 1, _leaf(2, 2), None))),
+    ],
+    "TwiceTheSamePoint": [(3, False, AFTER_DEL_3), (3, False, AFTER_DEL_3)],
+    "InvalidPointID": [(-1, True, FULL_TREE), (123, True, FULL_TREE)],
+}
+
+
+def test_find_minimum_golden(oracle):
+    # kdtree_test.go:388-411
+    k = oracle.Search(FIXTURE7, "kdtree")
+    assert [k.find_minimum(d) for d in (0, 1, 2)] == [4, 3, 3]
+    assert k.find_minimum(3) == -2  # "dim should be <3"
+
+
+@pytest.mark.parametrize("name", sorted(DELETE_CASES))
+def test_delete_point_golden_trees(oracle, name):
+    # kdtree_test.go:413-729 (expected tree after every step, error flag)
+    k = oracle.Search(FIXTURE7, "kdtree")
+    for pid, has_error, exp in DELETE_CASES[name]:
+        ok = k.delete_point(pid)
+        assert ok == (not has_error)
+        assert _tree(k) == exp
+
+
+def test_delete_all_points_on_a_line(oracle):
+    # kdtree_test.go:731-751
+    pts = np.array([[4, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0]], f32)
+    for kind in ("kdtree", "naive"):
+        k = oracle.Search(pts, kind)
+        for i in range(len(pts)):
+            assert k.delete_point(i)
+            ids, _ = k.nearest([pts[i]], 0.001)
+            assert ids[0] < 0
+
+
+def test_delete_point_random_cloud_equals_naive(oracle):
+    # kdtree_test.go:864-885 + testNearestRandomCloud :794-834 (incl. findMinimum agreement)
+    rng = np.random.default_rng(99)
+    for trial in range(10):
+        pts = (rng.random((100, 3), dtype=f32) * f32(10.0)).astype(f32)
+        k = oracle.Search(pts, "kdtree")
+        nv = oracle.Search(pts, "naive")
+        for i in rng.permutation(100 // 3):
+            assert k.delete_point(int(i)) and nv.delete_point(int(i))
+        for d in range(3):
+            a, b = k.find_minimum(d), nv.find_minimum(d)
+            assert pts[a, d] == pts[b, d]
+        for _ in range(100):
+            p = (rng.random(3, dtype=f32) * f32(10.0)).astype(f32)
+            mr = float(rng.random(dtype=f32) * f32(10.0))
+            a, b = k.nearest([p], mr), nv.nearest([p], mr)
+            assert a[0][0] == b[0][0] and a[1].tobytes() == b[1].tobytes()
+            ra, rb = k.range([p], mr), nv.range([p], mr)
+            assert ra[1].tolist() == rb[1].tolist() and ra[2].tobytes() == rb[2].tobytes()
+
+
+def check_min_dist_contract(pts, q, max_range, min_dist_sq, ids, dsq, exact_ids, exact_dsq, allow_early_miss=False):
+    """KDTree.MinDistSq (kdtree.go:19-22): the search may stop at the first candidate closer than
+    sqrt(MinDistSq).  Every answer is therefore either the exact nearest neighbour or a real point
+    with DistSq < MinDistSq (and inside maxRange); DistSq always belongs to the returned ID."""
+    mr2 = f32(max_range) * f32(max_range)
+    for i in range(len(q)):
+        if ids[i] == exact_ids[i] and dsq[i] == exact_dsq[i]:
+            continue
+        if ids[i] < 0:
+            # reference quirk (kdtree.go:100-106): with maxRange^2 < MinDistSq a first-leaf miss ends the search
+            assert allow_early_miss and mr2 < f32(min_dist_sq), i
+            assert dsq[i] == mr2
+            continue
+        d = pts[ids[i]] - q[i]
+        want = f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2]))
+        assert dsq[i] == want, i
+        assert dsq[i] < f32(min_dist_sq) and dsq[i] <= mr2, i
+        assert exact_dsq[i] <= dsq[i]
+
+
+def test_min_dist_sq_contract_on_kdtree(oracle):
+    # the property every MinDistSq answer of the reference satisfies; the GPU approximate mode is held to it too
+    rng = np.random.default_rng(5)
+    pts = (rng.random((5000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    q = (rng.random((3000, 3), dtype=f32) * f32(10.0)).astype(f32)
+    nv = oracle.Search(pts, "naive")
+    for mds in (0.01, 0.05, 0.5):
+        k = oracle.Search(pts, "kdtree", min_dist_sq=mds)
+        for mr in (0.1, 1.0, 20.0):
+            ids, d = k.nearest(q, mr)
+            eids, ed = nv.nearest(q, mr)
+            check_min_dist_contract(pts, q, mr, mds, ids, d, eids, ed, allow_early_miss=True)
+        approx_hits = int(np.sum(k.nearest(q, 20.0)[0] != nv.nearest(q, 20.0)[0]))
+        if mds >= 0.05:
+            assert approx_hits > 0  # the approximation really kicks in on this cloud
+
+
 # ---------------------------------------------------------- voxelgrid ------
 def _vg_cloud():
     # pc/filter/voxelgrid/voxelgrid_test.go:59-76 : fields x,y,z,label ; stride 16

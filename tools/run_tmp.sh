@@ -1,2 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r1_f.json 2> gpurun_out/bench_r1_f.err; tail -2 gpurun_out/bench_r1_f.err; python tools/show_bench.py gpurun_out/bench_r1_f.json | grep -E "VoxelGrid|^NN|^ICP|icp_|replay|terms"
+for st in 1 2 4 8; do echo "== lane stride $st"; PCG_ICP_LANE_STRIDE=$st python bench.py --only icp --steps 5 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print({m:(round(v['ms_per_alignment'],3), {k:round(x['avg_us'],1) for k,x in v['kernels'].items() if 'terms' in k}) for m,v in d['modes'].items()})"; done
