@@ -109,6 +109,9 @@ void pcg_index_free(pcg_index* idx);
 int64_t pcg_index_len(const pcg_index* idx);    /* Vec3RandomAccessor.Len */
 int32_t pcg_index_device(const pcg_index* idx);
 int64_t pcg_index_device_bytes(const pcg_index* idx); /* HBM held by the index */
+/* Test hook: copies the index's point slots (leaves*8 float4: x, y, z, original id as bits; tail padding
+ * has id 0xffffffff) to out; *slots receives their number.  Lets the tests check the build invariants. */
+pcg_status pcg_debug_index_slots(const pcg_index* idx, float* out, int64_t cap_slots, int64_t* slots);
 
 /* KDTree.Nearest for a batch (kdtree.go:83-92).  Exact search (MinDistSq == 0).
  * Result i is the (DistSq, ID)-lexicographic minimum over points with
@@ -162,6 +165,24 @@ int64_t pcg_range_total(const pcg_range_result* r);
 const int64_t* pcg_range_offsets(const pcg_range_result* r);       /* nq+1 entries */
 const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r); /* total entries */
 void pcg_range_free(pcg_range_result* r);
+
+/* ---- segmentation: RegionGrowing (pc/segmentation/regiongrowing/regiongrowing.go:11-56) ---- */
+/* regiongrowing.New(search, propertyIter): `search` is the index, the property is a uint32 field at byte
+ * label_off of the same records the index was built from (pc.Uint32RandomAccessor over the cloud).  The handle
+ * keeps its own device copy of (x, y, z, label); it borrows `search`, which must outlive it. */
+typedef struct pcg_region_growing pcg_region_growing;
+pcg_status pcg_region_growing_new(pcg_index* search, const void* data, int64_t n, int64_t stride,
+                                  const int64_t xyz_off[3], int64_t label_off, pcg_region_growing** out);
+void pcg_region_growing_free(pcg_region_growing* rg);
+/* RegionGrowing.Segment(p, maxRange) (regiongrowing.go:23-56): ids of the points reached from the Range
+ * neighbours of p through chains of points closer than maxRange that all carry the label of p's nearest
+ * neighbour, in the reference's breadth-first order (for Range lists in the canonical (DistSq, ID) order;
+ * the reference leaves equal-DistSq ties unordered and its own test sorts the result,
+ * regiongrowing_test.go:186).  Every level of the search is one batched Range on the device.
+ * indice must hold `cap` entries; if the result is larger the call fails with *n_out = size needed
+ * (pcg_index_len is always enough). */
+pcg_status pcg_region_growing_segment(pcg_region_growing* rg, const float p[3], float max_range, int64_t* indice,
+                                      int64_t cap, int64_t* n_out);
 
 /* ---- filter.Filter: VoxelGrid (pc/filter/voxelgrid/voxelgrid.go:35-187) ------ */
 /* chunk = Options.ChunkSize (option.go:7-18); any zero selects the un-chunked path

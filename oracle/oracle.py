@@ -78,6 +78,8 @@ def lib():
                                                   C.c_void_p, C.c_void_p]
         _lib.orc_icp_fit_gn.restype = C.c_int32
         _lib.orc_icp_fit_gn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_region_growing_segment.restype = C.c_int64
+        _lib.orc_region_growing_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
         _lib.orc_mat4_mul.argtypes = [C.c_void_p] * 3
         _lib.orc_mat4_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib.orc_translate.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
@@ -268,6 +270,16 @@ def icp_fit_gn(base: Search, target, params: IcpParams):
     it = C.c_int32(0)
     rc = lib().orc_icp_fit_gn(base._h, _p(t), len(t), C.byref(params), _p(trans), _p(ev), C.byref(it))
     return rc, trans, ev, it.value
+
+
+def region_growing_segment(search: Search, labels, p, max_range: float) -> np.ndarray:
+    """RegionGrowing.Segment (regiongrowing.go:23-56): point ids in BFS order."""
+    lab = np.ascontiguousarray(labels, np.uint32)
+    assert len(lab) == len(search)
+    pp = _f32(p)
+    out = np.empty(max(1, len(lab)), np.int64)
+    n = lib().orc_region_growing_segment(search._h, _p(lab), _p(pp), max_range, _p(out))
+    return out[:n].copy()
 
 
 def mat4_mul(a, b):

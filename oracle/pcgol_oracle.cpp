@@ -980,6 +980,39 @@ int icp_fit_gn(const Search& base, const float* target, int64_t n, const IcpPara
   return ORC_OK;
 }
 
+// ----------------------------------------------------------------------------
+// pc/segmentation/regiongrowing/regiongrowing.go:23-56 (RegionGrowing.Segment)
+// Range lists arrive in the canonical (DistSq, ID) order (the reference sorts by DistSq only and
+// leaves ties unordered, so the reference's own test sorts the result before comparing,
+// regiongrowing_test.go:186; with the canonical order the BFS order below is reproducible).
+// ----------------------------------------------------------------------------
+void region_growing_segment(const Search& search, const uint32_t* label, const Vec3& p, float max_range,
+                            std::vector<int64_t>& indice) {
+  indice.clear();
+  std::vector<Neighbor> nb;
+  search.range(p, max_range, nb);
+  if (nb.empty()) return;
+  const uint32_t target = label[nb[0].id];
+  std::vector<int64_t> next;
+  std::vector<uint8_t> to_visit((size_t)search.n, 0);
+  for (const Neighbor& n : nb) {
+    next.push_back(n.id);
+    to_visit[(size_t)n.id] = 1;
+  }
+  for (size_t head = 0; head < next.size(); head++) {
+    const int64_t id = next[head];
+    if (label[id] != target) continue;
+    indice.push_back(id);
+    search.range(search.at(id), max_range, nb);
+    for (const Neighbor& n : nb) {
+      if (!to_visit[(size_t)n.id]) {
+        next.push_back(n.id);
+        to_visit[(size_t)n.id] = 1;
+      }
+    }
+  }
+}
+
 template <typename F>
 void parallel_for(int64_t n, int threads, F f) {
   if (threads <= 1 || n < 2) {
@@ -1206,6 +1239,15 @@ int32_t orc_icp_fit_gn(void* base, const float* target, int64_t n, const IcpPara
   stat_ev8[7] = st.ev.dist_rms;
   *num_iteration = st.num_iteration;
   return rc;
+}
+
+// RegionGrowing.Segment; out must hold n entries; returns the number of indices (BFS order)
+int64_t orc_region_growing_segment(void* search, const uint32_t* label, const float* p, float max_range,
+                                   int64_t* out) {
+  std::vector<int64_t> ind;
+  region_growing_segment(*static_cast<Search*>(search), label, Vec3{{p[0], p[1], p[2]}}, max_range, ind);
+  std::memcpy(out, ind.data(), ind.size() * sizeof(int64_t));
+  return (int64_t)ind.size();
 }
 
 // mat helpers for the golden tests

@@ -8,6 +8,7 @@ from ._lib import PcgError, device_count, kernel_launch_count, E_INVALID_ARG
 from .pc import PointCloud, PointCloudHeader
 from .storage import Index, Neighbor
 from .filter import VoxelGrid, NoPointError, ReferencePanic
+from .segmentation import RegionGrowing
 from .icp import (ErrNotEnoughPairs, Evaluated, GaussNewtonUpdaterFactory, GradientDescentUpdaterFactory,
                   NearestPointCorresponder, PointToPointEvaluator, PointToPointICPGradient, Stat, STRICT, FAST,
                   WITH_HESSIAN)
@@ -17,4 +18,5 @@ __all__ = [
     "VoxelGrid", "NoPointError", "ReferencePanic", "ErrNotEnoughPairs", "Evaluated",
     "GradientDescentUpdaterFactory", "NearestPointCorresponder", "PointToPointEvaluator",
     "PointToPointICPGradient", "Stat", "STRICT", "FAST", "WITH_HESSIAN", "GaussNewtonUpdaterFactory", "E_INVALID_ARG",
+    "RegionGrowing",
 ]

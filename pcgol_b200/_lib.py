@@ -89,6 +89,7 @@ _sigs = {
     "pcg_device_synchronize": (_i32, [_i32]),
     "pcg_kernel_launch_count": (_i64, []),
     "pcg_debug_sequential_sum_f32": (_i32, [_vp, _i64, _i32, _i32, _vp]),
+    "pcg_debug_index_slots": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "pcg_profile_enable": (None, [_i32]),
     "pcg_profile_report": (_i64, [C.c_char_p, _i64]),
     "pcg_index_build": (_i32, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_vp)]),
@@ -109,6 +110,9 @@ _sigs = {
     "pcg_range_offsets": (_vp, [_vp]),
     "pcg_range_neighbors": (_vp, [_vp]),
     "pcg_range_free": (None, [_vp]),
+    "pcg_region_growing_new": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp)]),
+    "pcg_region_growing_free": (None, [_vp]),
+    "pcg_region_growing_segment": (_i32, [_vp, _vp, _f, _vp, _i64, C.POINTER(_i64)]),
     "pcg_voxelgrid_filter": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64)]),
     "pcg_voxelgrid_filter_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64), _vp]),
     "pcg_minmax_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),

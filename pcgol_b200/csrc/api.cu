@@ -82,6 +82,13 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
                            pcg_evaluated* ev_out, int32_t* converged);
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream);
+struct RegionGrowing;
+RegionGrowing* region_growing_new_device(const Index& search, const CloudView& v, int64_t label_off,
+                                         cudaStream_t stream);
+void region_growing_free(RegionGrowing* rg);
+int64_t region_growing_segment_device(const RegionGrowing& rg, const float p[3], float max_range,
+                                      DevBuf<uint32_t>& d_result, cudaStream_t stream);
+void region_growing_widen(const uint32_t* d_in, int64_t n, long long* d_out, cudaStream_t stream);
 float debug_sequential_sum(const float* d_x, int64_t n, bool exact_path, cudaStream_t stream, float* stats3);
 
 static void check_device(int device) {
@@ -144,6 +151,10 @@ struct pcg_index {
 };
 struct pcg_range_result {
   RangeResult r;
+};
+struct pcg_region_growing {
+  RegionGrowing* rg;
+  int device;
 };
 
 extern "C" {
@@ -329,6 +340,19 @@ int64_t pcg_index_len(const pcg_index* idx) { return idx ? idx->ix->n : 0; }
 int32_t pcg_index_device(const pcg_index* idx) { return idx ? idx->ix->device : -1; }
 int64_t pcg_index_device_bytes(const pcg_index* idx) { return idx ? idx->ix->bytes : 0; }
 
+pcg_status pcg_debug_index_slots(const pcg_index* idx, float* out, int64_t cap_slots, int64_t* slots) {
+  return guarded([&]() -> pcg_status {
+    if (!idx || !slots) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    const int64_t total = (int64_t)idx->ix->leaves * kLeaf;
+    *slots = idx->ix->n ? total : 0;
+    if (!out || idx->ix->n == 0) return PCG_OK;
+    if (cap_slots < total) throw StatusError{PCG_E_INVALID_ARG, "buffer too small"};
+    DeviceGuard g(idx->ix->device);
+    PCG_CUDA(cudaMemcpy(out, idx->ix->pts, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));
+    return PCG_OK;
+  });
+}
+
 pcg_status pcg_index_nearest_approx_dev(pcg_index* idx, const void* d_q, int64_t nq, int64_t q_stride,
                                         const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
                                         int32_t* d_ids, float* d_dist_sq, void* stream) {
@@ -467,6 +491,52 @@ int64_t pcg_range_total(const pcg_range_result* r) { return r ? r->r.total : 0; 
 const int64_t* pcg_range_offsets(const pcg_range_result* r) { return r ? r->r.offsets.data() : nullptr; }
 const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r) { return r ? r->r.neighbors : nullptr; }
 void pcg_range_free(pcg_range_result* r) { delete r; }
+
+// ---- region growing ---------------------------------------------------------------------
+pcg_status pcg_region_growing_new(pcg_index* search, const void* data, int64_t n, int64_t stride,
+                                  const int64_t xyz_off[3], int64_t label_off, pcg_region_growing** out) {
+  return guarded([&]() -> pcg_status {
+    if (!search || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *out = nullptr;
+    check_view_args(data, n, stride, xyz_off);
+    if (label_off < 0 || label_off + 4 > stride) throw StatusError{PCG_E_INVALID_ARG, "label offset outside the record"};
+    if (n != search->ix->n)
+      throw StatusError{PCG_E_INVALID_ARG, "the property accessor and the search must cover the same points"};
+    DeviceGuard g(search->ix->device);
+    cudaStream_t s = cudaStreamPerThread;
+    StagedCloud c(data, n, stride, xyz_off, s);
+    RegionGrowing* rg = region_growing_new_device(*search->ix, c.view, label_off, s);
+    PCG_CUDA(cudaStreamSynchronize(s));
+    *out = new pcg_region_growing{rg, search->ix->device};
+    return PCG_OK;
+  });
+}
+
+void pcg_region_growing_free(pcg_region_growing* rg) {
+  if (!rg) return;
+  region_growing_free(rg->rg);
+  delete rg;
+}
+
+pcg_status pcg_region_growing_segment(pcg_region_growing* rg, const float p[3], float max_range, int64_t* indice,
+                                      int64_t cap, int64_t* n_out) {
+  return guarded([&]() -> pcg_status {
+    if (!rg || !p || !n_out || cap < 0 || (cap && !indice)) throw StatusError{PCG_E_INVALID_ARG, "bad arguments"};
+    *n_out = 0;
+    DeviceGuard g(rg->device);
+    cudaStream_t s = cudaStreamPerThread;
+    DevBuf<uint32_t> d_result;
+    const int64_t m = region_growing_segment_device(*rg->rg, p, max_range, d_result, s);
+    *n_out = m;
+    if (m > cap) throw StatusError{PCG_E_INVALID_ARG, "result buffer too small (n_out holds the size needed)"};
+    if (m == 0) return PCG_OK;
+    DevBuf<long long> wide((size_t)m, s);
+    region_growing_widen(d_result.p, m, wide.p, s);
+    PCG_CUDA(cudaMemcpyAsync(indice, wide.p, (size_t)m * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    PCG_CUDA(cudaStreamSynchronize(s));
+    return PCG_OK;
+  });
+}
 
 // ---- voxel grid -------------------------------------------------------------------------
 static void check_vg_args(const float leaf[3], const int64_t chunk[3]) {

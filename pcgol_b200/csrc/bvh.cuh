@@ -447,4 +447,12 @@ void index_free(Index* ix);
 void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, cudaStream_t stream);
 constexpr int64_t kMinQueriesToReorder = 1 << 14;
 
+// Batched KDTree.Range building blocks (index.cu); both synchronise `stream`.
+void range_count_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
+                        int64_t* total_out, cudaStream_t stream);
+void range_fill_device(const Index& ix, const CloudView& q, float max_range, const long long* d_offsets,
+                       int64_t total, pcg_neighbor* d_out, cudaStream_t stream);
+// exclusive scan of uint32 counts into int64 offsets[n+1] (decoupled look-back)
+void scan_counts(const uint32_t* counts, long long* offsets, uint32_t n, cudaStream_t stream);
+
 }  // namespace pcg

@@ -50,7 +50,7 @@ constexpr int kTermThreads = 128;
 constexpr int kTerms = 9;  // Value, SumW, G0..G5, R
 constexpr int kHTerms = 9; // sum p (3) + second moments of p (6): the Gauss-Newton Hessian
 
-__device__ __noinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+__device__ __forceinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
                                                const double* __restrict__ hpartials, int nblocks, bool do_main,
                                                bool do_hess, float* s_sum, int* s_last);
 
@@ -82,7 +82,7 @@ __device__ __forceinline__ void block_sum_f64(const float* t, double (*s_red)[K]
 // APPROX: KDTree.MinDistSq > 0 on the base search (kdtree.go:19-22).  HESS: also accumulate the
 // nine moments of the normal equations (icp_math.cuh).
 template <int MODE, bool APPROX, bool HESS>
-__global__ void __launch_bounds__(kTermThreads, 16)
+__global__ void __launch_bounds__(kTermThreads)
     icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, float max_dist_sq,
                      float min_dist_sq, IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
                      double* __restrict__ partials, double* __restrict__ hpartials, int finalize) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ void icp_finalize(IcpState* __restrict__ st, const fl
 // Called by every CTA of icp_terms_kernel after it wrote its partials; the last one to arrive
 // reduces all of them (fixed order: lane-strided columns, then a shuffle tree).  do_main: the nine
 // Evaluate sums (FAST mode) followed by the tail; do_hess: the nine moments of the normal equations.
-__device__ __noinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
+__device__ __forceinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
                                                const double* __restrict__ hpartials, int nblocks, bool do_main,
                                                bool do_hess, float* s_sum, int* s_last) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -629,6 +629,7 @@ static void launch_terms(const Index& base, const CloudView& tgt, const uint32_t
                          int nblocks, int finalize, cudaStream_t stream) {
   const char* name = MODE == PCG_ICP_STRICT ? "(icp_terms_kernel<PCG_ICP_STRICT>)" : "(icp_terms_kernel<PCG_ICP_FAST>)";
   const bool approx = min_dist_sq > 0.f;
+  min_dist_sq = fminf(min_dist_sq, mdsq);  // only a real hit can end a search early: see nearest_device
 #define PCG_TERMS(A, H)                                                                                              \
   PCG_LAUNCH_NAMED(name, (icp_terms_kernel<MODE, A, H>), nblocks, kTermThreads, 0, stream, base.view(), tgt, perm, mdsq, \
                    min_dist_sq, st, terms, n_pad, partials, hpartials, finalize)
@@ -886,9 +887,9 @@ __global__ void __launch_bounds__(128)
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream) {
   if (tgt.n == 0) return;
-  if (min_dist_sq > 0.f)
+  if (min_dist_sq > 0.f)  // threshold capped at maxDist^2: see nearest_device
     PCG_LAUNCH(icp_pairs_kernel<true>, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist,
-               min_dist_sq, d_ids, d_dsq);
+               fminf(min_dist_sq, max_dist * max_dist), d_ids, d_dsq);
   else
     PCG_LAUNCH(icp_pairs_kernel<false>, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist, 0.f,
                d_ids, d_dsq);

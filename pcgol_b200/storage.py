@@ -53,7 +53,8 @@ class Index:
 
     def close(self):
         if getattr(self, "_h", None):
-            _lib.lib.pcg_index_free(self._h)
+            if getattr(self, "_shared", None) is None:  # a With() copy does not own the handle
+                _lib.lib.pcg_index_free(self._h)
             self._h = None
 
     __del__ = close
@@ -71,6 +72,14 @@ class Index:
 
     def raw_index_at(self, i: int) -> int:  # RawIndexAt
         return i
+
+    def debug_slots(self) -> np.ndarray:
+        """Test hook: the index's point slots as (slots, 4) float32 {x, y, z, original id bits}."""
+        m = C.c_int64(0)
+        _lib.check(_lib.lib.pcg_debug_index_slots(self._h, None, 0, C.byref(m)))
+        out = np.empty((max(m.value, 1), 4), np.float32)
+        _lib.check(_lib.lib.pcg_debug_index_slots(self._h, out.ctypes.data, m.value, C.byref(m)))
+        return out[: m.value]
 
     def device_bytes(self) -> int:
         return int(_lib.lib.pcg_index_device_bytes(self._h))
@@ -98,7 +107,6 @@ class Index:
         other = copy.copy(self)
         other.min_dist_sq = float(min_dist_sq)
         other._shared = self  # keeps the owner alive; only the owner frees the handle
-        other.close = lambda: None
         return other
 
     # -- KDTree.DeletePoint (kdtree.go:322-332) ---------------------------------

@@ -244,3 +244,40 @@ def test_gauss_newton_recovers_known_motion(pg, oracle):
     moved = oracle.mat4_transform(trans, target)
     assert np.abs(moved - base).max() < 2e-4
     assert stat.num_iteration <= 4
+
+
+# ------------------------------------------------------------- index build invariants ------
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 100, 2048, 2049, 5000, 70000, 300001])
+def test_index_slots_are_a_kd_partition(pg, n):
+    # The build orders the points like a KD-tree: under every node of the implicit tree the first
+    # half of the slots holds the points that rank lowest along ONE axis.  (Any order gives exact
+    # answers - the parity tests cover that - this pins the order that makes the boxes prune.)
+    rng = np.random.default_rng(n)
+    pts = (rng.random((n, 3), dtype=f32) * np.array([50, 30, 3], f32)).astype(f32)
+    if n >= 100:
+        pts[: n // 10] = pts[n // 10: 2 * (n // 10)]  # duplicates: ranks break ties, nothing is lost
+    slots = pg.Index(pts).debug_slots()
+    ids = slots[:, 3].view(np.uint32)
+    real = ids != 0xFFFFFFFF
+    assert real.sum() == n and np.all(real[:n]) and not real[n:].any()
+    assert np.array_equal(np.sort(ids[:n]), np.arange(n, dtype=np.uint32))  # a permutation
+    assert slots[:n, :3].tobytes() == pts[ids[:n]].tobytes()
+    assert np.all(np.isinf(slots[n:, :3]))
+    size = len(slots)
+    p2 = 8
+    while p2 < size:
+        p2 *= 2
+    xyz = slots[:n, :3]
+    seg = p2
+    checked = 0
+    while seg > 8:
+        for b in range(0, n, seg):
+            m, e = b + seg // 2, min(b + seg, n)
+            if m >= e:
+                continue
+            left, right = xyz[b:m], xyz[m:e]
+            assert np.any(left.max(axis=0) <= right.min(axis=0)), (seg, b)
+            checked += 1
+            if checked > 4000:
+                break
+        seg //= 2

@@ -296,6 +296,55 @@ def test_min_dist_sq_contract_on_kdtree(oracle):
             assert approx_hits > 0  # the approximation really kicks in on this cloud
 
 
+# ------------------------------------------------------ region growing ------
+def region_growing_scene(seed=0):
+    """regiongrowing_test.go:17-117: a floor and three boxes with labels 0/1/1/2 and +-0.01 noise.
+    (Go's math/rand stream is not reproducible here; the expected sets do not depend on the noise.)"""
+    def box(w, l, h, res):
+        def axis(width):
+            out, v = [], f32(-0.5) * f32(width)
+            while v <= f32(0.5) * f32(width):
+                out.append(v)
+                v = f32(v + f32(res))
+            return out
+        return np.array([[a, b, c] for a in axis(w) for b in axis(l) for c in axis(h)], f32)
+
+    objs = [((0, 0, 0), box(2, 2, 0.01, 0.1), 0), ((0, 0, 0.25), box(0.5, 0.5, 0.5, 0.1), 1),
+            ((0, 0.6, 0.4), box(0.3, 0.3, 0.8, 0.1), 1), ((1.5, 0, 0.25), box(0.25, 0.25, 0.5, 0.05), 2)]
+    rng = np.random.default_rng(seed)
+    pts, labels, indice, cnt = [], [], [], 0
+    for pos, p, lab in objs:
+        v = (p + np.array(pos, f32) + rng.uniform(-0.01, 0.01, p.shape).astype(f32)).astype(f32)
+        pts.append(v)
+        labels += [lab] * len(p)
+        indice.append(list(range(cnt, cnt + len(p))))
+        cnt += len(p)
+    return np.concatenate(pts), np.array(labels, np.uint32), indice
+
+
+REGION_CASES = {  # regiongrowing_test.go:119-155: name -> (p, maxRange, objects whose indices are expected)
+    "Label0": ((0.5, 0.1, 0), 0.15, [0]),
+    "Label1FirstBox": ((0.25, 0.15, 0.15), 0.15, [1]),
+    "Label1SecondBox": ((0, 0.45, 0.4), 0.15, [2]),
+    "Label1BothBoxes": ((0, 0.45, 0.4), 0.3, [1, 2]),
+    "Label3": ((1.4, 0.125, 0.2), 0.15, [3]),
+    "StillOnlyLabel3": ((1.4, 0.125, 0.2), 0.5, [3]),
+}
+
+
+@pytest.mark.parametrize("kind", ["kdtree", "naive"])
+def test_region_growing_golden(oracle, kind):
+    # regiongrowing_test.go:157-191 (result compared after sort.Ints)
+    pts, labels, indice = region_growing_scene()
+    s = oracle.Search(pts, kind)
+    for name, (p, mr, objs) in REGION_CASES.items():
+        got = oracle.region_growing_segment(s, labels, p, mr)
+        exp = sorted(i for o in objs for i in indice[o])
+        assert sorted(got.tolist()) == exp, name
+        assert len(set(got.tolist())) == len(got)
+    assert len(oracle.region_growing_segment(s, labels, (10, 10, 10), 0.15)) == 0  # regiongrowing.go:27-29
+
+
 # ---------------------------------------------------------- voxelgrid ------
 def _vg_cloud():
     # pc/filter/voxelgrid/voxelgrid_test.go:59-76 : fields x,y,z,label ; stride 16
