@@ -58,7 +58,14 @@ enum {
   PCG_E_NOT_ENOUGH_PAIRS = 5,
   PCG_E_CUDA = 6,
   PCG_E_NO_DEVICE = 7,
-  PCG_E_TOO_LARGE = 8
+  PCG_E_TOO_LARGE = 8,
+  /* pc.Unmarshal (pc/io.go): strconv.ErrSyntax / header validation errors, io.EOF / io.ErrUnexpectedEOF,
+   * lzf.ErrDataCorruption / "wrong uncompressed size" */
+  PCG_E_PCD_SYNTAX = 9,
+  PCG_E_PCD_EOF = 10,
+  PCG_E_PCD_CORRUPT = 11,
+  /* errors.New("invalid field name") (pc/pointcloud.go:115,189) */
+  PCG_E_INVALID_FIELD = 12
 };
 
 /* Mirrors Go's storage.Neighbor{ID int; DistSq float32} (pc/storage/search.go:8-11)
@@ -165,6 +172,46 @@ int64_t pcg_range_total(const pcg_range_result* r);
 const int64_t* pcg_range_offsets(const pcg_range_result* r);       /* nq+1 entries */
 const pcg_neighbor* pcg_range_neighbors(const pcg_range_result* r); /* total entries */
 void pcg_range_free(pcg_range_result* r);
+
+/* ---- pc.PointCloud resident in HBM + its PCD encodings (pc/pointcloud.go:9-78, pc/io.go) -------- */
+/* The steps either side of the hot path: a cloud is parsed / uploaded once, then VoxelGrid, the index
+ * build and ICP run on the resident records, and Marshal reads the result back once. */
+typedef struct pcg_cloud pcg_cloud;
+#define PCG_MAX_FIELDS 32
+typedef struct pcg_cloud_header { /* pc.PointCloudHeader + Points + len(Data) */
+  float version;
+  int32_t n_fields;
+  char fields[PCG_MAX_FIELDS][32];
+  char type[PCG_MAX_FIELDS][8];
+  int64_t size[PCG_MAX_FIELDS];
+  int64_t count[PCG_MAX_FIELDS];
+  int64_t width, height;
+  int32_t n_viewpoint;
+  float viewpoint[16];
+  int64_t points;
+  int64_t data_bytes;
+} pcg_cloud_header;
+/* pc.Unmarshal (io.go:32-45): ascii, binary and binary_compressed (LZF on the host, the field-major payload
+ * is transposed into records on the device, reproducing io.go:205-228 including its handling of COUNT > 1).
+ * Errors map to PCG_E_PCD_*; inputs on which the reference would panic (index out of range) give
+ * PCG_E_REF_WOULD_PANIC. */
+pcg_status pcg_pcd_unmarshal(const void* pcd, int64_t len, int32_t device, pcg_cloud** out);
+/* pc.Marshal (io.go:232-285): header text + records, always "DATA binary".  *len receives the size needed;
+ * the call fails with PCG_E_INVALID_ARG if cap is smaller. */
+pcg_status pcg_pcd_marshal(const pcg_cloud* c, void* buf, int64_t cap, int64_t* len);
+/* A cloud from a host record buffer (header->points records of stride sum(size*count)). */
+pcg_status pcg_cloud_upload(const pcg_cloud_header* header, const void* data, int32_t device, pcg_cloud** out);
+pcg_status pcg_cloud_get_header(const pcg_cloud* c, pcg_cloud_header* out);
+pcg_status pcg_cloud_download(const pcg_cloud* c, void* data, int64_t cap);
+const void* pcg_cloud_device_ptr(const pcg_cloud* c);
+void pcg_cloud_free(pcg_cloud* c);
+/* voxelGrid.Filter on a resident cloud: header cloned, Width = output points, Height = 1
+ * (voxelgrid.go:119-128).  x/y/z are resolved like PointCloud.Vec3Iterator (pointcloud.go:130-171). */
+pcg_status pcg_cloud_voxelgrid_filter(const pcg_cloud* in, const float leaf[3], const int64_t chunk[3],
+                                      pcg_cloud** out);
+/* kdtree.New(pp.Vec3Iterator()) on a resident cloud. */
+pcg_status pcg_cloud_index_build(const pcg_cloud* c, pcg_index** out);
+/* (pcg_cloud_icp_fit, the Fit with a resident target, is declared with the ICP entry points below.) */
 
 /* ---- segmentation: RegionGrowing (pc/segmentation/regiongrowing/regiongrowing.go:11-56) ---- */
 /* regiongrowing.New(search, propertyIter): `search` is the index, the property is a uint32 field at byte
@@ -285,6 +332,10 @@ pcg_status pcg_icp_fit(pcg_index* base, const void* target, int64_t n, int64_t s
 pcg_status pcg_icp_fit_dev(pcg_index* base, const void* d_target, int64_t n, int64_t stride,
                            const int64_t xyz_off[3], const pcg_icp_params* params, float trans[16],
                            pcg_icp_stat* stat, void* stream);
+
+/* PointToPointICPGradient.Fit with a resident target. */
+pcg_status pcg_cloud_icp_fit(pcg_index* base, const pcg_cloud* target, const pcg_icp_params* params, float trans[16],
+                             pcg_icp_stat* stat);
 
 /* Scan-pair farm: `count` independent (base, target) pairs, device resident, all on
  * `device`; builds one index per pair and runs the fits concurrently. status_out[i]

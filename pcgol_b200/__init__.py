@@ -9,6 +9,8 @@ from .pc import PointCloud, PointCloudHeader
 from .storage import Index, Neighbor
 from .filter import VoxelGrid, NoPointError, ReferencePanic
 from .segmentation import RegionGrowing
+from . import io
+from .io import DeviceCloud
 from .icp import (ErrNotEnoughPairs, Evaluated, GaussNewtonUpdaterFactory, GradientDescentUpdaterFactory,
                   NearestPointCorresponder, PointToPointEvaluator, PointToPointICPGradient, Stat, STRICT, FAST,
                   WITH_HESSIAN)
@@ -18,5 +20,5 @@ __all__ = [
     "VoxelGrid", "NoPointError", "ReferencePanic", "ErrNotEnoughPairs", "Evaluated",
     "GradientDescentUpdaterFactory", "NearestPointCorresponder", "PointToPointEvaluator",
     "PointToPointICPGradient", "Stat", "STRICT", "FAST", "WITH_HESSIAN", "GaussNewtonUpdaterFactory", "E_INVALID_ARG",
-    "RegionGrowing",
+    "RegionGrowing", "DeviceCloud", "io",
 ]

@@ -20,6 +20,10 @@ E_NOT_ENOUGH_PAIRS = 5
 E_CUDA = 6
 E_NO_DEVICE = 7
 E_TOO_LARGE = 8
+E_PCD_SYNTAX = 9
+E_PCD_EOF = 10
+E_PCD_CORRUPT = 11
+E_INVALID_FIELD = 12
 
 ICP_STRICT = 0
 ICP_FAST = 1
@@ -59,6 +63,19 @@ class Evaluated(C.Structure):
 
     _fields_ = [("value", C.c_float), ("gradient", C.c_float * 6), ("hessian", C.c_float * 36),
                 ("dist_rms", C.c_float)]
+
+
+MAX_FIELDS = 32
+
+
+class CloudHeader(C.Structure):
+    """pcg_cloud_header: pc.PointCloudHeader (pc/pointcloud.go:9-18) + Points + len(Data)."""
+
+    _fields_ = [("version", C.c_float), ("n_fields", C.c_int32), ("fields", (C.c_char * 32) * MAX_FIELDS),
+                ("type", (C.c_char * 8) * MAX_FIELDS), ("size", C.c_int64 * MAX_FIELDS),
+                ("count", C.c_int64 * MAX_FIELDS), ("width", C.c_int64), ("height", C.c_int64),
+                ("n_viewpoint", C.c_int32), ("viewpoint", C.c_float * 16), ("points", C.c_int64),
+                ("data_bytes", C.c_int64)]
 
 
 class IcpStat(C.Structure):
@@ -110,6 +127,16 @@ _sigs = {
     "pcg_range_offsets": (_vp, [_vp]),
     "pcg_range_neighbors": (_vp, [_vp]),
     "pcg_range_free": (None, [_vp]),
+    "pcg_pcd_unmarshal": (_i32, [_vp, _i64, _i32, C.POINTER(_vp)]),
+    "pcg_pcd_marshal": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
+    "pcg_cloud_upload": (_i32, [C.POINTER(CloudHeader), _vp, _i32, C.POINTER(_vp)]),
+    "pcg_cloud_get_header": (_i32, [_vp, C.POINTER(CloudHeader)]),
+    "pcg_cloud_download": (_i32, [_vp, _vp, _i64]),
+    "pcg_cloud_device_ptr": (_vp, [_vp]),
+    "pcg_cloud_free": (None, [_vp]),
+    "pcg_cloud_voxelgrid_filter": (_i32, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "pcg_cloud_index_build": (_i32, [_vp, C.POINTER(_vp)]),
+    "pcg_cloud_icp_fit": (_i32, [_vp, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat)]),
     "pcg_region_growing_new": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, C.POINTER(_vp)]),
     "pcg_region_growing_free": (None, [_vp]),
     "pcg_region_growing_segment": (_i32, [_vp, _vp, _f, _vp, _i64, C.POINTER(_i64)]),

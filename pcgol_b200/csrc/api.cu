@@ -3,6 +3,7 @@
 // run the device pipelines of voxelgrid.cu / index.cu / icp.cu and copy results back.
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -82,6 +83,11 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
                            pcg_evaluated* ev_out, int32_t* converged);
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream);
+struct CloudHeader;
+struct Cloud;
+void cloud_free(Cloud* c);
+Cloud* cloud_unmarshal(const uint8_t* pcd, int64_t len, int device, cudaStream_t stream);
+std::string cloud_marshal_header(const Cloud& c);
 struct RegionGrowing;
 RegionGrowing* region_growing_new_device(const Index& search, const CloudView& v, int64_t label_off,
                                          cudaStream_t stream);
@@ -134,6 +140,17 @@ struct StagedCloud {
   }
 };
 
+}  // namespace pcg
+struct pcg_index {
+  pcg::Index* ix;
+};
+namespace pcg {
+// shared with the other translation units that export C entry points (cloud.cu)
+pcg_status api_guard(const std::function<pcg_status()>& f) { return guarded(f); }
+pcg_index* api_wrap_index(Index* ix) { return new pcg_index{ix}; }
+Index* api_index_of(pcg_index* idx) { return idx->ix; }
+void api_check_device(int device) { check_device(device); }
+
 struct RangeResult {
   std::vector<int64_t> offsets;
   // plain heap memory: page-locking a result of hundreds of MB costs far more than the copy it would speed up
@@ -146,9 +163,6 @@ struct RangeResult {
 
 using namespace pcg;
 
-struct pcg_index {
-  Index* ix;
-};
 struct pcg_range_result {
   RangeResult r;
 };
@@ -172,6 +186,10 @@ const char* pcg_status_string(pcg_status s) {
     case PCG_E_CUDA: return "CUDA error";
     case PCG_E_NO_DEVICE: return "no usable CUDA device";
     case PCG_E_TOO_LARGE: return "problem too large";
+    case PCG_E_PCD_SYNTAX: return "PCD syntax error";
+    case PCG_E_PCD_EOF: return "PCD: unexpected end of data";
+    case PCG_E_PCD_CORRUPT: return "PCD: corrupt compressed data";
+    case PCG_E_INVALID_FIELD: return "invalid field name";
   }
   return "unknown status";
 }

@@ -431,6 +431,112 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// Levels whose segments fit one tile: the whole tail of the build in shared memory, one CTA per
+// kKdLocal slots.  Points get tile-local ids (their position in the tile's x-list), so the three
+// lists are 16-bit and the left/right marks live in shared memory; per level: axis per segment,
+// marks, two stable partitions.  Only the x-list is needed afterwards: it is the final order.
+constexpr int kKdLocalLog2 = 11;
+constexpr int kKdLocal = 1 << kKdLocalLog2;
+static_assert(kKdLocal == kKdTile, "the local kernel takes over where segments stop spanning tiles");
+
+__global__ void __launch_bounds__(256)
+    kd_local_kernel(CloudView v, const uint32_t* __restrict__ in0, const uint32_t* __restrict__ in1,
+                    const uint32_t* __restrict__ in2, uint32_t n, int log2S_first, int log2L,
+                    uint32_t* __restrict__ loc, uint32_t* __restrict__ order_out) {
+  __shared__ uint16_t s_list[2][3][kKdLocal];
+  __shared__ uint32_t s_gid[kKdLocal];
+  __shared__ uint8_t s_side[kKdLocal];
+  __shared__ uint8_t s_axis[kKdLocal / 16];
+  __shared__ uint32_t s_scan[rsort::kWarps];
+  __shared__ uint32_t s_excl[256];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t tile_base = blockIdx.x * kKdLocal;
+  const uint32_t cnt = min((uint32_t)kKdLocal, n - tile_base);
+  for (uint32_t i = tid; i < cnt; i += 256) {
+    const uint32_t g = in0[tile_base + i];
+    s_gid[i] = g;
+    loc[g] = i;
+    s_list[0][0][i] = (uint16_t)i;
+  }
+  __syncthreads();  // loc[] of this tile's points is complete (the three lists hold the same point set)
+  for (uint32_t i = tid; i < cnt; i += 256) {
+    s_list[0][1][i] = (uint16_t)loc[in1[tile_base + i]];
+    s_list[0][2][i] = (uint16_t)loc[in2[tile_base + i]];
+  }
+  __syncthreads();
+  int cur = 0;
+  const uint32_t base = tid * kKdTileItems;
+  for (int log2S = log2S_first; log2S > log2L; log2S--) {
+    const uint32_t S = 1u << log2S;
+    if (tid < ((uint32_t)kKdLocal >> log2S)) {
+      const uint32_t b = tid << log2S;
+      int axis = 3;
+      if (b < cnt) {
+        const uint32_t e = min(b + S, cnt), m = b + (S >> 1);
+        if (m < e) {
+          float ext[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const float lo = coord_of(v, s_gid[s_list[cur][c][b]], c), hi = coord_of(v, s_gid[s_list[cur][c][e - 1]], c);
+            float d = hi - lo;
+            if (!(d >= 0.f)) d = 0.f;
+            ext[c] = d;
+          }
+          axis = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+        }
+      }
+      s_axis[tid] = (uint8_t)axis;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += 256) {
+      const uint32_t seg = i >> log2S;
+      const int a = s_axis[seg];
+      if (a != 3) s_side[s_list[cur][a][i]] = i >= (seg << log2S) + (S >> 1) ? 1 : 0;
+    }
+    __syncthreads();
+    const uint32_t seg = base >> log2S, b = seg << log2S, m = b + (S >> 1);
+    const int axis = base < cnt ? s_axis[seg] : 3;
+#pragma unroll 1
+    for (int c = 0; c < 3; c++) {
+      const bool part = axis != 3 && axis != c;
+      uint16_t id[kKdTileItems];
+      uint32_t left_mask = 0, nl = 0;
+#pragma unroll
+      for (int j = 0; j < kKdTileItems; j++) {
+        id[j] = 0;
+        if (base + j < cnt) {
+          id[j] = s_list[cur][c][base + j];
+          if (part && !s_side[id[j]]) {
+            left_mask |= 1u << j;
+            nl++;
+          }
+        }
+      }
+      const uint32_t excl = rsort::block_excl_scan_256(nl, s_scan, nullptr);
+      s_excl[tid] = excl;
+      __syncthreads();
+      uint32_t lb = excl - s_excl[b / kKdTileItems];
+#pragma unroll
+      for (int j = 0; j < kKdTileItems; j++) {
+        const uint32_t pos = base + j;
+        if (pos < cnt) {
+          uint32_t dst = pos;
+          if (part) {
+            const bool is_left = (left_mask >> j) & 1u;
+            dst = is_left ? b + lb : m + ((pos - b) - lb);
+            lb += is_left ? 1u : 0u;
+          }
+          s_list[cur ^ 1][c][dst] = id[j];
+        }
+      }
+      __syncthreads();
+    }
+    cur ^= 1;
+  }
+  for (uint32_t i = tid; i < cnt; i += 256) order_out[tile_base + i] = s_gid[s_list[cur][0][i]];
+}
+
 // Writes the KD order into lists[.]; returns the buffer that holds it (a permutation of 0..n-1).
 static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t P, DevBuf<uint32_t> (&lists)[6],
                                        cudaStream_t stream) {
@@ -463,17 +569,22 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
   const uint32_t tiles = (uint32_t)div_up(n, kKdTile);
   DevBuf<uint8_t> seg_axis((size_t)P, stream), side(n, stream);
   DevBuf<uint32_t> tile_left((size_t)3 * tiles, stream);
-  for (int log2S = log2M; log2S > log2L; log2S--) {  // children of the last level are single leaves
+  int log2S = log2M;
+  for (; log2S > log2L && log2S > kKdLocalLog2; log2S--) {  // segments that span several tiles
     KdLists L;
     for (int c = 0; c < 3; c++) {
       L.in[c] = cur[c];
       L.out[c] = alt[c];
     }
     PCG_LAUNCH(kd_side_kernel, div_up(n, 256), 256, 0, stream, v, L, n, log2S, seg_axis.p, side.p);
-    if ((1u << log2S) > (uint32_t)kKdTile)
-      PCG_LAUNCH(kd_tile_count_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, tile_left.p);
+    PCG_LAUNCH(kd_tile_count_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, tile_left.p);
     PCG_LAUNCH(kd_scatter_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, tile_left.p);
     for (int c = 0; c < 3; c++) std::swap(cur[c], alt[c]);
+  }
+  if (log2S > log2L) {  // the rest (children of the last level are single leaves) in shared memory
+    DevBuf<uint32_t> loc(n, stream);  // point id -> tile-local id
+    PCG_LAUNCH(kd_local_kernel, tiles, 256, 0, stream, v, cur[0], cur[1], cur[2], n, log2S, log2L, loc.p, alt[0]);
+    return alt[0];
   }
   return cur[0];
 }

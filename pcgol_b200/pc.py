@@ -58,10 +58,28 @@ class PointCloud:
         raise KeyError("invalid field name")  # errors.New("invalid field name")
 
     def xyz_offsets(self) -> Tuple[int, int, int]:
-        """Byte offsets of x, y, z inside a record (pc/pointcloud.go:130-188)."""
-        if "xyz" in self.header.fields:
-            o = self.field_offset("xyz")
-            return (o, o + 4, o + 8)
+        """Byte offsets of x, y, z inside a record, resolved like PointCloud.Vec3Iterator
+        (pc/pointcloud.go:130-171): "xyz" if it comes before a complete x,y,z run, else consecutive
+        x,y,z, else (naiveVec3Iterator) the three fields wherever they are."""
+        h = self.header
+        state, first = 0, None
+        for name in h.fields:
+            if name == "xyz":
+                state, first = 3, name
+                break
+            if name == "x" and state == 0:
+                state, first = 1, name
+            elif name == "y" and state == 1:
+                state = 2
+            elif name == "z" and state == 2:
+                state = 3
+                break
+            else:
+                state = 0
+        if state == 3:
+            o = self.field_offset(first)
+            if self.stride() % 4 == 0 and o % 4 == 0:
+                return (o, o + 4, o + 8)
         return (self.field_offset("x"), self.field_offset("y"), self.field_offset("z"))
 
     def xyz(self) -> np.ndarray:

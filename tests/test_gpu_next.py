@@ -281,3 +281,161 @@ def test_index_slots_are_a_kd_partition(pg, n):
             if checked > 4000:
                 break
         seg //= 2
+
+
+# ------------------------------------------------------------- region growing (N1) ------
+def _labelled_cloud(pg, pts, labels):
+    rec = np.zeros(len(pts), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("label", "<u4")])
+    rec["x"], rec["y"], rec["z"], rec["label"] = pts[:, 0], pts[:, 1], pts[:, 2], labels
+    hdr = pg.PointCloudHeader(fields=["x", "y", "z", "label"], size=[4, 4, 4, 4], type=["F", "F", "F", "U"],
+                              count=[1, 1, 1, 1], width=len(pts))
+    return pg.PointCloud(hdr, rec.view(np.uint8))
+
+
+def test_region_growing_reference_cases(pg, oracle):
+    # regiongrowing_test.go:17-191: expected index sets; order checked against the oracle's FIFO order
+    from test_oracle_golden import REGION_CASES, region_growing_scene
+
+    pts, labels, indice = region_growing_scene()
+    cloud = _labelled_cloud(pg, pts, labels)
+    idx = pg.Index(cloud)
+    rg = pg.RegionGrowing(idx, cloud, "label")
+    nv = oracle.Search(pts, "naive")
+    for name, (p, mr, objs) in REGION_CASES.items():
+        got = rg.segment(p, mr)
+        exp = sorted(i for o in objs for i in indice[o])
+        assert sorted(got.tolist()) == exp, name
+        assert np.array_equal(got, oracle.region_growing_segment(nv, labels, p, mr)), name
+    assert len(rg.segment((10, 10, 10), 0.15)) == 0  # regiongrowing.go:27-29
+
+
+def test_region_growing_lidar_scan(pg, oracle, synth):
+    # a 120k-point scan: ground vs everything else; BFS order identical to the sequential oracle
+    pts = synth.lidar_scan(5)[::2].copy()
+    labels = (pts[:, 2] > 0.25).astype(np.uint32)
+    cloud = _labelled_cloud(pg, pts, labels)
+    idx = pg.Index(cloud)
+    rg = pg.RegionGrowing(idx, cloud, "label")
+    kd = oracle.Search(pts, "kdtree")
+    rng = np.random.default_rng(1)
+    for seed_id in rng.choice(len(pts), 4, replace=False):
+        p = pts[seed_id] + f32(0.01)
+        got = rg.segment(p, 0.3)
+        exp = oracle.region_growing_segment(kd, labels, p, 0.3)
+        assert np.array_equal(got, exp)
+        assert len(got) > 0 and np.all(labels[got] == labels[got[0]])
+
+
+def test_region_growing_after_delete(pg, oracle):
+    # DeletePoint on the search cuts the chain, exactly as it would in the reference
+    xs = np.arange(0, 40, dtype=f32) * f32(0.1)
+    pts = np.stack([xs, np.zeros_like(xs), np.zeros_like(xs)], 1).astype(f32)
+    labels = np.ones(len(pts), np.uint32)
+    cloud = _labelled_cloud(pg, pts, labels)
+    idx = pg.Index(cloud)
+    rg = pg.RegionGrowing(idx, cloud, "label")
+    nv = oracle.Search(pts, "naive")
+    assert sorted(rg.segment((0, 0, 0), 0.15).tolist()) == list(range(40))
+    idx.delete_point(20)
+    nv.delete_point(20)
+    got = rg.segment((0, 0, 0), 0.15)
+    assert np.array_equal(got, oracle.region_growing_segment(nv, labels, (0, 0, 0), 0.15))
+    assert sorted(got.tolist()) == list(range(20))
+
+
+# ------------------------------------------------------------- PCD I/O + resident pipeline (N2) ------
+PCD_ERR = {"strconv.ErrSyntax": "PcdSyntaxError", "io.EOF": "PcdEOF", "lzf.ErrDataCorruption": "PcdCorrupt"}
+
+
+def test_pcd_unmarshal_reference_vectors(pg):
+    # pc/io_test.go:16-255 through pcg_pcd_unmarshal: header, records byte for byte, error classes
+    from oracle import pcd as opcd
+    from test_oracle_golden import pcd_cases
+
+    for name, c in pcd_cases().items():
+        raw = bytes.fromhex(c["pcd_hex"])
+        if c["err"]:
+            with pytest.raises(getattr(pg.io, PCD_ERR[c["err"]])):
+                pg.io.unmarshal(raw)
+            continue
+        dc = pg.io.unmarshal(raw)
+        pp = dc.download()
+        eh, en, edata = opcd.unmarshal(raw)
+        assert pp.points == en and pp.data.tobytes() == edata, name
+        h = pp.header
+        assert (h.fields, h.size, h.type, h.count, h.width, h.height) == (eh.fields, eh.size, eh.type, eh.count,
+                                                                           eh.width, eh.height)
+        assert h.viewpoint == eh.viewpoint and f32(h.version) == f32(eh.version)
+        xyz, lab = pp.xyz(), pp.field_u32("label")
+        for i, e in enumerate(c["expected"]):
+            assert tuple(xyz[i]) == (f32(e[0]), f32(e[1]), f32(e[2])) and lab[i] == e[3], name
+        # Marshal -> bytes identical to the reference's Marshal (restated by the oracle)
+        assert pg.io.marshal(dc) == opcd.marshal(eh, en, edata), name
+    raw = bytes.fromhex(pcd_cases()["Binary"]["pcd_hex"])
+    assert pg.io.marshal(pg.io.unmarshal(raw)) == raw  # that vector was written by Marshal
+
+
+def test_pcd_binary_compressed_large(pg):
+    # a 50k-point, 4-field cloud through LZF (host) + the device transpose vs the oracle's literal loop
+    from oracle import pcd as opcd
+
+    rng = np.random.default_rng(8)
+    n = 50000
+    cols = [rng.random(n, dtype=f32) for _ in range(3)] + [rng.integers(0, 9, n, dtype=np.uint32).view(f32)]
+    soa = b"".join(c.tobytes() for c in cols)
+    # LZF stream made of literal runs only (valid LZF): chunks of <= 32 bytes
+    comp = bytearray()
+    for i in range(0, len(soa), 32):
+        chunk = soa[i:i + 32]
+        comp.append(len(chunk) - 1)
+        comp += chunk
+    head = (f"VERSION 0.7\nFIELDS x y z label\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH {n}\nHEIGHT 1\n"
+            f"VIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA binary_compressed\n").encode()
+    raw = head + np.array([len(comp), len(soa)], "<i4").tobytes() + bytes(comp)
+    eh, en, edata = opcd.unmarshal(raw)
+    pp = pg.io.unmarshal(raw).download()
+    assert pp.points == n and pp.data.tobytes() == edata
+    assert np.array_equal(pp.xyz()[:, 0], cols[0]) and np.array_equal(pp.field_u32("label"), cols[3].view(np.uint32))
+
+
+def test_resident_pipeline_matches_host_calls(pg, oracle, synth):
+    # Unmarshal -> VoxelGrid -> index -> ICP entirely on resident clouds == the host-buffer entry points
+    from oracle import pcd as opcd
+
+    base, target = synth.icp_pair(seed=4, n=30000)
+    data, stride, off = synth.with_fields(base, extra_u32=1)
+    hdr = opcd.Header(version=0.7, fields=["x", "y", "z", "label"], size=[4, 4, 4, 4], type=["F", "F", "F", "U"],
+                      count=[1, 1, 1, 1], width=len(base), height=1)
+    raw = opcd.marshal(hdr, len(base), data.tobytes())
+    dc = pg.io.unmarshal(raw)
+    assert dc.points == len(base)
+    # VoxelGrid on the resident cloud vs the host call vs the oracle
+    leaf, chunk = (0.2, 0.2, 0.2), (64, 64, 64)
+    small = dc.voxelgrid(leaf, chunk)
+    host_cloud = pg.PointCloud(pg.PointCloudHeader(fields=["x", "y", "z", "label"], size=[4] * 4, type=["F", "F", "F", "U"],
+                                                   count=[1] * 4, width=len(base)), data)
+    host_out = pg.VoxelGrid(leaf, chunk).filter(host_cloud)
+    got = small.download()
+    assert got.points == host_out.points and got.data.tobytes() == host_out.data[: host_out.points * stride].tobytes()
+    assert got.header.width == got.points and got.header.height == 1  # voxelgrid.go:119-128
+    rc, ref = oracle.voxelgrid_filter(data, stride, off, leaf, chunk, mode="sparse")
+    assert rc == oracle.OK and got.data.tobytes() == ref.tobytes()
+    # index + ICP on resident clouds: bit-identical to the host path (strict mode)
+    idx_res = small.index()
+    idx_host = pg.Index(host_out)
+    tgt = pg.DeviceCloud.upload(pg.PointCloud.from_xyz(target))
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+    t1, s1 = tgt.icp_fit(idx_res, icp)
+    t2, s2 = icp.fit(idx_host, target)
+    assert t1.tobytes() == t2.tobytes() and s1.num_iteration == s2.num_iteration
+    # round trip through Marshal
+    again = pg.io.unmarshal(pg.io.marshal(small)).download()
+    assert again.data.tobytes() == got.data.tobytes() and again.header.fields == got.header.fields
+
+
+def test_cloud_without_xyz_fields(pg):
+    pp = pg.PointCloud(pg.PointCloudHeader(fields=["a", "b", "c"], size=[4, 4, 4], type=["F", "F", "F"], count=[1, 1, 1],
+                                           width=2), np.zeros(24, np.uint8))
+    dc = pg.DeviceCloud.upload(pp)
+    with pytest.raises(pg.io.InvalidField):  # errors.New("invalid field name") pointcloud.go:115
+        dc.index()

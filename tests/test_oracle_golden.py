@@ -345,6 +345,61 @@ def test_region_growing_golden(oracle, kind):
     assert len(oracle.region_growing_segment(s, labels, (10, 10, 10), 0.15)) == 0  # regiongrowing.go:27-29
 
 
+# ------------------------------------------------------------ PCD I/O ------
+def pcd_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "pcd_cases.json")) as f:
+        return json.load(f)["cases"]
+
+
+PCD_ERRORS = {"strconv.ErrSyntax": "PcdSyntaxError", "io.EOF": "PcdEOF", "lzf.ErrDataCorruption": "PcdCorrupt"}
+
+
+def test_pcd_unmarshal_golden():
+    # pc/io_test.go:16-255 (vectors extracted by tools/gen_golden_pcd.py)
+    from oracle import pcd
+
+    for name, c in pcd_cases().items():
+        raw = bytes.fromhex(c["pcd_hex"])
+        if c["err"]:
+            with pytest.raises(getattr(pcd, PCD_ERRORS[c["err"]])):
+                pcd.unmarshal(raw)
+            continue
+        h, n, data = pcd.unmarshal(raw)
+        assert n == len(c["expected"]) and h.fields == ["x", "y", "z", "xyz", "label"] and h.stride() == 28
+        rec = np.frombuffer(data, np.uint8)[: n * 28].reshape(n, 28)
+        xyz = rec[:, :12].copy().view("<f4")
+        lab = rec[:, 24:28].copy().view("<u4").ravel()
+        for i, e in enumerate(c["expected"]):
+            assert tuple(xyz[i]) == (f32(e[0]), f32(e[1]), f32(e[2])), name  # Vec3.Equal
+            assert lab[i] == e[3], name
+    # the three encodings of the reference's fixture agree on x, y, z and label
+    a = pcd.unmarshal(bytes.fromhex(pcd_cases()["Ascii"]["pcd_hex"]))[2]
+    b = pcd.unmarshal(bytes.fromhex(pcd_cases()["Binary"]["pcd_hex"]))[2]
+    assert a == b
+
+
+def test_pcd_marshal_golden():
+    # pc/io_test.go:257-345: default / provided Viewpoint survive Marshal -> Unmarshal; header text of io.go:252-273
+    from oracle import pcd
+
+    h = pcd.Header(fields=["x", "y", "z"], size=[4, 4, 4], count=[1, 1, 1], type=["F", "F", "F"], width=3, height=1)
+    out = pcd.marshal(h, 3, bytes(36))
+    assert out.startswith(b"VERSION 0.0\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 3\nHEIGHT 1\n"
+                          b"VIEWPOINT 0.0000 0.0000 0.0000 1.0000 0.0000 0.0000 0.0000\nPOINTS 3\nDATA binary\n")
+    h2, n2, d2 = pcd.unmarshal(out)
+    assert h2.viewpoint == [0, 0, 0, 1, 0, 0, 0] and n2 == 3 and d2 == bytes(36)
+    vp = [1, 2, 3, -0.333, 0.003, 0.895, -0.298]
+    h.viewpoint = vp
+    h3 = pcd.unmarshal(pcd.marshal(h, 3, bytes(36)))[0]
+    assert h3.viewpoint == [float(f32(v)) for v in vp]
+    # the Binary golden re-marshals to itself (it was produced by Marshal: 4-decimal viewpoint)
+    raw = bytes.fromhex(pcd_cases()["Binary"]["pcd_hex"])
+    hb, nb, db = pcd.unmarshal(raw)
+    assert pcd.marshal(hb, nb, db) == raw
+
+
 # ---------------------------------------------------------- voxelgrid ------
 def _vg_cloud():
     # pc/filter/voxelgrid/voxelgrid_test.go:59-76 : fields x,y,z,label ; stride 16
