@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256)
   __shared__ uint16_t s_list[2][3][kKdLocal];
   __shared__ uint32_t s_gid[kKdLocal];
   __shared__ uint8_t s_side[kKdLocal];
-  __shared__ uint8_t s_axis[kKdLocal / 16];
+  __shared__ uint8_t s_axis[kKdLocal / kKdTileItems];  // segments are never smaller than one thread's items
   __shared__ uint32_t s_scan[rsort::kWarps];
   __shared__ uint32_t s_excl[256];
   const uint32_t tid = threadIdx.x;

@@ -138,6 +138,9 @@ struct VgParams {
   int64_t xs, ys;
   int64_t n_voxels;
   int32_t key_bits;
+  int32_t small;  // every count fits 30 bits: in-range points take the 32-bit arithmetic path
+  int64_t zs;
+  float rleaf[3], rchunk[3];  // 1/leaf, 1/chunk_size: quotient estimates (the exact division decides near integers)
 };
 
 PCG_HD bool go_int_hd(float f, long long* out) {
@@ -210,6 +213,12 @@ PCG_HD pcg_status vg_make_params(const float vmin[3], const float vmax[3], const
   P.n_voxels = (s[0] + 1) * (s[1] + 1) * (s[2] + 1);
   if (P.n_voxels <= 0) return PCG_E_REF_WOULD_PANIC;
   P.key_bits = bits_for(P.n_voxels);
+  P.zs = s[2];
+  for (int k = 0; k < 3; k++) {
+    P.rleaf[k] = im::div(1.f, leaf[k]);
+    P.rchunk[k] = P.chunked ? im::div(1.f, P.chunk_size[k]) : 0.f;
+  }
+  P.small = (P.n_voxels < (1ll << 30) && P.n_chunks < (1ll << 30) && s[0] >= 0 && s[1] >= 0 && s[2] >= 0) ? 1 : 0;
   int total_bits = P.key_bits + bits_for(P.n_chunks);
   if (total_bits > 64) return PCG_E_TOO_LARGE;
   if (total_bits == 0) total_bits = 1;
@@ -260,7 +269,8 @@ __device__ __forceinline__ void chunk_min(const VgParams& P, long long cid, floa
 
 // voxelgrid.go:76-79,88 (vec2cid) and :149-151 (voxel key) for one point:
 // (chunk id << key_bits) | (x + xs*(y + ys*z)).
-__device__ __forceinline__ unsigned long long voxel_key_of(const VgParams& P, const float3 pt, int* bad) {
+// General path: 64-bit arithmetic, every out-of-range case of the reference (aliasing, panics) handled.
+__device__ __noinline__ unsigned long long voxel_key_general(const VgParams& P, const float3 pt, int* bad) {
   long long cid = 0;
   float vc[3] = {P.vmin[0], P.vmin[1], P.vmin[2]};
   if (P.chunked) {
@@ -299,6 +309,105 @@ __device__ __forceinline__ unsigned long long voxel_key_of(const VgParams& P, co
   return ((unsigned long long)cid << P.key_bits) | (unsigned long long)key;
 }
 
+// Truncated quotients int(float32(a / d)) of three coordinates at once, branch-free on the common path.
+// q = a * (1/d) is within a few ulp of the correctly rounded quotient, so int(q) can differ from the
+// reference's int(a / d) only when an integer lies between the two, i.e. when q is (relatively) within 2^-19
+// of an integer.  Those lanes - and only those - evaluate the IEEE division.  Returns false when a quotient does
+// not fit 31 bits (NaN included): the general path then takes over.
+__device__ __forceinline__ bool div3_to_int32(const float a[3], const float d[3], const float r[3], int out[3]) {
+  float q[3];
+  bool ok = true, near = false;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    q[k] = __fmul_rn(a[k], r[k]);
+    const float qa = fabsf(q[k]);
+    ok = ok && qa < 1073741824.0f;
+    out[k] = __float2int_rz(q[k]);
+    const float fr = fabsf(__fsub_rn(q[k], (float)out[k]));  // exact: |q| < 2^30 leaves no rounding here
+    const float e = __fmul_rn(qa, 1.9073486e-6f);
+    near = near || fr <= e || fr >= __fsub_rn(1.0f, e);
+  }
+  if (!ok) return false;
+  if (near) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float ex = __fdiv_rn(a[k], d[k]);
+      ok = ok && fabsf(ex) < 1073741824.0f;
+      out[k] = __float2int_rz(ex);
+    }
+  }
+  return ok;
+}
+
+// The launch constants of the key arithmetic, read from shared memory once per thread.
+struct KeyConsts {
+  float vmin[3], leaf[3], rleaf[3], chunk_size[3], rchunk[3];
+  uint32_t nx, ny, n_chunks, xs, ys, zs, n_voxels;
+  int key_bits, chunked, small;
+  __device__ __forceinline__ explicit KeyConsts(const VgParams& P) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      vmin[k] = P.vmin[k];
+      leaf[k] = P.leaf[k];
+      rleaf[k] = P.rleaf[k];
+      chunk_size[k] = P.chunk_size[k];
+      rchunk[k] = P.rchunk[k];
+    }
+    nx = (uint32_t)P.nx;
+    ny = (uint32_t)P.ny;
+    n_chunks = (uint32_t)P.n_chunks;
+    xs = (uint32_t)P.xs;
+    ys = (uint32_t)P.ys;
+    zs = (uint32_t)P.zs;
+    n_voxels = (uint32_t)P.n_voxels;
+    key_bits = P.key_bits;
+    chunked = P.chunked;
+    small = P.small;
+  }
+};
+
+// voxelgrid.go:76-79,88 (vec2cid) and :149-151 (voxel key) for one point:
+// (chunk id << key_bits) | (x + xs*(y + ys*z)).  Points whose chunk and voxel coordinates are in range - all of
+// them on any input the reference accepts - are done in 32-bit arithmetic (same float operations, same
+// truncation).  Returns false when the point needs the general path.
+__device__ __forceinline__ bool voxel_key_fast(const KeyConsts& C, const float3 pt, unsigned long long* out) {
+  if (!C.small) return false;
+  uint32_t cid = 0;
+  float vc[3] = {C.vmin[0], C.vmin[1], C.vmin[2]};
+  const float p[3] = {pt.x, pt.y, pt.z};
+  bool fast = true;
+  if (C.chunked) {
+    float a[3];
+    int c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) a[k] = __fsub_rn(p[k], C.vmin[k]);
+    fast = div3_to_int32(a, C.chunk_size, C.rchunk, c);
+    fast = fast && (uint32_t)c[0] < C.nx && (uint32_t)c[1] < C.ny && c[2] >= 0;
+    const unsigned long long c64 = ((unsigned long long)(uint32_t)c[2] * C.ny + (uint32_t)c[1]) * C.nx + (uint32_t)c[0];
+    fast = fast && c64 < (unsigned long long)C.n_chunks;
+    cid = (uint32_t)c64;
+#pragma unroll
+    for (int k = 0; k < 3; k++) vc[k] = __fadd_rn(C.vmin[k], __fmul_rn((float)c[k], C.chunk_size[k]));  // voxelgrid.go:109-110
+  }
+  float a[3];
+  int x[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) a[k] = __fsub_rn(p[k], vc[k]);
+  fast = div3_to_int32(a, C.leaf, C.rleaf, x) && fast;
+  // coordinates inside [0, size+1] keep x + xs*(y + ys*z) below 2^32 when n_voxels < 2^30
+  fast = fast && (uint32_t)x[0] <= C.xs + 1u && (uint32_t)x[1] <= C.ys + 1u && (uint32_t)x[2] <= C.zs + 1u;
+  const uint32_t key = (uint32_t)x[0] + C.xs * ((uint32_t)x[1] + C.ys * (uint32_t)x[2]);
+  fast = fast && key < C.n_voxels;
+  *out = ((unsigned long long)cid << C.key_bits) | (unsigned long long)key;
+  return fast;
+}
+__device__ __forceinline__ unsigned long long voxel_key_of(const VgParams& P, const KeyConsts& C, const float3 pt,
+                                                           int* bad) {
+  unsigned long long k;
+  if (voxel_key_fast(C, pt, &k)) return k;
+  return voxel_key_general(P, pt, bad);
+}
+
 // Keys for the multi-kernel path; the digit histograms of the sort are accumulated here so the
 // keys are not read a second time.
 template <typename K>
@@ -311,12 +420,13 @@ __global__ void __launch_bounds__(256)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rounds = (v.n + stride - 1) / stride;
   int bad = 0;
+  const KeyConsts C(P);
   for (int64_t r = 0; r < rounds; r++) {
     const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < v.n;
     K out_key = 0;
     if (valid) {
-      out_key = (K)voxel_key_of(P, load_xyz(v, i), &bad);
+      out_key = (K)voxel_key_of(P, C, load_xyz(v, i), &bad);
       keys[i] = out_key;
     }
     rsort::hist_add_key(s_hist, out_key, valid, 0, passes);
@@ -507,9 +617,32 @@ static void run_sorted_reduce(const CloudView& v, const VgParams& P, int total_b
 // The host launches once and reads back 16 bytes.
 namespace cg = cooperative_groups;
 
+#ifdef PCG_VG_TIMING
+__device__ unsigned long long g_vg_stamps[64];
+__device__ int g_vg_nstamps;
+#define PCG_VG_STAMP()                                                          \
+  do {                                                                          \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+      unsigned long long t__;                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                   \
+      if (g_vg_nstamps < 64) g_vg_stamps[g_vg_nstamps++] = t__;                 \
+    }                                                                           \
+  } while (0)
+#else
+#define PCG_VG_STAMP() \
+  do {                 \
+  } while (0)
+#endif
+
 namespace fused {
-constexpr int kThreads = 512;
+#ifndef PCG_VG_THREADS
+#define PCG_VG_THREADS 512
+#endif
+constexpr int kThreads = PCG_VG_THREADS;
 constexpr int kWarps = kThreads / 32;
+constexpr int kParts = kThreads / (rsort::kRadix / 4);  // groups of 64 threads (4 digits each) that share the walk over the tiles
+constexpr int kIptSmall = 2048 / kThreads;         // tile of 2048 points (clouds up to 148 * 2048)
+constexpr int kIptLarge = 8192 / kThreads;         // tile of 8192 points
 
 struct Work {
   unsigned long long* acc;  // [6]: ~min / max packed (value bits, index), reduced with atomicMax; zero-initialised
@@ -517,7 +650,11 @@ struct Work {
   uint32_t* head_counts;    // [tiles]
   void* keys[2];            // n keys each (uint32 or uint64 depending on the bits needed)
   uint32_t* vals[2];
-  long long* result;        // [0] = records written, [1] = status | flags << 8 ; zero-initialised
+  long long* result;        // PINNED HOST memory (mapped): [0] = records written, [1] = status | flags << 8; the
+                            // kernel stores there directly, so the host needs no copy after the launch
+  unsigned long long* flags;  // device: kFlag* bits raised while the keys are computed; zero-initialised
+  float4* xyz4;             // n points as aligned {x, y, z, -}: the sorted gather of phase 3 is one 16-byte load per
+                            // point instead of three 4-byte loads scattered over two sectors
 };
 
 struct Args {
@@ -557,7 +694,7 @@ struct Smem {
   int status;
   int total_bits;
   uint32_t prefix;
-  uint32_t part[2][2][rsort::kRadix];  // [half][total|prefix][digit]
+  __align__(16) uint32_t part[kParts][2][rsort::kRadix];  // [part][total|prefix][digit]
   float mm[6];
 };
 
@@ -578,13 +715,47 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
   K keys[IPT];
   uint32_t vals[IPT];
   int bad = 0;
+  {
+    // The key arithmetic is a few hundred instructions: kept in a ROLLED loop (its code is fetched once and
+    // reused IPT times - fully unrolled it was instruction-fetch bound), results parked in shared memory.
+    K* s_park = reinterpret_cast<K*>(dyn);
+    bool general = false;
+    const KeyConsts C(P);
+#pragma unroll 2
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t pos = warp_base + i * 32 + lane;
+      unsigned long long k = ~0ull;
+      if (pos < n) {
+        const float3 pt = load_xyz(v, pos);
+        w.xyz4[pos] = make_float4(pt.x, pt.y, pt.z, 0.f);
+        if (!voxel_key_fast(C, pt, &k)) {
+          general = true;
+          k = ~0ull;
+        }
+      }
+      s_park[warp * (32 * IPT) + i * 32 + lane] = (K)k;
+    }
+    if (__any_sync(0xffffffffu, general)) {  // stragglers (out-of-range / non-finite coordinates): general path
+#pragma unroll 1
+      for (int i = 0; i < IPT; i++) {
+        const uint32_t pos = warp_base + i * 32 + lane;
+        if (pos < n && s_park[warp * (32 * IPT) + i * 32 + lane] == (K)~0ull) {
+          unsigned long long k;
+          if (!voxel_key_fast(C, load_xyz(v, pos), &k)) k = voxel_key_general(P, load_xyz(v, pos), &bad);
+          s_park[warp * (32 * IPT) + i * 32 + lane] = (K)k;
+        }
+      }
+    }
 #pragma unroll
-  for (int i = 0; i < IPT; i++) {
-    const uint32_t pos = warp_base + i * 32 + lane;
-    vals[i] = pos;
-    keys[i] = pos < n ? (K)voxel_key_of(P, load_xyz(v, pos), &bad) : (K)0;
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t pos = warp_base + i * 32 + lane;
+      vals[i] = pos;
+      keys[i] = pos < n ? s_park[warp * (32 * IPT) + i * 32 + lane] : (K)0;
+    }
+    __syncthreads();  // the parking area is the sort's staging buffer
   }
-  if (bad) atomicOr((unsigned long long*)&w.result[1], (unsigned long long)bad << 8);
+  if (bad) atomicOr(w.flags, (unsigned long long)bad);
+  PCG_VG_STAMP();  // keys done
 
   // ---- phase 2: stable LSD radix sort, one grid-wide exchange per digit
   K* s_keys = reinterpret_cast<K*>(dyn);
@@ -594,11 +765,18 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
     for (int i = tid; i < kWarps * rsort::kRadix; i += kThreads) (&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
     uint32_t offs[IPT];
+    uint32_t peers_of[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {  // the match instructions are independent: issue them back to back
+      const bool valid = (warp_base + i * 32 + lane) < n;
+      const uint32_t d = valid ? rsort::digit_of(keys[i], shift) : (uint32_t)rsort::kRadix;
+      peers_of[i] = __match_any_sync(0xffffffffu, d);
+    }
 #pragma unroll
     for (int i = 0; i < IPT; i++) {
       const bool valid = (warp_base + i * 32 + lane) < n;
       const uint32_t d = valid ? rsort::digit_of(keys[i], shift) : (uint32_t)rsort::kRadix;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t peers = peers_of[i];
       const int leader = __ffs(peers) - 1;
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       uint32_t pre = 0;
@@ -621,28 +799,48 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       }
       w.counts[tile * rsort::kRadix + tid] = count;
     }
+    PCG_VG_STAMP();  // ranked
     grid.sync();
+    PCG_VG_STAMP();  // sync A
     // offsets of this tile = counts of the preceding tiles (independent loads: no look-back chain);
-    // both halves of the CTA walk half of the tiles each
+    // every group of 256 threads walks its share of the tiles
     uint32_t total = 0, prefix = 0;
     {
-      const uint32_t d = tid & (rsort::kRadix - 1), half = tid >> 8;
-      const uint32_t t0 = half ? tiles / 2 : 0, t1 = half ? tiles : tiles / 2;
-      uint32_t tot = 0, pre = 0;
-#pragma unroll 8
-      for (uint32_t t = t0; t < t1; t++) {
-        const uint32_t c = __ldcg(&w.counts[t * rsort::kRadix + d]);
-        tot += c;
-        pre += t < tile ? c : 0u;
+      // thread = (4 consecutive digits, one share of the tiles): 16-byte loads, all of them independent
+      const uint32_t d4 = (tid & 63u) * 4u, part = tid >> 6;
+      const uint32_t t0 = part * tiles / kParts, t1 = (part + 1) * tiles / kParts;
+      uint4 tot = make_uint4(0, 0, 0, 0), pre = make_uint4(0, 0, 0, 0);
+      // every CTA reads the same table at the same moment: start at a CTA-specific tile so that the
+      // requests spread over the L2 slices (integer sums: the order is free)
+      const uint32_t len = t1 - t0;
+      uint32_t t = len ? t0 + tile % len : t0;
+#pragma unroll 4
+      for (uint32_t k = 0; k < len; k++) {
+        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(&w.counts[t * rsort::kRadix + d4]));
+        tot.x += c.x;
+        tot.y += c.y;
+        tot.z += c.z;
+        tot.w += c.w;
+        if (t < tile) {
+          pre.x += c.x;
+          pre.y += c.y;
+          pre.z += c.z;
+          pre.w += c.w;
+        }
+        t = t + 1 == t1 ? t0 : t + 1;
       }
-      sm.part[half][0][d] = tot;
-      sm.part[half][1][d] = pre;
+      *reinterpret_cast<uint4*>(&sm.part[part][0][d4]) = tot;
+      *reinterpret_cast<uint4*>(&sm.part[part][1][d4]) = pre;
       __syncthreads();
       if (tid < rsort::kRadix) {
-        total = sm.part[0][0][tid] + sm.part[1][0][tid];
-        prefix = sm.part[0][1][tid] + sm.part[1][1][tid];
+#pragma unroll
+        for (int k = 0; k < kParts; k++) {
+          total += sm.part[k][0][tid];
+          prefix += sm.part[k][1][tid];
+        }
       }
     }
+    PCG_VG_STAMP();  // walked
     const uint32_t digit_base = block_excl_scan(total, sm.scan, nullptr);
     const uint32_t dstart = block_excl_scan(count, sm.scan, nullptr);
     if (tid < rsort::kRadix) {
@@ -669,7 +867,9 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       ko[dst] = k;
       vo[dst] = s_vals[s];
     }
+    PCG_VG_STAMP();  // scattered
     grid.sync();
+    PCG_VG_STAMP();  // sync B
     cur ^= 1;
     if (shift + rsort::kRadixBits < sm.total_bits) {
 #pragma unroll
@@ -682,32 +882,47 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       }
     }
   }
+  PCG_VG_STAMP();  // sort done (incl. reload)
   const K* __restrict__ skeys = kbuf[cur];
   const uint32_t* __restrict__ svals = w.vals[cur];
 
   // ---- phase 3: segmented centroid (same arithmetic as voxel_reduce_kernel)
+  // Staging: key + raw point of every sorted position (independent gathers, all in flight at once).
+  // Thread t later walks positions t*IPT .. t*IPT+IPT-1: one pad word per IPT positions keeps the lanes of a warp
+  // on different banks (stride IPT would put them all on one or two).
+  constexpr int kPadTile = kTile + kTile / IPT;
+  auto pad = [](uint32_t l) { return l + l / (uint32_t)IPT; };
   K* s_key = reinterpret_cast<K*>(dyn);
-  float* s_p = reinterpret_cast<float*>(dyn + (size_t)kTile * sizeof(K));  // [3][kTile]
-  long long vc_cid = -1;  // sorted positions change chunk rarely: keep vcMin of the last chunk id
-  float vc[3] = {0.f, 0.f, 0.f};
-  for (uint32_t l = tid; l < tile_count; l += kThreads) {
-    const K key = __ldcg(&skeys[tile_base + l]);
-    const float3 pt = load_xyz(v, __ldcg(&svals[tile_base + l]));
-    const long long cid = (long long)((unsigned long long)key >> P.key_bits);
-    if (cid != vc_cid) {
-      chunk_min(P, cid, vc);
-      vc_cid = cid;
+  float* s_pt = reinterpret_cast<float*>(dyn + (size_t)kPadTile * sizeof(K));  // [3][kPadTile]
+  {
+    K kk[IPT];
+    uint32_t vv[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t l = i * kThreads + tid;
+      if (l < tile_count) {
+        kk[i] = __ldcg(&skeys[tile_base + l]);
+        vv[i] = __ldcg(&svals[tile_base + l]);
+      }
     }
-    s_key[l] = key;
-    s_p[l] = __fsub_rn(pt.x, vc[0]);
-    s_p[kTile + l] = __fsub_rn(pt.y, vc[1]);
-    s_p[2 * kTile + l] = __fsub_rn(pt.z, vc[2]);
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t l = i * kThreads + tid;
+      if (l < tile_count) {
+        const float4 pt = __ldcg(&w.xyz4[vv[i]]);
+        const uint32_t pl = pad(l);
+        s_key[pl] = kk[i];
+        s_pt[pl] = pt.x;
+        s_pt[kPadTile + pl] = pt.y;
+        s_pt[2 * kPadTile + pl] = pt.z;
+      }
+    }
   }
   __syncthreads();
   const uint32_t l0 = tid * IPT;
   K prev = 0;
   if (l0 > 0 && l0 - 1 < tile_count)
-    prev = s_key[l0 - 1];
+    prev = s_key[pad(l0 - 1)];
   else if (l0 == 0 && tile_base > 0)
     prev = __ldcg(&skeys[tile_base - 1]);
   uint32_t heads = 0, cnt = 0;
@@ -715,7 +930,7 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
   for (int j = 0; j < IPT; j++) {
     const uint32_t l = l0 + j;
     if (l < tile_count) {
-      const K k = s_key[l];
+      const K k = s_key[pad(l)];
       const bool h = (tile_base + l == 0) || k != prev;
       heads |= (h ? 1u : 0u) << j;
       cnt += h ? 1u : 0u;
@@ -725,7 +940,9 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
   uint32_t total_heads = 0;
   const uint32_t excl = block_excl_scan(cnt, sm.scan, &total_heads);
   if (tid == 0) w.head_counts[tile] = total_heads;
+  PCG_VG_STAMP();  // staged + heads
   grid.sync();
+  PCG_VG_STAMP();  // sync C
   if (warp == 0) {
     uint32_t part = 0;
     for (uint32_t t = lane; t < tile; t += 32) part += __ldcg(&w.head_counts[t]);
@@ -733,27 +950,25 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) {
       sm.prefix = part;
-      if (tile == tiles - 1) w.result[0] = (long long)(part + total_heads);
+      if (tile == tiles - 1) {  // the flags were raised before the sort's grid-wide barriers
+        w.result[1] = (long long)(__ldcg(w.flags) << 8);
+        w.result[0] = (long long)(part + total_heads);
+      }
     }
   }
   __syncthreads();
   uint64_t rank = (uint64_t)sm.prefix + excl;
   const int out_aligned = v.aligned && ((((uintptr_t)out) & 3) == 0);
+  // records that are exactly x,y,z (pc.Vec3Slice / xyz-only PCD): the first member's record is its point, already
+  // in shared memory - no gather from the input
+  const bool xyz_only = out_aligned && v.packed && v.stride == 12;
+  long long vc_cid = -1;  // sorted positions change chunk rarely: keep vcMin of the last chunk id
+  float vc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < IPT; j++) {
     if (!((heads >> j) & 1u)) continue;
     const uint32_t l = l0 + j;
-    const K key = s_key[l];
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t num = 0;
-    uint32_t ll = l;
-    do {
-      sx = __fadd_rn(sx, s_p[ll]);
-      sy = __fadd_rn(sy, s_p[kTile + ll]);
-      sz = __fadd_rn(sz, s_p[2 * kTile + ll]);
-      num++;
-      ll++;
-    } while (ll < tile_count && s_key[ll] == key);
+    const K key = s_key[pad(l)];
     {
       const long long cid = (long long)((unsigned long long)key >> P.key_bits);
       if (cid != vc_cid) {
@@ -761,6 +976,18 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
         vc_cid = cid;
       }
     }
+    const float fx = s_pt[pad(l)], fy = s_pt[kPadTile + pad(l)], fz = s_pt[2 * kPadTile + pad(l)];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t num = 0;
+    uint32_t ll = l;
+    do {  // p = pt - vcMin, sum += p in list order (voxelgrid.go:148-158)
+      const uint32_t pl = pad(ll);
+      sx = __fadd_rn(sx, __fsub_rn(s_pt[pl], vc[0]));
+      sy = __fadd_rn(sy, __fsub_rn(s_pt[kPadTile + pl], vc[1]));
+      sz = __fadd_rn(sz, __fsub_rn(s_pt[2 * kPadTile + pl], vc[2]));
+      num++;
+      ll++;
+    } while (ll < tile_count && s_key[pad(ll)] == key);
     if (ll == tile_count) {  // the voxel continues in the next tile(s)
       uint32_t g = tile_base + tile_count;
       while (g < n && __ldcg(&skeys[g]) == key) {
@@ -772,25 +999,39 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
         g++;
       }
     }
-    const uint32_t first = __ldcg(&svals[tile_base + l]);
-    uint8_t* dst = out + rank * (uint64_t)v.stride;
-    const uint8_t* src = v.data + (uint64_t)first * (uint64_t)v.stride;
-    if (out_aligned) {
-      const uint32_t* s4 = (const uint32_t*)src;
-      uint32_t* d4 = (uint32_t*)dst;
-      const int words = (int)(v.stride >> 2);
-      for (int b = 0; b < words; b++) d4[b] = __ldg(s4 + b);
-    } else {
-      for (int64_t b = 0; b < v.stride; b++) dst[b] = src[b];
-    }
+    float ox = fx, oy = fy, oz = fz;  // num == 1: the original bytes (voxelgrid.go:176-178)
     if (num > 1) {
       const float inv = __fdiv_rn(1.0f, (float)num);  // 1.0 / float32(n)   voxelgrid.go:179
-      store_f32_any(dst + v.off[0], __fadd_rn(__fmul_rn(sx, inv), vc[0]), out_aligned);
-      store_f32_any(dst + v.off[1], __fadd_rn(__fmul_rn(sy, inv), vc[1]), out_aligned);
-      store_f32_any(dst + v.off[2], __fadd_rn(__fmul_rn(sz, inv), vc[2]), out_aligned);
+      ox = __fadd_rn(__fmul_rn(sx, inv), vc[0]);
+      oy = __fadd_rn(__fmul_rn(sy, inv), vc[1]);
+      oz = __fadd_rn(__fmul_rn(sz, inv), vc[2]);
+    }
+    uint8_t* dst = out + rank * (uint64_t)v.stride;
+    if (xyz_only) {
+      float* d3 = reinterpret_cast<float*>(dst);
+      d3[0] = ox;
+      d3[1] = oy;
+      d3[2] = oz;
+    } else {
+      const uint32_t first = __ldcg(&svals[tile_base + l]);
+      const uint8_t* src = v.data + (uint64_t)first * (uint64_t)v.stride;
+      if (out_aligned) {
+        const uint32_t* s4 = (const uint32_t*)src;
+        uint32_t* d4 = (uint32_t*)dst;
+        const int words = (int)(v.stride >> 2);
+        for (int b = 0; b < words; b++) d4[b] = __ldg(s4 + b);
+      } else {
+        for (int64_t b = 0; b < v.stride; b++) dst[b] = src[b];
+      }
+      if (num > 1) {
+        store_f32_any(dst + v.off[0], ox, out_aligned);
+        store_f32_any(dst + v.off[1], oy, out_aligned);
+        store_f32_any(dst + v.off[2], oz, out_aligned);
+      }
     }
     rank++;
   }
+  PCG_VG_STAMP();  // reduced
 }
 
 template <int IPT>
@@ -803,6 +1044,10 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
   const uint32_t n = (uint32_t)v.n;
   const uint32_t tile_base = blockIdx.x * (uint32_t)kTile;
 
+#ifdef PCG_VG_TIMING
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_vg_nstamps = 0;
+#endif
+  PCG_VG_STAMP();  // start
   // ---- phase 0: MinMaxVec3 (pc/minmax.go:9-26), first occurrence wins (see minmax_kernel)
   unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
   for (int i = 0; i < IPT; i++) {
@@ -842,7 +1087,9 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
     for (int wv = 1; wv < kWarps; wv++) r = sm.red[wv][tid] > r ? sm.red[wv][tid] : r;
     if (r != 0ull) atomicMax(&w.acc[tid], r);
   }
+  PCG_VG_STAMP();  // minmax local
   grid.sync();
+  PCG_VG_STAMP();  // sync 0
   if (tid < 6) {
     const int k = tid, c = k % 3;
     const float3 p0 = load_xyz(v, 0);
@@ -873,6 +1120,7 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
     }
   }
   __syncthreads();
+  PCG_VG_STAMP();  // params
   if (sm.status != PCG_OK) return;  // every CTA computed the same status: uniform exit
   if (sm.total_bits <= 32)
     run<uint32_t, IPT>(v, w, out, sm, dyn, grid);
@@ -882,13 +1130,27 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
 
 template <int IPT>
 constexpr size_t dyn_smem_bytes() {
-  return (size_t)kThreads * IPT * 20;  // max(sort staging 12 B, reduce staging 8 + 12 B) per position
+  // max(sort staging 12 B, reduce staging (8 + 12) B with one pad slot per IPT positions) per position
+  return (size_t)(kThreads * IPT + kThreads) * 20;
 }
 
 }  // namespace fused
 
+#ifdef PCG_VG_TIMING
+}  // namespace pcg
+extern "C" int pcg_debug_vg_stamps(unsigned long long* out) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, pcg::g_vg_nstamps, sizeof(int));
+  cudaMemcpyFromSymbol(out, pcg::g_vg_stamps, sizeof(unsigned long long) * 64);
+  return n;
+}
+namespace pcg {
+#endif
+
 // Largest cloud the fused kernel takes: one tile per SM.
 static int64_t fused_capacity(int ipt) { return (int64_t)kNumSMs * fused::kThreads * ipt; }
+constexpr int kFusedIptSmall = fused::kIptSmall, kFusedIptLarge = fused::kIptLarge;
 
 template <int IPT>
 static void launch_fused(const CloudView& v, const fused::Args& args, const fused::Work& w, uint8_t* d_out,
@@ -919,20 +1181,24 @@ static void launch_fused(const CloudView& v, const fused::Args& args, const fuse
 static pcg_status voxelgrid_filter_fused(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                          uint8_t* d_out, int64_t* n_out, cudaStream_t stream) {
   const uint32_t n = (uint32_t)v.n;
-  const int ipt = v.n <= fused_capacity(4) ? 4 : 16;
+  const int ipt = v.n <= fused_capacity(kFusedIptSmall) ? kFusedIptSmall : kFusedIptLarge;
   const int tiles = div_up(v.n, (int64_t)fused::kThreads * ipt);
-  // one allocation: [acc 6 x u64 | result 2 x i64 | counts | head_counts | keys0 | keys1 | vals0 | vals1]
+  // one allocation: [acc 6 x u64 | flags | counts | head_counts | keys0 | keys1 | vals0 | vals1 | xyz4]
   const size_t head_bytes = 64 + 16 + 48;
   const size_t counts_bytes = ((size_t)tiles * rsort::kRadix + tiles) * sizeof(uint32_t);
   const size_t keys_bytes = ((size_t)n * 8 + 255) & ~(size_t)255;
   const size_t vals_bytes = ((size_t)n * 4 + 255) & ~(size_t)255;
   const size_t counts_pad = (counts_bytes + 255) & ~(size_t)255;
-  DevBuf<uint8_t> ws(128 + counts_pad + 2 * keys_bytes + 2 * vals_bytes, stream);
+  DevBuf<uint8_t> ws(128 + counts_pad + 2 * keys_bytes + 2 * vals_bytes + (size_t)n * sizeof(float4), stream);
   (void)head_bytes;
   PCG_CUDA(cudaMemsetAsync(ws.p, 0, 128, stream));
   fused::Work w;
   w.acc = (unsigned long long*)ws.p;
-  w.result = (long long*)(ws.p + 64);
+  w.flags = (unsigned long long*)(ws.p + 64);
+  long long* h = (long long*)pinned_scratch();  // cudaMallocHost memory: addressable from the device (UVA)
+  h[0] = 0;
+  h[1] = 0;
+  w.result = h;
   w.counts = (uint32_t*)(ws.p + 128);
   w.head_counts = w.counts + (size_t)tiles * rsort::kRadix;
   uint8_t* p = ws.p + 128 + counts_pad;
@@ -940,17 +1206,16 @@ static pcg_status voxelgrid_filter_fused(const CloudView& v, const float leaf[3]
   w.keys[1] = p + keys_bytes;
   w.vals[0] = (uint32_t*)(p + 2 * keys_bytes);
   w.vals[1] = (uint32_t*)(p + 2 * keys_bytes + vals_bytes);
+  w.xyz4 = (float4*)(p + 2 * keys_bytes + 2 * vals_bytes);  // 256-byte aligned like the blocks before it
   fused::Args args;
   for (int k = 0; k < 3; k++) {
     args.leaf[k] = leaf[k];
     args.chunk[k] = (long long)chunk[k];
   }
-  if (ipt == 4)
-    launch_fused<4>(v, args, w, d_out, stream);
+  if (ipt == kFusedIptSmall)
+    launch_fused<kFusedIptSmall>(v, args, w, d_out, stream);
   else
-    launch_fused<16>(v, args, w, d_out, stream);
-  long long* h = (long long*)pinned_scratch();
-  PCG_CUDA(cudaMemcpyAsync(h, w.result, 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    launch_fused<kFusedIptLarge>(v, args, w, d_out, stream);
   PCG_CUDA(cudaStreamSynchronize(stream));
   const pcg_status st = (pcg_status)(h[1] & 0xff);
   const int flags = (int)((h[1] >> 8) & 0xff);
@@ -970,7 +1235,7 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
   *n_out = 0;
   if (v.n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
   static const bool no_fused = getenv("PCG_VG_NO_FUSED") != nullptr;  // comparison runs only
-  if (!no_fused && v.n <= fused_capacity(16)) {
+  if (!no_fused && v.n <= fused_capacity(kFusedIptLarge)) {
     try {
       return voxelgrid_filter_fused(v, leaf, chunk, d_out, n_out, stream);
     } catch (const CudaError& e) {
