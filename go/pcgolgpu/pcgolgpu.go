@@ -10,7 +10,9 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"io"
 	"runtime"
+	"strconv"
 	"unsafe"
 
 	"github.com/seqsense/pcgol/mat"
@@ -24,6 +26,9 @@ import (
 // Status errors that have no counterpart in the reference (it would panic there).
 var ErrReferenceWouldPanic = errors.New("pcgolgpu: reference would panic (voxel/chunk index out of range)")
 
+// ErrDataCorruption stands for lzf.ErrDataCorruption (github.com/zhuyie/golzf) of pc.Unmarshal.
+var ErrDataCorruption = errors.New("lzf: data corruption")
+
 func statusError(s C.pcg_status) error {
 	switch s {
 	case C.PCG_OK:
@@ -34,6 +39,14 @@ func statusError(s C.pcg_status) error {
 		return icp.ErrNotEnoughPairs // pc/registration/icp/evaluator.go:15-17
 	case C.PCG_E_REF_WOULD_PANIC:
 		return ErrReferenceWouldPanic
+	case C.PCG_E_PCD_SYNTAX: // wraps the class of error pc.Unmarshal returns (pc/io_test.go:108-165)
+		return fmt.Errorf("%s: %w", C.GoString(C.pcg_last_error()), strconv.ErrSyntax)
+	case C.PCG_E_PCD_EOF:
+		return io.EOF
+	case C.PCG_E_PCD_CORRUPT:
+		return fmt.Errorf("%s: %w", C.GoString(C.pcg_last_error()), ErrDataCorruption)
+	case C.PCG_E_INVALID_FIELD:
+		return errors.New("invalid field name") // pc/pointcloud.go:115,189
 	}
 	return fmt.Errorf("pcgolgpu: status %d: %s", int(s), C.GoString(C.pcg_last_error()))
 }
@@ -64,6 +77,25 @@ func flatten(ra pc.Vec3RandomAccessor) (unsafe.Pointer, C.int64_t, C.int64_t, [3
 type Index struct {
 	pc.Vec3RandomAccessor // Vec3At / Len / RawIndexAt stay on the host accessor
 	h                     *C.pcg_index
+
+	// MinDistSq mirrors KDTree.MinDistSq (kdtree.go:19-22): larger than zero makes Nearest (and the ICP
+	// correspondences searched through this index) the approximate search.
+	MinDistSq float32
+	shared    bool // a With() copy: the handle belongs to the original
+}
+
+// With is KDTree.With (kdtree.go:58-65): a shallow copy sharing the device index.
+func (k *Index) With(minDistSq float32) *Index {
+	k2 := *k
+	k2.MinDistSq = minDistSq
+	k2.shared = true
+	return &k2
+}
+
+// DeletePoint is KDTree.DeletePoint (kdtree.go:322-332): the point stops matching any search.
+func (k *Index) DeletePoint(pID int) error {
+	id := C.int64_t(pID)
+	return statusError(C.pcg_index_delete_points(k.h, &id, 1))
 }
 
 var _ storage.Search = (*Index)(nil)
@@ -83,10 +115,10 @@ func NewIndex(ra pc.Vec3RandomAccessor, device int) (*Index, error) {
 }
 
 func (k *Index) Close() {
-	if k.h != nil {
+	if k.h != nil && !k.shared {
 		C.pcg_index_free(k.h)
-		k.h = nil
 	}
+	k.h = nil
 }
 
 // Nearest is KDTree.Nearest (kdtree.go:83-92) as a batch of one.
@@ -109,7 +141,8 @@ func (k *Index) NearestBatch(q pc.Vec3RandomAccessor, maxRange float32, out []st
 	if n == 0 {
 		return
 	}
-	s := C.pcg_index_nearest(k.h, p, n, stride, &off[0], C.float(maxRange), (*C.pcg_neighbor)(unsafe.Pointer(&out[0])))
+	s := C.pcg_index_nearest_approx(k.h, p, n, stride, &off[0], C.float(maxRange), C.float(k.MinDistSq),
+		(*C.pcg_neighbor)(unsafe.Pointer(&out[0])))
 	runtime.KeepAlive(keep)
 	runtime.KeepAlive(q)
 	if s != C.PCG_OK {
@@ -234,8 +267,9 @@ func (c *NearestPointCorresponder) Pairs(base storage.Search, target pc.Vec3Rand
 type Mode int32
 
 const (
-	Strict Mode = C.PCG_ICP_STRICT
-	Fast   Mode = C.PCG_ICP_FAST
+	Strict      Mode = C.PCG_ICP_STRICT
+	Fast        Mode = C.PCG_ICP_FAST
+	WithHessian Mode = C.PCG_ICP_WITH_HESSIAN // OR-ed in: Evaluate also fills Evaluated.Hessian
 )
 
 // PointToPointEvaluator implements icp.Evaluator (evaluator.go:32-36,69-189) with the default weight function.
@@ -245,14 +279,17 @@ type PointToPointEvaluator struct {
 	Mode         Mode
 }
 
-func (PointToPointEvaluator) HasGradient() bool { return true }
-func (PointToPointEvaluator) HasHessian() bool  { return false }
+func (PointToPointEvaluator) HasGradient() bool  { return true }
+func (e PointToPointEvaluator) HasHessian() bool { return e.Mode&WithHessian != 0 } // false by default, like evaluator.go:76
 
 func evaluatedFromC(e *C.pcg_evaluated) icp.Evaluated {
 	var out icp.Evaluated
 	out.Value = float32(e.value)
 	for i := 0; i < 6; i++ {
 		out.Gradient[i] = float32(e.gradient[i])
+	}
+	for i := 0; i < 36; i++ { // zero unless WithHessian / GaussNewton was selected
+		out.Hessian[i] = float32(e.hessian[i])
 	}
 	out.DistRMS = float32(e.dist_rms)
 	return out
@@ -263,8 +300,12 @@ func (e *PointToPointEvaluator) Evaluate(base storage.Search, target pc.Vec3Rand
 	p, n, stride, off, keep := flatten(target)
 	var ev C.pcg_evaluated
 	var np C.int64_t
-	s := C.pcg_icp_evaluate(idx.h, p, n, stride, &off[0], C.float(e.Corresponder.MaxDist), C.int32_t(e.MinPairs),
-		C.int32_t(e.Mode), &ev, &np)
+	var prm C.pcg_icp_params
+	prm.max_dist = C.float(e.Corresponder.MaxDist)
+	prm.min_pairs = C.int32_t(e.MinPairs)
+	prm.mode = C.int32_t(e.Mode)
+	prm.min_dist_sq = C.float(idx.MinDistSq)
+	s := C.pcg_icp_evaluate_params(idx.h, p, n, stride, &off[0], &prm, &ev, &np)
 	runtime.KeepAlive(keep)
 	if err := statusError(s); err != nil {
 		return nil, err
@@ -278,6 +319,9 @@ func (e *PointToPointEvaluator) Evaluate(base storage.Search, target pc.Vec3Rand
 type PointToPointICPGradient struct {
 	Evaluator      *PointToPointEvaluator
 	UpdaterFactory *icp.GradientDescentUpdaterFactory
+	// GaussNewton replaces the damped gradient step by the solution of the 6x6 normal equations accumulated
+	// with Evaluated.Hessian (not in the reference; Weight is then ignored).
+	GaussNewton bool
 }
 
 func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomAccessor) (mat.Mat4, icp.Stat, error) {
@@ -287,6 +331,10 @@ func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomA
 	prm.max_dist = C.float(r.Evaluator.Corresponder.MaxDist)
 	prm.min_pairs = C.int32_t(r.Evaluator.MinPairs)
 	prm.mode = C.int32_t(r.Evaluator.Mode)
+	prm.min_dist_sq = C.float(idx.MinDistSq)
+	if r.GaussNewton {
+		prm.updater = C.PCG_UPDATER_GAUSS_NEWTON
+	}
 	if f := r.UpdaterFactory; f != nil { // zero values select the reference defaults (updater.go:24-33)
 		for i := 0; i < 6; i++ {
 			prm.weight[i] = C.float(f.Weight[i])
@@ -300,4 +348,111 @@ func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomA
 	runtime.KeepAlive(keep)
 	stat := icp.Stat{Evaluated: evaluatedFromC(&st.evaluated), NumIteration: int(st.num_iteration)}
 	return trans, stat, statusError(s) // on ErrNotEnoughPairs: (trans so far, stat, err) like icp.go:51-53
+}
+
+// RegionGrowing is the drop-in for regiongrowing.New / Segment (pc/segmentation/regiongrowing/regiongrowing.go:11-56):
+// every breadth-first level is one batched Range on the device.
+type RegionGrowing struct {
+	h *C.pcg_region_growing
+	n int
+}
+
+// NewRegionGrowing takes the cloud the index was built from and the name of its uint32 property
+// (what pp.Uint32Iterator(field) would iterate).
+func NewRegionGrowing(search *Index, pp *pc.PointCloud, field string) (*RegionGrowing, error) {
+	off, err := xyzOffsets(pp)
+	if err != nil {
+		return nil, err
+	}
+	labelOff := 0
+	found := false
+	for i, fn := range pp.Fields {
+		if fn == field {
+			found = true
+			break
+		}
+		labelOff += pp.Size[i] * pp.Count[i]
+	}
+	if !found {
+		return nil, errors.New("invalid field name") // pointcloud.go:189
+	}
+	rg := &RegionGrowing{n: pp.Points}
+	var data unsafe.Pointer
+	if len(pp.Data) > 0 {
+		data = unsafe.Pointer(&pp.Data[0])
+	}
+	s := C.pcg_region_growing_new(search.h, data, C.int64_t(pp.Points), C.int64_t(pp.Stride()), &off[0],
+		C.int64_t(labelOff), &rg.h)
+	runtime.KeepAlive(pp)
+	if err := statusError(s); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(rg, (*RegionGrowing).Close)
+	return rg, nil
+}
+
+func (r *RegionGrowing) Close() {
+	if r.h != nil {
+		C.pcg_region_growing_free(r.h)
+		r.h = nil
+	}
+}
+
+// Segment is RegionGrowing.Segment (regiongrowing.go:23-56).
+func (r *RegionGrowing) Segment(p mat.Vec3, maxRange float32) []int {
+	out := make([]int, r.n+1) // Go int == int64 on the 64-bit targets this library supports
+	var m C.int64_t
+	s := C.pcg_region_growing_segment(r.h, (*C.float)(unsafe.Pointer(&p[0])), C.float(maxRange),
+		(*C.int64_t)(unsafe.Pointer(&out[0])), C.int64_t(r.n), &m)
+	if s != C.PCG_OK {
+		panic(statusError(s)) // Segment has no error return in the reference
+	}
+	return out[:m]
+}
+
+// DeviceCloud is a pc.PointCloud whose Data stays in HBM: Unmarshal -> VoxelGrid -> NewIndexFromCloud -> Fit
+// without host round trips (pc/io.go:32-45,232-285 for the encodings).
+type DeviceCloud struct{ h *C.pcg_cloud }
+
+// Unmarshal is pc.Unmarshal over a byte slice; ascii, binary and binary_compressed.
+func Unmarshal(pcd []byte, device int) (*DeviceCloud, error) {
+	var p unsafe.Pointer
+	if len(pcd) > 0 {
+		p = unsafe.Pointer(&pcd[0])
+	}
+	c := &DeviceCloud{}
+	if err := statusError(C.pcg_pcd_unmarshal(p, C.int64_t(len(pcd)), C.int32_t(device), &c.h)); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(c, (*DeviceCloud).Close)
+	return c, nil
+}
+
+// Marshal is pc.Marshal ("DATA binary").
+func (c *DeviceCloud) Marshal() ([]byte, error) {
+	var n C.int64_t
+	C.pcg_pcd_marshal(c.h, nil, 0, &n)
+	out := make([]byte, int(n))
+	if n == 0 {
+		return out, nil
+	}
+	return out, statusError(C.pcg_pcd_marshal(c.h, unsafe.Pointer(&out[0]), n, &n))
+}
+
+func (c *DeviceCloud) Close() {
+	if c.h != nil {
+		C.pcg_cloud_free(c.h)
+		c.h = nil
+	}
+}
+
+// VoxelGrid is voxelGrid.Filter on the resident cloud.
+func (c *DeviceCloud) VoxelGrid(leaf mat.Vec3, chunk [3]int) (*DeviceCloud, error) {
+	ck := [3]C.int64_t{C.int64_t(chunk[0]), C.int64_t(chunk[1]), C.int64_t(chunk[2])}
+	out := &DeviceCloud{}
+	if err := statusError(C.pcg_cloud_voxelgrid_filter(c.h, (*C.float)(unsafe.Pointer(&leaf[0])), &ck[0], &out.h)); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(out, (*DeviceCloud).Close)
+	return out, nil
 }

@@ -10,6 +10,10 @@
 //   pcgol::icp::{NearestPointCorresponder, PointToPointEvaluator,
 //                GradientDescentUpdaterFactory, PointToPointICPGradient, Stat, Evaluated}
 //                                                        pc/registration/icp/*.go
+//   pcgol::storage::Index::{MinDistSq, With, DeletePoint} kdtree.go:19-22,58-65,322-332
+//   pcgol::segmentation::RegionGrowing                   pc/segmentation/regiongrowing/regiongrowing.go:11-56
+//   pcgol::pc::{Unmarshal, Marshal, DeviceCloud}         pc/io.go:32-45,232-285 (+ a cloud resident in HBM)
+//   pcgol::icp::GaussNewtonUpdaterFactory                not in the reference: consumes Evaluated.Hessian
 //
 // Go returns (value, error); here errors are exceptions carrying the C status:
 //   pcgol::Error                    any failure (status(), what())
@@ -105,7 +109,15 @@ class Index : public Search {
     check(pcg_index_build(v.data, v.n, v.stride, v.off.data(), device, &h_));
   }
   explicit Index(const pc::Vec3Slice& ra, int device = 0) : Index(pc::view(ra), device) {}
+  explicit Index(pcg_index* adopted) : h_(adopted) {}  // e.g. from pc::DeviceCloud::BuildIndex
   ~Index() override { pcg_index_free(h_); }
+
+  // KDTree.MinDistSq (kdtree.go:19-22): > 0 turns Nearest / NearestBatch / the ICP correspondences into the
+  // approximate search (exact answer, or a real point closer than sqrt(MinDistSq)).
+  float MinDistSq = 0.f;
+  // KDTree.DeletePoint (kdtree.go:322-332); an id outside [0, Len()-1] throws (the reference returns an error).
+  void DeletePoint(int64_t pID) { check(pcg_index_delete_points(h_, &pID, 1)); }
+  void DeletePoints(const std::vector<int64_t>& ids) { check(pcg_index_delete_points(h_, ids.data(), (int64_t)ids.size())); }
   Index(const Index&) = delete;
   Index& operator=(const Index&) = delete;
 
@@ -113,7 +125,7 @@ class Index : public Search {
 
   Neighbor Nearest(const mat::Vec3& p, float maxRange) const override {
     pcg_neighbor nb;
-    check(pcg_index_nearest(h_, p.data(), 1, 12, nullptr, maxRange, &nb));
+    check(pcg_index_nearest_approx(h_, p.data(), 1, 12, nullptr, maxRange, MinDistSq, &nb));
     return Neighbor{nb.id, nb.dist_sq};
   }
   std::vector<Neighbor> Range(const mat::Vec3& p, float maxRange) const override {
@@ -123,7 +135,7 @@ class Index : public Search {
   // The batched calls the hot path uses.
   std::vector<Neighbor> NearestBatch(const pc::View& q, float maxRange) const {
     std::vector<pcg_neighbor> raw((size_t)q.n);
-    check(pcg_index_nearest(h_, q.data, q.n, q.stride, q.off.data(), maxRange, raw.data()));
+    check(pcg_index_nearest_approx(h_, q.data, q.n, q.stride, q.off.data(), maxRange, MinDistSq, raw.data()));
     std::vector<Neighbor> out((size_t)q.n);
     for (size_t i = 0; i < raw.size(); i++) out[i] = Neighbor{raw[i].id, raw[i].dist_sq};
     return out;
@@ -206,8 +218,8 @@ struct NearestPointCorresponder {  // correspondence.go:18-37
     std::vector<int64_t> b((size_t)target.n + 1), t((size_t)target.n + 1);
     std::vector<float> d((size_t)target.n + 1);
     int64_t m = 0;
-    check(pcg_icp_pairs(base.handle(), target.data, target.n, target.stride, target.off.data(), MaxDist, b.data(),
-                        t.data(), d.data(), &m));
+    check(pcg_icp_pairs_approx(base.handle(), target.data, target.n, target.stride, target.off.data(), MaxDist,
+                               base.MinDistSq, b.data(), t.data(), d.data(), &m));
     std::vector<PointToPointCorrespondence> out((size_t)m);
     for (int64_t i = 0; i < m; i++) out[(size_t)i] = {b[(size_t)i], t[(size_t)i], d[(size_t)i]};
     return out;
@@ -226,14 +238,20 @@ inline Evaluated from_c(const pcg_evaluated& e) {
 struct PointToPointEvaluator {  // evaluator.go:69-189
   NearestPointCorresponder Corresponder;
   int MinPairs = 0;
-  int Mode = PCG_ICP_STRICT;
+  int Mode = PCG_ICP_STRICT;  // | PCG_ICP_WITH_HESSIAN to fill Evaluated.Hessian
   bool HasGradient() const { return true; }
-  bool HasHessian() const { return false; }
+  bool HasHessian() const { return (Mode & PCG_ICP_WITH_HESSIAN) != 0; }  // false like evaluator.go:76 by default
   Evaluated Evaluate(const storage::Index& base, const pc::View& target) const {
     pcg_evaluated ev;
     int64_t np = 0;
-    pcg_status s = pcg_icp_evaluate(base.handle(), target.data, target.n, target.stride, target.off.data(),
-                                    Corresponder.MaxDist, MinPairs, Mode, &ev, &np);
+    pcg_icp_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.max_dist = Corresponder.MaxDist;
+    p.min_pairs = MinPairs;
+    p.mode = Mode;
+    p.min_dist_sq = base.MinDistSq;
+    pcg_status s = pcg_icp_evaluate_params(base.handle(), target.data, target.n, target.stride, target.off.data(), &p,
+                                           &ev, &np);
     if (s == PCG_E_NOT_ENOUGH_PAIRS) throw ErrNotEnoughPairs();
     check(s);
     return from_c(ev);
@@ -244,6 +262,12 @@ struct GradientDescentUpdaterFactory {  // updater.go:18-37 ; zero == reference 
   mat::Vec6 Weight{};
   mat::Vec6 Threshold{};
   int MaxIteration = 0;
+  int Kind = PCG_UPDATER_GRADIENT_DESCENT;
+};
+// Not in the reference: solves the normal equations accumulated with Evaluated.Hessian (the hook declared
+// by evaluator.go:25-36) instead of a damped gradient step; same convergence test and MaxIteration cap.
+struct GaussNewtonUpdaterFactory : GradientDescentUpdaterFactory {
+  GaussNewtonUpdaterFactory() { Kind = PCG_UPDATER_GAUSS_NEWTON; }
 };
 
 struct PointToPointICPGradient {  // icp.go:18-67
@@ -259,6 +283,8 @@ struct PointToPointICPGradient {  // icp.go:18-67
     std::memcpy(p.threshold, UpdaterFactory.Threshold.data(), sizeof(p.threshold));
     p.max_iteration = UpdaterFactory.MaxIteration;
     p.mode = Evaluator.Mode;
+    p.updater = UpdaterFactory.Kind;
+    p.min_dist_sq = base.MinDistSq;
     mat::Mat4 trans{};
     pcg_icp_stat st;
     pcg_status s = pcg_icp_fit(base.handle(), target.data, target.n, target.stride, target.off.data(), &p,
@@ -278,6 +304,90 @@ struct PointToPointICPGradient {  // icp.go:18-67
 };
 
 }  // namespace icp
+
+namespace segmentation {
+
+// regiongrowing.New(search, propertyIter) + Segment (regiongrowing.go:11-56): `labelOffset` is the byte offset
+// of the uint32 property inside the records of `pp` (pc.Uint32Iterator(name)).
+class RegionGrowing {
+ public:
+  RegionGrowing(const storage::Index& search, const pc::PointCloud& pp, int64_t labelOffset) : n_(pp.Points) {
+    check(pcg_region_growing_new(search.handle(), pp.Data.data(), pp.Points, pp.Stride, pp.XYZOffset.data(),
+                                 labelOffset, &h_));
+  }
+  ~RegionGrowing() { pcg_region_growing_free(h_); }
+  RegionGrowing(const RegionGrowing&) = delete;
+  RegionGrowing& operator=(const RegionGrowing&) = delete;
+  std::vector<int64_t> Segment(const mat::Vec3& p, float maxRange) const {
+    std::vector<int64_t> out((size_t)n_ + 1);
+    int64_t m = 0;
+    check(pcg_region_growing_segment(h_, p.data(), maxRange, out.data(), n_, &m));
+    out.resize((size_t)m);
+    return out;
+  }
+
+ private:
+  pcg_region_growing* h_ = nullptr;
+  int64_t n_;
+};
+
+}  // namespace segmentation
+
+namespace pc {
+
+// A pc.PointCloud whose Data stays in HBM: Unmarshal -> VoxelGrid -> BuildIndex -> ICP without host round trips.
+class DeviceCloud {
+ public:
+  explicit DeviceCloud(pcg_cloud* h) : h_(h) {}
+  ~DeviceCloud() { pcg_cloud_free(h_); }
+  DeviceCloud(const DeviceCloud&) = delete;
+  DeviceCloud& operator=(const DeviceCloud&) = delete;
+  DeviceCloud(DeviceCloud&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  pcg_cloud_header Header() const {
+    pcg_cloud_header h;
+    check(pcg_cloud_get_header(h_, &h));
+    return h;
+  }
+  std::vector<uint8_t> Download() const {
+    std::vector<uint8_t> d((size_t)Header().data_bytes);
+    check(pcg_cloud_download(h_, d.data(), (int64_t)d.size()));
+    return d;
+  }
+  DeviceCloud VoxelGrid(const mat::Vec3& leaf, std::array<int64_t, 3> chunk = {{0, 0, 0}}) const {
+    pcg_cloud* out = nullptr;
+    pcg_status s = pcg_cloud_voxelgrid_filter(h_, leaf.data(), chunk.data(), &out);
+    if (s == PCG_E_NO_POINT) throw ErrNoPoint();
+    check(s);
+    return DeviceCloud(out);
+  }
+  pcg_index* BuildIndex() const {  // wrap with storage::Index(handle)
+    pcg_index* idx = nullptr;
+    check(pcg_cloud_index_build(h_, &idx));
+    return idx;
+  }
+  pcg_cloud* handle() const { return h_; }
+
+ private:
+  pcg_cloud* h_;
+};
+
+// pc.Unmarshal (io.go:32-45): errors keep the reference's classes through Error::status()
+// (PCG_E_PCD_SYNTAX ~ strconv.ErrSyntax, PCG_E_PCD_EOF ~ io.EOF, PCG_E_PCD_CORRUPT ~ lzf.ErrDataCorruption).
+inline DeviceCloud Unmarshal(const std::vector<uint8_t>& pcd, int device = 0) {
+  pcg_cloud* c = nullptr;
+  check(pcg_pcd_unmarshal(pcd.data(), (int64_t)pcd.size(), device, &c));
+  return DeviceCloud(c);
+}
+// pc.Marshal (io.go:232-285): "DATA binary".
+inline std::vector<uint8_t> Marshal(const DeviceCloud& c) {
+  int64_t len = 0;
+  pcg_pcd_marshal(c.handle(), nullptr, 0, &len);
+  std::vector<uint8_t> out((size_t)len);
+  check(pcg_pcd_marshal(c.handle(), out.data(), len, &len));
+  return out;
+}
+
+}  // namespace pc
 }  // namespace pcgol
 
 #endif  // PCGOL_B200_HPP_

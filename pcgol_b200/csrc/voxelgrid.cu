@@ -1032,6 +1032,13 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
     rank++;
   }
   PCG_VG_STAMP();  // reduced
+#ifdef PCG_VG_TIMING
+  if (threadIdx.x == 0) {
+    unsigned long long t__;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+    atomicMax(&g_vg_stamps[63], t__);
+  }
+#endif
 }
 
 template <int IPT>
@@ -1045,7 +1052,10 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
   const uint32_t tile_base = blockIdx.x * (uint32_t)kTile;
 
 #ifdef PCG_VG_TIMING
-  if (blockIdx.x == 0 && threadIdx.x == 0) g_vg_nstamps = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    g_vg_nstamps = 0;
+    g_vg_stamps[63] = 0;
+  }
 #endif
   PCG_VG_STAMP();  // start
   // ---- phase 0: MinMaxVec3 (pc/minmax.go:9-26), first occurrence wins (see minmax_kernel)

@@ -217,6 +217,114 @@ static void TestPointToPointICPGradient() {
   }
 }
 
+
+// pc/storage/kdtree/kdtree_test.go:413-751 (DeletePoint): searches after deletion behave like naiveSearch.deletePoint
+static void TestKDtree_DeletePoint() {
+  pc::Vec3Slice pts{{{4, 1, 0}}, {{2, 2, 1}}, {{5, 0, 0}}, {{3, 0, 0}}, {{0, 1, 0}}, {{1, 0, 0}}, {{6, 2, 1}}};
+  storage::Index kdt(pts);
+  kdt.DeletePoint(5);
+  EXPECT(kdt.Nearest(pts[5], 0.001f).ID < 0, "point 5 was not deleted");
+  EXPECT(kdt.Nearest(pts[5], 1.5f).ID == 4, "nearest to deleted point 5 must be 4");
+  kdt.DeletePoint(5);  // "TwiceTheSamePoint": no error
+  EXPECT(kdt.Len() == 7, "Len() is the accessor's");
+  bool threw = false;
+  try {
+    kdt.DeletePoint(123);  // "InvalidPointID"
+  } catch (const Error& e) {
+    threw = e.status() == PCG_E_INVALID_ARG && std::string(e.what()).find("123 does not correspond") != std::string::npos;
+  }
+  EXPECT(threw, "expected an error when deleting a point that is not in the tree");
+  // kdtree_test.go:731-751: all points on a line
+  pc::Vec3Slice line{{{4, 0, 0}}, {{1, 0, 0}}, {{2, 0, 0}}, {{3, 0, 0}}};
+  storage::Index k2(line);
+  for (int i = 0; i < 4; i++) {
+    k2.DeletePoint(i);
+    EXPECT(k2.Nearest(line[i], 0.001f).ID < 0, "%d was not deleted", i);
+  }
+}
+
+// pc/registration/icp/icp_test.go:13-98 exactly as the reference runs it: kdtree.New(ra) with MinDistSq = 0.01
+static void TestPointToPointICPGradient_MinDistSq() {
+  pc::Vec3Slice base{{{-2.1f, 0, 0}}, {{-1, 1, 0}}, {{0, 2, 0}}, {{1, 1, 1}}, {{2, 0, 0}}};
+  storage::Index kdt(base);
+  kdt.MinDistSq = 0.01f;
+  const int indices[5] = {3, 1, 4, 0, 2};
+  for (const Mat4& delta : {Translate(0.25f, 0.125f, -0.125f), Rotate(1, 0, 0, 0.2f), Mul(Translate(0.2f, 0, 0), Rotate(0, 1, 0, 0.1f))}) {
+    pc::Vec3Slice target(5);
+    for (int i = 0; i < 5; i++) target[i] = Transform(delta, base[indices[i]]);
+    for (int gn = 0; gn < 2; gn++) {  // the reference's updater, then the Gauss-Newton one
+      icp::PointToPointICPGradient ppicp;
+      ppicp.Evaluator = icp::PointToPointEvaluator{icp::NearestPointCorresponder{2}, 3};
+      if (gn) ppicp.UpdaterFactory = icp::GaussNewtonUpdaterFactory();
+      auto fit = ppicp.Fit(kdt, pc::view(target));
+      float residual = 0;
+      for (int i = 0; i < 5; i++) residual += NormSq(Sub(Transform(fit.first, target[i]), base[indices[i]]));
+      EXPECT(0.05f >= residual / 5.0f, "MinDistSq fit (gn=%d): residual %f", gn, residual / 5.0f);
+    }
+  }
+  icp::PointToPointEvaluator e{icp::NearestPointCorresponder{2}, 3, PCG_ICP_STRICT | PCG_ICP_WITH_HESSIAN};
+  icp::Evaluated ev = e.Evaluate(kdt, pc::view(base));
+  EXPECT(e.HasHessian() && ev.Hessian[0] == 2.0f && ev.Hessian[7] == 2.0f, "H_tt = 2f*N*I = 2 (got %f)", ev.Hessian[0]);
+}
+
+// pc/segmentation/regiongrowing/regiongrowing_test.go (two labelled clusters joined by a chain of another label)
+static void TestRegionGrowingSegment() {
+  pc::PointCloud pp;
+  pp.Stride = 16;
+  const int n = 30;
+  pp.Points = pp.Width = n;
+  pp.Data.assign((size_t)n * 16, 0);
+  for (int i = 0; i < n; i++) {
+    const float xyz[3] = {0.1f * i, 0, 0};
+    const uint32_t label = (i >= 10 && i < 20) ? 7u : 1u;  // 1 1 1 ... 7 7 7 ... 1 1 1
+    std::memcpy(&pp.Data[(size_t)i * 16], xyz, 12);
+    std::memcpy(&pp.Data[(size_t)i * 16 + 12], &label, 4);
+  }
+  storage::Index kdt(pc::view(pp));
+  segmentation::RegionGrowing rg(kdt, pp, 12);
+  auto a = rg.Segment(Vec3{{0.0f, 0, 0}}, 0.15f);
+  EXPECT(a.size() == 10, "first label-1 run: expected 10 points, got %zu", a.size());
+  for (int64_t id : a) EXPECT(id < 10, "index %lld leaked across the label-7 run", (long long)id);
+  auto b = rg.Segment(Vec3{{1.5f, 0, 0}}, 0.15f);
+  EXPECT(b.size() == 10 && b[0] == 15, "label-7 run: expected 10 points starting at the seed's nearest, got %zu", b.size());
+  EXPECT(rg.Segment(Vec3{{10, 10, 10}}, 0.15f).empty(), "no neighbour -> empty result");
+}
+
+// pc/io_test.go:16-255 ("Binary" vector written by Marshal: Unmarshal -> Marshal reproduces it; error classes)
+static void TestUnmarshalMarshal() {
+  const char* head =
+      "VERSION 0.7\nFIELDS x y z label\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\nWIDTH 2\nHEIGHT 1\n"
+      "VIEWPOINT 0.0000 0.0000 0.0000 1.0000 0.0000 0.0000 0.0000\nPOINTS 2\nDATA binary\n";
+  std::vector<uint8_t> pcd(head, head + std::strlen(head));
+  const float pts[2][3] = {{0.352f, -0.151f, -0.106f}, {-0.473f, 0.292f, -0.731f}};
+  for (int i = 0; i < 2; i++) {
+    const uint32_t label = (uint32_t)i + 3;
+    pcd.insert(pcd.end(), (const uint8_t*)pts[i], (const uint8_t*)pts[i] + 12);
+    pcd.insert(pcd.end(), (const uint8_t*)&label, (const uint8_t*)&label + 4);
+  }
+  pc::DeviceCloud dc = pc::Unmarshal(pcd);
+  pcg_cloud_header h = dc.Header();
+  EXPECT(h.points == 2 && h.n_fields == 4 && std::string(h.fields[3]) == "label" && h.width == 2, "header");
+  EXPECT(pc::Marshal(dc) == pcd, "Marshal(Unmarshal(x)) != x");
+  auto status_of = [](const char* text) {
+    try {
+      pc::Unmarshal(std::vector<uint8_t>(text, text + std::strlen(text)));
+    } catch (const Error& e) {
+      return (int)e.status();
+    }
+    return 0;
+  };
+  EXPECT(status_of("VERSION X") == PCG_E_PCD_SYNTAX, "ErrorVersion -> strconv.ErrSyntax");
+  EXPECT(status_of("WIDTH X") == PCG_E_PCD_SYNTAX, "ErrorWidth -> strconv.ErrSyntax");
+  EXPECT(status_of("VERSION 0.7\nFIELDS x\nSIZE 4\nTYPE F\nCOUNT 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary_compressed\n") ==
+             PCG_E_PCD_EOF, "ErrorBinaryCompressedNCompressedEOF -> io.EOF");
+  // resident pipeline: VoxelGrid -> index -> Nearest
+  pc::DeviceCloud small = dc.VoxelGrid(Vec3{{10, 10, 10}}, {{4, 4, 4}});
+  EXPECT(small.Header().points == 1 && small.Header().width == 1 && small.Header().height == 1, "one voxel");
+  storage::Index idx(dc.BuildIndex());
+  EXPECT(idx.Nearest(Vec3{{0.35f, -0.15f, -0.1f}}, 1.0f).ID == 0, "index over the resident cloud");
+}
+
 int main() {
   if (pcg_device_count() < 1) {
     std::printf("no CUDA device: %s\n", pcg_last_error());
@@ -228,6 +336,10 @@ int main() {
   TestNearestPointCorresponder();
   TestPointToPointEvaluator();
   TestPointToPointICPGradient();
+  TestKDtree_DeletePoint();
+  TestPointToPointICPGradient_MinDistSq();
+  TestRegionGrowingSegment();
+  TestUnmarshalMarshal();
   std::printf(failures ? "FAILED (%d)\n" : "ok (%d failures)\n", failures);
   return failures ? 1 : 0;
 }

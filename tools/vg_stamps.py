@@ -15,6 +15,7 @@ for it in range(6):
     _lib.check(_lib.lib.pcg_voxelgrid_filter_dev(d.data_ptr(), len(pts), 12, off, lf, ck, 0, out.data_ptr(), C.byref(n), None))
     st = (C.c_ulonglong * 64)(); k = _lib.lib.pcg_debug_vg_stamps(st)
     t = np.array(st[:k], np.float64)
+    print("  last block ends", (st[63] - st[0]) / 1e3, "us after block 0 started; block 0 ended at", (st[k - 1] - st[0]) / 1e3)
     if it >= 2: acc = (t - t[0]) if acc is None else acc + (t - t[0])
 acc /= 4
 prev = 0.0
