@@ -392,6 +392,28 @@ pcg_status pcg_index_nearest_dev(pcg_index* idx, const void* d_q, int64_t nq, in
   return pcg_index_nearest_approx_dev(idx, d_q, nq, q_stride, q_xyz_off, max_range, 0.f, d_ids, d_dist_sq, stream);
 }
 
+// Large host batches are cut into slices that travel on a few streams: the upload of one slice, the
+// search of another and the download of a third overlap (two DMA engines + the SMs), so the call is bound
+// by the slower of PCIe and the kernel instead of their sum.  (Pageable caller memory still works; the
+// copies then serialise inside the driver.)
+constexpr int64_t kNearestSlice = 1 << 20;
+constexpr int kNearestStreams = 4;
+struct SliceStreams {
+  cudaStream_t s[kNearestStreams] = {nullptr, nullptr, nullptr, nullptr};
+  int device = -1;
+  ~SliceStreams() {
+    // the runtime may already be shutting down when thread-local storage is torn down: leak on purpose
+  }
+  void ensure(int dev) {
+    if (device == dev) return;
+    for (int i = 0; i < kNearestStreams; i++) {
+      if (s[i]) cudaStreamDestroy(s[i]);
+      PCG_CUDA(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    }
+    device = dev;
+  }
+};
+
 pcg_status pcg_index_nearest_approx(pcg_index* idx, const void* q, int64_t nq, int64_t q_stride,
                                     const int64_t q_xyz_off[3], float max_range, float min_dist_sq,
                                     pcg_neighbor* out) {
@@ -399,14 +421,36 @@ pcg_status pcg_index_nearest_approx(pcg_index* idx, const void* q, int64_t nq, i
     if (!idx) throw StatusError{PCG_E_INVALID_ARG, "null index"};
     if (nq && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
     if (!(min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
+    check_view_args(q, nq, q_stride, q_xyz_off);
     DeviceGuard g(idx->ix->device);
-    cudaStream_t s = cudaStreamPerThread;
-    StagedCloud c(q, nq, q_stride, q_xyz_off, s);
     if (nq == 0) return PCG_OK;
-    DevBuf<pcg_neighbor> d_out((size_t)nq, s);
-    nearest_device(*idx->ix, c.view, max_range, min_dist_sq, nullptr, nullptr, d_out.p, s);
-    PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)nq * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
-    PCG_CUDA(cudaStreamSynchronize(s));
+    if (nq < 2 * kNearestSlice) {
+      cudaStream_t s = cudaStreamPerThread;
+      StagedCloud c(q, nq, q_stride, q_xyz_off, s);
+      DevBuf<pcg_neighbor> d_out((size_t)nq, s);
+      nearest_device(*idx->ix, c.view, max_range, min_dist_sq, nullptr, nullptr, d_out.p, s);
+      PCG_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)nq * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+      PCG_CUDA(cudaStreamSynchronize(s));
+      return PCG_OK;
+    }
+    static thread_local SliceStreams streams;
+    streams.ensure(idx->ix->device);
+    const uint8_t* qb = (const uint8_t*)q;
+    try {
+      int k = 0;
+      for (int64_t b = 0; b < nq; b += kNearestSlice, k++) {
+        const int64_t m = std::min(kNearestSlice, nq - b);
+        cudaStream_t s = streams.s[k % kNearestStreams];
+        StagedCloud c(qb + b * q_stride, m, q_stride, q_xyz_off, s);  // stream-ordered: freed after the slice's work
+        DevBuf<pcg_neighbor> d_out((size_t)m, s);
+        nearest_device(*idx->ix, c.view, max_range, min_dist_sq, nullptr, nullptr, d_out.p, s);
+        PCG_CUDA(cudaMemcpyAsync(out + b, d_out.p, (size_t)m * sizeof(pcg_neighbor), cudaMemcpyDeviceToHost, s));
+      }
+    } catch (...) {  // nothing may still be writing into the caller's buffer when the error is reported
+      for (int i = 0; i < kNearestStreams; i++) cudaStreamSynchronize(streams.s[i]);
+      throw;
+    }
+    for (int i = 0; i < kNearestStreams; i++) PCG_CUDA(cudaStreamSynchronize(streams.s[i]));
     return PCG_OK;
   });
 }
