@@ -338,46 +338,33 @@ __global__ void __launch_bounds__(256)
   side[id] = i >= m ? 1 : 0;
 }
 
-// Level step 2 (only while a segment spans several tiles): left-going points of every tile, per list.
-__global__ void __launch_bounds__(256)
-    kd_tile_count_kernel(KdLists L, uint32_t n, int log2S, const uint8_t* __restrict__ seg_axis,
-                         const uint8_t* __restrict__ side, uint32_t tiles, uint32_t* __restrict__ tile_left) {
-  __shared__ uint32_t s_cnt[3];
-  if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t base = blockIdx.x * kKdTile + threadIdx.x * kKdTileItems;
-  const int axis = base < n ? seg_axis[base >> log2S] : 3;
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    uint32_t cnt = 0;
-    if (axis != 3 && axis != c) {
-#pragma unroll
-      for (int j = 0; j < kKdTileItems; j++)
-        if (base + j < n) cnt += side[L.in[c][base + j]] ? 0u : 1u;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt[c], cnt);
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) tile_left[threadIdx.x * tiles + blockIdx.x] = s_cnt[threadIdx.x];
-}
-
-// Level step 3: stable partition of the two lists that are not the split axis, inside every segment.
+// Level step 2: stable partition of the two lists that are not the split axis, inside every segment.
+// While a segment spans several tiles the left-counts of its earlier tiles arrive through a decoupled
+// look-back (tiles take their ids from a counter, so predecessors are always running; one packed word per
+// tile and list: state | level | count); the chain restarts at every segment's first tile.
+constexpr unsigned long long kKdAggregate = 1ull << 62, kKdInclusive = 2ull << 62;
 __global__ void __launch_bounds__(256)
     kd_scatter_kernel(KdLists L, uint32_t n, int log2S, const uint8_t* __restrict__ seg_axis,
-                      const uint8_t* __restrict__ side, uint32_t tiles, const uint32_t* __restrict__ tile_left) {
+                      const uint8_t* __restrict__ side, uint32_t tiles, uint32_t* __restrict__ tile_counter,
+                      unsigned long long* __restrict__ status) {
   __shared__ uint32_t s_scan[rsort::kWarps];
   __shared__ uint32_t s_excl[256];
   __shared__ uint32_t s_prefix;
+  __shared__ uint32_t s_tile;
   const uint32_t tid = threadIdx.x;
   const uint32_t S = 1u << log2S;
-  const uint32_t tile_base = blockIdx.x * kKdTile;
+  const bool big = S > (uint32_t)kKdTile;  // the segment spans S / kKdTile whole tiles: one segment per CTA
+  if (big) {
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+  }
+  const uint32_t tile = big ? s_tile : blockIdx.x;
+  const uint32_t tile_base = tile * kKdTile;
   const uint32_t base = tile_base + tid * kKdTileItems;
   const bool any = base < n;
-  const bool big = S > (uint32_t)kKdTile;  // the segment spans S / kKdTile whole tiles: one segment per CTA
   const uint32_t s = (big ? tile_base : base) >> log2S, b = s << log2S, m = b + (S >> 1);
   const int axis = any ? seg_axis[s] : 3;
+  const int cta_axis = big ? (int)seg_axis[s] : 3;  // uniform across the CTA when big (tile_base < n always)
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
     uint32_t id[kKdTileItems];
@@ -394,18 +381,42 @@ __global__ void __launch_bounds__(256)
         }
       }
     }
-    const uint32_t excl = rsort::block_excl_scan_256(cnt, s_scan, nullptr);
+    uint32_t total = 0;
+    const uint32_t excl = rsort::block_excl_scan_256(cnt, s_scan, &total);
     uint32_t seg_excl;  // lefts of this segment that precede this thread's items
     if (big) {
-      // whole CTA inside one segment: add the lefts of the segment's earlier tiles
-      const uint32_t first_tile = b / kKdTile;
-      uint32_t p = 0;
-      for (uint32_t t = first_tile + tid; t < blockIdx.x; t += 256) p += tile_left[c * tiles + t];
+      if (tid < 32) {  // warp 0 looks back 32 predecessor tiles per round
+        uint32_t prefix = 0;
+        if (cta_axis != 3 && cta_axis != c) {
+          volatile unsigned long long* st = status + (size_t)c * tiles;
+          const unsigned long long tag = (unsigned long long)(uint32_t)log2S << 48;
+          const uint32_t first_tile = b / kKdTile;
+          if (tile == first_tile) {
+            if (tid == 0) st[tile] = kKdInclusive | tag | total;
+          } else {
+            if (tid == 0) st[tile] = kKdAggregate | tag | total;
+            long long look = (long long)tile - 1;
+            for (;;) {
+              const long long idx = look - (long long)tid;
+              const bool before = idx < (long long)first_tile;  // ahead of the segment: contributes nothing, ends the walk
+              unsigned long long w = 0;
+              if (!before) w = st[idx];
+              const bool ready = before || ((w >> 62) != 0 && ((w >> 48) & 0xffu) == (unsigned long long)(uint32_t)log2S);
+              if (!__all_sync(0xffffffffu, ready)) continue;  // someone has not published at this level yet
+              const uint32_t stop = __ballot_sync(0xffffffffu, before || (w >> 62) == 2);
+              const int last = stop ? __ffs(stop) - 1 : 31;  // lanes 0..last contribute
+              uint32_t v = (!before && (int)tid <= last) ? (uint32_t)w : 0u;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-      if (tid == 0) s_prefix = 0;
-      __syncthreads();
-      if ((tid & 31) == 0 && p) atomicAdd(&s_prefix, p);
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              prefix += v;
+              if (stop) break;
+              look -= 32;
+            }
+            if (tid == 0) st[tile] = kKdInclusive | tag | (unsigned long long)(prefix + total);
+          }
+        }
+        if (tid == 0) s_prefix = prefix;
+      }
       __syncthreads();
       seg_excl = s_prefix + excl;
     } else {
@@ -430,7 +441,6 @@ __global__ void __launch_bounds__(256)
     __syncthreads();  // s_excl / s_prefix are reused by the next list
   }
 }
-
 
 // Levels whose segments fit one tile: the whole tail of the build in shared memory, one CTA per
 // kKdLocal slots.  Points get tile-local ids (their position in the tile's x-list), so the three
@@ -540,10 +550,11 @@ __global__ void __launch_bounds__(256)
 // Writes the KD order into lists[.]; returns the buffer that holds it (a permutation of 0..n-1).
 static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t P, DevBuf<uint32_t> (&lists)[6],
                                        cudaStream_t stream) {
-  DevBuf<uint32_t> keys[3], key_alt(n, stream);
+  DevBuf<uint32_t> keys[3], keys_alt[3];
   rsort::Sorter<uint32_t> sorter[3];
   for (int c = 0; c < 3; c++) {
     keys[c].alloc(n, stream);
+    keys_alt[c].alloc(n, stream);
     sorter[c].prepare(n, 0, 32, stream);
   }
   for (int c = 0; c < 6; c++) lists[c].alloc(n, stream);
@@ -552,13 +563,22 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
              sorter[1].hist(), sorter[2].hist(), sorter[0].passes);
   uint32_t* cur[3];
   uint32_t* alt[3];
-  for (int c = 0; c < 3; c++) {
-    uint32_t* kk[2] = {keys[c].p, key_alt.p};
-    uint32_t* vv[2] = {lists[c].p, lists[3 + c].p};
+  {
+    // the three axis sorts share every launch (blockIdx.y = axis)
+    uint32_t* kk[3][2];
+    uint32_t* vv[3][2];
+    for (int c = 0; c < 3; c++) {
+      kk[c][0] = keys[c].p;
+      kk[c][1] = keys_alt[c].p;
+      vv[c][0] = lists[c].p;
+      vv[c][1] = lists[3 + c].p;
+    }
     int res = 0;
-    sorter[c].run(kk, vv, /*identity_vals=*/true, /*keep_keys=*/false, stream, &res);
-    cur[c] = vv[res];
-    alt[c] = vv[res ^ 1];
+    rsort::run_batched<uint32_t>(sorter, 3, kk, vv, /*identity_vals=*/true, /*keep_keys=*/false, stream, &res);
+    for (int c = 0; c < 3; c++) {
+      cur[c] = vv[c][res];
+      alt[c] = vv[c][res ^ 1];
+    }
   }
   const uint32_t M = P * (uint32_t)kLeaf;  // slots of the complete tree
   if (P <= 1) return cur[0];
@@ -568,7 +588,9 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
   while ((1 << log2L) < kLeaf) log2L++;
   const uint32_t tiles = (uint32_t)div_up(n, kKdTile);
   DevBuf<uint8_t> seg_axis((size_t)P, stream), side(n, stream);
-  DevBuf<uint32_t> tile_left((size_t)3 * tiles, stream);
+  DevBuf<unsigned long long> status((size_t)3 * tiles + 32, stream);  // look-back words + one tile counter per level
+  PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
+  uint32_t* counters = reinterpret_cast<uint32_t*>(status.p + (size_t)3 * tiles);
   int log2S = log2M;
   for (; log2S > log2L && log2S > kKdLocalLog2; log2S--) {  // segments that span several tiles
     KdLists L;
@@ -577,8 +599,8 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
       L.out[c] = alt[c];
     }
     PCG_LAUNCH(kd_side_kernel, div_up(n, 256), 256, 0, stream, v, L, n, log2S, seg_axis.p, side.p);
-    PCG_LAUNCH(kd_tile_count_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, tile_left.p);
-    PCG_LAUNCH(kd_scatter_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, tile_left.p);
+    PCG_LAUNCH(kd_scatter_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, counters + log2S,
+               status.p);
     for (int c = 0; c < 3; c++) std::swap(cur[c], alt[c]);
   }
   if (log2S > log2L) {  // the rest (children of the last level are single leaves) in shared memory

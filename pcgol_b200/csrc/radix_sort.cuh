@@ -105,12 +105,30 @@ struct TileSmem {
   static constexpr size_t kBytes = (size_t)kTile * (sizeof(K) + sizeof(uint32_t));
 };
 
+// Up to kMaxBatch independent sorts of the same length advance together: blockIdx.y selects the sort.  (Three
+// axis sorts of the KD build in one launch per digit keep the machine full where one 1M-key pass does not.)
+constexpr int kMaxBatch = 3;
+template <typename K>
+struct PassArgs {
+  const K* keys_in[kMaxBatch];
+  K* keys_out[kMaxBatch];
+  const uint32_t* vals_in[kMaxBatch];
+  uint32_t* vals_out[kMaxBatch];
+  const uint32_t* hist[kMaxBatch];
+  uint32_t* tile_counter[kMaxBatch];
+  unsigned long long* status[kMaxBatch];
+};
+
 template <typename K, int IPT>
 __global__ void __launch_bounds__(kThreads)
-    onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out, const uint32_t* __restrict__ vals_in,
-                    uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t epoch,
-                    const uint32_t* __restrict__ hist, uint32_t* __restrict__ tile_counter,
-                    unsigned long long* __restrict__ status) {
+    onesweep_kernel(PassArgs<K> A, uint32_t n, int shift, uint32_t epoch) {
+  const K* __restrict__ keys_in = A.keys_in[blockIdx.y];
+  K* __restrict__ keys_out = A.keys_out[blockIdx.y];
+  const uint32_t* __restrict__ vals_in = A.vals_in[blockIdx.y];
+  uint32_t* __restrict__ vals_out = A.vals_out[blockIdx.y];
+  const uint32_t* __restrict__ hist = A.hist[blockIdx.y];
+  uint32_t* __restrict__ tile_counter = A.tile_counter[blockIdx.y];
+  unsigned long long* __restrict__ status = A.status[blockIdx.y];
   constexpr int kTile = kThreads * IPT;
   __shared__ uint32_t s_warp_hist[kWarps][kRadix];
   __shared__ uint32_t s_digit_start[kRadix];
@@ -224,9 +242,8 @@ inline int num_passes(int begin_bit, int end_bit) {
 }
 
 template <typename K, int IPT>
-inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, int shift,
-                        uint32_t epoch, const uint32_t* hist, uint32_t* counter, unsigned long long* status,
-                        cudaStream_t stream) {
+inline void launch_pass_batch(const PassArgs<K>& args, int batch, uint32_t n, int shift, uint32_t epoch,
+                              cudaStream_t stream) {
   constexpr size_t smem = TileSmem<K, IPT>::kBytes;
   static std::atomic<uint64_t> configured{0};  // bit per device; the attribute is per device
   int dev = 0;
@@ -236,8 +253,23 @@ inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vo
     configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   uint32_t tiles = (n + TileSmem<K, IPT>::kTile - 1) / TileSmem<K, IPT>::kTile;
-  PCG_LAUNCH((onesweep_kernel<K, IPT>), tiles, kThreads, smem, stream, kin, kout, vin, vout, n, shift, epoch, hist,
-             counter, status);
+  PCG_LAUNCH((onesweep_kernel<K, IPT>), dim3(tiles, (unsigned)batch), kThreads, smem, stream, args, n, shift, epoch);
+}
+
+template <typename K, int IPT>
+inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, int shift,
+                        uint32_t epoch, const uint32_t* hist, uint32_t* counter, unsigned long long* status,
+                        cudaStream_t stream) {
+  PassArgs<K> a;
+  std::memset(&a, 0, sizeof(a));
+  a.keys_in[0] = kin;
+  a.keys_out[0] = kout;
+  a.vals_in[0] = vin;
+  a.vals_out[0] = vout;
+  a.hist[0] = hist;
+  a.tile_counter[0] = counter;
+  a.status[0] = status;
+  launch_pass_batch<K, IPT>(a, 1, n, shift, epoch, stream);
 }
 
 inline int pick_ipt(uint32_t n) {
@@ -319,6 +351,42 @@ struct Sorter {
     *result = cur;
   }
 };
+
+// `batch` prepared sorters of identical length and bit range advance pass by pass in shared launches.
+// keys[b][2] / vals[b][2] as in Sorter::run; every sort ends on the same side (*result).
+template <typename K>
+void run_batched(Sorter<K>* sorters, int batch, K* (*keys)[2], uint32_t* (*vals)[2], bool identity_vals,
+                 bool keep_keys, cudaStream_t stream, int* result) {
+  *result = 0;
+  if (batch <= 0 || sorters[0].n == 0) return;
+  if (batch > kMaxBatch) throw StatusError{PCG_E_INVALID_ARG, "radix sort: batch too large"};
+  const Sorter<K>& s0 = sorters[0];
+  int cur = 0;
+  for (int p = 0; p < s0.passes; p++) {
+    const bool last = p == s0.passes - 1;
+    PassArgs<K> a;
+    std::memset(&a, 0, sizeof(a));
+    for (int b = 0; b < batch; b++) {
+      a.keys_in[b] = keys[b][cur];
+      a.keys_out[b] = (last && !keep_keys) ? nullptr : keys[b][cur ^ 1];
+      a.vals_in[b] = (p == 0 && identity_vals) ? nullptr : vals[b][cur];
+      a.vals_out[b] = vals[b][cur ^ 1];
+      a.hist[b] = sorters[b].head.p + (size_t)p * kRadix;
+      a.tile_counter[b] = sorters[b].head.p + sorters[b].hist_words + p;
+      a.status[b] = sorters[b].status.p;
+    }
+    const int shift = s0.begin_bit + p * kRadixBits;
+    const uint32_t epoch = (uint32_t)(p + 1);
+    if (s0.ipt == 4)
+      launch_pass_batch<K, 4>(a, batch, s0.n, shift, epoch, stream);
+    else if (s0.ipt == 8)
+      launch_pass_batch<K, 8>(a, batch, s0.n, shift, epoch, stream);
+    else
+      launch_pass_batch<K, 16>(a, batch, s0.n, shift, epoch, stream);
+    cur ^= 1;
+  }
+  *result = cur;
+}
 
 template <typename K>
 void sort_pairs(K* keys[2], uint32_t* vals[2], uint32_t n, int begin_bit, int end_bit, bool identity_vals,
