@@ -358,6 +358,20 @@ pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n,
  * 0..n-1 in d_order): coherent warps for repeated searches over the same cloud. */
 pcg_status pcg_query_order_dev(pcg_index* idx, const void* d_q, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                uint32_t* d_order, void* stream);
+/* The same sharded Fit with the loop resident on the device: no host round trip per iteration.  Every rank creates
+ * a shard over its slice of the target, then per iteration enqueues pcg_icp_shard_partial (16 float64 into
+ * d_partial16), all-reduces that buffer in stream order (NCCL) and enqueues pcg_icp_shard_finish, which applies the
+ * tail of Evaluate + gradientDescentUpdater.Update to the device-resident state; once converged / failed the
+ * remaining calls fall through.  pcg_icp_shard_result synchronises `stream` and returns the transform, Stat and
+ * whether the loop has ended (status PCG_E_NOT_ENOUGH_PAIRS like Fit).  Float64 sums, gradient-descent updater. */
+typedef struct pcg_icp_shard pcg_icp_shard;
+pcg_status pcg_icp_shard_new(pcg_index* base, const void* d_target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                             const pcg_icp_params* params, void* stream, pcg_icp_shard** out);
+void pcg_icp_shard_free(pcg_icp_shard* sh);
+pcg_status pcg_icp_shard_partial(pcg_icp_shard* sh, double* d_partial16, void* stream);
+pcg_status pcg_icp_shard_finish(pcg_icp_shard* sh, const double* d_reduced16, void* stream);
+pcg_status pcg_icp_shard_result(pcg_icp_shard* sh, float trans[16], pcg_icp_stat* stat, int32_t* done, void* stream);
+
 /* Host-side tail of Evaluate (evaluator.go:156-186) + Update (updater.go:44-71) from
  * all-reduced sums.  *iter is the updater's i; returns converged in *converged. */
 pcg_status pcg_icp_finish(const double partial16[16], const pcg_icp_params* params, int32_t* iter, float trans[16],

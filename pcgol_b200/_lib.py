@@ -153,6 +153,11 @@ _sigs = {
     "pcg_icp_fit_pairs_dev": (_i32, [_i32, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(IcpParams), _i32, _vp, _vp, _vp,
                                      _vp]),
     "pcg_icp_partial_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _i32, _vp, _vp, _vp]),
+    "pcg_icp_shard_new": (_i32, [_vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(_vp)]),
+    "pcg_icp_shard_free": (None, [_vp]),
+    "pcg_icp_shard_partial": (_i32, [_vp, _vp, _vp]),
+    "pcg_icp_shard_finish": (_i32, [_vp, _vp, _vp]),
+    "pcg_icp_shard_result": (_i32, [_vp, _vp, C.POINTER(IcpStat), C.POINTER(_i32), _vp]),
     "pcg_query_order_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "pcg_icp_finish": (_i32, [_vp, C.POINTER(IcpParams), C.POINTER(_i32), _vp, C.POINTER(Evaluated),
                               C.POINTER(_i32)]),

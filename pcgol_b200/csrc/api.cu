@@ -83,6 +83,12 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
                            pcg_evaluated* ev_out, int32_t* converged);
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream);
+struct IcpShard;
+IcpShard* icp_shard_new(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, cudaStream_t stream);
+void icp_shard_free(IcpShard* sh);
+void icp_shard_partial(IcpShard& sh, double* d_partial16, cudaStream_t stream);
+void icp_shard_finish(IcpShard& sh, const double* d_reduced16, cudaStream_t stream);
+pcg_status icp_shard_result(IcpShard& sh, float trans[16], pcg_icp_stat* stat, int32_t* done, cudaStream_t stream);
 struct CloudHeader;
 struct Cloud;
 void cloud_free(Cloud* c);
@@ -165,6 +171,10 @@ using namespace pcg;
 
 struct pcg_range_result {
   RangeResult r;
+};
+struct pcg_icp_shard {
+  IcpShard* sh;
+  int device;
 };
 struct pcg_region_growing {
   RegionGrowing* rg;
@@ -788,6 +798,54 @@ pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n,
     icp_partial_device(*base->ix, make_view(d_target, n, stride, xyz_off), max_dist, trans, first != 0, d_visit_order,
                        d_partial16, (cudaStream_t)stream);
     return PCG_OK;
+  });
+}
+
+pcg_status pcg_icp_shard_new(pcg_index* base, const void* d_target, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                             const pcg_icp_params* params, void* stream, pcg_icp_shard** out) {
+  return guarded([&]() -> pcg_status {
+    if (!base || !params || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *out = nullptr;
+    check_view_args(d_target, n, stride, xyz_off);
+    DeviceGuard g(base->ix->device);
+    IcpShard* sh = icp_shard_new(*base->ix, make_view(d_target, n, stride, xyz_off), *params, (cudaStream_t)stream);
+    *out = new pcg_icp_shard{sh, base->ix->device};
+    return PCG_OK;
+  });
+}
+void pcg_icp_shard_free(pcg_icp_shard* sh) {
+  if (!sh) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(sh->device);
+  cudaDeviceSynchronize();  // the stream-ordered workspace may still be in use
+  icp_shard_free(sh->sh);
+  if (prev >= 0) cudaSetDevice(prev);
+  delete sh;
+}
+pcg_status pcg_icp_shard_partial(pcg_icp_shard* sh, double* d_partial16, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!sh || !d_partial16) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(sh->device);
+    icp_shard_partial(*sh->sh, d_partial16, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+pcg_status pcg_icp_shard_finish(pcg_icp_shard* sh, const double* d_reduced16, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!sh || !d_reduced16) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(sh->device);
+    icp_shard_finish(*sh->sh, d_reduced16, (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+pcg_status pcg_icp_shard_result(pcg_icp_shard* sh, float trans[16], pcg_icp_stat* stat, int32_t* done, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!sh || !trans) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    DeviceGuard g(sh->device);
+    const pcg_status rc = icp_shard_result(*sh->sh, trans, stat, done, (cudaStream_t)stream);
+    if (rc == PCG_E_NOT_ENOUGH_PAIRS) set_error("not enough correspondence pairs");
+    return rc;
   });
 }
 

@@ -579,6 +579,7 @@ static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int
 __global__ void __launch_bounds__(kFinishThreads)
     icp_partial_reduce_kernel(IcpState* __restrict__ st, const double* __restrict__ partials, int nblocks,
                               double* __restrict__ out16) {
+  if (st->done) return;  // device-resident sharded loop: nothing was accumulated
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double s = 0.0;
   for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * kTerms + warp];
@@ -587,8 +588,18 @@ __global__ void __launch_bounds__(kFinishThreads)
   if (lane == 0) out16[warp] = s;
   if (tid == 0) {
     out16[9] = (double)st->pair_counter;
+    st->pair_counter = 0;  // the next iteration of a resident loop starts from zero
     for (int k = 10; k < 16; k++) out16[k] = 0.0;
   }
+}
+
+// Device-resident sharded loop: tail of Evaluate + Update from the all-reduced sums, identical on every rank.
+__global__ void icp_shard_finish_kernel(IcpState* __restrict__ st, const double* __restrict__ reduced16) {
+  if (threadIdx.x != 0 || st->done) return;
+  float sum9[kTerms];
+  for (int k = 0; k < kTerms; k++) sum9[k] = (float)reduced16[k];
+  st->pair_counter = (unsigned int)(long long)reduced16[9];  // icp_finalize takes the pair count from here
+  icp_finalize(st, sum9);
 }
 
 struct IcpWork {
@@ -809,6 +820,59 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
   launch_terms<PCG_ICP_FAST>(base, tgt, d_order, mdsq, 0.f, false, w.st.p, w.terms.p, w.n_pad, w.partials.p, nullptr,
                              w.nblocks, 0, stream);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
+}
+
+// ---- one large ICP, target sharded over GPUs, loop resident on the device -------------------------------
+// Per iteration and rank: terms kernel on the rank's slice (transform read from the device state) -> 16 float64
+// -> all-reduce by the caller (NCCL, stream-ordered) -> finish kernel.  No host round trip inside the loop; every
+// rank applies the identical update, so the transforms stay bit-identical without a broadcast.
+struct IcpShard {
+  const Index* base = nullptr;
+  CloudView tgt;
+  pcg_icp_params prm;
+  IcpWork w;
+};
+
+IcpShard* icp_shard_new(const Index& base, const CloudView& tgt, const pcg_icp_params& prm_in, cudaStream_t stream) {
+  pcg_icp_params prm = prm_in;
+  check_icp_params(prm);
+  if (prm.updater != PCG_UPDATER_GRADIENT_DESCENT || (prm.mode & PCG_ICP_WITH_HESSIAN))
+    throw StatusError{PCG_E_INVALID_ARG, "the sharded loop exchanges the nine Evaluate sums only (gradient-descent updater)"};
+  prm.mode = PCG_ICP_FAST;  // a sequential float32 sum has one order: it cannot be sharded
+  IcpShard* sh = new IcpShard();
+  try {
+    sh->base = &base;
+    sh->tgt = tgt;
+    sh->prm = prm;
+    icp_prepare(base, tgt, prm, false, sh->w, stream);
+  } catch (...) {
+    delete sh;
+    throw;
+  }
+  return sh;
+}
+
+void icp_shard_free(IcpShard* sh) { delete sh; }
+
+void icp_shard_partial(IcpShard& sh, double* d_partial16, cudaStream_t stream) {
+  const float mdsq = sh.prm.max_dist * sh.prm.max_dist;
+  launch_terms<PCG_ICP_FAST>(*sh.base, sh.tgt, sh.w.perm.p, mdsq, sh.prm.min_dist_sq, false, sh.w.st.p, sh.w.terms.p,
+                             sh.w.n_pad, sh.w.partials.p, nullptr, sh.w.nblocks, 0, stream);
+  PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, sh.w.st.p, sh.w.partials.p, sh.w.nblocks,
+             d_partial16);
+}
+
+void icp_shard_finish(IcpShard& sh, const double* d_reduced16, cudaStream_t stream) {
+  PCG_LAUNCH(icp_shard_finish_kernel, 1, 32, 0, stream, sh.w.st.p, d_reduced16);
+}
+
+pcg_status icp_shard_result(IcpShard& sh, float trans[16], pcg_icp_stat* stat, int32_t* done, cudaStream_t stream) {
+  IcpState h;
+  PCG_CUDA(cudaMemcpyAsync(&h, sh.w.st.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  state_to_outputs(h, trans, stat);
+  if (done) *done = h.done;
+  return (pcg_status)h.status;
 }
 
 // Tail of Evaluate + Update on the host from all-reduced sums (see pcg_icp_finish).

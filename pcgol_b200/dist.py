@@ -85,3 +85,40 @@ def make_gpu_partial(index, d_target_ptr: int, n: int, max_dist: float, stream: 
         return out
 
     return partial
+
+
+def sharded_icp_fit_device(index, d_target_ptr: int, n: int, params: _lib.IcpParams, group=None, stream: int = 0,
+                           stride: int = 12, off=(0, 4, 8), poll_every: int = 5):
+    """The same Fit with the loop resident on the device (pcg_icp_shard_*): per iteration the rank's slice is
+    reduced to 16 float64 on the GPU, all-reduced in stream order (NCCL over NVLink) and the tail of Evaluate +
+    Update runs on the device - no host round trip inside the loop.  `stream` must be torch's current stream (the
+    collective is ordered against it).  The end of the loop is polled every `poll_every` iterations (0 = never:
+    all MaxIteration iterations are enqueued; finished ones fall through).
+    Returns (status, trans16, IcpStat); identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    offs = (C.c_int64 * 3)(*off)
+    sh = C.c_void_p()
+    _lib.check(_lib.lib.pcg_icp_shard_new(index._h, d_target_ptr, n, stride, offs, C.byref(params), stream, C.byref(sh)))
+    try:
+        buf = torch.zeros(16, dtype=torch.float64, device="cuda")
+        max_iter = params.max_iteration or 20  # updater.go:31-33
+        trans = np.zeros(16, np.float32)
+        stat = _lib.IcpStat()
+        done = C.c_int32(0)
+        status = _lib.OK
+        collective = dist.is_available() and dist.is_initialized()
+        for it in range(max_iter):
+            _lib.check(_lib.lib.pcg_icp_shard_partial(sh, buf.data_ptr(), stream))
+            if collective:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+            _lib.check(_lib.lib.pcg_icp_shard_finish(sh, buf.data_ptr(), stream))
+            if poll_every and (it + 1) % poll_every == 0 and it + 1 < max_iter:
+                status = _lib.lib.pcg_icp_shard_result(sh, trans.ctypes.data, C.byref(stat), C.byref(done), stream)
+                if done.value:
+                    return status, trans, stat
+        status = _lib.lib.pcg_icp_shard_result(sh, trans.ctypes.data, C.byref(stat), C.byref(done), stream)
+        return status, trans, stat
+    finally:
+        _lib.lib.pcg_icp_shard_free(sh)

@@ -26,6 +26,17 @@ def test_sharded_icp_single_rank_matches_fast_fit():
     # same float64 partial sums folded in a different order -> identical after rounding to float32,
     # up to rare 1-ulp flips amplified over the iterations
     np.testing.assert_allclose(trans, ftrans, rtol=0, atol=1e-5)
+    # device-resident loop, one rank: the same reduction order as the host-driven loop -> the same bits
+    stream = torch.cuda.current_stream().cuda_stream
+    for poll in (0, 5):
+        rstatus, rtrans, rstat = pdist.sharded_icp_fit_device(idx, d_t.data_ptr(), len(target), p, stream=stream,
+                                                              poll_every=poll)
+        assert rstatus == 0 and rstat.num_iteration == iters
+        assert rtrans.tobytes() == trans.tobytes()
+    # ErrNotEnoughPairs travels through the resident loop like through Fit (icp.go:51-53)
+    far = torch.from_numpy((target + np.float32(500.0)).astype(np.float32)).cuda()
+    rstatus, rtrans, rstat = pdist.sharded_icp_fit_device(idx, far.data_ptr(), len(target), p, stream=stream)
+    assert rstatus == pg._lib.E_NOT_ENOUGH_PAIRS and rstat.num_iteration == 1
 
 
 def _free_port():
@@ -55,6 +66,11 @@ def _worker(rank, world, port, q):
         icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
         status, trans, ev, iters = pdist.sharded_icp_fit(
             pdist.make_gpu_partial(idx, d_t.data_ptr(), hi - lo, 1.0), icp.params())
+        # the same Fit with the loop resident on the device (no host round trip per iteration)
+        stream = torch.cuda.current_stream().cuda_stream
+        rstatus, rtrans, rstat = pdist.sharded_icp_fit_device(idx, d_t.data_ptr(), hi - lo, icp.params(), stream=stream)
+        assert rstatus == status and rstat.num_iteration == iters
+        assert rtrans.tobytes() == trans.tobytes(), "resident loop differs from the host-driven loop"
         # query sharding: disjoint slices of the same queries, index replicated, no collective
         q_all = synth.nn_queries(base, 50000, seed=5)
         qlo, qhi = pdist.shard_bounds(len(q_all), rank, world)
