@@ -331,14 +331,16 @@ constexpr int kReplayChunk = 256;
 constexpr int kReplayThreads = 512;
 constexpr int kReplayBatch = 256;  // chunk summaries staged in shared memory per round of the walk
 
-// Summary of one chunk as the walk consumes it.  Variant v = (accumulator negative ? 2 : 0) | parity
-// of its integer mantissa M (signed, 2^23 <= |M| < 2^24): the chunk is one exact integer add iff the
-// accumulator's exponent is `exp` and lo[v] <= M <= hi[v]; then M += tot[v].
+// Summary of one chunk as the walk consumes it, in the float domain.  p = parity of the accumulator's integer
+// mantissa M (acc = M * ulp, 2^23 <= |M| < 2^24).  The chunk is one exact add iff acc lies in [lo_pos[p], hi_pos[p]]
+// (positive accumulator) or in [lo_neg[p], hi_neg[p]] (negative): the interval is the set of accumulators of the
+// guessed binade that every running prefix keeps strictly inside it.  Then acc += t[p], t[p] = (integer total) *
+// ulp: both operands and the result are multiples of ulp below 2^24 * ulp, so the float addition is exact.
+// Unusable summaries hold empty intervals (lo = +inf, hi = -inf).
 struct __align__(16) ReplayChunk {
-  int lo[4], hi[4], tot[4];
-  int exp;    // binade of the guessed accumulator (999 when the summary is unusable)
-  float ulp;  // 2^(exp-23)
-  int pad_[2];
+  float t[2];
+  float lo_pos[2], hi_pos[2], lo_neg[2], hi_neg[2];
+  float pad_[2];
 };
 
 // Parity automaton of a run of elements: for start parity p, the integer increment, the parity
@@ -454,27 +456,26 @@ __global__ void __launch_bounds__(256)
   const bool all_regular = __all_sync(0xffffffffu, regular);
   if (lane == 0) {
     ReplayChunk rc;
-    const long long kLo = 1ll << 23, kHi = 1ll << 24, kClamp = 1ll << 30;
+    const long long kLo = 1ll << 23, kHi = 1ll << 24;
+    const float inf = __int_as_float(0x7f800000);
+    const bool usable = all_regular && e <= 100;  // 2^24 * ulp must stay finite
+    const float ulp = usable ? __uint_as_float((uint32_t)(e - 23 + 127) << 23) : 0.f;
 #pragma unroll
     for (int p = 0; p < 2; p++) {
       // every running value M + prefix must stay strictly inside the binade, with one unit of margin
       // (the pre-rounded terms are off by at most half a unit): positive M in [2^23+1, 2^24-1] - prefix, ...
-      long long lo_pos = kLo + 1 - m.mn[p], hi_pos = kHi - 1 - m.mx[p];
-      long long lo_neg = -kHi + 1 - m.mn[p], hi_neg = -kLo - 1 - m.mx[p];
-      lo_pos = max(-kClamp, min(kClamp, lo_pos));
-      hi_pos = max(-kClamp, min(kClamp, hi_pos));
-      lo_neg = max(-kClamp, min(kClamp, lo_neg));
-      hi_neg = max(-kClamp, min(kClamp, hi_neg));
-      const long long t = max(-kClamp, min(kClamp, m.off[p]));
-      rc.lo[p] = (int)lo_pos;
-      rc.hi[p] = (int)hi_pos;
-      rc.lo[2 + p] = (int)lo_neg;
-      rc.hi[2 + p] = (int)hi_neg;
-      rc.tot[p] = rc.tot[2 + p] = (int)t;
+      long long lo_pos = max(kLo + 1 - m.mn[p], kLo), hi_pos = min(kHi - 1 - m.mx[p], kHi - 1);
+      long long lo_neg = max(-kHi + 1 - m.mn[p], -(kHi - 1)), hi_neg = min(-kLo - 1 - m.mx[p], -kLo);
+      const bool tot_ok = m.off[p] > -kHi && m.off[p] < kHi;
+      const bool pos_ok = usable && tot_ok && lo_pos <= hi_pos, neg_ok = usable && tot_ok && lo_neg <= hi_neg;
+      // |integers| < 2^24 times a power of two: exact
+      rc.t[p] = (usable && tot_ok) ? __fmul_rn((float)m.off[p], ulp) : 0.f;
+      rc.lo_pos[p] = pos_ok ? __fmul_rn((float)lo_pos, ulp) : inf;
+      rc.hi_pos[p] = pos_ok ? __fmul_rn((float)hi_pos, ulp) : -inf;
+      rc.lo_neg[p] = neg_ok ? __fmul_rn((float)lo_neg, ulp) : inf;
+      rc.hi_neg[p] = neg_ok ? __fmul_rn((float)hi_neg, ulp) : -inf;
     }
-    rc.exp = all_regular ? e : 999;
-    rc.ulp = all_regular ? __uint_as_float((uint32_t)(e - 23 + 127) << 23) : 0.f;
-    rc.pad_[0] = rc.pad_[1] = 0;
+    rc.pad_[0] = rc.pad_[1] = 0.f;
     chunks[w] = rc;
   }
 }
@@ -505,43 +506,84 @@ __global__ void __launch_bounds__(kReplayThreads)
     }
     __syncthreads();
     if (warp == 0) {
-      ReplayChunk nxt = s_chunks[0];
-      for (int ci = 0; ci < batch; ci++) {
-        // the next summary is fetched before the (accumulator-dependent) work on this one: the walk's
-        // critical path is then a dozen dependent ALU operations per chunk, no shared-memory latency
-        const ReplayChunk rc = nxt;
-        nxt = s_chunks[min(ci + 1, batch - 1)];
-        const uint32_t bits = __float_as_uint(acc);
-        const int mag = (int)((bits & 0x7fffffu) | 0x800000u);  // acc = M * ulp, |M| = 2^23 | mantissa (exact)
-        const bool neg = (bits >> 31) != 0;
-        const int M = neg ? -mag : mag;
-        const bool odd = (mag & 1) != 0;
-        const int lo = neg ? (odd ? rc.lo[3] : rc.lo[2]) : (odd ? rc.lo[1] : rc.lo[0]);
-        const int hi = neg ? (odd ? rc.hi[3] : rc.hi[2]) : (odd ? rc.hi[1] : rc.hi[0]);
-        const int tot = odd ? rc.tot[1] : rc.tot[0];
-        const bool fast = ((int)((bits >> 23) & 0xff) - 127 == rc.exp) && M >= lo && M <= hi;
-        // |M + tot| < 2^24 -> exact in float; scaling by ulp (a normal power of two) is exact
-        if (fast) acc = __fmul_rn(__int2float_rn(M + tot), rc.ulp);
-        n_fast += fast ? 1u : 0u;
-        n_slow += fast ? 0u : 1u;
-        if (!fast) {  // replay the chunk like the reference
-          const int64_t base = (c0 + ci) * kReplayChunk;
+      // one step of the integer path: exact add if the accumulator lies in the chunk's safe interval
+      // (summaries travel as three 16-byte shared-memory loads into registers; selects, not indexed loads)
+      struct Rc {
+        float4 a, b, c;  // {t0,t1,lp0,lp1} {hp0,hp1,ln0,ln1} {hn0,hn1,-,-}
+      };
+      auto load_rc = [&](int i) {
+        const float4* q = reinterpret_cast<const float4*>(&s_chunks[i]);
+        Rc r;
+        r.a = q[0];
+        r.b = q[1];
+        r.c = q[2];
+        return r;
+      };
+      auto step = [](float a, const Rc rc, bool* fast) {
+        const bool p = (__float_as_uint(a) & 1u) != 0;
+        const float t = p ? rc.a.y : rc.a.x;
+        const float lp = p ? rc.a.w : rc.a.z, hp = p ? rc.b.y : rc.b.x;
+        const float ln = p ? rc.b.w : rc.b.z, hn = p ? rc.c.y : rc.c.x;
+        *fast = (a >= lp && a <= hp) || (a >= ln && a <= hn);
+        return __fadd_rn(a, t);
+      };
+      // the reference's own loop over one chunk (from shared memory)
+      auto replay = [&](float a, int64_t chunk) {
+        const int64_t base = chunk * kReplayChunk;
 #pragma unroll
-          for (int j = 0; j < kReplayChunk / 32; j++) {
-            const int64_t i = base + j * 32 + lane;
-            s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
-          }
-          __syncwarp();
-          const float4* b4 = reinterpret_cast<const float4*>(s_x);
+        for (int j = 0; j < kReplayChunk / 32; j++) {
+          const int64_t i = base + j * 32 + lane;
+          s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
+        }
+        __syncwarp();
+        const float4* b4 = reinterpret_cast<const float4*>(s_x);
 #pragma unroll 8
-          for (int j = 0; j < kReplayChunk / 4; j++) {
-            const float4 v = b4[j];
-            acc = __fadd_rn(acc, v.x);
-            acc = __fadd_rn(acc, v.y);
-            acc = __fadd_rn(acc, v.z);
-            acc = __fadd_rn(acc, v.w);
+        for (int j = 0; j < kReplayChunk / 4; j++) {
+          const float4 v = b4[j];
+          a = __fadd_rn(a, v.x);
+          a = __fadd_rn(a, v.y);
+          a = __fadd_rn(a, v.z);
+          a = __fadd_rn(a, v.w);
+        }
+        __syncwarp();
+        return a;
+      };
+      // Four chunks per round, speculatively: the data dependency between chunks is one select and one add; the
+      // interval tests run beside it and are looked at once per round.
+      int ci = 0;
+      for (; ci + 4 <= batch; ci += 4) {
+        const Rc r0 = load_rc(ci), r1 = load_rc(ci + 1), r2 = load_rc(ci + 2), r3 = load_rc(ci + 3);
+        bool f0, f1, f2, f3;
+        const float a1 = step(acc, r0, &f0);
+        const float a2 = step(a1, r1, &f1);
+        const float a3 = step(a2, r2, &f2);
+        const float a4 = step(a3, r3, &f3);
+        if (f0 && f1 && f2 && f3) {
+          acc = a4;
+          n_fast += 4;
+        } else {
+          for (int k = 0; k < 4; k++) {
+            bool f;
+            const float a = step(acc, load_rc(ci + k), &f);
+            if (f) {
+              acc = a;
+              n_fast++;
+            } else {
+              acc = replay(acc, c0 + ci + k);
+              n_slow++;
+            }
           }
-          __syncwarp();
+        }
+      }
+      for (; ci < batch; ci++) {
+        bool f;
+        const float a = step(acc, load_rc(ci), &f);
+        if (f) {
+          acc = a;
+          n_fast++;
+        } else {
+          acc = replay(acc, c0 + ci);
+          n_slow++;
         }
       }
     }

@@ -1,3 +1,6 @@
-python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/pytest_multi.log 2>&1; tail -5 gpurun_out/pytest_multi.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_r1b_n2.json 2> gpurun_out/bench_r1b_n2.err; tail -2 gpurun_out/bench_r1b_n2.err; python tools/show_bench.py gpurun_out/bench_r1b_n2.json | grep -E "^VoxelGrid|icp_sharded"
-python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r1b_n1s.json 2> gpurun_out/bench_r1b_n1s.err; python tools/show_bench.py gpurun_out/bench_r1b_n1s.json | grep -E "icp_sharded"
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -x -q -k "icp or sum or replay or strict or sequential" > gpurun_out/pytest_icp.log 2>&1; tail -4 gpurun_out/pytest_icp.log
+python tools/replay_stats.py
+python bench.py --only icp --steps 5 --warmup 3 > gpurun_out/bench_icp_w.json 2> gpurun_out/bench_icp_w.err; tail -1 gpurun_out/bench_icp_w.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_icp_w.json'))
+for m,v in d['modes'].items(): print(m, round(v['value'],1), round(v['ms_per_alignment'],3), {k:round(x['avg_us'],1) for k,x in v['kernels'].items()})"
