@@ -619,13 +619,17 @@ namespace cg = cooperative_groups;
 
 #ifdef PCG_VG_TIMING
 __device__ unsigned long long g_vg_stamps[64];
+__device__ unsigned long long g_vg_max[64];  // the same stamps, latest CTA
+__device__ unsigned long long g_vg_tile[3][160];  // per tile: reduce start, reduce end, voxel heads
 __device__ int g_vg_nstamps;
 #define PCG_VG_STAMP()                                                          \
   do {                                                                          \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+    if (threadIdx.x == 0) {                                                     \
       unsigned long long t__;                                                   \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                   \
-      if (g_vg_nstamps < 64) g_vg_stamps[g_vg_nstamps++] = t__;                 \
+      atomicMax(&g_vg_max[sm.stamp_i], t__);                                  \
+      if (blockIdx.x == 0 && g_vg_nstamps < 64) g_vg_stamps[g_vg_nstamps++] = t__; \
+      sm.stamp_i++;                                                           \
     }                                                                           \
   } while (0)
 #else
@@ -696,6 +700,16 @@ struct Smem {
   uint32_t prefix;
   __align__(16) uint32_t part[kParts][2][rsort::kRadix];  // [part][total|prefix][digit]
   float mm[6];
+  // the tile's last voxel when it runs on into the next tile(s): finished by warp 0 with parallel loads
+  struct {
+    unsigned long long key, rank;
+    float sx, sy, sz, fx, fy, fz, vc[3];
+    uint32_t num, l;
+    int pending;
+  } cont;
+#ifdef PCG_VG_TIMING
+  int stamp_i;  // thread 0's running stamp index
+#endif
 };
 
 template <typename K, int IPT>
@@ -943,6 +957,14 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
   PCG_VG_STAMP();  // staged + heads
   grid.sync();
   PCG_VG_STAMP();  // sync C
+#ifdef PCG_VG_TIMING
+  if (tid == 0 && tile < 160) {
+    unsigned long long t__;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
+    g_vg_tile[0][tile] = t__;
+    g_vg_tile[2][tile] = total_heads;
+  }
+#endif
   if (warp == 0) {
     uint32_t part = 0;
     for (uint32_t t = lane; t < tile; t += 32) part += __ldcg(&w.head_counts[t]);
@@ -950,6 +972,7 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) {
       sm.prefix = part;
+      sm.cont.pending = 0;
       if (tile == tiles - 1) {  // the flags were raised before the sort's grid-wide barriers
         w.result[1] = (long long)(__ldcg(w.flags) << 8);
         w.result[0] = (long long)(part + total_heads);
@@ -957,56 +980,23 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
     }
   }
   __syncthreads();
-  uint64_t rank = (uint64_t)sm.prefix + excl;
   const int out_aligned = v.aligned && ((((uintptr_t)out) & 3) == 0);
   // records that are exactly x,y,z (pc.Vec3Slice / xyz-only PCD): the first member's record is its point, already
   // in shared memory - no gather from the input
   const bool xyz_only = out_aligned && v.packed && v.stride == 12;
   long long vc_cid = -1;  // sorted positions change chunk rarely: keep vcMin of the last chunk id
   float vc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < IPT; j++) {
-    if (!((heads >> j) & 1u)) continue;
-    const uint32_t l = l0 + j;
-    const K key = s_key[pad(l)];
-    {
-      const long long cid = (long long)((unsigned long long)key >> P.key_bits);
-      if (cid != vc_cid) {
-        chunk_min(P, cid, vc);
-        vc_cid = cid;
-      }
-    }
-    const float fx = s_pt[pad(l)], fy = s_pt[kPadTile + pad(l)], fz = s_pt[2 * kPadTile + pad(l)];
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t num = 0;
-    uint32_t ll = l;
-    do {  // p = pt - vcMin, sum += p in list order (voxelgrid.go:148-158)
-      const uint32_t pl = pad(ll);
-      sx = __fadd_rn(sx, __fsub_rn(s_pt[pl], vc[0]));
-      sy = __fadd_rn(sy, __fsub_rn(s_pt[kPadTile + pl], vc[1]));
-      sz = __fadd_rn(sz, __fsub_rn(s_pt[2 * kPadTile + pl], vc[2]));
-      num++;
-      ll++;
-    } while (ll < tile_count && s_key[pad(ll)] == key);
-    if (ll == tile_count) {  // the voxel continues in the next tile(s)
-      uint32_t g = tile_base + tile_count;
-      while (g < n && __ldcg(&skeys[g]) == key) {
-        const float3 pt = load_xyz(v, __ldcg(&svals[g]));
-        sx = __fadd_rn(sx, __fsub_rn(pt.x, vc[0]));
-        sy = __fadd_rn(sy, __fsub_rn(pt.y, vc[1]));
-        sz = __fadd_rn(sz, __fsub_rn(pt.z, vc[2]));
-        num++;
-        g++;
-      }
-    }
+  // voxelgrid.go:173-184: the first member's record, x/y/z replaced by the centroid when there are several members
+  auto emit = [&](uint32_t l, uint32_t num, float sx, float sy, float sz, float fx, float fy, float fz,
+                  const float* vcm, uint64_t rk) {
     float ox = fx, oy = fy, oz = fz;  // num == 1: the original bytes (voxelgrid.go:176-178)
     if (num > 1) {
       const float inv = __fdiv_rn(1.0f, (float)num);  // 1.0 / float32(n)   voxelgrid.go:179
-      ox = __fadd_rn(__fmul_rn(sx, inv), vc[0]);
-      oy = __fadd_rn(__fmul_rn(sy, inv), vc[1]);
-      oz = __fadd_rn(__fmul_rn(sz, inv), vc[2]);
+      ox = __fadd_rn(__fmul_rn(sx, inv), vcm[0]);
+      oy = __fadd_rn(__fmul_rn(sy, inv), vcm[1]);
+      oz = __fadd_rn(__fmul_rn(sz, inv), vcm[2]);
     }
-    uint8_t* dst = out + rank * (uint64_t)v.stride;
+    uint8_t* dst = out + rk * (uint64_t)v.stride;
     if (xyz_only) {
       float* d3 = reinterpret_cast<float*>(dst);
       d3[0] = ox;
@@ -1029,14 +1019,95 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
         store_f32_any(dst + v.off[2], oz, out_aligned);
       }
     }
-    rank++;
+  };
+  // Voxels differ a lot in size (a few hundred members next to the sensor, one far away) and the members of one
+  // voxel must be added one after the other.  Walking "my 16 positions" would make a warp wait, 16 times over,
+  // for its longest voxel; instead the heads are compacted (s_src[r] = position of the tile's r-th voxel) and
+  // voxel r goes to thread r mod kThreads: a tile of few large voxels is one short round, and neighbouring
+  // lanes write neighbouring records.
+  uint16_t* s_src = reinterpret_cast<uint16_t*>(dyn + (size_t)kPadTile * 20);
+  {
+    uint32_t r = excl;
+#pragma unroll
+    for (int j = 0; j < IPT; j++)
+      if ((heads >> j) & 1u) s_src[r++] = (uint16_t)(l0 + j);
+  }
+  __syncthreads();
+  for (uint32_t r = tid; r < total_heads; r += kThreads) {
+    const uint32_t l = s_src[r];
+    const uint64_t rank = (uint64_t)sm.prefix + r;
+    const K key = s_key[pad(l)];
+    {
+      const long long cid = (long long)((unsigned long long)key >> P.key_bits);
+      if (cid != vc_cid) {
+        chunk_min(P, cid, vc);
+        vc_cid = cid;
+      }
+    }
+    const float fx = s_pt[pad(l)], fy = s_pt[kPadTile + pad(l)], fz = s_pt[2 * kPadTile + pad(l)];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t num = 0;
+    uint32_t ll = l;
+    do {  // p = pt - vcMin, sum += p in list order (voxelgrid.go:148-158)
+      const uint32_t pl = pad(ll);
+      sx = __fadd_rn(sx, __fsub_rn(s_pt[pl], vc[0]));
+      sy = __fadd_rn(sy, __fsub_rn(s_pt[kPadTile + pl], vc[1]));
+      sz = __fadd_rn(sz, __fsub_rn(s_pt[2 * kPadTile + pl], vc[2]));
+      num++;
+      ll++;
+    } while (ll < tile_count && s_key[pad(ll)] == key);
+    if (ll == tile_count && tile_base + tile_count < n) {
+      // the tile's last voxel may run on into the next tile(s): one thread walking those members would chain
+      // dependent global loads (key -> index -> point) - warp 0 finishes it below with the loads side by side
+      sm.cont.key = (unsigned long long)key;
+      sm.cont.rank = rank;
+      sm.cont.sx = sx;
+      sm.cont.sy = sy;
+      sm.cont.sz = sz;
+      sm.cont.fx = fx;
+      sm.cont.fy = fy;
+      sm.cont.fz = fz;
+      sm.cont.vc[0] = vc[0];
+      sm.cont.vc[1] = vc[1];
+      sm.cont.vc[2] = vc[2];
+      sm.cont.num = num;
+      sm.cont.l = l;
+      sm.cont.pending = 1;
+    } else {
+      emit(l, num, sx, sy, sz, fx, fy, fz, vc, rank);
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && sm.cont.pending) {
+    const K key = (K)sm.cont.key;
+    float sx = sm.cont.sx, sy = sm.cont.sy, sz = sm.cont.sz;
+    const float c0 = sm.cont.vc[0], c1 = sm.cont.vc[1], c2 = sm.cont.vc[2];
+    uint32_t num = sm.cont.num;
+    for (uint32_t g = tile_base + tile_count;; g += 32) {
+      const uint32_t idx = g + lane;
+      const bool match = idx < n && __ldcg(&skeys[idx]) == key;
+      const uint32_t m = __ballot_sync(0xffffffffu, match);
+      const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;  // members are consecutive: the leading matches
+      float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((int)lane < run) pt = __ldcg(&w.xyz4[__ldcg(&svals[idx])]);
+      for (int q = 0; q < run; q++) {  // the additions stay in list order (every lane carries the same sums)
+        sx = __fadd_rn(sx, __fsub_rn(__shfl_sync(0xffffffffu, pt.x, q), c0));
+        sy = __fadd_rn(sy, __fsub_rn(__shfl_sync(0xffffffffu, pt.y, q), c1));
+        sz = __fadd_rn(sz, __fsub_rn(__shfl_sync(0xffffffffu, pt.z, q), c2));
+      }
+      num += (uint32_t)run;
+      if (run < 32) break;
+    }
+    if (lane == 0) emit(sm.cont.l, num, sx, sy, sz, sm.cont.fx, sm.cont.fy, sm.cont.fz, sm.cont.vc, sm.cont.rank);
   }
   PCG_VG_STAMP();  // reduced
 #ifdef PCG_VG_TIMING
+  __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long t__;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));
     atomicMax(&g_vg_stamps[63], t__);
+    if (tile < 160) g_vg_tile[1][tile] = t__;
   }
 #endif
 }
@@ -1052,6 +1123,7 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
   const uint32_t tile_base = blockIdx.x * (uint32_t)kTile;
 
 #ifdef PCG_VG_TIMING
+  if (threadIdx.x == 0) sm.stamp_i = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     g_vg_nstamps = 0;
     g_vg_stamps[63] = 0;
@@ -1140,8 +1212,9 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
 
 template <int IPT>
 constexpr size_t dyn_smem_bytes() {
-  // max(sort staging 12 B, reduce staging (8 + 12) B with one pad slot per IPT positions) per position
-  return (size_t)(kThreads * IPT + kThreads) * 20;
+  // max(sort staging 12 B, reduce staging (8 + 12) B with one pad slot per IPT positions) per position,
+  // + 2 B per position for the compacted list of voxel heads
+  return (size_t)(kThreads * IPT + kThreads) * 20 + (size_t)kThreads * IPT * 2;
 }
 
 }  // namespace fused
@@ -1153,6 +1226,10 @@ extern "C" int pcg_debug_vg_stamps(unsigned long long* out) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(&n, pcg::g_vg_nstamps, sizeof(int));
   cudaMemcpyFromSymbol(out, pcg::g_vg_stamps, sizeof(unsigned long long) * 64);
+  cudaMemcpyFromSymbol(out + 64, pcg::g_vg_max, sizeof(unsigned long long) * 64);
+  cudaMemcpyFromSymbol(out + 128, pcg::g_vg_tile, sizeof(unsigned long long) * 480);
+  unsigned long long z[64] = {0};
+  cudaMemcpyToSymbol(pcg::g_vg_max, z, sizeof(z));
   return n;
 }
 namespace pcg {
