@@ -823,8 +823,11 @@ __global__ void __launch_bounds__(128)
 }
 
 // One query per thread (no work fetching): kept for comparison runs (PCG_NN_KERNEL=simple).
+#ifndef PCG_NN_THREADS
+#define PCG_NN_THREADS 128
+#endif
 template <bool APPROX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PCG_NN_THREADS)
     nearest_simple_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
                           float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
                           pcg_neighbor* __restrict__ aos) {
@@ -887,12 +890,12 @@ void nearest_device(const Index& ix, const CloudView& q, float max_range, float 
   if (min_dist_sq > 0.f) {  // KDTree.MinDistSq > 0: approximate search (kdtree.go:19-22)
     // a miss keeps DistSq == maxRange^2: capping the threshold there means only a real hit can end the search
     // early (the reference's early miss for maxRange^2 < MinDistSq, kdtree.go:100-106, is not reproduced)
-    PCG_LAUNCH(nearest_simple_kernel<true>, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq,
+    PCG_LAUNCH(nearest_simple_kernel<true>, div_up(q.n, PCG_NN_THREADS), PCG_NN_THREADS, 0, stream, ix.view(), q, perm.p, mrsq,
                fminf(min_dist_sq, mrsq), d_ids, d_dist_sq, d_aos);
     return;
   }
   if (simple) {
-    PCG_LAUNCH(nearest_simple_kernel<false>, div_up(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, 0.f, d_ids,
+    PCG_LAUNCH(nearest_simple_kernel<false>, div_up(q.n, PCG_NN_THREADS), PCG_NN_THREADS, 0, stream, ix.view(), q, perm.p, mrsq, 0.f, d_ids,
                d_dist_sq, d_aos);
     return;
   }

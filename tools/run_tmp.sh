@@ -1,5 +1,9 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py tests/test_gpu_next.py tests/test_gpu_multi.py -x -q -k "icp or sum or replay or strict or hessian or gauss or shard or pipeline" > gpurun_out/pytest_icp.log 2>&1; tail -4 gpurun_out/pytest_icp.log
-python bench.py --only icp --steps 5 --warmup 3 > gpurun_out/bench_icp_x.json 2> gpurun_out/bench_icp_x.err; tail -1 gpurun_out/bench_icp_x.err
-python -c "
-import json; d=json.load(open('gpurun_out/bench_icp_x.json'))
-for m,v in d['modes'].items(): print(m, round(v['value'],1), round(v['ms_per_alignment'],3), {k:round(x['avg_us'],1) for k,x in v['kernels'].items()})"
+for v in q8 qmorton q8morton; do
+  export PCG_LIB=$PWD/build_variants/libpcg_$v.so
+  python bench.py --only nn --steps 5 --warmup 3 > gpurun_out/bench_nn_$v.json 2> gpurun_out/bench_nn_$v.err
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_nn_$v.json')); print('$v', round(d['value']/1e6,1), round(d['ms_per_step'],3), {k:(x['launches'],round(x['avg_us'],1)) for k,x in d['kernels'].items()})"
+  python bench.py --only icp --steps 5 --warmup 3 > gpurun_out/bench_icp_$v.json 2> gpurun_out/bench_icp_$v.err
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_icp_$v.json')); print('$v', {m:(round(v['value'],1), round([x['avg_us'] for k,x in v['kernels'].items() if 'terms' in k][0],1)) for m,v in d['modes'].items()})"
+done
