@@ -412,8 +412,8 @@ __device__ __forceinline__ unsigned long long voxel_key_of(const VgParams& P, co
 // keys are not read a second time.
 template <typename K>
 __global__ void __launch_bounds__(256)
-    voxel_key_kernel(CloudView v, VgParams P, K* __restrict__ keys, int* __restrict__ flags,
-                     uint32_t* __restrict__ hist, int passes) {
+    voxel_key_kernel(CloudView v, VgParams P, K* __restrict__ keys, float4* __restrict__ xyz4,
+                     int* __restrict__ flags, uint32_t* __restrict__ hist, int passes) {
   __shared__ uint32_t s_hist[rsort::kMaxPasses * rsort::kRadix];
   rsort::hist_zero(s_hist, passes);
   __syncthreads();
@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(256)
     const bool valid = i < v.n;
     K out_key = 0;
     if (valid) {
-      out_key = (K)voxel_key_of(P, C, load_xyz(v, i), &bad);
+      const float3 pt = load_xyz(v, i);
+      xyz4[i] = make_float4(pt.x, pt.y, pt.z, 0.f);  // aligned copy: the sorted gather is one 16-byte load per point
+      out_key = (K)voxel_key_of(P, C, pt, &bad);
       keys[i] = out_key;
     }
     rsort::hist_add_key(s_hist, out_key, valid, 0, passes);
@@ -450,39 +452,58 @@ constexpr int kSegTile = kSegThreads * kSegItems;
 template <typename K>
 __global__ void __launch_bounds__(kSegThreads)
     voxel_reduce_kernel(CloudView v, VgParams P, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
-                        uint8_t* __restrict__ out, uint32_t* __restrict__ tile_counter,
+                        const float4* __restrict__ xyz4, uint8_t* __restrict__ out, uint32_t* __restrict__ tile_counter,
                         unsigned long long* __restrict__ status, long long* __restrict__ n_out) {
-  __shared__ float s_p[3][kSegTile];
+  __shared__ float s_pt[3][kSegTile];  // raw points of the tile's sorted slice
   __shared__ K s_key[kSegTile];
+  __shared__ uint16_t s_src[kSegTile];  // position of the tile's r-th voxel head
   __shared__ uint32_t s_scan[rsort::kWarps];
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_prefix;
-  const uint32_t tid = threadIdx.x;
+  __shared__ struct {
+    unsigned long long key, rank;
+    float sx, sy, sz, fx, fy, fz, vc[3];
+    uint32_t num, l;
+    int pending;
+  } s_cont;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n = (uint32_t)v.n;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  if (tid == 0) {
+    s_tile = atomicAdd(tile_counter, 1u);
+    s_cont.pending = 0;
+  }
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t tile_base = tile * kSegTile;
   const uint32_t tile_count = min((uint32_t)kSegTile, n - tile_base);
 
-  // Phase A (striped: coalesced key/index loads, independent gathers)
+  // Phase A (striped: coalesced key/index loads, independent 16-byte gathers)
+  {
+    K kk[kSegItems];
+    uint32_t vv[kSegItems];
 #pragma unroll
-  for (int j = 0; j < kSegItems; j++) {
-    const uint32_t l = j * kSegThreads + tid;
-    if (l < tile_count) {
-      const K key = keys[tile_base + l];
-      const float3 pt = load_xyz(v, vals[tile_base + l]);
-      float vc[3];
-      chunk_min(P, (long long)((unsigned long long)key >> P.key_bits), vc);
-      s_key[l] = key;
-      s_p[0][l] = __fsub_rn(pt.x, vc[0]);
-      s_p[1][l] = __fsub_rn(pt.y, vc[1]);
-      s_p[2][l] = __fsub_rn(pt.z, vc[2]);
+    for (int j = 0; j < kSegItems; j++) {
+      const uint32_t l = j * kSegThreads + tid;
+      if (l < tile_count) {
+        kk[j] = keys[tile_base + l];
+        vv[j] = vals[tile_base + l];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kSegItems; j++) {
+      const uint32_t l = j * kSegThreads + tid;
+      if (l < tile_count) {
+        const float4 pt = __ldg(&xyz4[vv[j]]);
+        s_key[l] = kk[j];
+        s_pt[0][l] = pt.x;
+        s_pt[1][l] = pt.y;
+        s_pt[2][l] = pt.z;
+      }
     }
   }
   __syncthreads();
 
-  // Phase B (blocked: thread t owns positions 4t .. 4t+3)
+  // Phase B (blocked: thread t looks at positions 4t .. 4t+3): voxel heads, compacted
   const uint32_t l0 = tid * kSegItems;
   K prev = 0;
   if (l0 > 0 && l0 - 1 < tile_count)
@@ -503,6 +524,12 @@ __global__ void __launch_bounds__(kSegThreads)
   }
   uint32_t total = 0;
   const uint32_t excl = rsort::block_excl_scan_256(cnt, s_scan, &total);
+  {
+    uint32_t r = excl;
+#pragma unroll
+    for (int j = 0; j < kSegItems; j++)
+      if ((heads >> j) & 1u) s_src[r++] = (uint16_t)(l0 + j);
+  }
   if (tid == 0) {
     volatile unsigned long long* st = status;
     unsigned long long prefix = 0;
@@ -525,55 +552,103 @@ __global__ void __launch_bounds__(kSegThreads)
     if ((uint64_t)tile_base + kSegTile >= n) *n_out = (long long)(prefix + total);
   }
   __syncthreads();
-  uint64_t rank = s_prefix + excl;
   const int out_aligned = v.aligned && ((((uintptr_t)out) & 3) == 0);
 
-#pragma unroll
-  for (int j = 0; j < kSegItems; j++) {
-    if (!((heads >> j) & 1u)) continue;
-    const uint32_t l = l0 + j;
-    const K key = s_key[l];
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t num = 0;
-    uint32_t ll = l;
-    do {  // members inside this tile: shared memory
-      sx = __fadd_rn(sx, s_p[0][ll]);
-      sy = __fadd_rn(sy, s_p[1][ll]);
-      sz = __fadd_rn(sz, s_p[2][ll]);
-      num++;
-      ll++;
-    } while (ll < tile_count && s_key[ll] == key);
-    float vc[3];
-    chunk_min(P, (long long)((unsigned long long)key >> P.key_bits), vc);
-    if (ll == tile_count) {  // the voxel continues in the next tile(s): finish from global memory
-      uint32_t g = tile_base + tile_count;
-      while (g < n && keys[g] == key) {
-        const float3 pt = load_xyz(v, vals[g]);
-        sx = __fadd_rn(sx, __fsub_rn(pt.x, vc[0]));
-        sy = __fadd_rn(sy, __fsub_rn(pt.y, vc[1]));
-        sz = __fadd_rn(sz, __fsub_rn(pt.z, vc[2]));
-        num++;
-        g++;
-      }
-    }
+  // voxelgrid.go:173-184: the first member's record, x/y/z replaced by the centroid when there are several members
+  auto emit = [&](uint32_t l, uint32_t num, float sx, float sy, float sz, float fx, float fy, float fz,
+                  const float* vcm, uint64_t rk) {
     const uint32_t first = vals[tile_base + l];
-    uint8_t* dst = out + rank * (uint64_t)v.stride;
+    uint8_t* dst = out + rk * (uint64_t)v.stride;
     const uint8_t* src = v.data + (uint64_t)first * (uint64_t)v.stride;
     if (out_aligned) {
       const uint32_t* s4 = (const uint32_t*)src;
       uint32_t* d4 = (uint32_t*)dst;
       const int words = (int)(v.stride >> 2);
-      for (int b = 0; b < words; b++) d4[b] = __ldg(s4 + b);
+      if (v.packed && words == 3) {  // xyz-only records: the point itself
+        d4[0] = __float_as_uint(fx);
+        d4[1] = __float_as_uint(fy);
+        d4[2] = __float_as_uint(fz);
+      } else {
+        for (int b = 0; b < words; b++) d4[b] = __ldg(s4 + b);
+      }
     } else {
       for (int64_t b = 0; b < v.stride; b++) dst[b] = src[b];
     }
     if (num > 1) {
       const float inv = __fdiv_rn(1.0f, (float)num);  // 1.0 / float32(n)   voxelgrid.go:179
-      store_f32_any(dst + v.off[0], __fadd_rn(__fmul_rn(sx, inv), vc[0]), out_aligned);
-      store_f32_any(dst + v.off[1], __fadd_rn(__fmul_rn(sy, inv), vc[1]), out_aligned);
-      store_f32_any(dst + v.off[2], __fadd_rn(__fmul_rn(sz, inv), vc[2]), out_aligned);
+      store_f32_any(dst + v.off[0], __fadd_rn(__fmul_rn(sx, inv), vcm[0]), out_aligned);
+      store_f32_any(dst + v.off[1], __fadd_rn(__fmul_rn(sy, inv), vcm[1]), out_aligned);
+      store_f32_any(dst + v.off[2], __fadd_rn(__fmul_rn(sz, inv), vcm[2]), out_aligned);
     }
-    rank++;
+  };
+
+  // One voxel per thread per round (see the fused kernel): the members of a voxel are added in list order out of
+  // shared memory (voxelgrid.go:148-158) - the float32 sum is the reference's.
+  long long vc_cid = -1;
+  float vc[3] = {0.f, 0.f, 0.f};
+  for (uint32_t r = tid; r < total; r += kSegThreads) {
+    const uint32_t l = s_src[r];
+    const uint64_t rank = s_prefix + r;
+    const K key = s_key[l];
+    {
+      const long long cid = (long long)((unsigned long long)key >> P.key_bits);
+      if (cid != vc_cid) {
+        chunk_min(P, cid, vc);
+        vc_cid = cid;
+      }
+    }
+    const float fx = s_pt[0][l], fy = s_pt[1][l], fz = s_pt[2][l];
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    uint32_t num = 0;
+    uint32_t ll = l;
+    do {
+      sx = __fadd_rn(sx, __fsub_rn(s_pt[0][ll], vc[0]));
+      sy = __fadd_rn(sy, __fsub_rn(s_pt[1][ll], vc[1]));
+      sz = __fadd_rn(sz, __fsub_rn(s_pt[2][ll], vc[2]));
+      num++;
+      ll++;
+    } while (ll < tile_count && s_key[ll] == key);
+    if (ll == tile_count && tile_base + tile_count < n) {  // may run on into the next tile(s): finished by warp 0
+      s_cont.key = (unsigned long long)key;
+      s_cont.rank = rank;
+      s_cont.sx = sx;
+      s_cont.sy = sy;
+      s_cont.sz = sz;
+      s_cont.fx = fx;
+      s_cont.fy = fy;
+      s_cont.fz = fz;
+      s_cont.vc[0] = vc[0];
+      s_cont.vc[1] = vc[1];
+      s_cont.vc[2] = vc[2];
+      s_cont.num = num;
+      s_cont.l = l;
+      s_cont.pending = 1;
+    } else {
+      emit(l, num, sx, sy, sz, fx, fy, fz, vc, rank);
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && s_cont.pending) {
+    const K key = (K)s_cont.key;
+    float sx = s_cont.sx, sy = s_cont.sy, sz = s_cont.sz;
+    const float c0 = s_cont.vc[0], c1 = s_cont.vc[1], c2 = s_cont.vc[2];
+    uint32_t num = s_cont.num;
+    for (uint32_t g = tile_base + tile_count;; g += 32) {
+      const uint32_t idx = g + lane;
+      const bool match = idx < n && keys[idx] == key;
+      const uint32_t m = __ballot_sync(0xffffffffu, match);
+      const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;  // members are consecutive: the leading matches
+      float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((int)lane < run) pt = __ldg(&xyz4[vals[idx]]);
+      for (int q = 0; q < run; q++) {  // the additions stay in list order (every lane carries the same sums)
+        sx = __fadd_rn(sx, __fsub_rn(__shfl_sync(0xffffffffu, pt.x, q), c0));
+        sy = __fadd_rn(sy, __fsub_rn(__shfl_sync(0xffffffffu, pt.y, q), c1));
+        sz = __fadd_rn(sz, __fsub_rn(__shfl_sync(0xffffffffu, pt.z, q), c2));
+      }
+      num += (uint32_t)run;
+      if (run < 32) break;
+    }
+    if (lane == 0) emit(s_cont.l, num, sx, sy, sz, s_cont.fx, s_cont.fy, s_cont.fz, s_cont.vc, s_cont.rank);
   }
 }
 
@@ -583,10 +658,12 @@ static void run_sorted_reduce(const CloudView& v, const VgParams& P, int total_b
   const uint32_t n = (uint32_t)v.n;
   DevBuf<K> keys0(n, stream), keys1(n, stream);
   DevBuf<uint32_t> vals0(n, stream), vals1(n, stream);
+  DevBuf<float4> xyz4(n, stream);
   rsort::Sorter<K> sorter;
   sorter.prepare(n, 0, total_bits, stream);
   const int kblocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
-  PCG_LAUNCH((voxel_key_kernel<K>), kblocks, 256, 0, stream, v, P, keys0.p, d_flags, sorter.hist(), sorter.passes);
+  PCG_LAUNCH((voxel_key_kernel<K>), kblocks, 256, 0, stream, v, P, keys0.p, xyz4.p, d_flags, sorter.hist(),
+             sorter.passes);
   K* kk[2] = {keys0.p, keys1.p};
   uint32_t* vbuf[2] = {vals0.p, vals1.p};
   int res = 0;
@@ -595,8 +672,8 @@ static void run_sorted_reduce(const CloudView& v, const VgParams& P, int total_b
   DevBuf<unsigned long long> status((size_t)tiles + 1, stream);
   PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
   uint32_t* counter = (uint32_t*)(status.p + tiles);
-  PCG_LAUNCH((voxel_reduce_kernel<K>), tiles, kSegThreads, 0, stream, v, P, kk[res], vbuf[res], d_out, counter,
-             status.p, d_n_out);
+  PCG_LAUNCH((voxel_reduce_kernel<K>), tiles, kSegThreads, 0, stream, v, P, kk[res], vbuf[res], xyz4.p, d_out,
+             counter, status.p, d_n_out);
 }
 
 // ======================================================================================

@@ -456,3 +456,20 @@ def test_nearest_large_host_batch_is_sliced(pg, oracle, synth):
     if len(ties):
         nids, _ = oracle.Search(pts, "naive").nearest(q[ties], 0.8)
         assert np.array_equal(ids[ties], nids)
+
+
+def test_voxelgrid_multi_kernel_path_small_inputs():
+    # Clouds above 1.2M points take the multi-kernel pipeline (keys -> onesweep passes -> voxel_reduce_kernel); the
+    # 50M-point test covers it at scale, this one runs the whole VoxelGrid parity suite through it at small sizes
+    # (PCG_VG_NO_FUSED is read once per process, hence the child process).
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, PCG_VG_NO_FUSED="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_parity.py"),
+                        os.path.join(here, "test_gpu_edges.py"), "-k", "voxel or Voxel"], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
