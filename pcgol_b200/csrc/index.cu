@@ -305,126 +305,112 @@ struct KdLists {
   uint32_t* out[3];
 };
 
-// Level step 1: axis of every segment that splits at this level + the side of each of its points.
-// Segment s covers positions [s*S, min((s+1)*S, n)); it splits at m = s*S + S/2 when m < its end.
-__global__ void __launch_bounds__(256)
-    kd_side_kernel(CloudView v, KdLists L, uint32_t n, int log2S, uint8_t* __restrict__ seg_axis,
-                   uint8_t* __restrict__ side) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t S = 1u << log2S;
-  const uint32_t group = S < 32u ? S : 32u;  // positions of one warp that share a segment
-  const uint32_t leader = lane & ~(group - 1u);
-  int axis = 3;
-  const bool in_range = i < n;
-  const uint32_t s = i >> log2S, b = s << log2S;
-  const uint32_t e = min(b + S, n), m = b + (S >> 1);
-  if (in_range && lane == leader && m < e) {
-    float ext[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const float lo = coord_of(v, L.in[c][b], c), hi = coord_of(v, L.in[c][e - 1], c);
-      float d = hi - lo;
-      if (!(d >= 0.f)) d = 0.f;  // NaN ends
-      ext[c] = d;
-    }
-    axis = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
-  }
-  axis = __shfl_sync(0xffffffffu, axis, leader);
-  if (!in_range) return;
-  if (i == b) seg_axis[s] = (uint8_t)axis;
-  if (axis == 3) return;
-  const uint32_t id = axis == 0 ? L.in[0][i] : (axis == 1 ? L.in[1][i] : L.in[2][i]);
-  side[id] = i >= m ? 1 : 0;
-}
-
-// Level step 2: stable partition of the two lists that are not the split axis, inside every segment.
-// While a segment spans several tiles the left-counts of its earlier tiles arrive through a decoupled
-// look-back (tiles take their ids from a counter, so predecessors are always running; one packed word per
-// tile and list: state | level | count); the chain restarts at every segment's first tile.
+// One level of the build while a segment still spans several tiles (one segment per CTA).  Segment s covers
+// positions [s*S, min((s+1)*S, n)) and splits at m = s*S + S/2 when m lies before its end:
+//   axis   = widest extent, read off the ends of the segment's three sorted lists (that IS its bounding box);
+//   pivot  = the element at position m of the list of that axis; a point goes left iff it ranks before the pivot
+//            in that list, i.e. iff (key, id) < (pivot key, pivot id) - the lists were sorted stably by key from
+//            the identity, so ties are in id order - which every thread decides from the point's own coordinate;
+//   the two other lists are partitioned stably; the left-counts of the segment's earlier tiles arrive through a
+//   decoupled look-back (tiles take their ids from a counter, so predecessors are always running; one packed word
+//   per tile and list: state | level | count), restarted at every segment's first tile.
 constexpr unsigned long long kKdAggregate = 1ull << 62, kKdInclusive = 2ull << 62;
 __global__ void __launch_bounds__(256)
-    kd_scatter_kernel(KdLists L, uint32_t n, int log2S, const uint8_t* __restrict__ seg_axis,
-                      const uint8_t* __restrict__ side, uint32_t tiles, uint32_t* __restrict__ tile_counter,
-                      unsigned long long* __restrict__ status) {
+    kd_level_kernel(CloudView v, KdLists L, uint32_t n, int log2S, uint32_t tiles, uint32_t* __restrict__ tile_counter,
+                    unsigned long long* __restrict__ status) {
   __shared__ uint32_t s_scan[rsort::kWarps];
-  __shared__ uint32_t s_excl[256];
   __shared__ uint32_t s_prefix;
   __shared__ uint32_t s_tile;
+  __shared__ int s_axis;
+  __shared__ uint32_t s_pivot_key, s_pivot_id;
   const uint32_t tid = threadIdx.x;
   const uint32_t S = 1u << log2S;
-  const bool big = S > (uint32_t)kKdTile;  // the segment spans S / kKdTile whole tiles: one segment per CTA
-  if (big) {
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_base = tile * kKdTile;  // < n: there are ceil(n / kKdTile) tiles
+  const uint32_t s = tile_base >> log2S, b = s << log2S, m = b + (S >> 1);
+  const uint32_t e = min(b + S, n);
+  if (tid == 0) {
+    int axis = 3;
+    if (m < e) {
+      float ext[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float lo = coord_of(v, L.in[c][b], c), hi = coord_of(v, L.in[c][e - 1], c);
+        float d = hi - lo;
+        if (!(d >= 0.f)) d = 0.f;  // NaN ends
+        ext[c] = d;
+      }
+      axis = (ext[0] >= ext[1] && ext[0] >= ext[2]) ? 0 : (ext[1] >= ext[2] ? 1 : 2);
+      const uint32_t pid = L.in[axis][m];
+      s_pivot_id = pid;
+      s_pivot_key = ord_bits(coord_of(v, pid, axis));
+    }
+    s_axis = axis;
   }
-  const uint32_t tile = big ? s_tile : blockIdx.x;
-  const uint32_t tile_base = tile * kKdTile;
+  __syncthreads();
+  const int axis = s_axis;
+  const uint32_t pkey = s_pivot_key, pid = s_pivot_id;
   const uint32_t base = tile_base + tid * kKdTileItems;
-  const bool any = base < n;
-  const uint32_t s = (big ? tile_base : base) >> log2S, b = s << log2S, m = b + (S >> 1);
-  const int axis = any ? seg_axis[s] : 3;
-  const int cta_axis = big ? (int)seg_axis[s] : 3;  // uniform across the CTA when big (tile_base < n always)
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
     uint32_t id[kKdTileItems];
     uint32_t left_mask = 0, cnt = 0;
-    const bool part = any && axis != 3 && axis != c;
+    const bool part = axis != 3 && axis != c;
 #pragma unroll
     for (int j = 0; j < kKdTileItems; j++) {
       id[j] = 0;
-      if (base + j < n) {
-        id[j] = L.in[c][base + j];
-        if (part && !side[id[j]]) {
-          left_mask |= 1u << j;
-          cnt++;
+      if (base + j < n) id[j] = L.in[c][base + j];
+    }
+    if (part) {
+#pragma unroll
+      for (int j = 0; j < kKdTileItems; j++) {
+        if (base + j < n) {
+          const uint32_t key = ord_bits(coord_of(v, id[j], axis));
+          if (key < pkey || (key == pkey && id[j] < pid)) {
+            left_mask |= 1u << j;
+            cnt++;
+          }
         }
       }
     }
     uint32_t total = 0;
     const uint32_t excl = rsort::block_excl_scan_256(cnt, s_scan, &total);
-    uint32_t seg_excl;  // lefts of this segment that precede this thread's items
-    if (big) {
-      if (tid < 32) {  // warp 0 looks back 32 predecessor tiles per round
-        uint32_t prefix = 0;
-        if (cta_axis != 3 && cta_axis != c) {
-          volatile unsigned long long* st = status + (size_t)c * tiles;
-          const unsigned long long tag = (unsigned long long)(uint32_t)log2S << 48;
-          const uint32_t first_tile = b / kKdTile;
-          if (tile == first_tile) {
-            if (tid == 0) st[tile] = kKdInclusive | tag | total;
-          } else {
-            if (tid == 0) st[tile] = kKdAggregate | tag | total;
-            long long look = (long long)tile - 1;
-            for (;;) {
-              const long long idx = look - (long long)tid;
-              const bool before = idx < (long long)first_tile;  // ahead of the segment: contributes nothing, ends the walk
-              unsigned long long w = 0;
-              if (!before) w = st[idx];
-              const bool ready = before || ((w >> 62) != 0 && ((w >> 48) & 0xffu) == (unsigned long long)(uint32_t)log2S);
-              if (!__all_sync(0xffffffffu, ready)) continue;  // someone has not published at this level yet
-              const uint32_t stop = __ballot_sync(0xffffffffu, before || (w >> 62) == 2);
-              const int last = stop ? __ffs(stop) - 1 : 31;  // lanes 0..last contribute
-              uint32_t v = (!before && (int)tid <= last) ? (uint32_t)w : 0u;
+    if (tid < 32) {  // warp 0 looks back 32 predecessor tiles per round
+      uint32_t prefix = 0;
+      if (part) {
+        volatile unsigned long long* st = status + (size_t)c * tiles;
+        const unsigned long long tag = (unsigned long long)(uint32_t)log2S << 48;
+        const uint32_t first_tile = b / kKdTile;
+        if (tile == first_tile) {
+          if (tid == 0) st[tile] = kKdInclusive | tag | total;
+        } else {
+          if (tid == 0) st[tile] = kKdAggregate | tag | total;
+          long long look = (long long)tile - 1;
+          for (;;) {
+            const long long idx = look - (long long)tid;
+            const bool before = idx < (long long)first_tile;  // ahead of the segment: contributes nothing, ends the walk
+            unsigned long long w = 0;
+            if (!before) w = st[idx];
+            const bool ready = before || ((w >> 62) != 0 && ((w >> 48) & 0xffu) == (unsigned long long)(uint32_t)log2S);
+            if (!__all_sync(0xffffffffu, ready)) continue;  // someone has not published at this level yet
+            const uint32_t stop = __ballot_sync(0xffffffffu, before || (w >> 62) == 2);
+            const int last = stop ? __ffs(stop) - 1 : 31;  // lanes 0..last contribute
+            uint32_t val = (!before && (int)tid <= last) ? (uint32_t)w : 0u;
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              prefix += v;
-              if (stop) break;
-              look -= 32;
-            }
-            if (tid == 0) st[tile] = kKdInclusive | tag | (unsigned long long)(prefix + total);
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            prefix += val;
+            if (stop) break;
+            look -= 32;
           }
+          if (tid == 0) st[tile] = kKdInclusive | tag | (unsigned long long)(prefix + total);
         }
-        if (tid == 0) s_prefix = prefix;
       }
-      __syncthreads();
-      seg_excl = s_prefix + excl;
-    } else {
-      s_excl[tid] = excl;
-      __syncthreads();
-      seg_excl = excl - s_excl[(b - tile_base) / kKdTileItems];  // b >= tile_base: segments are tile-aligned here
+      if (tid == 0) s_prefix = prefix;
     }
-    uint32_t lb = seg_excl;
+    __syncthreads();
+    uint32_t lb = s_prefix + excl;  // lefts of this segment that precede this thread's items
 #pragma unroll
     for (int j = 0; j < kKdTileItems; j++) {
       const uint32_t pos = base + j;
@@ -438,7 +424,7 @@ __global__ void __launch_bounds__(256)
         L.out[c][dst] = id[j];
       }
     }
-    __syncthreads();  // s_excl / s_prefix are reused by the next list
+    __syncthreads();  // s_prefix is reused by the next list
   }
 }
 
@@ -587,7 +573,6 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
   int log2L = 0;
   while ((1 << log2L) < kLeaf) log2L++;
   const uint32_t tiles = (uint32_t)div_up(n, kKdTile);
-  DevBuf<uint8_t> seg_axis((size_t)P, stream), side(n, stream);
   DevBuf<unsigned long long> status((size_t)3 * tiles + 32, stream);  // look-back words + one tile counter per level
   PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
   uint32_t* counters = reinterpret_cast<uint32_t*>(status.p + (size_t)3 * tiles);
@@ -598,9 +583,7 @@ static const uint32_t* kd_order_device(const CloudView& v, uint32_t n, uint32_t 
       L.in[c] = cur[c];
       L.out[c] = alt[c];
     }
-    PCG_LAUNCH(kd_side_kernel, div_up(n, 256), 256, 0, stream, v, L, n, log2S, seg_axis.p, side.p);
-    PCG_LAUNCH(kd_scatter_kernel, tiles, 256, 0, stream, L, n, log2S, seg_axis.p, side.p, tiles, counters + log2S,
-               status.p);
+    PCG_LAUNCH(kd_level_kernel, tiles, 256, 0, stream, v, L, n, log2S, tiles, counters + log2S, status.p);
     for (int c = 0; c < 3; c++) std::swap(cur[c], alt[c]);
   }
   if (log2S > log2L) {  // the rest (children of the last level are single leaves) in shared memory
