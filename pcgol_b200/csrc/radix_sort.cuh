@@ -377,9 +377,11 @@ void run_batched(Sorter<K>* sorters, int batch, K* (*keys)[2], uint32_t* (*vals)
     }
     const int shift = s0.begin_bit + p * kRadixBits;
     const uint32_t epoch = (uint32_t)(p + 1);
-    if (s0.ipt == 4)
+    // tile size for the work of the whole batch (the workspace was sized for the smaller tiles of one sort)
+    const int ipt = std::max(s0.ipt, pick_ipt((uint32_t)std::min<uint64_t>((uint64_t)s0.n * (uint64_t)batch, 0xffffffffull)));
+    if (ipt == 4)
       launch_pass_batch<K, 4>(a, batch, s0.n, shift, epoch, stream);
-    else if (s0.ipt == 8)
+    else if (ipt == 8)
       launch_pass_batch<K, 8>(a, batch, s0.n, shift, epoch, stream);
     else
       launch_pass_batch<K, 16>(a, batch, s0.n, shift, epoch, stream);

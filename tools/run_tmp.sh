@@ -1,4 +1,4 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_all3.log 2>&1; tail -3 gpurun_out/pytest_all3.log
-python bench.py > gpurun_out/bench_r1_i.json 2> gpurun_out/bench_r1_i.err; tail -1 gpurun_out/bench_r1_i.err; python tools/show_bench.py gpurun_out/bench_r1_i.json 2>/dev/null | grep -E "^VoxelGrid|^NN|^ICP|icp_|roofline"
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_i.json 2> gpurun_out/bench_ref_i.err; head -c 300 gpurun_out/bench_ref_i.json
+python -m pytest tests/test_gpu_next.py tests/test_gpu_parity.py -x -q -k "slots or nearest or Nearest or range or icp" > gpurun_out/pytest_kd6.log 2>&1; tail -3 gpurun_out/pytest_kd6.log
+python tools/build_prof.py 15625 2>/dev/null | head -3
+for i in 1 2; do python bench.py --no-extra --steps 20 --warmup 5 > gpurun_out/bench_vg_n$i.json 2> gpurun_out/bench_vg_n$i.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_vg_n$i.json')); print(round(d['value'],1), d['ms_per_step'], json.dumps(d['e2e'])[:330])"; done
