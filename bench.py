@@ -747,7 +747,7 @@ def run_ours(args):
         args.gpus = world
     peak = measured_peak()
     if args.only:
-        r = (bench_nn if args.only == "nn" else bench_icp)(pg, torch, dist, rank, args, peak)
+        r = {"nn": bench_nn, "icp": bench_icp, "farm": bench_icp_farm}[args.only](pg, torch, dist, rank, args, peak)
         r.pop("_check", None)
         if rank == 0:
             emit({"profiling_aid": args.only, **r})
@@ -813,7 +813,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="primary VoxelGrid line only")
     ap.add_argument("--config5", action="store_true", help="add the 50M-point map workload (slow; not in the default run)")
-    ap.add_argument("--only", default=None, choices=["nn", "icp"],
+    ap.add_argument("--only", default=None, choices=["nn", "icp", "farm"],
                     help="profiling aid: run just this extra workload and print its object (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
