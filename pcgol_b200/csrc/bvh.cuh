@@ -442,6 +442,7 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream);
 // d_ids: n point ids, already validated against [0, ix.n). Enqueues on `stream`.
 void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream);
 void index_free(Index* ix);
+void index_free_async(Index* ix, cudaStream_t stream);  // caller is on ix->device; `stream` ordered after the last use
 // Queries visited in Morton order make the threads of a warp walk the same part of the tree.
 // Writes a permutation (sorted position -> query index) into d_perm[q.n].
 void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, cudaStream_t stream);

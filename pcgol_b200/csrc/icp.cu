@@ -791,6 +791,38 @@ pcg_status icp_fit_device(const Index& base, const CloudView& tgt, const pcg_icp
   return (pcg_status)h.status;
 }
 
+constexpr int kFarmMaxStreams = 32;
+struct FarmResources {
+  int device = -1, n_streams = 0;
+  cudaStream_t streams[kFarmMaxStreams];
+  cudaEvent_t start = nullptr, done[kFarmMaxStreams];
+  IcpState* results = nullptr;  // pinned
+  size_t capacity = 0;
+};
+static FarmResources& farm_resources(int device, int count) {
+  static thread_local FarmResources r;  // never destroyed: the runtime may be gone when the thread ends
+  if (r.device != device) {
+    if (r.device >= 0) throw StatusError{PCG_E_INVALID_ARG, "pcg_icp_fit_pairs_dev: one device per calling thread"};
+    const char* e = getenv("PCG_FARM_STREAMS");  // pairs in flight (tuning runs)
+    r.n_streams = std::max(1, std::min(kFarmMaxStreams, e ? atoi(e) : 8));
+    for (int s = 0; s < r.n_streams; s++) {
+      PCG_CUDA(cudaStreamCreateWithFlags(&r.streams[s], cudaStreamNonBlocking));
+      PCG_CUDA(cudaEventCreateWithFlags(&r.done[s], cudaEventDisableTiming));
+    }
+    PCG_CUDA(cudaEventCreateWithFlags(&r.start, cudaEventDisableTiming));
+    r.device = device;
+  }
+  if ((size_t)count > r.capacity) {
+    if (r.results) cudaFreeHost(r.results);
+    r.results = nullptr;
+    r.capacity = 0;
+    const size_t cap = std::max<size_t>(64, (size_t)count * 2);
+    PCG_CUDA(cudaMallocHost((void**)&r.results, cap * sizeof(IcpState)));
+    r.capacity = cap;
+  }
+  return r;
+}
+
 // Scan-pair farm (BASELINE config 4): independent pairs round-robined over a few
 // streams so that index builds and fits of different pairs overlap.
 void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_t* n_base,
@@ -802,17 +834,16 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
   const int total = im::make_updater(prm).max_iteration;
   if (total > kMaxEnqueuedIterations)
     throw StatusError{PCG_E_INVALID_ARG, "pcg_icp_fit_pairs_dev supports MaxIteration <= 64"};
-  constexpr int kStreams = 8;
-  const int ns = std::min<int>(kStreams, count);
-  cudaStream_t streams[kStreams];
-  cudaEvent_t start, done[kStreams];
-  for (int s = 0; s < ns; s++) PCG_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
-  PCG_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
-  for (int s = 0; s < ns; s++) PCG_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+  // Streams, events and the pinned result buffer live as long as the calling thread: creating them per call costs
+  // milliseconds (cudaMallocHost synchronises the device) against ~20 ms of work for 64 pairs.
+  FarmResources& res = farm_resources(device, count);
+  const int ns = std::min<int>(res.n_streams, count);
+  cudaStream_t* streams = res.streams;
+  cudaEvent_t start = res.start;
+  cudaEvent_t* done = res.done;
   PCG_CUDA(cudaEventRecord(start, stream));
   for (int s = 0; s < ns; s++) PCG_CUDA(cudaStreamWaitEvent(streams[s], start, 0));
-  PinnedBuf results((size_t)count * sizeof(IcpState));
-  IcpState* h = (IcpState*)results.p;
+  IcpState* h = res.results;
   {
     std::vector<IcpWork> works((size_t)count);
     std::vector<Index*> indices((size_t)count, nullptr);
@@ -836,21 +867,15 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
       PCG_CUDA(cudaStreamSynchronize(stream));
     } catch (...) {
       for (int s = 0; s < ns; s++) cudaStreamSynchronize(streams[s]);
-      for (auto* ix : indices) index_free(ix);
+      for (auto* ix : indices) index_free_async(ix, stream);
       works.clear();
-      for (int s = 0; s < ns; s++) cudaStreamDestroy(streams[s]);
       throw;
     }
-    for (auto* ix : indices) index_free(ix);
+    for (auto* ix : indices) index_free_async(ix, stream);  // every pair's stream has been synchronised
   }
   for (int i = 0; i < count; i++) {
     state_to_outputs(h[i], trans_out ? trans_out + 16 * (size_t)i : nullptr, stat_out ? &stat_out[i] : nullptr);
     if (status_out) status_out[i] = (pcg_status)h[i].status;
-  }
-  cudaEventDestroy(start);
-  for (int s = 0; s < ns; s++) {
-    cudaEventDestroy(done[s]);
-    cudaStreamDestroy(streams[s]);
   }
 }
 

@@ -694,6 +694,17 @@ void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cuda
   PCG_LAUNCH(delete_points_kernel, div_up(n, 256), 256, 0, stream, ix.pts, ix.inv, d_ids, n);
 }
 
+// For owners that know the stream the index was last used on (the scan-pair farm): cudaFree synchronises
+// the whole device, a stream-ordered free does not.
+void index_free_async(Index* ix, cudaStream_t stream) {
+  if (!ix) return;
+  if (ix->pts) cudaFreeAsync(ix->pts, stream);
+  if (ix->boxes) cudaFreeAsync(ix->boxes, stream);
+  if (ix->bbox) cudaFreeAsync(ix->bbox, stream);
+  if (ix->inv) cudaFreeAsync(ix->inv, stream);
+  delete ix;
+}
+
 #ifdef PCG_NN_STATS
 }  // namespace pcg
 extern "C" void pcg_debug_nn_stats(unsigned long long out[4]) {
