@@ -51,7 +51,6 @@ struct IcpState {
 // last block's fold over all partials like few, large blocks (fast mode: 41.6 us at 256 threads, 46 at 128, 73 at 32).
 constexpr int kTermThreadsStrict = 32;
 constexpr int kTermThreadsReduce = 256;
-constexpr int kTermThreadsMax = kTermThreadsReduce;
 inline int term_threads(int mode, bool hess) {
   return ((mode & ~PCG_ICP_WITH_HESSIAN) == PCG_ICP_STRICT && !hess) ? kTermThreadsStrict : kTermThreadsReduce;
 }

@@ -1,3 +1,2 @@
-python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_r1c_n2.json 2> gpurun_out/bench_r1c_n2.err; tail -2 gpurun_out/bench_r1c_n2.err; python tools/show_bench.py gpurun_out/bench_r1c_n2.json 2>/dev/null | grep -E "^VoxelGrid|^NN|^ICP|icp_"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | head -c 300
+# scratch script for gpurun calls during development (overwritten freely)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
