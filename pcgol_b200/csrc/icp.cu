@@ -799,9 +799,11 @@ struct FarmResources {
   size_t capacity = 0;
 };
 static FarmResources& farm_resources(int device, int count) {
-  static thread_local FarmResources r;  // never destroyed: the runtime may be gone when the thread ends
+  constexpr int kMaxDevices = 64;
+  if (device < 0 || device >= kMaxDevices) throw StatusError{PCG_E_INVALID_ARG, "device ordinal out of range"};
+  static thread_local FarmResources per_device[kMaxDevices];  // never destroyed: the runtime may be gone at thread exit
+  FarmResources& r = per_device[device];
   if (r.device != device) {
-    if (r.device >= 0) throw StatusError{PCG_E_INVALID_ARG, "pcg_icp_fit_pairs_dev: one device per calling thread"};
     const char* e = getenv("PCG_FARM_STREAMS");  // pairs in flight (tuning runs)
     r.n_streams = std::max(1, std::min(kFarmMaxStreams, e ? atoi(e) : 8));
     for (int s = 0; s < r.n_streams; s++) {
