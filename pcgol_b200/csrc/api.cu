@@ -63,6 +63,11 @@ void ensure_pool(int device) {
 pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], uint8_t* d_out,
                                    int64_t* n_out, cudaStream_t stream);
 void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
+int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
+                                         int64_t* hist_out, int64_t cap, cudaStream_t stream);
+pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
+                                          int64_t cid_lo, int64_t cid_hi, uint8_t* d_out, int64_t* n_out,
+                                          cudaStream_t stream);
 void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
                     float* d_dist_sq, pcg_neighbor* d_aos, cudaStream_t stream);
 void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
@@ -652,6 +657,38 @@ pcg_status pcg_voxelgrid_filter(const void* data, int64_t n, int64_t stride, con
       PCG_CUDA(cudaStreamSynchronize(s));
     }
     return rc;
+  });
+}
+
+pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                             const float leaf[3], const int64_t chunk[3], int32_t device,
+                                             int64_t* hist, int64_t cap, int64_t* n_chunks, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!n_chunks) throw StatusError{PCG_E_INVALID_ARG, "null n_chunks"};
+    *n_chunks = 0;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    DeviceGuard g(device);
+    *n_chunks = voxelgrid_chunk_histogram_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, hist, cap,
+                                                 (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_voxelgrid_filter_chunks_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                           const float leaf[3], const int64_t chunk[3], int64_t cid_lo, int64_t cid_hi,
+                                           int32_t device, void* d_out, int64_t* n_out, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!n_out) throw StatusError{PCG_E_INVALID_ARG, "null n_out"};
+    *n_out = 0;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    if (n && !d_out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(device);
+    return voxelgrid_filter_chunks_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, cid_lo, cid_hi,
+                                          (uint8_t*)d_out, n_out, (cudaStream_t)stream);
   });
 }
 

@@ -10,7 +10,7 @@
 // record and overwrites x,y,z when the voxel has more than one member.
 #include <cooperative_groups.h>
 
-#include "common.cuh"
+#include "bvh.cuh"
 #include "icp_math.cuh"
 #include "radix_sort.cuh"
 
@@ -1438,6 +1438,164 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
     throw StatusError{PCG_E_REF_WOULD_PANIC,
                       "reference would panic: voxel or chunk index out of range (voxelgrid.go:46,89,151)"};
   *n_out = h_n;
+  return PCG_OK;
+}
+
+
+// ======================================================================================
+// One large VoxelGrid over several GPUs: chunks are independent units in the reference
+// (voxelgrid.go:102-116), so rank r filters the chunks [cid_lo, cid_hi) of the replicated cloud and the ranks'
+// outputs, concatenated in rank order, are the reference's output.  MinMaxVec3, the grid and the chunk table are
+// those of the WHOLE cloud; the points of the range are compacted in index order (the stable sort then keeps the
+// reference's accumulation order), sorted and reduced by the kernels above.
+__global__ void __launch_bounds__(256)
+    chunk_hist_kernel(CloudView v, VgParams P, unsigned int* __restrict__ hist, int* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  int bad = 0;
+  const KeyConsts C(P);
+  const unsigned long long key = voxel_key_of(P, C, load_xyz(v, i), &bad);
+  if (bad) atomicOr(flags, bad);
+  atomicAdd(&hist[key >> P.key_bits], 1u);
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256)
+    range_key_kernel(CloudView v, VgParams P, unsigned long long cid_lo, unsigned long long cid_hi,
+                     K* __restrict__ keys, float4* __restrict__ xyz4, uint32_t* __restrict__ in_range,
+                     int* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  int bad = 0;
+  const KeyConsts C(P);
+  const float3 pt = load_xyz(v, i);
+  const unsigned long long key = voxel_key_of(P, C, pt, &bad);
+  const unsigned long long cid = key >> P.key_bits;
+  const bool in = cid >= cid_lo && cid < cid_hi;
+  // an input the reference would panic on fails on every rank, whichever range the offending point falls in
+  if (bad) atomicOr(flags, bad);
+  keys[i] = (K)key;
+  xyz4[i] = make_float4(pt.x, pt.y, pt.z, 0.f);
+  in_range[i] = in ? 1u : 0u;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256)
+    range_compact_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ in_range,
+                         const long long* __restrict__ offs, uint32_t n, K* __restrict__ keys_out,
+                         uint32_t* __restrict__ vals_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !in_range[i]) return;
+  const long long o = offs[i];  // index order is kept: equal keys stay in the reference's accumulation order
+  keys_out[o] = keys[i];
+  vals_out[o] = i;
+}
+
+static void vg_params_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], VgParams* P,
+                             int* total_bits, cudaStream_t stream) {
+  if (v.n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
+  float vmin[3], vmax[3];
+  minmax_device(v, vmin, vmax, stream);
+  const long long chunk_ll[3] = {(long long)chunk[0], (long long)chunk[1], (long long)chunk[2]};
+  const pcg_status prc = vg_make_params(vmin, vmax, leaf, chunk_ll, P, total_bits);
+  if (prc != PCG_OK) throw StatusError{prc, vg_status_message(prc)};
+}
+
+static void throw_on_flags(int h_flags) {
+  if (h_flags & kFlagUndefined)
+    throw StatusError{PCG_E_REF_UNDEFINED, "a voxel coordinate is not finite / out of int64 range"};
+  if (h_flags & kFlagPanic)
+    throw StatusError{PCG_E_REF_WOULD_PANIC,
+                      "reference would panic: voxel or chunk index out of range (voxelgrid.go:46,89,151)"};
+}
+
+// Points per chunk id (the loop order of voxelgrid.go:102-116), for balancing the ranges over the ranks.
+int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
+                                         int64_t* hist_out, int64_t cap, cudaStream_t stream) {
+  VgParams P;
+  int total_bits = 0;
+  vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
+  if (P.n_chunks > ((int64_t)1 << 26)) throw StatusError{PCG_E_TOO_LARGE, "more than 2^26 chunks"};
+  if (!hist_out || cap < P.n_chunks) return P.n_chunks;  // size query
+  DevBuf<unsigned int> hist((size_t)P.n_chunks, stream);
+  DevBuf<int> d_flags(1, stream);
+  PCG_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), stream));
+  PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
+  PCG_LAUNCH(chunk_hist_kernel, div_up(v.n, 256), 256, 0, stream, v, P, hist.p, d_flags.p);
+  std::vector<unsigned int> h((size_t)P.n_chunks);
+  int h_flags = 0;
+  PCG_CUDA(cudaMemcpyAsync(h.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaMemcpyAsync(&h_flags, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  throw_on_flags(h_flags);
+  for (int64_t c = 0; c < P.n_chunks; c++) hist_out[c] = (int64_t)h[(size_t)c];
+  return P.n_chunks;
+}
+
+template <typename K>
+static void run_range_reduce(const CloudView& v, const VgParams& P, int total_bits, unsigned long long cid_lo,
+                             unsigned long long cid_hi, uint8_t* d_out, long long* d_n_out, int* d_flags,
+                             cudaStream_t stream) {
+  const uint32_t n = (uint32_t)v.n;
+  DevBuf<K> keys_all(n, stream);
+  DevBuf<float4> xyz4(n, stream);
+  DevBuf<uint32_t> in_range(n, stream);
+  DevBuf<long long> offs((size_t)n + 1, stream);
+  PCG_LAUNCH((range_key_kernel<K>), div_up(n, 256), 256, 0, stream, v, P, cid_lo, cid_hi, keys_all.p, xyz4.p, in_range.p,
+             d_flags);
+  scan_counts(in_range.p, offs.p, n, stream);
+  long long m = 0;
+  PCG_CUDA(cudaMemcpyAsync(&m, offs.p + n, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  if (m == 0) return;  // *d_n_out stays 0
+  const uint32_t nr = (uint32_t)m;
+  DevBuf<K> keys0(nr, stream), keys1(nr, stream);
+  DevBuf<uint32_t> vals0(nr, stream), vals1(nr, stream);
+  PCG_LAUNCH((range_compact_kernel<K>), div_up(n, 256), 256, 0, stream, keys_all.p, in_range.p, offs.p, n, keys0.p,
+             vals0.p);
+  rsort::Sorter<K> sorter;
+  sorter.prepare(nr, 0, total_bits, stream);
+  sorter.histogram(keys0.p, stream);
+  K* kk[2] = {keys0.p, keys1.p};
+  uint32_t* vbuf[2] = {vals0.p, vals1.p};
+  int res = 0;
+  sorter.run(kk, vbuf, /*identity_vals=*/false, /*keep_keys=*/true, stream, &res);
+  const int tiles = div_up(nr, kSegTile);
+  DevBuf<unsigned long long> status((size_t)tiles + 1, stream);
+  PCG_CUDA(cudaMemsetAsync(status.p, 0, status.bytes(), stream));
+  uint32_t* counter = (uint32_t*)(status.p + tiles);
+  CloudView vr = v;
+  vr.n = nr;  // length of the sorted list; records and points are still addressed by their original index
+  PCG_LAUNCH((voxel_reduce_kernel<K>), tiles, kSegThreads, 0, stream, vr, P, kk[res], vbuf[res], xyz4.p, d_out,
+             counter, status.p, d_n_out);
+}
+
+// Filter restricted to the chunks [cid_lo, cid_hi). Synchronises `stream`.
+pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
+                                          int64_t cid_lo, int64_t cid_hi, uint8_t* d_out, int64_t* n_out,
+                                          cudaStream_t stream) {
+  *n_out = 0;
+  VgParams P;
+  int total_bits = 0;
+  vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
+  if (cid_lo < 0 || cid_hi < cid_lo) throw StatusError{PCG_E_INVALID_ARG, "bad chunk range"};
+  DevBuf<long long> d_n(1, stream);
+  DevBuf<int> d_flags(1, stream);
+  PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
+  PCG_CUDA(cudaMemsetAsync(d_n.p, 0, sizeof(long long), stream));
+  if (total_bits <= 32)
+    run_range_reduce<uint32_t>(v, P, total_bits, (unsigned long long)cid_lo, (unsigned long long)cid_hi, d_out, d_n.p,
+                               d_flags.p, stream);
+  else
+    run_range_reduce<unsigned long long>(v, P, total_bits, (unsigned long long)cid_lo, (unsigned long long)cid_hi,
+                                         d_out, d_n.p, d_flags.p, stream);
+  long long* ph_n = (long long*)pinned_scratch();
+  int* ph_flags = (int*)(pinned_scratch() + 16);
+  PCG_CUDA(cudaMemcpyAsync(ph_n, d_n.p, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaMemcpyAsync(ph_flags, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  throw_on_flags(*ph_flags);
+  *n_out = *ph_n;
   return PCG_OK;
 }
 

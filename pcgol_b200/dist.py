@@ -33,6 +33,55 @@ def round_robin(count: int, rank: int, world: int) -> List[int]:
     return list(range(rank, count, world))
 
 
+def chunk_ranges(hist, world: int) -> List[Tuple[int, int]]:
+    """Contiguous chunk-id ranges [lo, hi) per rank, balanced by points: rank r starts at the first chunk whose
+    cumulative point count reaches r/world of the cloud.  Covers [0, len(hist)) without gaps; ranges may be empty."""
+    hist = np.asarray(hist, np.int64)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = (total * r) // world
+        c = int(np.searchsorted(cum, target, side="left"))
+        cuts.append(min(max(c, cuts[-1]), len(hist)))
+    cuts.append(len(hist))
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def sharded_voxelgrid(d_ptr: int, n: int, leaf, chunk, rank: int, world: int, d_out_ptr: int, device: int = 0,
+                      stream: int = 0, stride: int = 12, off=(0, 4, 8), group=None):
+    """One large voxelGrid.Filter over `world` GPUs: the cloud is replicated, rank r filters a range of
+    chunk ids (chunks are independent in the reference, voxelgrid.go:102-116) chosen from the chunk histogram so that
+    every rank gets about n/world points, and the outputs concatenated in rank order are the reference's output.
+    Writes this rank's records to d_out_ptr (capacity n*stride bytes is always enough) and returns
+    (n_out_local, counts_of_all_ranks, (cid_lo, cid_hi)); the only collective is the all-gather of the counts."""
+    lf = (C.c_float * 3)(*[float(x) for x in leaf])
+    ck = (C.c_int64 * 3)(*[int(x) for x in chunk])
+    offs = (C.c_int64 * 3)(*off)
+    n_chunks = C.c_int64(0)
+    _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, None, 0,
+                                                         C.byref(n_chunks), stream))
+    hist = np.zeros(max(1, n_chunks.value), np.int64)
+    _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, hist.ctypes.data,
+                                                         len(hist), C.byref(n_chunks), stream))
+    lo, hi = chunk_ranges(hist[: n_chunks.value], world)[rank]
+    n_out = C.c_int64(0)
+    _lib.check(_lib.lib.pcg_voxelgrid_filter_chunks_dev(d_ptr, n, stride, offs, lf, ck, lo, hi, device, d_out_ptr,
+                                                       C.byref(n_out), stream))
+    counts = [n_out.value]
+    try:
+        import torch
+        import torch.distributed as dist
+        if world > 1 and dist.is_available() and dist.is_initialized():
+            t = torch.tensor([n_out.value], dtype=torch.int64, device="cuda" if dist.get_backend(group) == "nccl" else "cpu")
+            gathered = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t, group=group)
+            counts = [int(g.item()) for g in gathered]
+    except ImportError:
+        pass
+    return n_out.value, counts, (lo, hi)
+
+
 def sharded_icp_fit(partial_fn: Callable[[np.ndarray, bool], "object"], params: _lib.IcpParams,
                     group=None, all_reduce: Optional[Callable] = None):
     """PointToPointICPGradient.Fit (icp.go:23-67) over a target split across ranks.

@@ -120,3 +120,23 @@ def test_sharded_icp_world2_gloo(oracle):
     rc, etrans, _, eit = oracle.icp_fit(search, target, oracle.icp_params(0.5, f64_accumulate=True))
     assert rc == oracle.OK and eit == iters
     np.testing.assert_allclose(trans, etrans, rtol=0, atol=1e-6)
+
+
+def test_chunk_ranges_partition_the_chunk_table():
+    # host logic of the sharded VoxelGrid: contiguous, gap-free, balanced by points
+    from pcgol_b200 import dist as pdist
+
+    rng = np.random.default_rng(0)
+    for trial in range(50):
+        nchunks = int(rng.integers(1, 400))
+        hist = rng.integers(0, 5000, nchunks) * (rng.random(nchunks) < 0.6)
+        for world in (1, 2, 3, 4, 8):
+            r = pdist.chunk_ranges(hist, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == nchunks
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert all(lo <= hi for lo, hi in r)
+            pts = [int(hist[lo:hi].sum()) for lo, hi in r]
+            assert sum(pts) == int(hist.sum())
+            if hist.sum() > 0:  # no rank exceeds its share by more than the largest chunk
+                assert max(pts) <= hist.sum() / world + hist.max()
+    assert pdist.chunk_ranges([0, 0, 0], 2) == [(0, 0), (0, 3)] or pdist.chunk_ranges([0, 0, 0], 2)[-1][1] == 3

@@ -71,11 +71,19 @@ def _worker(rank, world, port, q):
         rstatus, rtrans, rstat = pdist.sharded_icp_fit_device(idx, d_t.data_ptr(), hi - lo, icp.params(), stream=stream)
         assert rstatus == status and rstat.num_iteration == iters
         assert rtrans.tobytes() == trans.tobytes(), "resident loop differs from the host-driven loop"
+        # one large VoxelGrid: cloud replicated, chunk ranges per rank, all-gather of the counts
+        scan = synth.lidar_scan(3, n_az=2000)
+        d_scan = torch.from_numpy(scan).cuda()
+        d_vg = torch.empty(len(scan) * 12, dtype=torch.uint8, device="cuda")
+        m, counts, _ = pdist.sharded_voxelgrid(d_scan.data_ptr(), len(scan), (0.1, 0.1, 0.1), (32, 32, 32), rank, world,
+                                               d_vg.data_ptr(), device=rank)
+        vg_bytes = d_vg[: m * 12].cpu().numpy().tobytes()
+        assert counts[rank] == m and len(counts) == world
         # query sharding: disjoint slices of the same queries, index replicated, no collective
         q_all = synth.nn_queries(base, 50000, seed=5)
         qlo, qhi = pdist.shard_bounds(len(q_all), rank, world)
         ids, dsq = idx.nearest_batch(q_all[qlo:qhi], 1.0)
-        q.put((rank, status, trans.tobytes(), iters, qlo, ids.tobytes(), dsq.tobytes()))
+        q.put((rank, status, trans.tobytes(), iters, qlo, ids.tobytes(), dsq.tobytes(), vg_bytes, counts))
     finally:
         dist.destroy_process_group()
 
@@ -112,3 +120,8 @@ def test_sharded_icp_and_queries_world2_nccl():
     got_ids = np.concatenate([np.frombuffer(r[5], np.int64) for r in res])
     got_dsq = np.concatenate([np.frombuffer(r[6], np.float32) for r in res])
     assert np.array_equal(got_ids, ids) and got_dsq.tobytes() == dsq.tobytes()
+    # sharded VoxelGrid: rank outputs in rank order == the single-GPU Filter, counts all-gathered
+    scan = synth.lidar_scan(3, n_az=2000)
+    full = pg.VoxelGrid((0.1, 0.1, 0.1), (32, 32, 32)).filter(pg.PointCloud.from_xyz(scan))
+    assert b"".join(r[7] for r in res) == full.data[: full.points * 12].tobytes()
+    assert res[0][8] == res[1][8] and sum(res[0][8]) == full.points

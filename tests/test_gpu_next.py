@@ -473,3 +473,60 @@ def test_voxelgrid_multi_kernel_path_small_inputs():
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+# ------------------------------------------------- one large VoxelGrid sharded by chunk ranges (§8e) ------
+@pytest.mark.parametrize("layout", [(12, (0, 4, 8)), (20, (4, 8, 12))])
+def test_sharded_voxelgrid_concatenation_is_the_reference_output(pg, oracle, synth, layout):
+    # every "rank" (emulated on one GPU) filters its chunk-id range of the replicated cloud; the outputs in rank order
+    # must be the reference's output byte for byte, for any number of ranks
+    import torch
+    from pcgol_b200 import dist as pdist
+
+    stride, off = layout
+    scan = synth.lidar_scan(3, n_az=3000)  # ~190k points
+    if stride == 12:
+        data = scan.view(np.uint8).reshape(-1).copy()
+    else:
+        rec = np.zeros((len(scan), stride), np.uint8)
+        rng = np.random.default_rng(1)
+        rec[:] = rng.integers(0, 255, rec.shape, dtype=np.uint8)
+        for k in range(3):
+            rec[:, off[k]:off[k] + 4] = scan[:, k].copy().view(np.uint8).reshape(-1, 4)
+        data = rec.reshape(-1)
+    n = len(scan)
+    leaf, chunk = (0.1, 0.1, 0.1), (32, 32, 32)
+    rc, exp = oracle.voxelgrid_filter(data, stride, off, leaf, chunk, mode="sparse")
+    assert rc == oracle.OK
+    d_in = torch.from_numpy(data).cuda()
+    d_out = torch.empty(n * stride, dtype=torch.uint8, device="cuda")
+    for world in (1, 2, 3, 7):
+        parts, counts = [], []
+        for rank in range(world):
+            m, cnts, (lo, hi) = pdist.sharded_voxelgrid(d_in.data_ptr(), n, leaf, chunk, rank, world, d_out.data_ptr(),
+                                                        stride=stride, off=off)
+            parts.append(d_out[: m * stride].cpu().numpy().copy())
+            counts.append(m)
+        got = np.concatenate(parts)
+        assert got.tobytes() == exp.tobytes(), world
+        if world > 1:
+            assert max(counts) < 0.8 * sum(counts)  # the ranges are balanced by points, not by chunk count
+
+
+def test_sharded_voxelgrid_errors_and_unchunked(pg, synth):
+    import ctypes as C
+    import torch
+    from pcgol_b200 import _lib, dist as pdist
+
+    scan = synth.lidar_scan(3, n_az=500)
+    d_in = torch.from_numpy(scan).cuda()
+    d_out = torch.empty(len(scan) * 12, dtype=torch.uint8, device="cuda")
+    # un-chunked filter == the single chunk 0: rank 0 of 2 gets everything or nothing, the concatenation is complete
+    full = pg.VoxelGrid((0.2, 0.2, 0.2)).filter(pg.PointCloud.from_xyz(scan))
+    tot = 0
+    for rank in range(2):
+        m, _, _ = pdist.sharded_voxelgrid(d_in.data_ptr(), len(scan), (0.2, 0.2, 0.2), (0, 0, 0), rank, 2, d_out.data_ptr())
+        tot += m
+    assert tot == full.points
+    with pytest.raises(pg.PcgError):  # empty cloud: "no point" (pc/minmax.go:10-12)
+        pdist.sharded_voxelgrid(d_in.data_ptr(), 0, (0.2, 0.2, 0.2), (4, 4, 4), 0, 2, d_out.data_ptr())

@@ -1,3 +1,1 @@
-timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_edges.py tests/test_gpu_next.py tests/test_gpu_parity.py -x -q -k "not 50m and not large_host and not lidar_scan and not multi_kernel and not min_dist_sq_contract" > gpurun_out/memcheck2.log 2>&1; echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|rror" gpurun_out/memcheck2.log | head -8
-PCG_VG_NO_FUSED=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_edges.py -x -q -k "voxel or Voxel" > gpurun_out/memcheck3.log 2>&1; echo "memcheck(multi-kernel VG) rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/memcheck3.log | head -4
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_edges.py -x -q -k "voxel or Voxel" > gpurun_out/racecheck2.log 2>&1; echo "racecheck(VG) rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/racecheck2.log | head -4
+python -m pytest tests/test_gpu_next.py tests/test_gpu_multi.py -x -q -k "sharded" > gpurun_out/pytest_sh.log 2>&1; tail -6 gpurun_out/pytest_sh.log
