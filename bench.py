@@ -641,6 +641,46 @@ def bench_config5(pg, torch, dist, rank, args, peak):
     return out
 
 
+def bench_voxelgrid_sharded(pg, torch, dist, rank, args, peak):
+    """BASELINE config 5 (VoxelGrid part) over the job's GPUs: ONE 50M-point Filter, the cloud replicated, every rank
+    filtering a balanced range of chunk ids (dist.sharded_voxelgrid); strong scaling, the step includes the chunk
+    histogram, its read-back and the all-gather of the counts."""
+    from pcgol_b200 import dist as pdist, synth
+
+    big = synth.tiled_map(10, 5)
+    n = len(big)
+    dev = torch.device("cuda")
+    device = torch.cuda.current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+    world = dist.get_world_size() if dist is not None else 1
+    d_in = torch.from_numpy(big).to(dev)
+    d_out = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+    box = [None]
+
+    def step(i):
+        box[0] = pdist.sharded_voxelgrid(d_in.data_ptr(), n, LEAF, CHUNK, rank, world, d_out.data_ptr(), device=device,
+                                         stream=stream)
+
+    step(0)
+    step(1)
+    ms = timed_region(dist, torch, step, 5)
+    n_local, counts, (lo, hi) = box[0]
+    report = profile_kernels(pg, torch, step, 2) or {}
+    kernels = {k: round(v["total_ms"] / 2, 4) for k, v in report.items()}
+    vg = pg.VoxelGrid(LEAF, CHUNK, device=device)
+    full = [0]
+
+    def whole(i):
+        full[0] = vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr(), stream)
+
+    whole(0)
+    ms1 = timed_region(dist, torch, whole, 5)
+    return {"points": n, "world": world, "ms_per_step": ms / 5, "value_mpts": n / (ms / 5 / 1e3) / 1e6,
+            "counts_per_rank": counts, "voxels_out": int(sum(counts)), "rank0_chunk_range": [int(lo), int(hi)],
+            "unsharded_ms_per_step": ms1 / 5, "unsharded_voxels_out": int(full[0]), "scaling": "strong",
+            "rank0_kernel_ms_per_step": kernels}
+
+
 def bench_icp_sharded(pg, torch, dist, rank, args, peak):
     """BASELINE config 5 (ICP part): ONE alignment of a 1M-pt scan against a 1M-pt base, target sharded over the
     ranks, base index replicated, 16 float64 sums all-reduced over NCCL each iteration."""
@@ -748,7 +788,7 @@ def run_ours(args):
         args.gpus = world
     peak = measured_peak()
     if args.only:
-        r = {"nn": bench_nn, "icp": bench_icp, "farm": bench_icp_farm}[args.only](pg, torch, dist, rank, args, peak)
+        r = {"nn": bench_nn, "icp": bench_icp, "farm": bench_icp_farm, "vgshard": bench_voxelgrid_sharded}[args.only](pg, torch, dist, rank, args, peak)
         r.pop("_check", None)
         if rank == 0:
             emit({"profiling_aid": args.only, **r})
@@ -814,7 +854,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="primary VoxelGrid line only")
     ap.add_argument("--config5", action="store_true", help="add the 50M-point map workload (slow; not in the default run)")
-    ap.add_argument("--only", default=None, choices=["nn", "icp", "farm"],
+    ap.add_argument("--only", default=None, choices=["nn", "icp", "farm", "vgshard"],
                     help="profiling aid: run just this extra workload and print its object (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -247,12 +247,14 @@ pcg_status pcg_voxelgrid_filter_dev(const void* d_data, int64_t n, int64_t strid
  * concatenated in ascending chunk id), so with the cloud replicated every rank filters a range of chunk ids and the
  * ranks' outputs, concatenated in rank order, are the reference's output byte for byte.
  * pcg_voxelgrid_chunk_histogram_dev: points per chunk id (hist == NULL or cap too small: only *n_chunks is set) - what
- * a caller balances the ranges with.  pcg_voxelgrid_filter_chunks_dev: the Filter restricted to chunk ids
+ * a caller balances the ranges with; sample_step = 1 counts every point, s > 1 one run of 32 points out of every 32*s
+ * (any partition of the chunk ids gives the reference's output, the histogram only balances the load).  pcg_voxelgrid_filter_chunks_dev: the Filter restricted to chunk ids
  * [cid_lo, cid_hi); MinMaxVec3, the voxel grid and the chunk table are those of the whole cloud.  An un-chunked filter
  * (any ChunkSize component zero) is the single chunk 0. */
 pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                              const float leaf[3], const int64_t chunk[3], int32_t device,
-                                             int64_t* hist, int64_t cap, int64_t* n_chunks, void* stream);
+                                             int64_t sample_step, int64_t* hist, int64_t cap, int64_t* n_chunks,
+                                             void* stream);
 pcg_status pcg_voxelgrid_filter_chunks_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                            const float leaf[3], const int64_t chunk[3], int64_t cid_lo, int64_t cid_hi,
                                            int32_t device, void* d_out, int64_t* n_out, void* stream);

@@ -142,7 +142,8 @@ _sigs = {
     "pcg_region_growing_segment": (_i32, [_vp, _vp, _f, _vp, _i64, C.POINTER(_i64)]),
     "pcg_voxelgrid_filter": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64)]),
     "pcg_voxelgrid_filter_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, C.POINTER(_i64), _vp]),
-    "pcg_voxelgrid_chunk_histogram_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, C.POINTER(_i64), _vp]),
+    "pcg_voxelgrid_chunk_histogram_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i64),
+                                          _vp]),
     "pcg_voxelgrid_filter_chunks_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _vp, C.POINTER(_i64),
                                                _vp]),
     "pcg_minmax_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp]),

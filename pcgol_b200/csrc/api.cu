@@ -64,7 +64,7 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
                                    int64_t* n_out, cudaStream_t stream);
 void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
-                                         int64_t* hist_out, int64_t cap, cudaStream_t stream);
+                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream);
 pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                           int64_t cid_lo, int64_t cid_hi, uint8_t* d_out, int64_t* n_out,
                                           cudaStream_t stream);
@@ -662,7 +662,8 @@ pcg_status pcg_voxelgrid_filter(const void* data, int64_t n, int64_t stride, con
 
 pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                              const float leaf[3], const int64_t chunk[3], int32_t device,
-                                             int64_t* hist, int64_t cap, int64_t* n_chunks, void* stream) {
+                                             int64_t sample_step, int64_t* hist, int64_t cap, int64_t* n_chunks,
+                                             void* stream) {
   return guarded([&]() -> pcg_status {
     if (!n_chunks) throw StatusError{PCG_E_INVALID_ARG, "null n_chunks"};
     *n_chunks = 0;
@@ -670,7 +671,8 @@ pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int6
     check_view_args(d_data, n, stride, xyz_off);
     check_vg_args(leaf, chunk);
     DeviceGuard g(device);
-    *n_chunks = voxelgrid_chunk_histogram_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, hist, cap,
+    *n_chunks = voxelgrid_chunk_histogram_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, sample_step, hist,
+                                                 cap,
                                                  (cudaStream_t)stream);
     return PCG_OK;
   });

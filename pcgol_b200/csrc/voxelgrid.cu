@@ -1449,45 +1449,71 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
 // those of the WHOLE cloud; the points of the range are compacted in index order (the stable sort then keeps the
 // reference's accumulation order), sorted and reduced by the kernels above.
 __global__ void __launch_bounds__(256)
-    chunk_hist_kernel(CloudView v, VgParams P, unsigned int* __restrict__ hist, int* __restrict__ flags) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= v.n) return;
+    chunk_hist_kernel(CloudView v, VgParams P, int64_t sample_step, unsigned int* __restrict__ hist,
+                      int* __restrict__ flags) {
+  // a sampled histogram takes one run of 32 consecutive points out of every 32*sample_step (coalesced, and a warp
+  // still sees neighbouring points)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (t >> 5) * 32 * sample_step + (t & 31);
+  const bool live = i < v.n;
   int bad = 0;
   const KeyConsts C(P);
-  const unsigned long long key = voxel_key_of(P, C, load_xyz(v, i), &bad);
+  unsigned long long cid = ~0ull;
+  if (live) cid = voxel_key_of(P, C, load_xyz(v, i), &bad) >> P.key_bits;
   if (bad) atomicOr(flags, bad);
-  atomicAdd(&hist[key >> P.key_bits], 1u);
+  // scans are spatially coherent: a warp's 32 points fall into a few chunks, so one lane per distinct chunk adds
+  const unsigned peers = __match_any_sync(0xffffffffu, cid);
+  if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[cid], (unsigned)__popc(peers));
 }
 
 template <typename K>
 __global__ void __launch_bounds__(256)
     range_key_kernel(CloudView v, VgParams P, unsigned long long cid_lo, unsigned long long cid_hi,
-                     K* __restrict__ keys, float4* __restrict__ xyz4, uint32_t* __restrict__ in_range,
+                     K* __restrict__ keys, float4* __restrict__ xyz4, uint32_t* __restrict__ block_counts,
                      int* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= v.n) return;
-  int bad = 0;
-  const KeyConsts C(P);
-  const float3 pt = load_xyz(v, i);
-  const unsigned long long key = voxel_key_of(P, C, pt, &bad);
-  const unsigned long long cid = key >> P.key_bits;
-  const bool in = cid >= cid_lo && cid < cid_hi;
-  // an input the reference would panic on fails on every rank, whichever range the offending point falls in
-  if (bad) atomicOr(flags, bad);
-  keys[i] = (K)key;
-  xyz4[i] = make_float4(pt.x, pt.y, pt.z, 0.f);
-  in_range[i] = in ? 1u : 0u;
+  bool in = false;
+  if (i < v.n) {
+    int bad = 0;
+    const KeyConsts C(P);
+    const float3 pt = load_xyz(v, i);
+    const unsigned long long key = voxel_key_of(P, C, pt, &bad);
+    const unsigned long long cid = key >> P.key_bits;
+    in = cid >= cid_lo && cid < cid_hi;
+    // an input the reference would panic on fails on every rank, whichever range the offending point falls in
+    if (bad) atomicOr(flags, bad);
+    keys[i] = (K)key;
+    if (in) xyz4[i] = make_float4(pt.x, pt.y, pt.z, 0.f);  // the gather only reads the range's own points
+  }
+  const int cnt = __syncthreads_count(in);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)cnt;
 }
 
+// Ordered compaction of the range's points: block offsets from the scan of block_counts, rank inside the block by
+// ballot.  Index order is kept, so equal keys stay in the reference's accumulation order through the stable sort.
 template <typename K>
 __global__ void __launch_bounds__(256)
-    range_compact_kernel(const K* __restrict__ keys, const uint32_t* __restrict__ in_range,
-                         const long long* __restrict__ offs, uint32_t n, K* __restrict__ keys_out,
+    range_compact_kernel(const K* __restrict__ keys, const long long* __restrict__ block_offs, uint32_t n, int key_bits,
+                         unsigned long long cid_lo, unsigned long long cid_hi, K* __restrict__ keys_out,
                          uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t wsum[8];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !in_range[i]) return;
-  const long long o = offs[i];  // index order is kept: equal keys stay in the reference's accumulation order
-  keys_out[o] = keys[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool in = false;
+  K key = 0;
+  if (i < n) {
+    key = keys[i];
+    const unsigned long long cid = (unsigned long long)key >> key_bits;
+    in = cid >= cid_lo && cid < cid_hi;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, in);
+  if (lane == 0) wsum[warp] = (uint32_t)__popc(b);
+  __syncthreads();
+  if (!in) return;
+  uint32_t base = 0;
+  for (int w = 0; w < warp; w++) base += wsum[w];
+  const long long o = block_offs[blockIdx.x] + base + __popc(b & ((1u << lane) - 1u));
+  keys_out[o] = key;
   vals_out[o] = i;
 }
 
@@ -1511,7 +1537,8 @@ static void throw_on_flags(int h_flags) {
 
 // Points per chunk id (the loop order of voxelgrid.go:102-116), for balancing the ranges over the ranks.
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
-                                         int64_t* hist_out, int64_t cap, cudaStream_t stream) {
+                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream) {
+  if (sample_step < 1) throw StatusError{PCG_E_INVALID_ARG, "sample_step < 1"};
   VgParams P;
   int total_bits = 0;
   vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
@@ -1521,7 +1548,9 @@ int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3]
   DevBuf<int> d_flags(1, stream);
   PCG_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), stream));
   PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
-  PCG_LAUNCH(chunk_hist_kernel, div_up(v.n, 256), 256, 0, stream, v, P, hist.p, d_flags.p);
+  const int64_t runs = div_up(div_up(v.n, (int64_t)32), sample_step);
+  PCG_LAUNCH(chunk_hist_kernel, (unsigned)div_up(runs * 32, (int64_t)256), 256, 0, stream, v, P, sample_step, hist.p,
+             d_flags.p);
   std::vector<unsigned int> h((size_t)P.n_chunks);
   int h_flags = 0;
   PCG_CUDA(cudaMemcpyAsync(h.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -1539,20 +1568,21 @@ static void run_range_reduce(const CloudView& v, const VgParams& P, int total_bi
   const uint32_t n = (uint32_t)v.n;
   DevBuf<K> keys_all(n, stream);
   DevBuf<float4> xyz4(n, stream);
-  DevBuf<uint32_t> in_range(n, stream);
-  DevBuf<long long> offs((size_t)n + 1, stream);
-  PCG_LAUNCH((range_key_kernel<K>), div_up(n, 256), 256, 0, stream, v, P, cid_lo, cid_hi, keys_all.p, xyz4.p, in_range.p,
+  const uint32_t blocks = (uint32_t)div_up(n, 256);
+  DevBuf<uint32_t> block_counts(blocks, stream);
+  DevBuf<long long> offs((size_t)blocks + 1, stream);
+  PCG_LAUNCH((range_key_kernel<K>), blocks, 256, 0, stream, v, P, cid_lo, cid_hi, keys_all.p, xyz4.p, block_counts.p,
              d_flags);
-  scan_counts(in_range.p, offs.p, n, stream);
+  scan_counts(block_counts.p, offs.p, blocks, stream);
   long long m = 0;
-  PCG_CUDA(cudaMemcpyAsync(&m, offs.p + n, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaMemcpyAsync(&m, offs.p + blocks, sizeof(long long), cudaMemcpyDeviceToHost, stream));
   PCG_CUDA(cudaStreamSynchronize(stream));
   if (m == 0) return;  // *d_n_out stays 0
   const uint32_t nr = (uint32_t)m;
   DevBuf<K> keys0(nr, stream), keys1(nr, stream);
   DevBuf<uint32_t> vals0(nr, stream), vals1(nr, stream);
-  PCG_LAUNCH((range_compact_kernel<K>), div_up(n, 256), 256, 0, stream, keys_all.p, in_range.p, offs.p, n, keys0.p,
-             vals0.p);
+  PCG_LAUNCH((range_compact_kernel<K>), blocks, 256, 0, stream, keys_all.p, offs.p, n, P.key_bits, cid_lo, cid_hi,
+             keys0.p, vals0.p);
   rsort::Sorter<K> sorter;
   sorter.prepare(nr, 0, total_bits, stream);
   sorter.histogram(keys0.p, stream);

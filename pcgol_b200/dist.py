@@ -49,7 +49,7 @@ def chunk_ranges(hist, world: int) -> List[Tuple[int, int]]:
 
 
 def sharded_voxelgrid(d_ptr: int, n: int, leaf, chunk, rank: int, world: int, d_out_ptr: int, device: int = 0,
-                      stream: int = 0, stride: int = 12, off=(0, 4, 8), group=None):
+                      stream: int = 0, stride: int = 12, off=(0, 4, 8), group=None, sample_step: Optional[int] = None):
     """One large voxelGrid.Filter over `world` GPUs: the cloud is replicated, rank r filters a range of
     chunk ids (chunks are independent in the reference, voxelgrid.go:102-116) chosen from the chunk histogram so that
     every rank gets about n/world points, and the outputs concatenated in rank order are the reference's output.
@@ -58,12 +58,16 @@ def sharded_voxelgrid(d_ptr: int, n: int, leaf, chunk, rank: int, world: int, d_
     lf = (C.c_float * 3)(*[float(x) for x in leaf])
     ck = (C.c_int64 * 3)(*[int(x) for x in chunk])
     offs = (C.c_int64 * 3)(*off)
+    # balancing needs proportions, not counts: large clouds are sampled (every rank computes the same histogram)
+    step = int(sample_step) if sample_step else (16 if n >= (1 << 22) else 1)
     n_chunks = C.c_int64(0)
-    _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, None, 0,
-                                                         C.byref(n_chunks), stream))
-    hist = np.zeros(max(1, n_chunks.value), np.int64)
-    _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, hist.ctypes.data,
+    hist = np.zeros(1 << 16, np.int64)  # enough for most maps; a larger chunk table asks again with its exact size
+    _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, step, hist.ctypes.data,
                                                          len(hist), C.byref(n_chunks), stream))
+    if n_chunks.value > len(hist):
+        hist = np.zeros(n_chunks.value, np.int64)
+        _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_dev(d_ptr, n, stride, offs, lf, ck, device, step, hist.ctypes.data,
+                                                             len(hist), C.byref(n_chunks), stream))
     lo, hi = chunk_ranges(hist[: n_chunks.value], world)[rank]
     n_out = C.c_int64(0)
     _lib.check(_lib.lib.pcg_voxelgrid_filter_chunks_dev(d_ptr, n, stride, offs, lf, ck, lo, hi, device, d_out_ptr,

@@ -500,15 +500,16 @@ def test_sharded_voxelgrid_concatenation_is_the_reference_output(pg, oracle, syn
     assert rc == oracle.OK
     d_in = torch.from_numpy(data).cuda()
     d_out = torch.empty(n * stride, dtype=torch.uint8, device="cuda")
-    for world in (1, 2, 3, 7):
+    # a sampled histogram (one run of 32 points out of 32*step) only changes where the ranges are cut
+    for world, step in ((1, 1), (2, 1), (3, 1), (7, 1), (2, 5), (3, 16)):
         parts, counts = [], []
         for rank in range(world):
             m, cnts, (lo, hi) = pdist.sharded_voxelgrid(d_in.data_ptr(), n, leaf, chunk, rank, world, d_out.data_ptr(),
-                                                        stride=stride, off=off)
+                                                        stride=stride, off=off, sample_step=step)
             parts.append(d_out[: m * stride].cpu().numpy().copy())
             counts.append(m)
         got = np.concatenate(parts)
-        assert got.tobytes() == exp.tobytes(), world
+        assert got.tobytes() == exp.tobytes(), (world, step)
         if world > 1:
             assert max(counts) < 0.8 * sum(counts)  # the ranges are balanced by points, not by chunk count
 
