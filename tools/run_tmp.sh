@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_next.py tests/test_gpu_multi.py -x -q -k "sharded" > gpurun_out/pytest_sh.log 2>&1; tail -4 gpurun_out/pytest_sh.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --only vgshard > gpurun_out/vgshard_n2.json 2> gpurun_out/vgshard_n2.err; tail -2 gpurun_out/vgshard_n2.err; cat gpurun_out/vgshard_n2.json
+python -m pytest tests -x -q -m gpu > gpurun_out/pytest_final.log 2>&1; tail -4 gpurun_out/pytest_final.log
+python bench.py > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err; tail -2 gpurun_out/bench_final_n1.err; head -c 1500 gpurun_out/bench_final_n1.json
