@@ -180,6 +180,30 @@ class VoxelGrid {
     return out;
   }
 
+  // One large Filter over several GPUs (chunks are independent units, voxelgrid.go:102-116): points per chunk id of a
+  // device-resident cloud, to cut [0, n_chunks) into one range per rank ...
+  std::vector<int64_t> ChunkHistogramDev(const void* d_data, int64_t n, int64_t stride,
+                                         const std::array<int64_t, 3>& xyzOff, int64_t sampleStep = 1,
+                                         void* stream = nullptr) const {
+    int64_t chunks = 0;
+    check(pcg_voxelgrid_chunk_histogram_dev(d_data, n, stride, xyzOff.data(), leaf_.data(), chunk_.data(), device_,
+                                            sampleStep, nullptr, 0, &chunks, stream));
+    std::vector<int64_t> hist((size_t)chunks, 0);
+    check(pcg_voxelgrid_chunk_histogram_dev(d_data, n, stride, xyzOff.data(), leaf_.data(), chunk_.data(), device_,
+                                            sampleStep, hist.data(), chunks, &chunks, stream));
+    return hist;
+  }
+  // ... and the Filter restricted to chunk ids [cidLo, cidHi): the ranks' outputs in rank order are Filter's output.
+  int64_t FilterChunksDev(const void* d_data, int64_t n, int64_t stride, const std::array<int64_t, 3>& xyzOff,
+                          int64_t cidLo, int64_t cidHi, void* d_out, void* stream = nullptr) const {
+    int64_t m = 0;
+    pcg_status s = pcg_voxelgrid_filter_chunks_dev(d_data, n, stride, xyzOff.data(), leaf_.data(), chunk_.data(), cidLo,
+                                                   cidHi, device_, d_out, &m, stream);
+    if (s == PCG_E_NO_POINT) throw pc::ErrNoPoint();
+    check(s);
+    return m;
+  }
+
  private:
   mat::Vec3 leaf_;
   std::array<int64_t, 3> chunk_;
