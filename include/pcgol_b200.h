@@ -248,9 +248,10 @@ pcg_status pcg_voxelgrid_filter_dev(const void* d_data, int64_t n, int64_t strid
  * ranks' outputs, concatenated in rank order, are the reference's output byte for byte.
  * pcg_voxelgrid_chunk_histogram_dev: points per chunk id (hist == NULL or cap too small: only *n_chunks is set) - what
  * a caller balances the ranges with; sample_step = 1 counts every point, s > 1 one run of 32 points out of every 32*s
- * (any partition of the chunk ids gives the reference's output, the histogram only balances the load).  pcg_voxelgrid_filter_chunks_dev: the Filter restricted to chunk ids
- * [cid_lo, cid_hi); MinMaxVec3, the voxel grid and the chunk table are those of the whole cloud.  An un-chunked filter
- * (any ChunkSize component zero) is the single chunk 0. */
+ * (any partition of the chunk ids gives the reference's output, the histogram only balances the load).
+ * pcg_voxelgrid_filter_chunks_dev: the Filter restricted to chunk ids [cid_lo, cid_hi); MinMaxVec3, the voxel grid and the chunk table are those of the whole cloud.  For an un-chunked
+ * filter (any ChunkSize component zero; one chunk) the ids are the top <= 12 bits of the voxel key instead: voxels are
+ * independent and emitted in ascending key order (voxelgrid.go:172-184), so key ranges concatenate the same way. */
 pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                              const float leaf[3], const int64_t chunk[3], int32_t device,
                                              int64_t sample_step, int64_t* hist, int64_t cap, int64_t* n_chunks,

@@ -1449,8 +1449,8 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
 // those of the WHOLE cloud; the points of the range are compacted in index order (the stable sort then keeps the
 // reference's accumulation order), sorted and reduced by the kernels above.
 __global__ void __launch_bounds__(256)
-    chunk_hist_kernel(CloudView v, VgParams P, int64_t sample_step, unsigned int* __restrict__ hist,
-                      int* __restrict__ flags) {
+    chunk_hist_kernel(CloudView v, VgParams P, int shift, unsigned long long n_ids, int64_t sample_step,
+                      unsigned int* __restrict__ hist, int* __restrict__ flags) {
   // a sampled histogram takes one run of 32 consecutive points out of every 32*sample_step (coalesced, and a warp
   // still sees neighbouring points)
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1459,16 +1459,16 @@ __global__ void __launch_bounds__(256)
   int bad = 0;
   const KeyConsts C(P);
   unsigned long long cid = ~0ull;
-  if (live) cid = voxel_key_of(P, C, load_xyz(v, i), &bad) >> P.key_bits;
+  if (live) cid = voxel_key_of(P, C, load_xyz(v, i), &bad) >> shift;
   if (bad) atomicOr(flags, bad);
   // scans are spatially coherent: a warp's 32 points fall into a few chunks, so one lane per distinct chunk adds
   const unsigned peers = __match_any_sync(0xffffffffu, cid);
-  if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[cid], (unsigned)__popc(peers));
+  if (live && cid < n_ids && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[cid], (unsigned)__popc(peers));
 }
 
 template <typename K>
 __global__ void __launch_bounds__(256)
-    range_key_kernel(CloudView v, VgParams P, unsigned long long cid_lo, unsigned long long cid_hi,
+    range_key_kernel(CloudView v, VgParams P, int shift, unsigned long long cid_lo, unsigned long long cid_hi,
                      K* __restrict__ keys, float4* __restrict__ xyz4, uint32_t* __restrict__ block_counts,
                      int* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1478,7 +1478,7 @@ __global__ void __launch_bounds__(256)
     const KeyConsts C(P);
     const float3 pt = load_xyz(v, i);
     const unsigned long long key = voxel_key_of(P, C, pt, &bad);
-    const unsigned long long cid = key >> P.key_bits;
+    const unsigned long long cid = key >> shift;
     in = cid >= cid_lo && cid < cid_hi;
     // an input the reference would panic on fails on every rank, whichever range the offending point falls in
     if (bad) atomicOr(flags, bad);
@@ -1493,7 +1493,7 @@ __global__ void __launch_bounds__(256)
 // ballot.  Index order is kept, so equal keys stay in the reference's accumulation order through the stable sort.
 template <typename K>
 __global__ void __launch_bounds__(256)
-    range_compact_kernel(const K* __restrict__ keys, const long long* __restrict__ block_offs, uint32_t n, int key_bits,
+    range_compact_kernel(const K* __restrict__ keys, const long long* __restrict__ block_offs, uint32_t n, int shift,
                          unsigned long long cid_lo, unsigned long long cid_hi, K* __restrict__ keys_out,
                          uint32_t* __restrict__ vals_out) {
   __shared__ uint32_t wsum[8];
@@ -1503,7 +1503,7 @@ __global__ void __launch_bounds__(256)
   K key = 0;
   if (i < n) {
     key = keys[i];
-    const unsigned long long cid = (unsigned long long)key >> key_bits;
+    const unsigned long long cid = (unsigned long long)key >> shift;
     in = cid >= cid_lo && cid < cid_hi;
   }
   const unsigned b = __ballot_sync(0xffffffffu, in);
@@ -1535,7 +1535,15 @@ static void throw_on_flags(int h_flags) {
                       "reference would panic: voxel or chunk index out of range (voxelgrid.go:46,89,151)"};
 }
 
-// Points per chunk id (the loop order of voxelgrid.go:102-116), for balancing the ranges over the ranks.
+// The ids a sharded Filter is cut by: chunk ids when the filter is chunked (the loop of voxelgrid.go:102-116); for an
+// un-chunked filter (one chunk) the top <= 12 bits of the voxel key - voxels are independent and emitted in ascending
+// key order (voxelgrid.go:172-184), so contiguous key ranges concatenate to the reference's output just the same.
+static int range_shift(const VgParams& P) { return P.n_chunks > 1 ? P.key_bits : std::max(0, P.key_bits - 12); }
+static int64_t range_ids(const VgParams& P) {
+  return P.n_chunks > 1 ? (int64_t)P.n_chunks : (int64_t)(((unsigned long long)(P.n_voxels - 1)) >> range_shift(P)) + 1;
+}
+
+// Points per id, for balancing the ranges over the ranks.
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                          int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream) {
   if (sample_step < 1) throw StatusError{PCG_E_INVALID_ARG, "sample_step < 1"};
@@ -1543,22 +1551,24 @@ int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3]
   int total_bits = 0;
   vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
   if (P.n_chunks > ((int64_t)1 << 26)) throw StatusError{PCG_E_TOO_LARGE, "more than 2^26 chunks"};
-  if (!hist_out || cap < P.n_chunks) return P.n_chunks;  // size query
-  DevBuf<unsigned int> hist((size_t)P.n_chunks, stream);
+  const int64_t ids = range_ids(P);
+  const int shift = range_shift(P);
+  if (!hist_out || cap < ids) return ids;  // size query
+  DevBuf<unsigned int> hist((size_t)ids, stream);
   DevBuf<int> d_flags(1, stream);
   PCG_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), stream));
   PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
   const int64_t runs = div_up(div_up(v.n, (int64_t)32), sample_step);
-  PCG_LAUNCH(chunk_hist_kernel, (unsigned)div_up(runs * 32, (int64_t)256), 256, 0, stream, v, P, sample_step, hist.p,
-             d_flags.p);
-  std::vector<unsigned int> h((size_t)P.n_chunks);
+  PCG_LAUNCH(chunk_hist_kernel, (unsigned)div_up(runs * 32, (int64_t)256), 256, 0, stream, v, P, shift,
+             (unsigned long long)ids, sample_step, hist.p, d_flags.p);
+  std::vector<unsigned int> h((size_t)ids);
   int h_flags = 0;
   PCG_CUDA(cudaMemcpyAsync(h.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, stream));
   PCG_CUDA(cudaMemcpyAsync(&h_flags, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   PCG_CUDA(cudaStreamSynchronize(stream));
   throw_on_flags(h_flags);
-  for (int64_t c = 0; c < P.n_chunks; c++) hist_out[c] = (int64_t)h[(size_t)c];
-  return P.n_chunks;
+  for (int64_t c = 0; c < ids; c++) hist_out[c] = (int64_t)h[(size_t)c];
+  return ids;
 }
 
 template <typename K>
@@ -1571,7 +1581,8 @@ static void run_range_reduce(const CloudView& v, const VgParams& P, int total_bi
   const uint32_t blocks = (uint32_t)div_up(n, 256);
   DevBuf<uint32_t> block_counts(blocks, stream);
   DevBuf<long long> offs((size_t)blocks + 1, stream);
-  PCG_LAUNCH((range_key_kernel<K>), blocks, 256, 0, stream, v, P, cid_lo, cid_hi, keys_all.p, xyz4.p, block_counts.p,
+  const int shift = range_shift(P);
+  PCG_LAUNCH((range_key_kernel<K>), blocks, 256, 0, stream, v, P, shift, cid_lo, cid_hi, keys_all.p, xyz4.p, block_counts.p,
              d_flags);
   scan_counts(block_counts.p, offs.p, blocks, stream);
   long long m = 0;
@@ -1581,7 +1592,7 @@ static void run_range_reduce(const CloudView& v, const VgParams& P, int total_bi
   const uint32_t nr = (uint32_t)m;
   DevBuf<K> keys0(nr, stream), keys1(nr, stream);
   DevBuf<uint32_t> vals0(nr, stream), vals1(nr, stream);
-  PCG_LAUNCH((range_compact_kernel<K>), blocks, 256, 0, stream, keys_all.p, offs.p, n, P.key_bits, cid_lo, cid_hi,
+  PCG_LAUNCH((range_compact_kernel<K>), blocks, 256, 0, stream, keys_all.p, offs.p, n, shift, cid_lo, cid_hi,
              keys0.p, vals0.p);
   rsort::Sorter<K> sorter;
   sorter.prepare(nr, 0, total_bits, stream);

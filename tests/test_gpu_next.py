@@ -514,7 +514,7 @@ def test_sharded_voxelgrid_concatenation_is_the_reference_output(pg, oracle, syn
             assert max(counts) < 0.8 * sum(counts)  # the ranges are balanced by points, not by chunk count
 
 
-def test_sharded_voxelgrid_errors_and_unchunked(pg, synth):
+def test_sharded_voxelgrid_errors_and_unchunked(pg, oracle, synth):
     import ctypes as C
     import torch
     from pcgol_b200 import _lib, dist as pdist
@@ -522,12 +522,19 @@ def test_sharded_voxelgrid_errors_and_unchunked(pg, synth):
     scan = synth.lidar_scan(3, n_az=500)
     d_in = torch.from_numpy(scan).cuda()
     d_out = torch.empty(len(scan) * 12, dtype=torch.uint8, device="cuda")
-    # un-chunked filter == the single chunk 0: rank 0 of 2 gets everything or nothing, the concatenation is complete
-    full = pg.VoxelGrid((0.2, 0.2, 0.2)).filter(pg.PointCloud.from_xyz(scan))
-    tot = 0
-    for rank in range(2):
-        m, _, _ = pdist.sharded_voxelgrid(d_in.data_ptr(), len(scan), (0.2, 0.2, 0.2), (0, 0, 0), rank, 2, d_out.data_ptr())
-        tot += m
-    assert tot == full.points
+    # un-chunked filter: the ids are prefixes of the voxel key (voxels are independent and emitted in ascending key
+    # order, voxelgrid.go:172-184), so the concatenation is again the reference's output and every rank gets a share
+    leaf = (0.2, 0.2, 0.2)
+    data = scan.view(np.uint8).reshape(-1).copy()
+    rc, exp = oracle.voxelgrid_filter(data, 12, (0, 4, 8), leaf, (0, 0, 0), mode="sparse")
+    assert rc == oracle.OK
+    for world in (2, 5):
+        parts, counts = [], []
+        for rank in range(world):
+            m, _, _ = pdist.sharded_voxelgrid(d_in.data_ptr(), len(scan), leaf, (0, 0, 0), rank, world, d_out.data_ptr())
+            parts.append(d_out[: m * 12].cpu().numpy().copy())
+            counts.append(m)
+        assert np.concatenate(parts).tobytes() == exp.tobytes(), world
+        assert min(counts) > 0
     with pytest.raises(pg.PcgError):  # empty cloud: "no point" (pc/minmax.go:10-12)
         pdist.sharded_voxelgrid(d_in.data_ptr(), 0, (0.2, 0.2, 0.2), (4, 4, 4), 0, 2, d_out.data_ptr())

@@ -1,2 +1,1 @@
-python -m pytest tests -x -q -m gpu > gpurun_out/pytest_final.log 2>&1; tail -4 gpurun_out/pytest_final.log
-python bench.py > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err; tail -2 gpurun_out/bench_final_n1.err; head -c 1500 gpurun_out/bench_final_n1.json
+python -m pytest tests/test_gpu_next.py -x -q -k "sharded" > gpurun_out/pytest_sh.log 2>&1; tail -12 gpurun_out/pytest_sh.log
