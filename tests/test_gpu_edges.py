@@ -183,3 +183,30 @@ def test_strict_replay_is_the_sequential_float32_sum(pg):
         got = _seq_sum(pg, x, exact=True)
         assert got_seq.tobytes() == f32(exp).tobytes() or (np.isnan(exp) and np.isnan(got_seq)), name
         assert got.tobytes() == got_seq.tobytes() or (np.isnan(got) and np.isnan(got_seq)), (name, got, got_seq)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", [(0, 0, 0), (128, 128, 128), (4096, 4096, 4096)])
+def test_voxelgrid_keys_wider_than_32_bits(pg, oracle, chunk):
+    # leaf 1 mm over a 4 x 3 x 1.5 m box: 1.8e10 voxels un-chunked (35-bit keys), 9216 chunks x 22-bit keys chunked;
+    # the 64-bit sort-key path of the plain Filter and of the sharded one (3 ranks emulated on one GPU)
+    import torch
+    from pcgol_b200 import dist as pdist
+
+    rng = np.random.default_rng(77)
+    n = 30000
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([4.0, 3.0, 1.5], f32)).astype(f32)
+    xyz[: n // 2] = (xyz[: n // 2] * f32(0.01)).astype(f32)  # half of the points share voxels near the origin
+    xyz -= xyz.min(axis=0)
+    leaf = (0.001, 0.001, 0.001)
+    rc, exp, grc, got = _vg_both(pg, oracle, xyz, leaf, chunk)
+    assert rc == oracle.OK and grc == 0
+    assert got.tobytes() == exp.tobytes()
+    assert len(exp) < n * 12  # some voxels do hold several points
+    d_in = torch.from_numpy(xyz).cuda()
+    d_out = torch.empty(n * 12, dtype=torch.uint8, device="cuda")
+    parts = []
+    for rank in range(3):
+        m, _, _ = pdist.sharded_voxelgrid(d_in.data_ptr(), n, leaf, chunk, rank, 3, d_out.data_ptr())
+        parts.append(d_out[: m * 12].cpu().numpy().copy())
+    assert np.concatenate(parts).tobytes() == exp.tobytes()

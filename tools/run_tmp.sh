@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_next.py -x -q -k "sharded" > gpurun_out/pytest_sh.log 2>&1; tail -12 gpurun_out/pytest_sh.log
+python -m pytest tests/test_gpu_edges.py -x -q -k "wider" > gpurun_out/pytest_wide.log 2>&1; tail -25 gpurun_out/pytest_wide.log
