@@ -210,3 +210,51 @@ def test_voxelgrid_keys_wider_than_32_bits(pg, oracle, chunk):
         m, _, _ = pdist.sharded_voxelgrid(d_in.data_ptr(), n, leaf, chunk, rank, 3, d_out.data_ptr())
         parts.append(d_out[: m * 12].cpu().numpy().copy())
     assert np.concatenate(parts).tobytes() == exp.tobytes()
+
+
+@pytest.mark.gpu
+def test_one_handle_many_threads(pg):
+    # the reference's KDTree.Nearest / Range are goroutine-safe (sync.Pool, kdtree.go:44-50; CI runs -race): eight OS
+    # threads share one index handle and also run Filters and Fits side by side; every result must equal the
+    # single-threaded one bit for bit
+    import threading
+
+    from pcgol_b200 import synth
+
+    scan = synth.lidar_scan(5, n_az=600)  # ~38k points
+    rng = np.random.default_rng(5)
+    idx = pg.Index(scan)
+    queries = [(scan[rng.choice(len(scan), 4000)] + rng.normal(0, 0.1, (4000, 3))).astype(f32) for _ in range(8)]
+    vg = pg.VoxelGrid((0.1, 0.1, 0.1), (32, 32, 32))
+    cloud = pg.PointCloud.from_xyz(scan)
+    c, s = np.cos(0.02), np.sin(0.02)
+    target = (scan[::3] @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], f32).T + f32(0.05)).astype(f32)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+
+    def work(k):
+        ids, dsq = idx.nearest_batch(queries[k], 0.5)
+        off, rids, rdsq = idx.range_batch(queries[k][:500], 0.3)
+        out = vg.filter(cloud).data.tobytes()
+        trans, stat = icp.fit(idx, target)
+        return ids.tobytes(), dsq.tobytes(), off.tobytes(), rids.tobytes(), rdsq.tobytes(), out, trans.tobytes(), \
+            stat.num_iteration
+
+    expected = [work(k) for k in range(8)]
+    got = [None] * 8
+    errors = []
+
+    def run(k):
+        try:
+            for _ in range(3):
+                got[k] = work(k)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(8):
+        assert got[k] == expected[k], k
