@@ -334,7 +334,12 @@ __global__ void __launch_bounds__(32)
 //      otherwise the chunk is replayed element by element like the reference (from shared memory).
 // The result is the reference's float32 sum, bit for bit, for any input; LiDAR residuals take the
 // element-wise path only around the few binade crossings of each accumulator.
-constexpr int kReplayChunk = 256;
+#ifndef PCG_REPLAY_CHUNK
+#define PCG_REPLAY_CHUNK 256
+#endif
+constexpr int kReplayChunk = PCG_REPLAY_CHUNK;        // elements folded into one summary
+constexpr int kReplayPerLane = kReplayChunk / 32;     // consecutive elements per lane when a warp folds a chunk
+static_assert(kReplayChunk % 128 == 0 || kReplayChunk == 64 || kReplayChunk == 32, "chunk = whole float4 rows per warp");
 constexpr int kReplayThreads = 512;
 constexpr int kReplayBatch = 256;  // chunk summaries staged in shared memory per round of the walk
 
@@ -385,10 +390,10 @@ __global__ void __launch_bounds__(256)
   if (w >= nchunks * streams) return;
   const int64_t k = w / nchunks, c = w - k * nchunks;
   const float* __restrict__ x = terms + k * n_pad;
-  const int64_t base = c * kReplayChunk + lane * 8;
+  const int64_t base = c * kReplayChunk + lane * kReplayPerLane;
   double s = 0.0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) s += (base + j < n) ? (double)x[base + j] : 0.0;
+  for (int j = 0; j < kReplayPerLane; j++) s += (base + j < n) ? (double)x[base + j] : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) chunk_sums[w] = s;
@@ -414,14 +419,14 @@ __global__ void __launch_bounds__(256)
   const int e = float_exponent(guess);
   bool regular = guess != 0.f && e > -100 && e < 128;  // not zero / (near) denormal / inf / nan
   const double scale = regular ? __longlong_as_double((long long)(1023 + 23 - e) << 52) : 0.0;  // 2^(23-e), exact
-  const int64_t base = c * kReplayChunk + lane * 8;
+  const int64_t base = c * kReplayChunk + lane * kReplayPerLane;
   ParityMap m;
   m.off[0] = m.off[1] = 0;
   m.mn[0] = m.mn[1] = 0x7fffffffffffffffll;
   m.mx[0] = m.mx[1] = -0x7fffffffffffffffll;
   m.np = 2;  // identity: parity p stays p
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
+  for (int j = 0; j < kReplayPerLane; j++) {
     const float xv = (base + j < n) ? x[base + j] : 0.f;
     const double y = (double)xv * scale;  // exact: power-of-two scaling inside double's range
     double q = floor(y);
