@@ -59,33 +59,40 @@ int main(int argc, char** argv) {
     vector<double> csum(nch), psub((size_t)(n + SUB - 1) / SUB + 1, 0.0);
     for (ll c = 0; c < nch; c++) { double s = 0; for (ll i = c * CH; i < min(n, (c + 1) * CH); i++) s += x[i]; csum[c] = s; }
     { double s = 0; for (ll i = 0; i < n; i++) { if (i % SUB == 0) psub[i / SUB] = s; s += x[i]; } }
-    float acc = 0.f, seq = 0.f; double g = 0; ll slow = 0, c_unus = 0, c_bin = 0, c_cross = 0, c_margin = 0, b_slow_sub = 0, c_onepass = 0, d_slow_sub = 0;
+    float acc = 0.f, seq = 0.f; double g = 0; ll slow = 0, c_unus = 0, c_bin = 0, c_cross = 0, c_margin = 0, b_slow_sub = 0, c_onepass = 0, d_slow_sub = 0, e_slow_sub = 0, pred_miss = 0, pred_extra = 0;
     for (ll c = 0; c < nch; c++) {
       const float guess = (float)g; g += csum[c];
       const Summary s = summarize(x, c * CH, CH, n, fexp(guess), guess_regular(guess));
       float nxt;
-      if (fast_ok(s, acc, &nxt)) { acc = nxt; }
+      // prediction available when the summaries are built: does the GUESS accumulator pass the interval test?
+      float dummy; const bool predicted_fast = fast_ok(s, guess, &dummy);
+      if (fast_ok(s, acc, &nxt)) { acc = nxt; if (!predicted_fast) pred_extra++; }
       else {
         slow++;
+        if (predicted_fast) pred_miss++;
         // why
         bool crossing = false; { float a = acc; const int e0 = fexp(a); for (ll i = c * CH; i < min(n, (c + 1) * CH); i++) { a += x[i]; if (a == 0.f || fexp(a) != e0) crossing = true; } }
         if (!s.usable) c_unus++; else if (acc == 0.f || fexp(acc) != s.e) c_bin++; else if (crossing) c_cross++; else c_margin++;
         // C: one more warp pass with the TRUE binade of the accumulator settles the chunk in one add
         { const Summary t = summarize(x, c * CH, CH, n, fexp(acc), guess_regular(acc)); float o; if (fast_ok(t, acc, &o)) c_onepass++; }
         // B: sub-chunk summaries with their own f64-prefix guesses; D: sub-chunk summaries in the true binade
-        float a = acc, ad = acc;
+        float a = acc, ad = acc, ae = acc;
         for (ll b = c * CH; b < min(n, (c + 1) * (ll)CH); b += SUB) {
           const float gs = (float)psub[b / SUB]; const Summary t = summarize(x, b, SUB, n, fexp(gs), guess_regular(gs)); float o;
           if (fast_ok(t, a, &o)) a = o; else { b_slow_sub++; for (ll i = b; i < min(n, b + SUB); i++) a += x[i]; }
           const Summary td = summarize(x, b, SUB, n, fexp(ad), guess_regular(ad));
           if (fast_ok(td, ad, &o)) ad = o; else { d_slow_sub++; for (ll i = b; i < min(n, b + SUB); i++) ad += x[i]; }
+          // E: sub-chunk maps exist only for the chunk's guessed binade and its two neighbours
+          const int ee = fexp(ae); const bool have = ae != 0.f && abs(ee - s.e) <= 1;
+          const Summary te = summarize(x, b, SUB, n, ee, have && guess_regular(ae));
+          if (have && fast_ok(te, ae, &o)) ae = o; else { e_slow_sub++; for (ll i = b; i < min(n, b + SUB); i++) ae += x[i]; }
         }
         for (ll i = c * CH; i < min(n, (c + 1) * (ll)CH); i++) acc += x[i];
-        if (bits(a) != bits(acc) || bits(ad) != bits(acc)) { printf("MODEL ERROR in sub-chunk path, stream %d chunk %lld\n", k, c); return 2; }
+        if (bits(a) != bits(acc) || bits(ad) != bits(acc) || bits(ae) != bits(acc)) { printf("MODEL ERROR in sub-chunk path, stream %d chunk %lld\n", k, c); return 2; }
       }
     }
     for (ll i = 0; i < n; i++) seq += x[i];
-    printf("%-6s %6lld %6lld | %13lld %8lld %8lld %8lld | %10lld %10lld %10lld | %s\n", names[k], nch, slow, c_unus, c_bin, c_cross, c_margin, b_slow_sub, c_onepass, d_slow_sub, bits(seq) == bits(acc) ? "exact" : "MISMATCH");
+    printf("%-6s %6lld %6lld | %13lld %8lld %8lld %8lld | %10lld %10lld %10lld | %s  E:slow-sub %lld  predicted-fast-but-slow %lld, predicted-slow-but-fast %lld\n", names[k], nch, slow, c_unus, c_bin, c_cross, c_margin, b_slow_sub, c_onepass, d_slow_sub, bits(seq) == bits(acc) ? "exact" : "MISMATCH", e_slow_sub, pred_miss, pred_extra);
     worst_slow = max(worst_slow, slow); worst_b = max(worst_b, b_slow_sub); worst_d = max(worst_d, d_slow_sub);
   }
   printf("slowest stream: %lld replayed chunks (%lld element adds) now; two-level: %lld sub-chunks (%lld adds) with prefix guesses, %lld (%lld adds) in the true binade\n",
