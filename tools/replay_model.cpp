@@ -48,9 +48,30 @@ static bool fast_ok(const Summary& s, float acc, float* out) {
 static bool guess_regular(float g) { const int e = fexp(g); return g != 0.f && e > -100 && e < 128; }
 int main(int argc, char** argv) {
   const char* path = argc > 1 ? argv[1] : "/tmp/rpm/iterN.bin"; const int CH = argc > 2 ? atoi(argv[2]) : 256; const int SUB = argc > 3 ? atoi(argv[3]) : 32;
-  FILE* f = fopen(path, "rb"); if (!f) { perror(path); return 1; } fseek(f, 0, SEEK_END); const long sz = ftell(f); fseek(f, 0, SEEK_SET);
-  const ll n = sz / 4 / 9; vector<float> all((size_t)n * 9); if (fread(all.data(), 4, all.size(), f) != all.size()) return 1; fclose(f);
-  const char* names[9] = {"Value", "SumW", "G0", "G1", "G2", "G3", "G4", "G5", "R"};
+  ll n; vector<float> all;
+  const char* names_icp[9] = {"Value", "SumW", "G0", "G1", "G2", "G3", "G4", "G5", "R"};
+  const char* names_syn[9] = {"unif", "ties", "heavy", "altern", "const", "ints", "zeroX", "grow", "sparse"};
+  const char** names = names_icp;
+  if (!strcmp(path, "selftest")) {  // adversarial synthetic streams: ties, sign changes, mixed magnitudes, zero crossings
+    names = names_syn; n = 70001; all.resize((size_t)n * 9); uint64_t st = argc > 4 ? strtoull(argv[4], 0, 10) : 12345;
+    auto rnd = [&]() { st += 0x9e3779b97f4a7c15ull; uint64_t z = st; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; return z ^ (z >> 31); };
+    auto uni = [&]() { return (double)(rnd() >> 11) / 9007199254740992.0; };
+    auto nrm = [&]() { return sqrt(-2 * log(uni() + 1e-300)) * cos(6.283185307179586 * uni()); };
+    for (ll i = 0; i < n; i++) {
+      all[0 * n + i] = (float)(2 * uni() - 1);
+      all[1 * n + i] = (float)((double)((ll)(rnd() % 8193) - 4096) / 1024.0);           // multiples of 2^-10: exact ties
+      all[2 * n + i] = (float)(nrm() * exp(3 * nrm()));
+      all[3 * n + i] = (float)((i & 1 ? -1.0 : 1.0) + 1e-4 * nrm());
+      all[4 * n + i] = 0.1f;
+      all[5 * n + i] = (float)(1e-3 * (double)((ll)(rnd() % 2001) - 1000));
+      all[6 * n + i] = (float)(sin(i * 0.001) * (1 + 0.01 * nrm()));                     // sum oscillates through zero
+      all[7 * n + i] = (float)(ldexp(1.0, (int)(i / 3000)) * (uni() - 0.3));             // grows over 23 binades
+      all[8 * n + i] = (rnd() % 50 == 0) ? (float)(1000 * nrm()) : 0.f;
+    }
+  } else {
+    FILE* f = fopen(path, "rb"); if (!f) { perror(path); return 1; } fseek(f, 0, SEEK_END); const long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    n = sz / 4 / 9; all.resize((size_t)n * 9); if (fread(all.data(), 4, all.size(), f) != all.size()) return 1; fclose(f);
+  }
   printf("%s: n = %lld, chunk %d, sub-chunk %d\n", path, n, CH, SUB);
   printf("%-6s %6s %6s | slow: %7s %8s %8s %8s | %10s %10s %10s | %s\n", "stream", "chunks", "slow", "unusabl", "binade!=", "crossing", "margin", "B:slow-sub", "C:1-pass", "D:slow-sub", "check");
   ll worst_slow = 0, worst_b = 0, worst_d = 0;
