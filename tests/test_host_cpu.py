@@ -120,3 +120,19 @@ def test_icp_finish_host_matches_oracle(oracle):
         et, econv = oracle.icp_update(oracle.icp_params(1.0), trial % 20, oracle.rotate(0, 0, 1, 0.05 * trial), ev8)
         assert bool(conv.value) == econv
         assert trans.tobytes() == et.tobytes()
+
+
+def test_replay_model_selftest(tmp_path):
+    # tools/replay_model.cpp restates the strict-ICP replay rules (binade summaries, parity automaton, interval test,
+    # neighbour-binade sub-chunk maps) on the CPU; on adversarial streams every variant must reproduce the sequential
+    # float32 sum bit for bit
+    import subprocess
+
+    exe = tmp_path / "replay_model"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-o", str(exe), os.path.join(ROOT, "tools", "replay_model.cpp")],
+                   check=True)
+    for seed in ("1", "7"):
+        out = subprocess.run([str(exe), "selftest", "256", "32", seed], check=True, capture_output=True, text=True).stdout
+        rows = [ln for ln in out.splitlines() if "| exact" in ln or "MISMATCH" in ln]
+        assert len(rows) == 9 and all("| exact" in ln for ln in rows), out
+        assert "MODEL ERROR" not in out
