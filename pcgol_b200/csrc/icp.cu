@@ -18,7 +18,6 @@
 //                      is set the remaining launches fall through.
 #include <algorithm>
 #include <cstdlib>
-#include <mutex>
 #include <vector>
 
 #include "bvh.cuh"
@@ -966,10 +965,8 @@ static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int
   static const bool v1 = getenv("PCG_REPLAY_V1") != nullptr;  // comparison runs
   if (!v1) {
     const size_t smem = 2 * sizeof(W2Buf);
-    static std::once_flag once;
-    std::call_once(once, [&] {
-      PCG_CUDA(cudaFuncSetAttribute(icp_replay_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    });
+    // per device, and cheap: set on every launch
+    PCG_CUDA(cudaFuncSetAttribute(icp_replay_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PCG_LAUNCH(icp_replay_walk2_kernel, streams, kReplayThreads, smem, stream, st, terms, n, n_pad, nchunks, streams,
                chunks);
     return;
