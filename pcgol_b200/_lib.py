@@ -108,6 +108,7 @@ _sigs = {
     "pcg_debug_sequential_sum_f32": (_i32, [_vp, _i64, _i32, _i32, _vp]),
     "pcg_debug_index_slots": (_i32, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "pcg_profile_enable": (None, [_i32]),
+    "pcg_debug_set_vg_path": (None, [_i32]),
     "pcg_profile_report": (_i64, [C.c_char_p, _i64]),
     "pcg_index_build": (_i32, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_vp)]),
     "pcg_index_build_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _vp, C.POINTER(_vp)]),
@@ -194,6 +195,11 @@ def kernel_launch_count() -> int:
 
 def profile_enable(on: bool) -> None:
     lib.pcg_profile_enable(1 if on else 0)
+
+
+def set_vg_path(path: int) -> None:
+    """Test hook: 0 automatic, 1 LSD pipeline, 2 cooperative kernel, 3 partition pipeline."""
+    lib.pcg_debug_set_vg_path(int(path))
 
 
 def profile_report() -> dict:

@@ -63,6 +63,7 @@ void ensure_pool(int device) {
 pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], uint8_t* d_out,
                                    int64_t* n_out, cudaStream_t stream);
 void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
+extern std::atomic<int> g_vg_path;
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                          int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream);
 pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
@@ -219,6 +220,7 @@ int32_t pcg_device_count(void) {
 int64_t pcg_kernel_launch_count(void) { return g_launches.load(); }
 
 void pcg_profile_enable(int32_t on) { g_profile.store(on ? 1 : 0); }
+void pcg_debug_set_vg_path(int32_t path) { g_vg_path.store(path); }
 
 pcg_status pcg_debug_sequential_sum_f32(const float* x, int64_t n, int32_t device, int32_t exact_path, float* out) {
   return guarded([&]() -> pcg_status {

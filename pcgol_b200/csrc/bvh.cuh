@@ -53,70 +53,9 @@ __device__ __forceinline__ uint64_t nn_init(float max_range_sq) {
   return (uint64_t)__float_as_uint(max_range_sq) << 32;
 }
 
-// Exact nearest neighbour. `best` must be nn_init(maxRange^2) (or a tighter bound);
-// on return it is unchanged for a miss, else (DistSq bits << 32 | original index) and
-// best_pos is the winner's position in ix.pts.
-__device__ __forceinline__ void nn_traverse(const IndexView& ix, float qx, float qy, float qz, uint64_t& best,
-                                            uint32_t& best_pos) {
-  if (ix.n == 0) return;
-  if (qx != qx || qy != qy || qz != qz) return;  // NaN never compares below the bound in the reference
-  uint32_t stack_node[kMaxStack];
-  float stack_d[kMaxStack];
-  int sp = 0;
-  float bestd = __uint_as_float((uint32_t)(best >> 32));
-  {
-    float d = box_dist_sq(ix.boxes[2], ix.boxes[3], qx, qy, qz);
-    if (!(d <= bestd)) return;
-  }
-  const uint32_t P = ix.P;
-  uint32_t node = 1;
-  for (;;) {
-    while (node < P) {
-      const float4* cb = ix.boxes + 4 * (size_t)node;
-      const float4 l0 = __ldg(cb), h0 = __ldg(cb + 1), l1 = __ldg(cb + 2), h1 = __ldg(cb + 3);
-      const float d0 = box_dist_sq(l0, h0, qx, qy, qz);
-      const float d1 = box_dist_sq(l1, h1, qx, qy, qz);
-      const bool first0 = d0 <= d1;
-      const float dn = first0 ? d0 : d1, df = first0 ? d1 : d0;
-      const uint32_t near_node = 2 * node + (first0 ? 0u : 1u), far_node = 2 * node + (first0 ? 1u : 0u);
-      if (!(dn <= bestd)) {
-        node = 0;
-        break;
-      }
-      if (df <= bestd) {
-        stack_node[sp] = far_node;
-        stack_d[sp] = df;
-        sp++;
-      }
-      node = near_node;
-    }
-    if (node) {
-      const uint32_t base = (node - P) * kLeaf;
-      const float4* lp = ix.pts + base;
-#pragma unroll
-      for (int j = 0; j < kLeaf; j++) {
-        const float4 p = __ldg(lp + j);
-        const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
-        const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
-        if (packed < best) {
-          best = packed;
-          best_pos = base + j;
-        }
-      }
-      bestd = __uint_as_float((uint32_t)(best >> 32));
-    }
-    node = 0;
-    while (sp > 0) {
-      --sp;
-      if (stack_d[sp] <= bestd) {
-        node = stack_node[sp];
-        break;
-      }
-    }
-    if (!node) break;
-  }
-}
-
+// Exact nearest neighbour: nn_traverse4 below.  `best` must be nn_init(maxRange^2) or a tighter bound that belongs
+// to a real point (a warm start); on return it is unchanged for a miss, else (DistSq bits << 32 | original index)
+// and best_pos is the winner's position in ix.pts.
 // 4-ary view of the same heap: a step looks at the four grandchildren 4k..4k+3 of node k (their
 // boxes are one aligned 128-byte line), so the chain of dependent loads per descent is half as
 // long.  Children are ordered by their box distance with the child slot packed into the two
@@ -226,149 +165,6 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
       }
     }
     if (!node) break;
-  }
-}
-
-// Measured on B200: the 4-ary walk is 18 % faster for 10M LiDAR queries (9.25 vs 10.9 ms) and 14 %
-// for a 100k-point ICP iteration. -DPCG_BVH2 keeps the binary walk for comparison builds.
-#ifdef PCG_BVH2
-#define PCG_NN_TRAVERSE nn_traverse
-#else
-#define PCG_NN_TRAVERSE nn_traverse4<false>
-#endif
-
-// Persistent, work-fetching form of nn_traverse for batches.  Per-query work varies by an
-// order of magnitude (dense near field vs. sparse far field, amount of backtracking), so
-// with one query per thread most lanes of a warp idle behind its slowest query.  Here every
-// warp owns a chunk of the (Morton-ordered) query list and a lane that finishes its query
-// immediately takes the next one from the chunk; chunks come from one global counter
-// (one atomic per kQueryChunk queries).  `load(slot, x, y, z)` returns false when the slot
-// needs no search; `done(slot, x, y, z, best, pos, hit)` consumes a finished query.
-constexpr uint32_t kQueryChunk = 256;
-
-template <typename Load, typename Done>
-__device__ __forceinline__ void nn_persistent(const IndexView& ix, uint32_t n_queries, float max_range_sq,
-                                              unsigned int* __restrict__ counter, int leaf_votes, Load load,
-                                              Done done) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t P = ix.P;
-  const uint64_t init = nn_init(max_range_sq);
-  uint32_t stack_node[kMaxStack];
-  float stack_d[kMaxStack];
-  int sp = 0;
-  uint32_t node = 0;  // 0 == this lane has no query in flight
-  uint32_t slot = 0, best_pos = 0;
-  uint64_t best = init;
-  float bestd = max_range_sq, qx = 0.f, qy = 0.f, qz = 0.f;
-  uint32_t chunk_next = 0, chunk_end = 0;  // warp-uniform
-  bool drained = false;                    // warp-uniform: the global list is exhausted
-
-  for (;;) {
-    // ---- refill idle lanes from the warp's chunk
-    uint32_t idle = __ballot_sync(0xffffffffu, node == 0);
-    while (idle && !drained) {
-      if (chunk_next == chunk_end) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(counter, kQueryChunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_queries) {
-          drained = true;
-          break;
-        }
-        chunk_next = base;
-        chunk_end = min(base + kQueryChunk, n_queries);
-      }
-      const uint32_t take = min((uint32_t)__popc(idle), chunk_end - chunk_next);
-      const uint32_t rank = __popc(idle & lt_mask);
-      if (node == 0 && rank < take) {
-        slot = chunk_next + rank;
-        best = init;
-        bestd = max_range_sq;
-        best_pos = 0;
-        sp = 0;
-        bool search = load(slot, qx, qy, qz) && ix.n != 0 && qx == qx && qy == qy && qz == qz;
-        if (search) {
-          const float d = box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz);
-          search = d <= bestd;
-        }
-        if (search)
-          node = 1;
-        else
-          done(slot, qx, qy, qz, best, best_pos, false);  // stays idle, refilled by the next round
-      }
-      chunk_next += take;
-      idle = __ballot_sync(0xffffffffu, node == 0);
-    }
-    if (__ballot_sync(0xffffffffu, node != 0) == 0) {
-      if (drained) break;
-      continue;
-    }
-    // ---- inner nodes: one step per round for every lane that holds one.  Lanes that reached a
-    // leaf wait; the leaves are scanned together once enough lanes hold one (or nobody can
-    // step any more), so both phases run with most lanes active.
-    for (;;) {
-      const bool inner = node != 0 && node < P;
-      const uint32_t inner_mask = __ballot_sync(0xffffffffu, inner);
-      const uint32_t leaf_mask = __ballot_sync(0xffffffffu, node >= P && node != 0xffffffffu);
-      if (inner_mask == 0 || __popc(leaf_mask) >= leaf_votes) break;
-      if (inner) {
-        const float4* cb = ix.boxes + 4 * (size_t)node;
-        const float4 l0 = __ldg(cb), h0 = __ldg(cb + 1), l1 = __ldg(cb + 2), h1 = __ldg(cb + 3);
-        const float d0 = box_dist_sq(l0, h0, qx, qy, qz);
-        const float d1 = box_dist_sq(l1, h1, qx, qy, qz);
-        const bool first0 = d0 <= d1;
-        const float dn = first0 ? d0 : d1, df = first0 ? d1 : d0;
-        const uint32_t near_node = 2 * node + (first0 ? 0u : 1u), far_node = 2 * node + (first0 ? 1u : 0u);
-        if (!(dn <= bestd)) {
-          // both children pruned: pop right away so the lane keeps stepping
-          node = 0xffffffffu;
-          while (sp > 0) {
-            --sp;
-            if (stack_d[sp] <= bestd) {
-              node = stack_node[sp];
-              break;
-            }
-          }
-        } else {
-          if (df <= bestd) {
-            stack_node[sp] = far_node;
-            stack_d[sp] = df;
-            sp++;
-          }
-          node = near_node;
-        }
-      }
-    }
-    if (node != 0) {
-      if (node != 0xffffffffu && node >= P) {
-        const uint32_t base = (node - P) * kLeaf;
-        const float4* lp = ix.pts + base;
-#pragma unroll
-        for (int j = 0; j < kLeaf; j++) {
-          const float4 p = __ldg(lp + j);
-          const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
-          const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
-          if (packed < best) {
-            best = packed;
-            best_pos = base + j;
-          }
-        }
-        bestd = __uint_as_float((uint32_t)(best >> 32));
-        node = 0xffffffffu;
-      }
-      if (node == 0xffffffffu) {
-        node = 0;
-        while (sp > 0) {
-          --sp;
-          if (stack_d[sp] <= bestd) {
-            node = stack_node[sp];
-            break;
-          }
-        }
-        if (node == 0) done(slot, qx, qy, qz, best, best_pos, best != init);
-      }
-    }
   }
 }
 

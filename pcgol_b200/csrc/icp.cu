@@ -90,9 +90,9 @@ __device__ __forceinline__ void block_sum_f64(const float* t, double (*s_red)[K]
 // nine moments of the normal equations (icp_math.cuh).
 template <int MODE, bool APPROX, bool HESS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-    icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, float max_dist_sq,
-                     float min_dist_sq, IcpState* __restrict__ st, float* __restrict__ terms, int64_t n_pad,
-                     double* __restrict__ partials, double* __restrict__ hpartials, int finalize) {
+    icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, uint32_t* __restrict__ warm,
+                     float max_dist_sq, float min_dist_sq, IcpState* __restrict__ st, float* __restrict__ terms,
+                     int64_t n_pad, double* __restrict__ partials, double* __restrict__ hpartials, int finalize) {
   if (st->done) return;
   __shared__ float s_m[16];
   __shared__ int s_first;
@@ -123,11 +123,22 @@ __global__ void __launch_bounds__(THREADS)
     uint64_t best = nn_init(max_dist_sq);
     const uint64_t init = best;
     uint32_t pos = 0;
-#ifdef PCG_BVH2
-    PCG_NN_TRAVERSE(base, x0, y0, z0, best, pos);
-#else
-    nn_traverse4<APPROX>(base, x0, y0, z0, best, pos, min_dist_sq);
-#endif
+    // warm start: the point this target matched in the previous iteration (the transform moves little per
+    // iteration) is a real candidate, so starting from its distance leaves the (DistSq, ID) arg-min unchanged
+    // and prunes almost all backtracking
+    const uint32_t w0 = warm ? warm[slot] : 0xffffffffu;
+    if (w0 != 0xffffffffu) {
+      const float4 c = __ldg(base.pts + w0);
+      const float d = dist_sq_ref(c.x, c.y, c.z, x0, y0, z0);
+      const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
+      if (packed < best) {
+        best = packed;
+        pos = w0;
+      }
+    }
+    if (!(APPROX && best != init && __uint_as_float((uint32_t)(best >> 32)) < min_dist_sq))
+      nn_traverse4<APPROX>(base, x0, y0, z0, best, pos, min_dist_sq);
+    if (warm && best != init) warm[slot] = pos;
     if (best != init) {  // correspondence.go:27-29
       matched = 1;
       const float4 pb = __ldg(base.pts + pos);
@@ -380,82 +391,7 @@ __device__ __forceinline__ long long shfl_down_ll(long long v, int d) {
 
 __device__ __forceinline__ int float_exponent(float f) { return (int)((__float_as_uint(f) >> 23) & 0xff) - 127; }
 
-#ifdef PCG_REPLAY_V2
-// ---- variant under evaluation (-DPCG_REPLAY_V2, off by default) --------------------------------------------------
-// Measured on the default walk: 27k cycles for the 391 one-add steps of a 100k-element stream + 2.1k cycles per
-// replayed chunk, and every replayed chunk holds a true binade crossing (tools/replay_model.cpp).  V2 attacks the
-// 2.1k: the summaries kernel flags the chunks the walk will replay and adds 32-element maps for binades e-1, e, e+1;
-// in the walk kernel the 15 idle warps stage the flagged chunks' elements and maps in shared memory one batch ahead,
-// so a flagged chunk costs eight interval tests plus 32 sequential adds for the sub-chunk that holds the crossing.
-constexpr int kReplaySubRecords = 24;                    // 3 binades x 8 sub-chunks per flagged chunk
-constexpr int kReplayChunkRecords = 1 + kReplaySubRecords;  // summary records allocated per chunk
-static_assert(kReplayChunk == 256, "V2 sub-chunks are 4 lanes x 8 elements");
-
-// Parity map of this lane's kReplayPerLane elements in units of binade eb's ulp (the loop of the summaries kernel).
-__device__ __forceinline__ ParityMap replay_lane_map(const float* __restrict__ x, int64_t base, int64_t n, int eb,
-                                                     bool* sane_io) {
-  const bool ok = *sane_io;
-  const double scale = ok ? __longlong_as_double((long long)(1023 + 23 - eb) << 52) : 0.0;  // 2^(23-eb), exact
-  ParityMap m;
-  m.off[0] = m.off[1] = 0;
-  m.mn[0] = m.mn[1] = 0x7fffffffffffffffll;
-  m.mx[0] = m.mx[1] = -0x7fffffffffffffffll;
-  m.np = 2;
-  bool sane_all = ok;
-#pragma unroll
-  for (int j = 0; j < kReplayPerLane; j++) {
-    const float xv = (base + j < n) ? x[base + j] : 0.f;
-    const double y = (double)xv * scale;
-    double q = floor(y);
-    const bool sane = fabs(y) < 1.0e12;
-    if (!sane) {
-      sane_all = false;
-      q = 0.0;
-    }
-    const double frac = sane ? y - q : 0.0;
-    const long long qi = (long long)q;
-    ParityMap el;
-    if (frac == 0.5) {
-      el.off[0] = qi + (qi & 1);
-      el.off[1] = qi + ((qi + 1) & 1);
-      el.np = 0;
-    } else {
-      const long long r = qi + (frac > 0.5 ? 1 : 0);
-      el.off[0] = el.off[1] = r;
-      el.np = (r & 1) ? 1 : 2;
-    }
-    el.mn[0] = el.mx[0] = el.off[0];
-    el.mn[1] = el.mx[1] = el.off[1];
-    m = compose(m, el);
-  }
-  *sane_io = sane_all;
-  return m;
-}
-
-// The record the walk consumes, from a folded map in units of binade eb's ulp (same rules as the chunk summaries).
-__device__ __forceinline__ ReplayChunk replay_make_summary(const ParityMap& m, int eb, bool usable) {
-  ReplayChunk rc;
-  const long long kLo = 1ll << 23, kHi = 1ll << 24;
-  const float inf = __int_as_float(0x7f800000);
-  const float ulp = usable ? __uint_as_float((uint32_t)(eb - 23 + 127) << 23) : 0.f;
-#pragma unroll
-  for (int p = 0; p < 2; p++) {
-    long long lo_pos = max(kLo + 1 - m.mn[p], kLo), hi_pos = min(kHi - 1 - m.mx[p], kHi - 1);
-    long long lo_neg = max(-kHi + 1 - m.mn[p], -(kHi - 1)), hi_neg = min(-kLo - 1 - m.mx[p], -kLo);
-    const bool tot_ok = m.off[p] > -kHi && m.off[p] < kHi;
-    const bool pos_ok = usable && tot_ok && lo_pos <= hi_pos, neg_ok = usable && tot_ok && lo_neg <= hi_neg;
-    rc.t[p] = (usable && tot_ok) ? __fmul_rn((float)m.off[p], ulp) : 0.f;
-    rc.lo_pos[p] = pos_ok ? __fmul_rn((float)lo_pos, ulp) : inf;
-    rc.hi_pos[p] = pos_ok ? __fmul_rn((float)hi_pos, ulp) : -inf;
-    rc.lo_neg[p] = neg_ok ? __fmul_rn((float)lo_neg, ulp) : inf;
-    rc.hi_neg[p] = neg_ok ? __fmul_rn((float)hi_neg, ulp) : -inf;
-  }
-  rc.pad_[0] = rc.pad_[1] = 0.f;
-  return rc;
-}
-#else
 constexpr int kReplayChunkRecords = 1;
-#endif
 
 // Phase A (whole GPU): float64 sum of every chunk of every stream; one warp per chunk.
 __global__ void __launch_bounds__(256)
@@ -543,9 +479,6 @@ __global__ void __launch_bounds__(256)
     if ((lane & (2 * o - 1)) == 0) m = compose(m, right);
   }
   const bool all_regular = __all_sync(0xffffffffu, regular);
-#ifdef PCG_REPLAY_V2
-  int flagged = 0;
-#endif
   if (lane == 0) {
     ReplayChunk rc;
     const long long kLo = 1ll << 23, kHi = 1ll << 24;
@@ -568,50 +501,8 @@ __global__ void __launch_bounds__(256)
       rc.hi_neg[p] = neg_ok ? __fmul_rn((float)hi_neg, ulp) : -inf;
     }
     rc.pad_[0] = rc.pad_[1] = 0.f;
-#ifdef PCG_REPLAY_V2
-    {
-      // will the walk leave the one-add path here?  The guess accumulator answers for the true one (CPU model on real
-      // term streams: no miss, no false alarm).  1 = flagged, sub-chunk maps follow; 2 = flagged, no usable binade.
-      const int p = (int)(__float_as_uint(guess) & 1u);
-      const bool fast = (guess >= rc.lo_pos[p] && guess <= rc.hi_pos[p]) || (guess >= rc.lo_neg[p] && guess <= rc.hi_neg[p]);
-      flagged = fast ? 0 : (usable ? 1 : 2);
-      rc.pad_[0] = (float)flagged;
-      rc.pad_[1] = (float)e;
-    }
-#endif
     chunks[w] = rc;
   }
-#ifdef PCG_REPLAY_V2
-  flagged = __shfl_sync(0xffffffffu, flagged, 0);
-  if (flagged == 1) {
-    // 32-element sub-chunk maps for the guessed binade and its two neighbours: the accumulator of a flagged chunk
-    // changes binade inside it, almost always to a neighbour.  Lane groups of four fold their 4 x 8 elements.
-    ReplayChunk* __restrict__ subs = chunks + nchunks * streams + w * (int64_t)kReplaySubRecords;
-#pragma unroll 1
-    for (int bi = 0; bi < 3; bi++) {
-      const int eb = e - 1 + bi;
-      bool sane = eb > -100 && eb <= 100;
-      ParityMap mb = replay_lane_map(x, base, n, eb, &sane);
-#pragma unroll
-      for (int o = 1; o < 4; o <<= 1) {
-        ParityMap right;
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-          right.off[p] = shfl_down_ll(mb.off[p], o);
-          right.mn[p] = shfl_down_ll(mb.mn[p], o);
-          right.mx[p] = shfl_down_ll(mb.mx[p], o);
-        }
-        right.np = __shfl_down_sync(0xffffffffu, mb.np, o);
-        if ((lane & (2 * o - 1)) == 0) mb = compose(mb, right);
-      }
-      const unsigned sane_mask = __ballot_sync(0xffffffffu, sane);
-      if ((lane & 3) == 0) {
-        const bool group_sane = ((sane_mask >> lane) & 0xfu) == 0xfu;
-        subs[bi * 8 + (lane >> 2)] = replay_make_summary(mb, eb, group_sane);
-      }
-    }
-  }
-#endif
 }
 
 // Phase C (one CTA per stream): in-order walk with the true accumulator.  The chunk summaries are
@@ -741,218 +632,6 @@ __global__ void __launch_bounds__(kReplayThreads)
   }
 }
 
-#ifdef PCG_REPLAY_V2
-constexpr int kW2Batch = 64;  // chunk summaries per round of the walk, double buffered
-constexpr int kW2Slots = 12;  // flagged chunks per round staged ahead (elements + sub-chunk maps); more fall back
-struct W2Slot {
-  float x[kReplayChunk];
-  ReplayChunk sub[kReplaySubRecords];
-};
-struct W2Buf {
-  ReplayChunk chunks[kW2Batch];
-  short slot[kW2Batch];  // staged slot of a chunk of the batch, -1 = none
-  W2Slot slots[kW2Slots];
-};
-static_assert(sizeof(W2Slot) % 16 == 0 && sizeof(W2Buf) % 16 == 0, "16-byte copies");
-
-// Phase C, variant: warp 0 walks batch b out of one shared-memory buffer while warps 1..15 stage batch b+1 into the
-// other - its summaries and, for the flagged chunks, the elements and the sub-chunk maps.
-__global__ void __launch_bounds__(kReplayThreads)
-    icp_replay_walk2_kernel(IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad,
-                            int64_t nchunks, int streams, const ReplayChunk* __restrict__ chunks_all) {
-  if (st->done) return;
-  extern __shared__ __align__(16) unsigned char w2_smem[];
-  W2Buf* bufs = reinterpret_cast<W2Buf*>(w2_smem);
-  __shared__ __align__(16) float s_x[kReplayChunk];  // chunks that were replayed without a staged slot
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int k = blockIdx.x;
-  const float* __restrict__ x = terms + (int64_t)k * n_pad;
-  const ReplayChunk* __restrict__ chunks = chunks_all + (int64_t)k * nchunks;
-  const ReplayChunk* __restrict__ subs = chunks_all + nchunks * streams + (int64_t)k * nchunks * kReplaySubRecords;
-  const int nbatches = (int)((nchunks + kW2Batch - 1) / kW2Batch);
-  constexpr int kHelpers = kReplayThreads / 32 - 1;
-
-  auto stage = [&](int b) {  // helper warps only
-    W2Buf& B = bufs[b & 1];
-    const int64_t c0 = (int64_t)b * kW2Batch;
-    const int cnt = (int)min((int64_t)kW2Batch, nchunks - c0);
-    {
-      const int4* src = reinterpret_cast<const int4*>(chunks + c0);
-      int4* dst = reinterpret_cast<int4*>(B.chunks);
-      const int words = cnt * (int)(sizeof(ReplayChunk) / sizeof(int4));
-      for (int i = tid - 32; i < words; i += kHelpers * 32) dst[i] = src[i];
-    }
-    // every helper warp ranks the flagged chunks of the batch by itself (two chunks per lane)
-    const float f0 = lane < cnt ? __ldg(&chunks[c0 + lane].pad_[0]) : 0.f;
-    const float f1 = lane + 32 < cnt ? __ldg(&chunks[c0 + lane + 32].pad_[0]) : 0.f;
-    const unsigned m0 = __ballot_sync(0xffffffffu, f0 != 0.f), m1 = __ballot_sync(0xffffffffu, f1 != 0.f);
-    const unsigned lt = (1u << lane) - 1u;
-    const int r0 = __popc(m0 & lt), r1 = __popc(m0) + __popc(m1 & lt);
-    if (warp == 1) {
-      B.slot[lane] = (short)((f0 != 0.f && r0 < kW2Slots) ? r0 : -1);
-      B.slot[lane + 32] = (short)((f1 != 0.f && r1 < kW2Slots) ? r1 : -1);
-    }
-    const int total = min(__popc(m0) + __popc(m1), kW2Slots);
-    for (int r = warp - 1; r < total; r += kHelpers) {
-      // the r-th flagged chunk of the batch: r-th set bit of (m1:m0)
-      const unsigned who0 = __ballot_sync(0xffffffffu, f0 != 0.f && r0 == r);
-      const unsigned who1 = __ballot_sync(0xffffffffu, f1 != 0.f && r1 == r);
-      const int ci = who0 ? (__ffs(who0) - 1) : (32 + __ffs(who1) - 1);
-      const float fv = who0 ? __shfl_sync(0xffffffffu, f0, __ffs(who0) - 1) : __shfl_sync(0xffffffffu, f1, __ffs(who1) - 1);
-      W2Slot& S = B.slots[r];
-      const int64_t base = (c0 + ci) * kReplayChunk;
-#pragma unroll
-      for (int j = 0; j < kReplayChunk / 32; j++) {
-        const int64_t i = base + j * 32 + lane;
-        S.x[j * 32 + lane] = i < n ? x[i] : 0.f;
-      }
-      if (fv == 1.f) {
-        const int4* src = reinterpret_cast<const int4*>(subs + (c0 + ci) * kReplaySubRecords);
-        int4* dst = reinterpret_cast<int4*>(S.sub);
-        constexpr int words = kReplaySubRecords * (int)(sizeof(ReplayChunk) / sizeof(int4));
-        for (int i = lane; i < words; i += 32) dst[i] = src[i];
-      }
-    }
-  };
-
-  float acc = 0.f;
-  unsigned int n_fast = 0, n_slow = 0;
-  const long long t_walk0 = clock64();
-  if (warp != 0) stage(0);
-  __syncthreads();
-  for (int b = 0; b < nbatches; b++) {
-    if (warp != 0) {
-      if (b + 1 < nbatches) stage(b + 1);
-    } else {
-      const W2Buf& B = bufs[b & 1];
-      const int64_t c0 = (int64_t)b * kW2Batch;
-      const int batch = (int)min((int64_t)kW2Batch, nchunks - c0);
-      struct Rc {
-        float4 a, b, c;  // {t0,t1,lp0,lp1} {hp0,hp1,ln0,ln1} {hn0,hn1,flag,binade}
-      };
-      auto load_rc = [&](const ReplayChunk* rcp) {
-        const float4* q = reinterpret_cast<const float4*>(rcp);
-        Rc r;
-        r.a = q[0];
-        r.b = q[1];
-        r.c = q[2];
-        return r;
-      };
-      auto step = [](float a, const Rc rc, bool* fast) {
-        const bool p = (__float_as_uint(a) & 1u) != 0;
-        const float t = p ? rc.a.y : rc.a.x;
-        const float lp = p ? rc.a.w : rc.a.z, hp = p ? rc.b.y : rc.b.x;
-        const float ln = p ? rc.b.w : rc.b.z, hn = p ? rc.c.y : rc.c.x;
-        *fast = (a >= lp && a <= hp) || (a >= ln && a <= hn);
-        return __fadd_rn(a, t);
-      };
-      // the reference's own loop over `count` elements held in shared memory
-      auto sequential = [](float a, const float* xs, int count) {
-        const float4* b4 = reinterpret_cast<const float4*>(xs);
-#pragma unroll 8
-        for (int j = 0; j < count / 4; j++) {
-          const float4 v = b4[j];
-          a = __fadd_rn(a, v.x);
-          a = __fadd_rn(a, v.y);
-          a = __fadd_rn(a, v.z);
-          a = __fadd_rn(a, v.w);
-        }
-        return a;
-      };
-      auto replay = [&](float a, int ci, const Rc& rc) {
-        const int sl = B.slot[ci];
-        if (sl < 0) {  // not staged (more flagged chunks than slots, or a chunk the guess did not flag)
-          const int64_t base = (c0 + ci) * kReplayChunk;
-#pragma unroll
-          for (int j = 0; j < kReplayChunk / 32; j++) {
-            const int64_t i = base + j * 32 + lane;
-            s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
-          }
-          __syncwarp();
-          a = sequential(a, s_x, kReplayChunk);
-          __syncwarp();
-          return a;
-        }
-        const W2Slot& S = B.slots[sl];
-        if (rc.c.z != 1.f) return sequential(a, S.x, kReplayChunk);
-        const int e = (int)rc.c.w;
-#pragma unroll 1
-        for (int sub = 0; sub < 8; sub++) {
-          const int bi = float_exponent(a) - e + 1;  // zero / denormal accumulators fall outside 0..2
-          bool done = false;
-          if (bi >= 0 && bi <= 2) {
-            bool f;
-            const float a1 = step(a, load_rc(&S.sub[bi * 8 + sub]), &f);
-            if (f) {
-              a = a1;
-              done = true;
-            }
-          }
-          if (!done) a = sequential(a, S.x + sub * 32, 32);
-        }
-        return a;
-      };
-      int ci = 0;
-      for (; ci + 4 <= batch; ci += 4) {
-        const Rc r0 = load_rc(&B.chunks[ci]), r1 = load_rc(&B.chunks[ci + 1]), r2 = load_rc(&B.chunks[ci + 2]),
-                 r3 = load_rc(&B.chunks[ci + 3]);
-        bool f0, f1, f2, f3;
-        const float a1 = step(acc, r0, &f0);
-        const float a2 = step(a1, r1, &f1);
-        const float a3 = step(a2, r2, &f2);
-        const float a4 = step(a3, r3, &f3);
-        if (f0 && f1 && f2 && f3) {
-          acc = a4;
-          n_fast += 4;
-        } else {
-          for (int q = 0; q < 4; q++) {
-            bool f;
-            const Rc rq = load_rc(&B.chunks[ci + q]);
-            const float a = step(acc, rq, &f);
-            if (f) {
-              acc = a;
-              n_fast++;
-            } else {
-              acc = replay(acc, ci + q, rq);
-              n_slow++;
-            }
-          }
-        }
-      }
-      for (; ci < batch; ci++) {
-        bool f;
-        const Rc rq = load_rc(&B.chunks[ci]);
-        const float a = step(acc, rq, &f);
-        if (f) {
-          acc = a;
-          n_fast++;
-        } else {
-          acc = replay(acc, ci, rq);
-          n_slow++;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    st->sums[k] = acc;
-    if (gridDim.x == 1) {  // test hook launch: expose the walk statistics
-      st->sums[9] = (float)n_fast;
-      st->sums[10] = (float)n_slow;
-      st->sums[11] = (float)(clock64() - t_walk0);
-    }
-    __threadfence();
-    const unsigned int t = atomicAdd(&st->ticket, 1u);
-    if (t == (unsigned int)kTerms - 1u) {
-      __threadfence();
-      float sum9[kTerms];
-      for (int j = 0; j < kTerms; j++) sum9[j] = __ldcg(&st->sums[j]);
-      st->ticket = 0;
-      icp_finalize(st, sum9);
-    }
-  }
-}
-#endif  // PCG_REPLAY_V2
 
 // Launches the three phases for `streams` accumulators (9 in a Fit, 1 from the test hook).
 static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int64_t n_pad, int streams,
@@ -961,17 +640,6 @@ static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int
   const int blocks = div_up(nchunks * streams, 256 / 32);
   PCG_LAUNCH(icp_replay_sums_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums);
   PCG_LAUNCH(icp_replay_summaries_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums, chunks);
-#ifdef PCG_REPLAY_V2
-  static const bool v1 = getenv("PCG_REPLAY_V1") != nullptr;  // comparison runs
-  if (!v1) {
-    const size_t smem = 2 * sizeof(W2Buf);
-    // per device, and cheap: set on every launch
-    PCG_CUDA(cudaFuncSetAttribute(icp_replay_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PCG_LAUNCH(icp_replay_walk2_kernel, streams, kReplayThreads, smem, stream, st, terms, n, n_pad, nchunks, streams,
-               chunks);
-    return;
-  }
-#endif
   PCG_LAUNCH(icp_replay_walk_kernel, streams, kReplayThreads, 0, stream, st, terms, n, n_pad, nchunks, chunks);
 }
 
@@ -1008,6 +676,7 @@ struct IcpWork {
   DevBuf<double> partials;
   DevBuf<double> hpartials;  // [nblocks][9] when the normal equations are accumulated
   DevBuf<uint32_t> perm;
+  DevBuf<uint32_t> warm;              // per visit slot: position in the index of the previous iteration's match
   DevBuf<ReplayChunk> replay_chunks;  // strict replay: [9][chunks]
   DevBuf<double> replay_sums;         // strict replay: [9][chunks]
   int nblocks = 0;
@@ -1035,16 +704,16 @@ static void check_icp_params(const pcg_icp_params& prm) {
 
 // One launch of the fused correspondence + terms kernel for the (mode, MinDistSq, Hessian) combination.
 template <int MODE>
-static void launch_terms(const Index& base, const CloudView& tgt, const uint32_t* perm, float mdsq, float min_dist_sq,
-                         bool hess, IcpState* st, float* terms, int64_t n_pad, double* partials, double* hpartials,
+static void launch_terms(const Index& base, const CloudView& tgt, const uint32_t* perm, uint32_t* warm, float mdsq,
+                         float min_dist_sq, bool hess, IcpState* st, float* terms, int64_t n_pad, double* partials, double* hpartials,
                          int nblocks, int finalize, cudaStream_t stream) {
   const char* name = MODE == PCG_ICP_STRICT ? "(icp_terms_kernel<PCG_ICP_STRICT>)" : "(icp_terms_kernel<PCG_ICP_FAST>)";
   const bool approx = min_dist_sq > 0.f;
   min_dist_sq = fminf(min_dist_sq, mdsq);  // only a real hit can end a search early: see nearest_device
   // nblocks was sized with term_threads(MODE, hess): strict without the Hessian moments walks in 32-thread blocks
 #define PCG_TERMS(A, H, T)                                                                                         \
-  PCG_LAUNCH_NAMED(name, (icp_terms_kernel<MODE, A, H, T>), nblocks, T, 0, stream, base.view(), tgt, perm, mdsq,   \
-                   min_dist_sq, st, terms, n_pad, partials, hpartials, finalize)
+  PCG_LAUNCH_NAMED(name, (icp_terms_kernel<MODE, A, H, T>), nblocks, T, 0, stream, base.view(), tgt, perm, warm,    \
+                   mdsq, min_dist_sq, st, terms, n_pad, partials, hpartials, finalize)
   constexpr int kT = MODE == PCG_ICP_STRICT ? kTermThreadsStrict : kTermThreadsReduce;
   if (approx && hess)
     PCG_TERMS(true, true, kTermThreadsReduce);
@@ -1068,15 +737,11 @@ static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, cons
   const bool hess = (prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON;
   for (int it = 0; it < iterations; it++) {
     if (mode == PCG_ICP_STRICT) {
-      launch_terms<PCG_ICP_STRICT>(base, tgt, w.perm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
+      launch_terms<PCG_ICP_STRICT>(base, tgt, w.perm.p, w.warm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
                                    w.partials.p, w.hpartials.p, w.nblocks, 1, stream);
-      static const bool sequential_replay = getenv("PCG_ICP_REPLAY_SEQ") != nullptr;  // comparison runs only
-      if (sequential_replay)
-        PCG_LAUNCH(icp_replay_kernel, kTerms, 32, 0, stream, w.st.p, w.terms.p, tgt.n, w.n_pad);
-      else
-        launch_exact_replay(w.st.p, w.terms.p, tgt.n, w.n_pad, kTerms, w.replay_chunks.p, w.replay_sums.p, stream);
+      launch_exact_replay(w.st.p, w.terms.p, tgt.n, w.n_pad, kTerms, w.replay_chunks.p, w.replay_sums.p, stream);
     } else {
-      launch_terms<PCG_ICP_FAST>(base, tgt, w.perm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
+      launch_terms<PCG_ICP_FAST>(base, tgt, w.perm.p, w.warm.p, mdsq, prm.min_dist_sq, hess, w.st.p, w.terms.p, w.n_pad,
                                  w.partials.p, w.hpartials.p, w.nblocks, 1, stream);
     }
   }
@@ -1093,6 +758,10 @@ static void icp_prepare(const Index& base, const CloudView& tgt, const pcg_icp_p
   }
   w.n_pad = (tgt.n + 3) & ~(int64_t)3;
   w.st.alloc(1, stream);
+  if (!evaluate_only && tgt.n > 0) {
+    w.warm.alloc((size_t)tgt.n, stream);
+    PCG_CUDA(cudaMemsetAsync(w.warm.p, 0xff, w.warm.bytes(), stream));
+  }
   if ((prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON)
     w.hpartials.alloc((size_t)w.nblocks * kHTerms, stream);
   if ((prm.mode & ~PCG_ICP_WITH_HESSIAN) == PCG_ICP_STRICT) {
@@ -1155,8 +824,7 @@ static FarmResources& farm_resources(int device, int count) {
   static thread_local FarmResources per_device[kMaxDevices];  // never destroyed: the runtime may be gone at thread exit
   FarmResources& r = per_device[device];
   if (r.device != device) {
-    const char* e = getenv("PCG_FARM_STREAMS");  // pairs in flight (tuning runs)
-    r.n_streams = std::max(1, std::min(kFarmMaxStreams, e ? atoi(e) : 8));
+    r.n_streams = std::min(kFarmMaxStreams, 8);  // pairs in flight
     for (int s = 0; s < r.n_streams; s++) {
       PCG_CUDA(cudaStreamCreateWithFlags(&r.streams[s], cudaStreamNonBlocking));
       PCG_CUDA(cudaEventCreateWithFlags(&r.done[s], cudaEventDisableTiming));
@@ -1247,7 +915,7 @@ void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist,
   h.num_iteration = first ? 0 : 1;  // only "is this the first Evaluate" matters to the terms kernel
   PCG_CUDA(cudaMemcpyAsync(w.st.p, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   const float mdsq = max_dist * max_dist;
-  launch_terms<PCG_ICP_FAST>(base, tgt, d_order, mdsq, 0.f, false, w.st.p, w.terms.p, w.n_pad, w.partials.p, nullptr,
+  launch_terms<PCG_ICP_FAST>(base, tgt, d_order, nullptr, mdsq, 0.f, false, w.st.p, w.terms.p, w.n_pad, w.partials.p, nullptr,
                              w.nblocks, 0, stream);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, w.st.p, w.partials.p, w.nblocks, d_partial16);
 }
@@ -1286,7 +954,7 @@ void icp_shard_free(IcpShard* sh) { delete sh; }
 
 void icp_shard_partial(IcpShard& sh, double* d_partial16, cudaStream_t stream) {
   const float mdsq = sh.prm.max_dist * sh.prm.max_dist;
-  launch_terms<PCG_ICP_FAST>(*sh.base, sh.tgt, sh.w.perm.p, mdsq, sh.prm.min_dist_sq, false, sh.w.st.p, sh.w.terms.p,
+  launch_terms<PCG_ICP_FAST>(*sh.base, sh.tgt, sh.w.perm.p, sh.w.warm.p, mdsq, sh.prm.min_dist_sq, false, sh.w.st.p, sh.w.terms.p,
                              sh.w.n_pad, sh.w.partials.p, nullptr, sh.w.nblocks, 0, stream);
   PCG_LAUNCH(icp_partial_reduce_kernel, 1, kFinishThreads, 0, stream, sh.w.st.p, sh.w.partials.p, sh.w.nblocks,
              d_partial16);
@@ -1368,11 +1036,7 @@ __global__ void __launch_bounds__(128)
   uint64_t best = nn_init(max_dist_sq);
   const uint64_t init = best;
   uint32_t pos = 0;
-#ifdef PCG_BVH2
-  PCG_NN_TRAVERSE(base, p.x, p.y, p.z, best, pos);
-#else
   nn_traverse4<APPROX>(base, p.x, p.y, p.z, best, pos, min_dist_sq);
-#endif
   const bool hit = best != init;
   ids[i] = hit ? (int32_t)(uint32_t)best : -1;
   dsq[i] = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_dist_sq;

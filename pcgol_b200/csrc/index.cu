@@ -10,7 +10,6 @@
 
 namespace pcg {
 
-constexpr int kMortonBitsPerAxis = 16;
 
 __device__ __forceinline__ uint32_t ord_bits(float f) {
   uint32_t b = __float_as_uint(f);
@@ -113,40 +112,6 @@ __device__ __forceinline__ unsigned long long hilbert_key(uint32_t x0, uint32_t 
   X[1] ^= t;
   X[2] ^= t;
   return (spread16(X[0]) << 2) | (spread16(X[1]) << 1) | spread16(X[2]);
-}
-
-__global__ void __launch_bounds__(256)
-    morton_kernel(CloudView v, const uint32_t* __restrict__ bbox6, unsigned long long* __restrict__ keys) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= v.n) return;
-  float lo[3], ext = 0.f;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    lo[k] = ord_to_float(bbox6[k]);
-    float hi = ord_to_float(bbox6[3 + k]);
-    ext = fmaxf(ext, hi - lo[k]);
-  }
-  const float scale = (ext > 0.f && isfinite(ext)) ? (float)(1 << kMortonBitsPerAxis) / ext : 0.f;
-  float3 p = load_xyz(v, i);
-  float c[3] = {p.x, p.y, p.z};
-  unsigned long long key = 0;
-  bool finite = isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]);
-  if (finite) {
-    uint32_t u[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float q = (c[k] - lo[k]) * scale;
-      u[k] = (uint32_t)fminf(fmaxf(q, 0.f), (float)((1 << kMortonBitsPerAxis) - 1));
-    }
-#ifdef PCG_MORTON
-    key = spread16(u[0]) | (spread16(u[1]) << 1) | (spread16(u[2]) << 2);
-#else
-    key = hilbert_key<kMortonBitsPerAxis>(u[0], u[1], u[2]);
-#endif
-  } else {
-    key = (1ull << (3 * kMortonBitsPerAxis)) - 1;  // non-finite points go last; they never match a query
-  }
-  keys[i] = key;
 }
 
 __global__ void __launch_bounds__(256)
@@ -617,22 +582,7 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
     int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
     PCG_LAUNCH(bbox_kernel, blocks, 256, 0, stream, v, ix->bbox);
 
-    // PCG_INDEX_ORDER=hilbert keeps the space-filling-curve order (one 48-bit sort) for comparison runs
-    static const bool hilbert_order = [] {
-      const char* e = getenv("PCG_INDEX_ORDER");
-      return e && strcmp(e, "hilbert") == 0;
-    }();
-    if (hilbert_order) {
-      DevBuf<unsigned long long> keys0(n, stream), keys1(n, stream);
-      DevBuf<uint32_t> vals0(n, stream), vals1(n, stream);
-      PCG_LAUNCH(morton_kernel, div_up(n, 256), 256, 0, stream, v, ix->bbox, keys0.p);
-      unsigned long long* kk[2] = {keys0.p, keys1.p};
-      uint32_t* vv[2] = {vals0.p, vals1.p};
-      int res = 0;
-      rsort::sort_pairs<unsigned long long>(kk, vv, n, 0, 3 * kMortonBitsPerAxis, /*identity_vals=*/true,
-                                            /*keep_keys=*/false, stream, &res);
-      PCG_LAUNCH(gather_points_kernel, div_up(padded, 256), 256, 0, stream, v, vv[res], ix->pts, (uint32_t)padded);
-    } else {
+    {
       DevBuf<uint32_t> lists[6];
       const uint32_t* order = kd_order_device(v, n, P, lists, stream);
       PCG_LAUNCH(gather_points_kernel, div_up(padded, 256), 256, 0, stream, v, order, ix->pts, (uint32_t)padded);
@@ -752,11 +702,7 @@ __global__ void __launch_bounds__(256)
         float t = (c[k] - lo[k]) * scale;  // queries outside the box clamp to its faces; NaN -> 0
         u[k] = (uint32_t)fminf(fmaxf(t, 0.f), cells - 1.f);
       }
-#ifdef PCG_MORTON
-      key = (uint32_t)(spread16(u[0]) | (spread16(u[1]) << 1) | (spread16(u[2]) << 2));
-#else
       key = (uint32_t)hilbert_key<kQueryBitsPerAxis>(u[0], u[1], u[2]);
-#endif
       keys[i] = key;
     }
     rsort::hist_add_key(s_hist, key, valid, 0, passes);
@@ -784,79 +730,53 @@ void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, c
 }
 
 // ---- KDTree.Nearest, batched (kdtree.go:83-92) -----------------------------------------
-__global__ void __launch_bounds__(128)
-    nearest_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
-                   int32_t* __restrict__ ids, float* __restrict__ dist_sq, pcg_neighbor* __restrict__ aos,
-                   unsigned int* __restrict__ counter, int leaf_votes) {
-  nn_persistent(
-      ix, (uint32_t)q.n, max_range_sq, counter, leaf_votes,
-      [&](uint32_t slot, float& x, float& y, float& z) {
-        // Morton-ordered visit; results still land at the query's own index
-        const float3 p = load_xyz(q, perm ? perm[slot] : slot);
-        x = p.x;
-        y = p.y;
-        z = p.z;
-        return true;
-      },
-      [&](uint32_t slot, float, float, float, uint64_t best, uint32_t, bool hit) {
-        const uint32_t i = perm ? perm[slot] : slot;
-        const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
-        const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
-        if (ids) {
-          ids[i] = id;
-          dist_sq[i] = d;
-        }
-        if (aos) {
-          pcg_neighbor nb;
-          nb.id = (int64_t)id;
-          nb.dist_sq = d;
-          nb.pad_ = 0;
-          aos[i] = nb;
-        }
-      });
-}
-
-// One query per thread (no work fetching): kept for comparison runs (PCG_NN_KERNEL=simple).
-#ifndef PCG_NN_THREADS
-#define PCG_NN_THREADS 128
-#endif
+// One thread walks `per_thread` consecutive queries of the (Hilbert-ordered) visit list.  Consecutive queries are
+// neighbours in space, so the winner of one query is a real point close to the next one: its distance is a valid
+// upper bound to start the next walk with (it is one of the candidates the search would see anyway, so the
+// (DistSq, ID) arg-min is unchanged), and almost all backtracking is pruned from the first step.
+constexpr int kNnThreads = 128;
 template <bool APPROX>
-__global__ void __launch_bounds__(PCG_NN_THREADS)
-    nearest_simple_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, float max_range_sq,
-                          float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
-                          pcg_neighbor* __restrict__ aos) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= q.n) return;
-  if (perm) i = perm[i];
-  float3 p = load_xyz(q, i);
-  uint64_t best = nn_init(max_range_sq);
-  const uint64_t init = best;
-  uint32_t pos = 0;
-#ifdef PCG_BVH2
-  PCG_NN_TRAVERSE(ix, p.x, p.y, p.z, best, pos);
-#else
-  nn_traverse4<APPROX>(ix, p.x, p.y, p.z, best, pos, min_dist_sq);
-#endif
-  const bool hit = best != init;
-  const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
-  const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
-  if (ids) {
-    ids[i] = id;
-    dist_sq[i] = d;
+__global__ void __launch_bounds__(kNnThreads)
+    nearest_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, int per_thread, float max_range_sq,
+                   float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
+                   pcg_neighbor* __restrict__ aos) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t init = nn_init(max_range_sq);
+  uint32_t warm = 0xffffffffu;
+  for (int k = 0; k < per_thread; k++) {
+    const int64_t slot = t * per_thread + k;
+    if (slot >= q.n) return;
+    const int64_t i = perm ? (int64_t)perm[slot] : slot;
+    const float3 p = load_xyz(q, i);
+    uint64_t best = init;
+    uint32_t pos = 0;
+    if (warm != 0xffffffffu) {
+      const float4 c = __ldg(ix.pts + warm);
+      const float d = dist_sq_ref(c.x, c.y, c.z, p.x, p.y, p.z);
+      const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
+      if (packed < best) {
+        best = packed;
+        pos = warm;
+      }
+    }
+    if (!(APPROX && best != init && __uint_as_float((uint32_t)(best >> 32)) < min_dist_sq))
+      nn_traverse4<APPROX>(ix, p.x, p.y, p.z, best, pos, min_dist_sq);
+    const bool hit = best != init;
+    if (hit) warm = pos;
+    const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
+    const float d = hit ? __uint_as_float((uint32_t)(best >> 32)) : max_range_sq;
+    if (ids) {
+      ids[i] = id;
+      dist_sq[i] = d;
+    }
+    if (aos) {
+      pcg_neighbor nb;
+      nb.id = (int64_t)id;
+      nb.dist_sq = d;
+      nb.pad_ = 0;
+      aos[i] = nb;
+    }
   }
-  if (aos) {
-    pcg_neighbor nb;
-    nb.id = (int64_t)id;
-    nb.dist_sq = d;
-    nb.pad_ = 0;
-    aos[i] = nb;
-  }
-}
-
-// Persistent launch: enough CTAs to fill the machine, capped by the amount of work.
-static int persistent_blocks(int64_t n_queries, int threads) {
-  const int64_t by_work = (n_queries + kQueryChunk - 1) / kQueryChunk * 32 / threads + 1;
-  return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)kNumSMs * (2048 / threads), by_work));
 }
 
 void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
@@ -868,33 +788,18 @@ void nearest_device(const Index& ix, const CloudView& q, float max_range, float 
     perm.alloc((size_t)q.n, stream);
     query_order_device(ix, q, perm.p, stream);
   }
-  DevBuf<unsigned int> counter(1, stream);
-  PCG_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned int), stream));
-  static const int leaf_votes = [] {
-    const char* e = getenv("PCG_NN_LEAF_VOTES");
-    return e ? atoi(e) : 16;
-  }();
-  // Measured on B200 (10M LiDAR-shaped queries vs 1M points): the one-query-per-thread kernel
-  // wins over the work-fetching one (14.3 vs 16.4 ms) — divergent sub-warps overlap each
-  // other's L2 latency, the converged rounds of the persistent kernel expose it.
-  static const bool simple = [] {
-    const char* e = getenv("PCG_NN_KERNEL");
-    return !(e && strcmp(e, "persistent") == 0);
-  }();
+  // queries per thread: as many as still leave every SM a few thousand threads
+  const int per_thread = !perm.p ? 1 : (q.n >= (int64_t)kNumSMs * 2048 * 8 ? 8 : (q.n >= (int64_t)kNumSMs * 2048 * 2 ? 4 : 2));
+  const int blocks = div_up(div_up(q.n, per_thread), kNnThreads);
   if (min_dist_sq > 0.f) {  // KDTree.MinDistSq > 0: approximate search (kdtree.go:19-22)
     // a miss keeps DistSq == maxRange^2: capping the threshold there means only a real hit can end the search
     // early (the reference's early miss for maxRange^2 < MinDistSq, kdtree.go:100-106, is not reproduced)
-    PCG_LAUNCH(nearest_simple_kernel<true>, div_up(q.n, PCG_NN_THREADS), PCG_NN_THREADS, 0, stream, ix.view(), q, perm.p, mrsq,
+    PCG_LAUNCH(nearest_kernel<true>, blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq,
                fminf(min_dist_sq, mrsq), d_ids, d_dist_sq, d_aos);
     return;
   }
-  if (simple) {
-    PCG_LAUNCH(nearest_simple_kernel<false>, div_up(q.n, PCG_NN_THREADS), PCG_NN_THREADS, 0, stream, ix.view(), q, perm.p, mrsq, 0.f, d_ids,
-               d_dist_sq, d_aos);
-    return;
-  }
-  PCG_LAUNCH(nearest_kernel, persistent_blocks(q.n, 128), 128, 0, stream, ix.view(), q, perm.p, mrsq, d_ids,
-             d_dist_sq, d_aos, counter.p, leaf_votes);
+  PCG_LAUNCH(nearest_kernel<false>, blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq, 0.f, d_ids,
+             d_dist_sq, d_aos);
 }
 
 // ---- KDTree.Range, batched (kdtree.go:148-197) -----------------------------------------

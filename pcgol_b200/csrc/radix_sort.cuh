@@ -273,11 +273,6 @@ inline void launch_pass(const K* kin, K* kout, const uint32_t* vin, uint32_t* vo
 }
 
 inline int pick_ipt(uint32_t n) {
-  static const int forced = [] {
-    const char* e = getenv("PCG_SORT_IPT");
-    return e ? atoi(e) : 0;
-  }();
-  if (forced == 4 || forced == 8 || forced == 16) return forced;
   // largest tile that still gives every SM about four CTAs
   for (int ipt : {16, 8}) {
     if ((uint64_t)n >= (uint64_t)kNumSMs * 4 * kThreads * ipt) return ipt;
