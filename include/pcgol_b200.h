@@ -103,10 +103,9 @@ int64_t pcg_kernel_launch_count(void);
  * element by element, and SM cycles of the in-order walk. */
 pcg_status pcg_debug_sequential_sum_f32(const float* x, int64_t n, int32_t device, int32_t exact_path, float* out);
 void pcg_profile_enable(int32_t on);
-/* Test hook: which VoxelGrid pipeline pcg_voxelgrid_filter* runs. 0 = automatic (sample-partition pipeline, LSD
- * radix pipeline when a partition bucket overflows or the cloud is too large for the splitter table), 1 = LSD
- * pipeline, 2 = single cooperative kernel (clouds up to 1.2M points), 3 = partition pipeline.  Every path produces
- * the same bytes; the parity tests run all of them. */
+/* Test hook: which VoxelGrid pipeline pcg_voxelgrid_filter* runs. 0 = automatic (one cooperative kernel up to 1.2M
+ * points, the multi-kernel LSD radix pipeline above), 1 = always the multi-kernel pipeline.  Both produce the same
+ * bytes; the parity tests run both. */
 void pcg_debug_set_vg_path(int32_t path);
 int64_t pcg_profile_report(char* buf, int64_t cap);
 

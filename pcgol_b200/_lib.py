@@ -198,7 +198,7 @@ def profile_enable(on: bool) -> None:
 
 
 def set_vg_path(path: int) -> None:
-    """Test hook: 0 automatic, 1 LSD pipeline, 2 cooperative kernel, 3 partition pipeline."""
+    """Test hook: 0 automatic, 1 always the multi-kernel LSD pipeline."""
     lib.pcg_debug_set_vg_path(int(path))
 
 

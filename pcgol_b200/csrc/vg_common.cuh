@@ -320,9 +320,4 @@ inline void vg_throw_on_flags(int h_flags) {
                       "reference would panic: voxel or chunk index out of range (voxelgrid.go:46,89,151)"};
 }
 
-// vg_partition.cu
-bool vgp_eligible(int64_t n);
-bool voxelgrid_filter_partition(const CloudView& v, const float leaf[3], const int64_t chunk[3], uint8_t* d_out,
-                                int64_t* n_out, cudaStream_t stream);
-
 }  // namespace pcg

@@ -1099,15 +1099,11 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
                                    int64_t* n_out, cudaStream_t stream) {
   *n_out = 0;
   if (v.n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
-  // Paths: the sample-partition pipeline (vg_partition.cu) is the product path; the LSD pipeline below takes over
-  // when a bucket of the partition overflows or the cloud needs more buckets than the splitter table holds.
-  // g_vg_path is a test hook (pcg_debug_set_vg_path): 0 = automatic, 1 = LSD pipeline, 2 = fused cooperative
-  // kernel, 3 = partition pipeline.
+  // Clouds of up to 1.2M points: the whole Filter in one cooperative kernel; larger ones: the multi-kernel LSD
+  // pipeline below.  g_vg_path is a test hook (pcg_debug_set_vg_path): 1 forces the multi-kernel pipeline so that the
+  // parity tests cover it at every size.
   const int path = g_vg_path.load(std::memory_order_relaxed);
-  if ((path == 0 || path == 3) && vgp_eligible(v.n)) {
-    if (voxelgrid_filter_partition(v, leaf, chunk, d_out, n_out, stream)) return PCG_OK;
-  }
-  if (path == 2 && v.n <= fused_capacity(kFusedIptLarge)) {
+  if (path != 1 && v.n <= fused_capacity(kFusedIptLarge)) {
     try {
       return voxelgrid_filter_fused(v, leaf, chunk, d_out, n_out, stream);
     } catch (const CudaError& e) {

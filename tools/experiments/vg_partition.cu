@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    splitters_kernel(const uint32_t* __restrict__ sorted, uint32_t n_samples, uint32_t n_buckets,
+    splitters_kernel(const uint32_t* __restrict__ sorted, uint32_t n_samples, uint32_t n_buckets, uint32_t padded,
                      uint32_t* __restrict__ spl) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j + 1 < n_buckets) spl[j] = sorted[(uint64_t)(j + 1) * n_samples / n_buckets];
+  if (j >= padded) return;
+  spl[j] = j + 1 < n_buckets ? sorted[(uint64_t)(j + 1) * n_samples / n_buckets] : 0xffffffffu;
 }
 
 // ---- partition -------------------------------------------------------------------------------------------------
@@ -256,15 +257,13 @@ __global__ void __launch_bounds__(kPartThreads, 4)
         if (!voxel_key_fast(C, pt, &key)) key = voxel_key_general(st->P, pt, &bad);
         const uint32_t sk = (uint32_t)(key >> shift);
         // bucket = number of splitters <= key >> shift (the table is read-only and small: it lives in L1)
+        // (branch-free: the table is padded with 0xffffffff up to 2 * top entries)
         uint32_t lo = 0;
-        for (uint32_t step = top; step; step >>= 1) {
-          const uint32_t t = lo + step;
-          if (t <= n_spl && __ldg(&spl[t - 1]) <= sk) lo = t;
-        }
-        b = lo;
+        for (uint32_t step = top; step; step >>= 1) lo += __ldg(&spl[lo + step - 1]) <= sk ? step : 0u;
+        b = min(lo, n_spl);
         const unsigned long long kmin = b ? (unsigned long long)__ldg(&spl[b - 1]) << shift : 0ull;
         const unsigned long long r = key - kmin;
-        over = over || (r >> 32) != 0;
+        over = over || (r >> 32) != 0 || (uint32_t)r == 0xffffffffu;  // (0xffffffff marks an empty hash slot in bucket_kernel)
         rel = (uint32_t)r;
       }
       // rank among the warp's points of the same bucket, in index order (item-major, lane-minor)
@@ -329,32 +328,53 @@ __global__ void __launch_bounds__(kPartThreads, 4)
   if (over) atomicOr(&st->overflow, 1u);
 }
 
-// ---- bucket: order, sort, reduce -------------------------------------------------------------------------------
-constexpr int kBktThreads = 512;
+// ---- bucket: group by voxel, order, reduce -----------------------------------------------------------------------
+// One CTA per bucket, everything in shared memory, no radix passes:
+//   1  every record's key goes into a hash table (open addressing): slot -> member count; the first record of a key
+//      appends it to the list of distinct keys.  The number of distinct keys = voxels of the bucket is published
+//      for the look-back at once, so no later bucket ever waits for this one's work
+//   2  the distinct keys (a few hundred) are sorted (bitonic): voxel u = u-th smallest key; exclusive scan of the
+//      member counts = first position of every voxel
+//   3  records are scattered into their voxel's range (atomic fill: arbitrary order inside the voxel), then every
+//      record counts the members of its voxel with a smaller point index: that is its place in the reference's
+//      accumulation order (voxelgrid.go:148-158 adds the points in iteration order)
+//   4  points gathered in final order; one thread per voxel adds its members sequentially; record + centroid written
+//      at the voxel's slot of the output (bucket offsets by decoupled look-back)
+// A voxel with more than kMaxMembers points makes step 3 quadratic: the bucket raises the overflow flag and the
+// caller runs the LSD pipeline.
+constexpr int kBktThreads = 256;
 constexpr int kBktWarps = kBktThreads / 32;
-constexpr int kBktIpt = kCap / kBktThreads;  // 8
+constexpr int kBktIpt = kCap / kBktThreads;  // 16 rows of 256 records
+constexpr int kHashMax = 2 * kCap;
+constexpr uint32_t kMaxMembers = 255;
 
 struct BucketSmem {
-  uint32_t key[kCap];               // staging: keys
-  uint16_t pos[kCap];               // staging: payload (position of the record in the bucket region / run number)
-  uint16_t hist[kBktWarps][256];    // digit counts per warp; later the positions of the voxel heads
   union {
-    uint32_t hset[2 * kCap];   // distinct keys of the bucket (open addressing)
     struct {
-      uint32_t chunk[kCap];    // run r: index >> kChunkShift of its records
-      uint16_t start[kCap];    // first record
-      uint16_t rank[kCap];     // rank of the run by chunk
-      uint16_t nstart[kCap];   // length by rank, then (scanned) first position in index order
-      uint16_t rec_run[kCap];  // run of record l
-    } run;
-    float xyz[3][kCap];        // points in sorted order
+      uint32_t hkey[kHashMax];      // slot -> key (0xffffffff = empty), later slot -> voxel
+      uint32_t hcnt[kHashMax / 2];  // slot -> member count, two 16-bit counters per word; later the fill cursors
+    } h;
+    float xyz[3][kCap];             // points in final order (steps 4)
   } u;
+  uint32_t dkey[kCap];     // distinct keys, sorted in step 2
+  uint16_t dslot[kCap];    // their hash slots; from step 3 on: final position -> record
+  uint16_t vstart[kCap + 2];  // first position of voxel u (vstart[U] = m)
+  uint32_t g_idx[kCap];    // grouped position -> point index
+  union {
+    struct {
+      uint16_t g_l[kCap];  // grouped position -> record
+      uint16_t g_u[kCap];  // grouped position -> voxel
+    } g;
+    struct {               // scratch of the distinct-key sort (step 2)
+      uint16_t hist[kBktWarps][256];
+      uint32_t digit_start[256];
+    } r;
+  } w;
   uint32_t scan[kBktWarps];
-  uint32_t digit_start[256];
-  uint32_t bucket, maxkey, minchunk, maxchunk, distinct;
+  uint32_t bucket, distinct, heavy, maxkey;
   unsigned long long look[kBktWarps][2];
-  unsigned long long prefix;
 };
+static_assert(sizeof(BucketSmem) <= 113 * 1024, "two buckets per SM");
 
 __device__ __forceinline__ uint32_t bkt_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -382,27 +402,33 @@ __device__ __forceinline__ uint32_t bkt_excl_scan(uint32_t v, uint32_t* s_warp, 
   return base + incl - v;
 }
 
-// Stable LSD radix sort (8-bit digits) of the `count` (key, payload) pairs in sm.key / sm.pos, in place, on key bits
-// [0, nbits).  Position p = warp * 256 + i * 32 + lane is the order the ranks follow.  All threads call; ends with
-// a barrier.
-__device__ __forceinline__ void bkt_radix_sort(BucketSmem& sm, uint32_t count, int nbits) {
+__device__ __forceinline__ uint32_t cnt_get(const uint32_t* hcnt, uint32_t s) { return (hcnt[s >> 1] >> (16 * (s & 1))) & 0xffffu; }
+__device__ __forceinline__ uint32_t cnt_inc(uint32_t* hcnt, uint32_t s) {  // returns the counter's previous value
+  return (atomicAdd(&hcnt[s >> 1], 1u << (16 * (s & 1))) >> (16 * (s & 1))) & 0xffffu;
+}
+
+// Stable LSD radix sort (8-bit digits) of the `count` (key, payload) pairs in sm.dkey / sm.dslot, in place, on key
+// bits [0, nbits).  All threads call; ends with a barrier.
+__device__ __forceinline__ void bkt_sort_distinct(BucketSmem& sm, uint32_t count, int nbits) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t warp_base = warp * (32u * kBktIpt);
+  constexpr uint32_t kPerWarp = 32u * kBktIpt;
+  const uint32_t warp_base = warp * kPerWarp;
   if (nbits <= 0 || count <= 1) return;
   uint32_t keys[kBktIpt], pp[kBktIpt];
 #pragma unroll
   for (int i = 0; i < kBktIpt; i++) {
     const uint32_t p = warp_base + i * 32 + lane;
-    keys[i] = p < count ? sm.key[p] : 0u;
-    pp[i] = p < count ? sm.pos[p] : 0u;
+    keys[i] = p < count ? sm.dkey[p] : 0u;
+    pp[i] = p < count ? sm.dslot[p] : 0u;
   }
-  const uint32_t used_warps = (count + 32u * kBktIpt - 1) / (32u * kBktIpt);  // warps that hold any pair
+  const uint32_t used_warps = (count + kPerWarp - 1) / kPerWarp;  // warps that hold any pair
   for (int shift = 0; shift < nbits; shift += 8) {
-    for (uint32_t i = tid; i < used_warps * 128u; i += kBktThreads) reinterpret_cast<uint32_t*>(&sm.hist[0][0])[i] = 0;
+    for (uint32_t i = tid; i < used_warps * 128u; i += kBktThreads) reinterpret_cast<uint32_t*>(&sm.w.r.hist[0][0])[i] = 0;
     __syncthreads();
     uint32_t offs[kBktIpt];
 #pragma unroll
     for (int i = 0; i < kBktIpt; i++) {
+      offs[i] = 0;
       if (warp_base + i * 32 < count) {  // warp-uniform
         const bool valid = warp_base + i * 32 + lane < count;
         const uint32_t d = valid ? ((keys[i] >> shift) & 255u) : 256u;
@@ -410,8 +436,8 @@ __device__ __forceinline__ void bkt_radix_sort(BucketSmem& sm, uint32_t count, i
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (valid && (int)lane == leader) {
-          pre = sm.hist[warp][d];
-          sm.hist[warp][d] = (uint16_t)(pre + __popc(peers));
+          pre = sm.w.r.hist[warp][d];
+          sm.w.r.hist[warp][d] = (uint16_t)(pre + __popc(peers));
         }
         pre = __shfl_sync(0xffffffffu, pre, leader);
         offs[i] = pre + __popc(peers & ((1u << lane) - 1u));
@@ -420,23 +446,23 @@ __device__ __forceinline__ void bkt_radix_sort(BucketSmem& sm, uint32_t count, i
     }
     __syncthreads();
     uint32_t cnt = 0;
-    if (tid < 256) {
+    {  // thread = digit: exclusive offsets of the warps' counts
       for (uint32_t w = 0; w < used_warps; w++) {
-        const uint32_t c = sm.hist[w][tid];
-        sm.hist[w][tid] = (uint16_t)cnt;
+        const uint32_t c = sm.w.r.hist[w][tid];
+        sm.w.r.hist[w][tid] = (uint16_t)cnt;
         cnt += c;
       }
     }
     const uint32_t dstart = bkt_excl_scan(cnt, sm.scan, nullptr);
-    if (tid < 256) sm.digit_start[tid] = dstart;
+    sm.w.r.digit_start[tid] = dstart;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kBktIpt; i++) {
-      if (warp_base + i * 32 + lane < count) {
+      if (warp_base + i * 32 < count && warp_base + i * 32 + lane < count) {
         const uint32_t d = (keys[i] >> shift) & 255u;
-        const uint32_t at = sm.digit_start[d] + sm.hist[warp][d] + offs[i];
-        sm.key[at] = keys[i];
-        sm.pos[at] = (uint16_t)pp[i];
+        const uint32_t at = sm.w.r.digit_start[d] + sm.w.r.hist[warp][d] + offs[i];
+        sm.dkey[at] = keys[i];
+        sm.dslot[at] = (uint16_t)pp[i];
       }
     }
     __syncthreads();
@@ -444,9 +470,9 @@ __device__ __forceinline__ void bkt_radix_sort(BucketSmem& sm, uint32_t count, i
 #pragma unroll
       for (int i = 0; i < kBktIpt; i++) {
         const uint32_t p = warp_base + i * 32 + lane;
-        if (p < count) {
-          keys[i] = sm.key[p];
-          pp[i] = sm.pos[p];
+        if (warp_base + i * 32 < count && p < count) {
+          keys[i] = sm.dkey[p];
+          pp[i] = sm.dslot[p];
         }
       }
     }
@@ -464,10 +490,9 @@ __global__ void __launch_bounds__(kBktThreads, 2)
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     sm.bucket = atomicAdd(&st->ticket_bucket, 1u);  // dynamic id: every predecessor is running or done
-    sm.maxkey = 0;
-    sm.minchunk = 0xffffffffu;
-    sm.maxchunk = 0;
     sm.distinct = 0;
+    sm.heavy = 0;
+    sm.maxkey = 0;
   }
   __syncthreads();
   const uint32_t bucket = sm.bucket;
@@ -475,212 +500,129 @@ __global__ void __launch_bounds__(kBktThreads, 2)
   const float4* __restrict__ brec = rec + (size_t)bucket * kCap;
   const uint32_t* __restrict__ bkey = key32 + (size_t)bucket * kCap;
   volatile unsigned long long* stv = status;
-  const uint32_t l0 = tid * kBktIpt;
-  constexpr uint32_t kEmpty = 0xffffffffu;
+  constexpr uint32_t kEmpty = 0xffffffffu;  // never a key: partition_kernel raises the overflow flag for it
 
-  uint32_t total_heads = 0;
-  uint32_t keys[kBktIpt];
+  uint32_t U = 0;
   if (m > 0) {
-    // ---- 1. load (striped); chunk ids to shared memory.  The number of distinct keys (= voxels of the bucket) is
-    // counted with a hash set and published at once: no later bucket ever waits for this one's sort.
+    // ---- 1. hash the keys
     uint32_t hslots = 256;  // power of two >= 2 m
     while (hslots < 2 * m) hslots *= 2;
-    for (uint32_t i = tid; i < hslots; i += kBktThreads) sm.u.hset[i] = kEmpty;
-    uint32_t mx = 0, cmin = 0xffffffffu, cmax = 0;
-#pragma unroll
-    for (int i = 0; i < kBktIpt; i++) {
-      const uint32_t l = i * kBktThreads + tid;
-      keys[i] = 0;
-      if (l < m) {
-        keys[i] = __ldcs(bkey + l);
-        const uint32_t c = __float_as_uint(__ldg(&brec[l].w)) >> kChunkShift;
-        sm.key[l] = c;
-        mx = max(mx, keys[i]);
-        cmin = min(cmin, c);
-        cmax = max(cmax, c);
-      }
-    }
+    for (uint32_t i = tid; i < hslots; i += kBktThreads) sm.u.h.hkey[i] = kEmpty;
+    for (uint32_t i = tid; i < hslots / 2; i += kBktThreads) sm.u.h.hcnt[i] = 0;
     __syncthreads();
-    uint32_t fresh = 0;
     const int hshift = 32 - (31 - __clz(hslots));
+    uint32_t slot2[kBktIpt / 2];  // the records' hash slots, two per register
+    uint32_t idx[kBktIpt];        // their point indices
+    uint32_t mx = 0;
 #pragma unroll
     for (int i = 0; i < kBktIpt; i++) {
+      if ((i & 1) == 0) slot2[i / 2] = 0;
+      idx[i] = 0;
       const uint32_t l = i * kBktThreads + tid;
-      if (l < m) {
-        const uint32_t k = keys[i] == kEmpty ? kEmpty - 1 : keys[i];  // the marker itself shares a slot with its
-        uint32_t h = (k * 0x9e3779b1u) >> hshift;                      // neighbour (corrected below)
+      if (i * kBktThreads < m && l < m) {
+        const uint32_t k = __ldcs(bkey + l);
+        idx[i] = __float_as_uint(__ldg(&brec[l].w));
+        mx = max(mx, k);
+        uint32_t h = (k * 0x9e3779b1u) >> hshift;
         for (;;) {
-          const uint32_t old = atomicCAS(&sm.u.hset[h], kEmpty, k);
+          const uint32_t old = atomicCAS(&sm.u.h.hkey[h], kEmpty, k);
           if (old == kEmpty) {
-            fresh++;
+            const uint32_t at = atomicAdd(&sm.distinct, 1u);
+            sm.dkey[at] = k;
+            sm.dslot[at] = (uint16_t)h;
             break;
           }
           if (old == k) break;
           h = (h + 1) & (hslots - 1);
         }
+        cnt_inc(sm.u.h.hcnt, h);
+        slot2[i / 2] |= h << (16 * (i & 1));
       }
     }
-    // keys 0xffffffff and 0xfffffffe were counted as one: both present -> one more voxel
-    bool has_e = false, has_e1 = false;
 #pragma unroll
-    for (int i = 0; i < kBktIpt; i++) {
-      const uint32_t l = i * kBktThreads + tid;
-      has_e = has_e || (l < m && keys[i] == kEmpty);
-      has_e1 = has_e1 || (l < m && keys[i] == kEmpty - 1);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-      cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, d));
-      cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, d));
-      fresh += __shfl_xor_sync(0xffffffffu, fresh, d);
-    }
-    if (lane == 0) {
-      if (mx) atomicMax(&sm.maxkey, mx);
-      atomicMin(&sm.minchunk, cmin);
-      atomicMax(&sm.maxchunk, cmax);
-      if (fresh) atomicAdd(&sm.distinct, fresh);
-    }
-    const int both = __syncthreads_or(has_e ? 1 : 0) && __syncthreads_or(has_e1 ? 1 : 0);
-    total_heads = sm.distinct + (both ? 1u : 0u);
-  }
-  if (tid == 0) stv[bucket] = ((bucket == 0 ? 2ull : 1ull) << 62) | (unsigned long long)total_heads;
-  if (m > 0) {
-    // ---- 2. runs (blocked): a run = consecutive records of one chunk (one warp's reservation)
-    uint32_t headmask = 0, cnt = 0;
-    {
-      uint32_t prev = l0 > 0 && l0 - 1 < m ? sm.key[l0 - 1] : 0xffffffffu;
-#pragma unroll
-      for (int j = 0; j < kBktIpt; j++) {
-        const uint32_t l = l0 + j;
-        if (l < m) {
-          const uint32_t c = sm.key[l];
-          const bool h = l == 0 || c != prev;
-          headmask |= (h ? 1u : 0u) << j;
-          cnt += h ? 1u : 0u;
-          prev = c;
-        }
-      }
-    }
-    uint32_t runs = 0;
-    const uint32_t rexcl = bkt_excl_scan(cnt, sm.scan, &runs);  // (its barriers also retire the hash set)
-    uint32_t my_chunk[kBktIpt];
-    {
-      uint32_t r = rexcl;  // runs before this thread's first head; a record's run = heads up to and including it - 1
-#pragma unroll
-      for (int j = 0; j < kBktIpt; j++) {
-        const uint32_t l = l0 + j;
-        my_chunk[j] = 0;
-        if (l < m) {
-          if ((headmask >> j) & 1u) {
-            my_chunk[j] = sm.key[l];
-            sm.u.run.chunk[r] = my_chunk[j];
-            sm.u.run.start[r] = (uint16_t)l;
-            r++;
-          }
-          sm.u.run.rec_run[l] = (uint16_t)(r - 1);
-        }
-      }
-    }
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0 && mx) atomicMax(&sm.maxkey, mx);
     __syncthreads();
-    const bool ordered = runs <= 1;
-    if (!ordered) {
-      // ---- 3. rank of every run by chunk id (unique per run): radix sort of (chunk - min chunk, run)
-      const uint32_t minchunk = sm.minchunk;
-      const int cbits = 32 - __clz(sm.maxchunk - minchunk);  // >= 1: two runs have different chunks
-      {
-        uint32_t r = rexcl;
-#pragma unroll
-        for (int j = 0; j < kBktIpt; j++) {
-          if ((headmask >> j) & 1u) {
-            sm.key[r] = my_chunk[j] - minchunk;
-            sm.pos[r] = (uint16_t)r;
-            r++;
-          }
-        }
-      }
-      __syncthreads();
-      bkt_radix_sort(sm, runs, cbits);
-      // ---- 4. first position of every run in index order: exclusive scan of the lengths by rank
-      uint32_t len[kBktIpt], sum = 0;
+    U = sm.distinct;
+    if (tid == 0) stv[bucket] = ((bucket == 0 ? 2ull : 1ull) << 62) | (unsigned long long)U;
+    // ---- 2. sort the distinct keys (with their slots)
+    bkt_sort_distinct(sm, U, sm.maxkey ? 32 - __clz(sm.maxkey) : 0);
+    // ---- first position of every voxel; slot -> voxel
+    {
+      const uint32_t u0 = tid * kBktIpt;
+      uint32_t len[kBktIpt], sum = 0, big = 0;
 #pragma unroll
       for (int j = 0; j < kBktIpt; j++) {
-        len[j] = 0;
-        if (l0 + j < runs) {
-          const uint32_t r = sm.pos[l0 + j];
-          sm.u.run.rank[r] = (uint16_t)(l0 + j);
-          len[j] = (r + 1 < runs ? (uint32_t)sm.u.run.start[r + 1] : m) - sm.u.run.start[r];
-        }
+        len[j] = u0 + j < U ? cnt_get(sm.u.h.hcnt, sm.dslot[u0 + j]) : 0u;
+        big = max(big, len[j]);
         sum += len[j];
       }
-      uint32_t e = bkt_excl_scan(sum, sm.scan, nullptr);
+      if (big > kMaxMembers) sm.heavy = 1;
+      uint32_t e = bkt_excl_scan(sum, sm.scan, nullptr);  // (its barriers also order the count reads before the resets)
 #pragma unroll
       for (int j = 0; j < kBktIpt; j++) {
-        if (l0 + j < runs) sm.u.run.nstart[l0 + j] = (uint16_t)e;
+        if (u0 + j < U) {
+          const uint32_t s = sm.dslot[u0 + j];
+          sm.vstart[u0 + j] = (uint16_t)e;
+          sm.u.h.hkey[s] = u0 + j;
+        }
         e += len[j];
       }
-      __syncthreads();
+      if (tid == 0) sm.vstart[U] = (uint16_t)m;
+      for (uint32_t i = tid; i < hslots / 2; i += kBktThreads) sm.u.h.hcnt[i] = 0;
     }
-    // ---- 5. records in index order -> staging (key, position in the region)
+    __syncthreads();
+    if (sm.heavy) {  // uniform
+      if (tid == 0) atomicOr(&st->overflow, 2u);
+    }
+    // ---- 3. records into their voxel's range, then into the reference's accumulation order
 #pragma unroll
     for (int i = 0; i < kBktIpt; i++) {
       const uint32_t l = i * kBktThreads + tid;
-      if (l < m) {
-        uint32_t np = l;
-        if (!ordered) {
-          const uint32_t r = sm.u.run.rec_run[l];
-          np = (uint32_t)sm.u.run.nstart[sm.u.run.rank[r]] + (l - sm.u.run.start[r]);
-        }
-        sm.key[np] = keys[i];
-        sm.pos[np] = (uint16_t)l;
+      if (i * kBktThreads < m && l < m) {
+        const uint32_t s = (slot2[i / 2] >> (16 * (i & 1))) & 0xffffu;
+        const uint32_t u = sm.u.h.hkey[s];
+        const uint32_t p = (uint32_t)sm.vstart[u] + cnt_inc(sm.u.h.hcnt, s);
+        sm.w.g.g_l[p] = (uint16_t)l;
+        sm.w.g.g_u[p] = (uint16_t)u;
+        sm.g_idx[p] = idx[i];
       }
     }
     __syncthreads();
-    // ---- 6. stable LSD radix sort on the bits the keys of this bucket use
-    const uint32_t maxkey = sm.maxkey;
-    bkt_radix_sort(sm, m, maxkey ? 32 - __clz(maxkey) : 0);
-    // ---- 7. points in sorted order (the run table is dead)
-#pragma unroll
-    for (int i = 0; i < kBktIpt; i++) {
-      const uint32_t l = i * kBktThreads + tid;
-      if (l < m) {
-        const float4 r4 = __ldg(&brec[sm.pos[l]]);
-        sm.u.xyz[0][l] = r4.x;
-        sm.u.xyz[1][l] = r4.y;
-        sm.u.xyz[2][l] = r4.z;
-      }
-    }
-    // ---- 8. voxel heads (blocked), compacted
-    headmask = 0;
-    cnt = 0;
-    {
-      uint32_t prev = l0 > 0 && l0 - 1 < m ? sm.key[l0 - 1] : 0u;
-#pragma unroll
-      for (int j = 0; j < kBktIpt; j++) {
-        const uint32_t l = l0 + j;
-        if (l < m) {
-          const uint32_t k = sm.key[l];
-          const bool h = l == 0 || k != prev;
-          headmask |= (h ? 1u : 0u) << j;
-          cnt += h ? 1u : 0u;
-          prev = k;
+    if (!sm.heavy) {
+#pragma unroll 1
+      for (int i = 0; i < kBktIpt; i++) {
+        const uint32_t p = i * kBktThreads + tid;
+        if (p < m) {
+          const uint32_t l = sm.w.g.g_l[p], u = sm.w.g.g_u[p];
+          const uint32_t a = sm.vstart[u], e = sm.vstart[u + 1];
+          const uint32_t mine = sm.g_idx[p];
+          uint32_t r = 0;
+          for (uint32_t j = a; j < e; j++) r += sm.g_idx[j] < mine ? 1u : 0u;
+          sm.dslot[a + r] = (uint16_t)l;
         }
       }
     }
-    const uint32_t hexcl = bkt_excl_scan(cnt, sm.scan, nullptr);  // also orders the xyz stores before the walk
-    {
-      uint16_t* s_src = &sm.hist[0][0];
-      uint32_t r = hexcl;
+    __syncthreads();
+    // ---- 4. points in final order (the hash table is dead)
 #pragma unroll
-      for (int j = 0; j < kBktIpt; j++)
-        if ((headmask >> j) & 1u) s_src[r++] = (uint16_t)(l0 + j);
+    for (int i = 0; i < kBktIpt; i++) {
+      const uint32_t p = i * kBktThreads + tid;
+      if (i * kBktThreads < m && p < m) {
+        const float4 r4 = __ldg(&brec[sm.dslot[p]]);
+        sm.u.xyz[0][p] = r4.x;
+        sm.u.xyz[1][p] = r4.y;
+        sm.u.xyz[2][p] = r4.z;
+      }
     }
+  } else if (tid == 0) {
+    stv[bucket] = ((bucket == 0 ? 2ull : 1ull) << 62);
   }
-  // ---- 9. output slot of the bucket's first voxel: look-back over the preceding buckets, one status word per
-  // thread (every running bucket has published its count already; only finished ones hold inclusive sums)
+  // ---- output slot of the bucket's first voxel: look-back over the preceding buckets, one status word per thread
+  // (every running bucket has published its count already; only finished ones hold inclusive sums)
   unsigned long long prefix = 0;
   if (bucket > 0) {
-    int64_t hi = (int64_t)bucket - 1;  // window [hi - 511, hi], thread t reads hi - t
+    int64_t hi = (int64_t)bucket - 1;  // window [hi - 255, hi], thread t reads hi - t
     for (;;) {
       const int64_t idx = hi - (int64_t)tid;
       unsigned long long w = 2ull << 62;  // before the first bucket: an inclusive 0
@@ -708,25 +650,23 @@ __global__ void __launch_bounds__(kBktThreads, 2)
       if (found) break;
       hi -= kBktThreads;
     }
-    if (tid == 0) stv[bucket] = (2ull << 62) | (prefix + total_heads);
+    if (tid == 0) stv[bucket] = (2ull << 62) | (prefix + U);
   }
-  if (tid == 0 && bucket == n_buckets - 1) st->n_out = (long long)(prefix + total_heads);
+  if (tid == 0 && bucket == n_buckets - 1) st->n_out = (long long)(prefix + U);
   __syncthreads();
-  if (m == 0) return;
-  // ---- 10. one voxel per thread per round: members added in list order (voxelgrid.go:148-158), record of the
-  // first member with the centroid (voxelgrid.go:173-184)
+  if (m == 0 || sm.heavy) return;
+  // ---- one voxel per thread per round: members added in list order (voxelgrid.go:148-158), record of the first
+  // member with the centroid (voxelgrid.go:173-184)
   const VgParams& P = st->P;
   const int out_aligned = v.aligned && ((((uintptr_t)out) & 3) == 0);
   const bool xyz_only = out_aligned && v.packed && v.stride == 12;
   const unsigned long long kmin = bucket ? (unsigned long long)__ldg(&spl[bucket - 1]) << st->shift : 0ull;
-  const uint16_t* s_src = &sm.hist[0][0];
   const int key_bits = P.key_bits;
   long long vc_cid = -1;
   float vc[3] = {0.f, 0.f, 0.f};
-  for (uint32_t r = tid; r < total_heads; r += kBktThreads) {
-    const uint32_t l = s_src[r];
-    const uint32_t end = r + 1 < total_heads ? s_src[r + 1] : m;
-    const unsigned long long key = kmin + sm.key[l];
+  for (uint32_t r = tid; r < U; r += kBktThreads) {
+    const uint32_t l = sm.vstart[r], end = sm.vstart[r + 1];
+    const unsigned long long key = kmin + sm.dkey[r];
     const long long cid = (long long)(key >> key_bits);
     if (cid != vc_cid) {
       chunk_min(P, cid, vc);
@@ -754,7 +694,7 @@ __global__ void __launch_bounds__(kBktThreads, 2)
       d3[1] = oy;
       d3[2] = oz;
     } else {
-      const uint32_t first = __float_as_uint(__ldg(&brec[sm.pos[l]].w));
+      const uint32_t first = __float_as_uint(__ldg(&brec[sm.dslot[l]].w));
       const uint8_t* src = v.data + (uint64_t)first * (uint64_t)v.stride;
       if (out_aligned) {
         const uint32_t* s4 = (const uint32_t*)src;
@@ -796,7 +736,9 @@ bool voxelgrid_filter_partition(const CloudView& v, const float leaf[3], const i
   State* st = reinterpret_cast<State*>(small.p);
   uint32_t* cursor = reinterpret_cast<uint32_t*>(small.p + state_bytes);
   unsigned long long* status = reinterpret_cast<unsigned long long*>(small.p + state_bytes + cursor_bytes);
-  DevBuf<uint32_t> spl(std::max<uint32_t>(n_buckets, 1u), stream);
+  uint32_t spl_padded = 2;  // 2 * (largest power of two <= n_buckets - 1), at least 2
+  while (spl_padded < 2 * n_buckets) spl_padded *= 2;
+  DevBuf<uint32_t> spl(spl_padded, stream);
   DevBuf<float4> rec((size_t)n_buckets * kCap, stream);
   DevBuf<uint32_t> key32((size_t)n_buckets * kCap, stream);
 
@@ -812,7 +754,8 @@ bool voxelgrid_filter_partition(const CloudView& v, const float leaf[3], const i
     uint32_t* vv[2] = {sv0.p, sv1.p};
     int res = 0;
     sorter.run(kk, vv, /*identity_vals=*/true, /*keep_keys=*/true, stream, &res);
-    PCG_LAUNCH(splitters_kernel, div_up(n_buckets, 256), 256, 0, stream, kk[res], n_samples, n_buckets, spl.p);
+    PCG_LAUNCH(splitters_kernel, div_up(spl_padded, 256), 256, 0, stream, kk[res], n_samples, n_buckets, spl_padded,
+               spl.p);
   }
   {
     static std::atomic<uint64_t> configured{0};
