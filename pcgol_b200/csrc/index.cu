@@ -730,10 +730,11 @@ void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, c
 }
 
 // ---- KDTree.Nearest, batched (kdtree.go:83-92) -----------------------------------------
-// One thread walks `per_thread` consecutive queries of the (Hilbert-ordered) visit list.  Consecutive queries are
-// neighbours in space, so the winner of one query is a real point close to the next one: its distance is a valid
-// upper bound to start the next walk with (it is one of the candidates the search would see anyway, so the
-// (DistSq, ID) arg-min is unchanged), and almost all backtracking is pruned from the first step.
+// A warp walks `per_thread` consecutive runs of 32 queries of the (Hilbert-ordered) visit list; lane l takes query l
+// of every run, so the lanes of a warp always hold neighbouring queries (their walks touch the same nodes).  Queries
+// 32 positions apart are still neighbours in space, so the winner of a lane's previous query is a real point close to
+// its next one: its distance is a valid upper bound to start the next walk with (it is one of the candidates the
+// search would see anyway, so the (DistSq, ID) arg-min is unchanged) and prunes most of the backtracking.
 constexpr int kNnThreads = 128;
 template <bool APPROX>
 __global__ void __launch_bounds__(kNnThreads)
@@ -741,10 +742,11 @@ __global__ void __launch_bounds__(kNnThreads)
                    float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
                    pcg_neighbor* __restrict__ aos) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t first = (t >> 5) * 32 * per_thread + (t & 31);
   const uint64_t init = nn_init(max_range_sq);
   uint32_t warm = 0xffffffffu;
   for (int k = 0; k < per_thread; k++) {
-    const int64_t slot = t * per_thread + k;
+    const int64_t slot = first + (int64_t)k * 32;
     if (slot >= q.n) return;
     const int64_t i = perm ? (int64_t)perm[slot] : slot;
     const float3 p = load_xyz(q, i);
