@@ -384,6 +384,23 @@ pcg_status pcg_query_order_dev(pcg_index* idx, const void* d_q, int64_t n, int64
  * tail of Evaluate + gradientDescentUpdater.Update to the device-resident state; once converged / failed the
  * remaining calls fall through.  pcg_icp_shard_result synchronises `stream` and returns the transform, Stat and
  * whether the loop has ended (status PCG_E_NOT_ENOUGH_PAIRS like Fit).  Float64 sums, gradient-descent updater. */
+/* ---- multi-GPU from ONE process (the Go shim has no ranks): the device list is the list of index replicas.
+ * pcg_index_replicate copies a built index to another device (NVLink peer copy; the replica is bit-identical).
+ * pcg_icp_fit_multi* = PointToPointICPGradient.Fit (icp.go:23-67) with the target split over the replicas' devices:
+ * one persistent cooperative kernel per device runs the whole loop; per iteration every device stores its ten float64
+ * partial sums into every peer's exchange buffer over NVLink (peer-mapped memory, no library collective, no kernel
+ * launch, no host round trip), waits on flags and applies the identical update.  Fast mode, gradient-descent
+ * updater, exact nearest neighbour (min_dist_sq == 0).  The transform equals the single-GPU fast Fit up to the
+ * rounding of the float64 sums.  n_dev == 1 is allowed (no exchange).  _dev: d_targets[r] (n_targets[r] records) is
+ * device memory on the device of bases[r]; the host variant cuts `target` into contiguous slices itself. */
+pcg_status pcg_index_replicate(pcg_index* src, int32_t device, pcg_index** out);
+pcg_status pcg_icp_fit_multi_dev(int32_t n_dev, pcg_index* const* bases, const void* const* d_targets,
+                                 const int64_t* n_targets, int64_t stride, const int64_t xyz_off[3],
+                                 const pcg_icp_params* params, float trans[16], pcg_icp_stat* stat);
+pcg_status pcg_icp_fit_multi(int32_t n_dev, pcg_index* const* bases, const void* target, int64_t n, int64_t stride,
+                             const int64_t xyz_off[3], const pcg_icp_params* params, float trans[16],
+                             pcg_icp_stat* stat);
+
 typedef struct pcg_icp_shard pcg_icp_shard;
 pcg_status pcg_icp_shard_new(pcg_index* base, const void* d_target, int64_t n, int64_t stride, const int64_t xyz_off[3],
                              const pcg_icp_params* params, void* stream, pcg_icp_shard** out);

@@ -90,6 +90,9 @@ pcg_status icp_finish_host(const double partial16[16], const pcg_icp_params& prm
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream);
 struct IcpShard;
+pcg_status icp_fit_multi_device(int n_dev, const Index* const* bases, const void* const* d_targets,
+                                const int64_t* n_targets, int64_t stride, const int64_t xyz_off[3],
+                                const pcg_icp_params& prm, float trans[16], pcg_icp_stat* stat);
 IcpShard* icp_shard_new(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, cudaStream_t stream);
 void icp_shard_free(IcpShard* sh);
 void icp_shard_partial(IcpShard& sh, double* d_partial16, cudaStream_t stream);
@@ -839,6 +842,83 @@ pcg_status pcg_icp_partial_dev(pcg_index* base, const void* d_target, int64_t n,
     icp_partial_device(*base->ix, make_view(d_target, n, stride, xyz_off), max_dist, trans, first != 0, d_visit_order,
                        d_partial16, (cudaStream_t)stream);
     return PCG_OK;
+  });
+}
+
+// ---- multi-GPU entry points for a single-process caller (device list = the devices of the index replicas) ----
+pcg_status pcg_index_replicate(pcg_index* src, int32_t device, pcg_index** out) {
+  return guarded([&]() -> pcg_status {
+    if (!src || !out) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *out = nullptr;
+    check_device(device);
+    *out = new pcg_index{index_replicate(*src->ix, device)};
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_icp_fit_multi_dev(int32_t n_dev, pcg_index* const* bases, const void* const* d_targets,
+                                 const int64_t* n_targets, int64_t stride, const int64_t xyz_off[3],
+                                 const pcg_icp_params* params, float trans[16], pcg_icp_stat* stat) {
+  return guarded([&]() -> pcg_status {
+    if (!bases || !d_targets || !n_targets || !params || !trans) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (n_dev < 1 || n_dev > 8) throw StatusError{PCG_E_INVALID_ARG, "1 to 8 devices"};
+    const Index* ix[8];
+    for (int r = 0; r < n_dev; r++) {
+      if (!bases[r]) throw StatusError{PCG_E_INVALID_ARG, "null index"};
+      ix[r] = bases[r]->ix;
+    }
+    return icp_fit_multi_device(n_dev, ix, d_targets, n_targets, stride, xyz_off, *params, trans, stat);
+  });
+}
+
+pcg_status pcg_icp_fit_multi(int32_t n_dev, pcg_index* const* bases, const void* target, int64_t n, int64_t stride,
+                             const int64_t xyz_off[3], const pcg_icp_params* params, float trans[16],
+                             pcg_icp_stat* stat) {
+  return guarded([&]() -> pcg_status {
+    if (!bases || !params || !trans) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (n_dev < 1 || n_dev > 8) throw StatusError{PCG_E_INVALID_ARG, "1 to 8 devices"};
+    check_view_args(target, n, stride, xyz_off);
+    // contiguous slices of the target, one per device (the order of the float64 partial sums follows the devices)
+    const Index* ix[8];
+    void* d_tgt[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const void* d_ctgt[8];
+    int64_t cnt[8];
+    int prev = -1;
+    cudaGetDevice(&prev);
+    auto release = [&]() {
+      for (int r = 0; r < n_dev; r++)
+        if (d_tgt[r]) {
+          cudaSetDevice(ix[r]->device);
+          cudaFree(d_tgt[r]);
+        }
+      if (prev >= 0) cudaSetDevice(prev);
+    };
+    try {
+      for (int r = 0; r < n_dev; r++) {
+        if (!bases[r]) throw StatusError{PCG_E_INVALID_ARG, "null index"};
+        ix[r] = bases[r]->ix;
+      }
+      for (int r = 0; r < n_dev; r++) {
+        const int64_t lo = n * r / n_dev, hi = n * (r + 1) / n_dev;
+        cnt[r] = hi - lo;
+        PCG_CUDA(cudaSetDevice(ix[r]->device));
+        PCG_CUDA(cudaMalloc(&d_tgt[r], (size_t)std::max<int64_t>(1, cnt[r] * stride)));
+        if (cnt[r])
+          PCG_CUDA(cudaMemcpyAsync(d_tgt[r], (const uint8_t*)target + lo * stride, (size_t)(cnt[r] * stride),
+                                   cudaMemcpyHostToDevice, cudaStreamPerThread));
+        d_ctgt[r] = d_tgt[r];
+      }
+      for (int r = 0; r < n_dev; r++) {
+        PCG_CUDA(cudaSetDevice(ix[r]->device));
+        PCG_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+      }
+      const pcg_status rc = icp_fit_multi_device(n_dev, ix, d_ctgt, cnt, stride, xyz_off, *params, trans, stat);
+      release();
+      return rc;
+    } catch (...) {
+      release();
+      throw;
+    }
   });
 }
 

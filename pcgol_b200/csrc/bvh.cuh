@@ -238,6 +238,7 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream);
 // d_ids: n point ids, already validated against [0, ix.n). Enqueues on `stream`.
 void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream);
 void index_free(Index* ix);
+Index* index_replicate(const Index& src, int device);
 void index_free_async(Index* ix, cudaStream_t stream);  // caller is on ix->device; `stream` ordered after the last use
 // Queries visited in Morton order make the threads of a warp walk the same part of the tree.
 // Writes a permutation (sorted position -> query index) into d_perm[q.n].

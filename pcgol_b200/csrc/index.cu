@@ -596,6 +596,47 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
   return ix;
 }
 
+void index_free(Index* ix);
+// A copy of a built index on another device (device-to-device over NVLink when the devices are peers, staged
+// through the host by the runtime otherwise): the replica every GPU needs for sharded queries and the sharded ICP.
+// Much cheaper than a second build, and bit-identical to the source by construction.
+Index* index_replicate(const Index& src, int device) {
+  Index* ix = new Index();
+  ix->device = device;
+  ix->n = src.n;
+  ix->leaves = src.leaves;
+  ix->P = src.P;
+  if (src.n == 0) return ix;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  try {
+    PCG_CUDA(cudaSetDevice(src.device));
+    PCG_CUDA(cudaDeviceSynchronize());  // the source may still be building on some stream
+    PCG_CUDA(cudaSetDevice(device));
+    const size_t pts_bytes = (size_t)src.leaves * kLeaf * sizeof(float4);
+    const size_t box_bytes = (size_t)4 * src.P * sizeof(float4);
+    PCG_CUDA(cudaMalloc((void**)&ix->pts, pts_bytes));
+    PCG_CUDA(cudaMalloc((void**)&ix->boxes, box_bytes));
+    PCG_CUDA(cudaMalloc((void**)&ix->bbox, 8 * sizeof(uint32_t)));
+    PCG_CUDA(cudaMemcpyPeer(ix->pts, device, src.pts, src.device, pts_bytes));
+    PCG_CUDA(cudaMemcpyPeer(ix->boxes, device, src.boxes, src.device, box_bytes));
+    PCG_CUDA(cudaMemcpyPeer(ix->bbox, device, src.bbox, src.device, 8 * sizeof(uint32_t)));
+    ix->bytes = (int64_t)(pts_bytes + box_bytes);
+    if (src.inv) {  // DeletePoint was used: the tombstone table travels too
+      PCG_CUDA(cudaMalloc((void**)&ix->inv, (size_t)src.n * sizeof(uint32_t)));
+      PCG_CUDA(cudaMemcpyPeer(ix->inv, device, src.inv, src.device, (size_t)src.n * sizeof(uint32_t)));
+      ix->bytes += src.n * (int64_t)sizeof(uint32_t);
+    }
+    PCG_CUDA(cudaDeviceSynchronize());
+  } catch (...) {
+    if (prev >= 0) cudaSetDevice(prev);
+    index_free(ix);
+    throw;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return ix;
+}
+
 void index_free(Index* ix) {
   if (!ix) return;
   int prev = -1;

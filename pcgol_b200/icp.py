@@ -163,6 +163,33 @@ class PointToPointICPGradient:
                                       C.byref(stat), stream)
         return self._finish(rc, trans, stat)
 
+    def fit_multi(self, bases: Sequence[Index], target) -> Tuple[np.ndarray, Stat]:
+        """Fit with the target split over the devices of `bases` (replicas of one index, see Index.replicate):
+        one process, NVLink peer exchange of the partial sums inside the per-device kernels.  Fast mode."""
+        data, n, stride, off = as_vec3_buffer(target)
+        p = self.params(bases[0])
+        k = len(bases)
+        hs = (C.c_void_p * k)(*[b._h for b in bases])
+        trans = np.zeros(16, np.float32)
+        stat = _lib.IcpStat()
+        rc = _lib.lib.pcg_icp_fit_multi(k, hs, data.ctypes.data, n, stride, _off(off), C.byref(p), trans.ctypes.data,
+                                        C.byref(stat))
+        return self._finish(rc, trans, stat)
+
+    def fit_multi_dev(self, bases: Sequence[Index], d_targets: Sequence[int], n_targets: Sequence[int],
+                      stride: int = 12, off=(0, 4, 8)) -> Tuple[np.ndarray, Stat]:
+        """Device-resident variant: d_targets[r] (n_targets[r] records) lives on the device of bases[r]."""
+        p = self.params(bases[0])
+        k = len(bases)
+        hs = (C.c_void_p * k)(*[b._h for b in bases])
+        pt = (C.c_void_p * k)(*d_targets)
+        nt = (C.c_int64 * k)(*n_targets)
+        trans = np.zeros(16, np.float32)
+        stat = _lib.IcpStat()
+        rc = _lib.lib.pcg_icp_fit_multi_dev(k, hs, pt, nt, stride, _off(off), C.byref(p), trans.ctypes.data,
+                                            C.byref(stat))
+        return self._finish(rc, trans, stat)
+
     def fit_pairs_dev(self, d_base, n_base, d_target, n_target, device: int = 0, stream: int = 0, stride: int = 12,
                       off=(0, 4, 8)):
         """Scan-pair farm: lists of device pointers / sizes. Returns (trans (k,16), num_iteration, status)."""

@@ -51,6 +51,17 @@ class Index:
         _lib.check(_lib.lib.pcg_index_build_dev(d_ptr, n, stride, _off(off), device, stream, C.byref(self._h)))
         return self
 
+    def replicate(self, device: int) -> "Index":
+        """A bit-identical copy of the built index on another device (NVLink peer copy, no rebuild)."""
+        other = Index.__new__(Index)
+        other._cloud = self._cloud
+        other._xyz = self._xyz
+        other.device = device
+        other.min_dist_sq = self.min_dist_sq
+        other._h = C.c_void_p()
+        _lib.check(_lib.lib.pcg_index_replicate(self._h, device, C.byref(other._h)))
+        return other
+
     def close(self):
         if getattr(self, "_h", None):
             if getattr(self, "_shared", None) is None:  # a With() copy does not own the handle

@@ -39,6 +39,62 @@ def test_sharded_icp_single_rank_matches_fast_fit():
     assert rstatus == pg._lib.E_NOT_ENOUGH_PAIRS and rstat.num_iteration == 1
 
 
+def test_fit_multi_one_device_matches_fast_fit():
+    """pcg_icp_fit_multi with a single replica: the persistent kernel without any exchange.  Same float64 partial sums
+    as the single-GPU fast Fit, folded in a different order."""
+    import pcgol_b200 as pg
+    from pcgol_b200 import synth
+
+    base, target = synth.icp_pair(seed=3, n=30000, n_az=500)
+    idx = pg.Index(base)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    ftrans, fstat = icp.fit(idx, target)
+    mtrans, mstat = icp.fit_multi([idx], target)
+    assert mstat.num_iteration == fstat.num_iteration and mstat.n_pairs == fstat.n_pairs
+    np.testing.assert_allclose(mtrans, ftrans, rtol=0, atol=1e-6)
+    # ErrNotEnoughPairs travels through the persistent loop like through Fit (icp.go:51-53)
+    with pytest.raises(pg.ErrNotEnoughPairs) as ei:
+        icp.fit_multi([idx], (target + np.float32(500.0)).astype(np.float32))
+    assert ei.value.stat.num_iteration == 1
+    # strict order cannot be sharded: the entry point always runs the fast mode, whatever the evaluator says
+    strict = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+    strans, _ = strict.fit_multi([idx], target)
+    assert strans.tobytes() == mtrans.tobytes()
+
+
+def test_fit_multi_peer_exchange_matches_single_gpu():
+    """One process, several GPUs: index replicas by peer copy, target split, ten float64 sums exchanged over NVLink
+    inside the per-device kernels.  Transform within 1e-6 of the single-GPU fast Fit and of the float64 oracle's."""
+    import torch
+
+    import pcgol_b200 as pg
+    from oracle import oracle as orc
+    from pcgol_b200 import synth
+
+    ndev = min(torch.cuda.device_count(), 8)
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    base, target = synth.icp_pair(seed=4, n=60000, n_az=900)
+    idx = pg.Index(base)
+    replicas = [idx] + [idx.replicate(d) for d in range(1, ndev)]
+    q = synth.nn_queries(base, 20000, seed=5)
+    ids0, dsq0 = idx.nearest_batch(q, 1.0)
+    for r in replicas[1:]:  # a replica answers exactly like the source
+        ids, dsq = r.nearest_batch(q, 1.0)
+        assert np.array_equal(ids, ids0) and dsq.tobytes() == dsq0.tobytes()
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    ftrans, fstat = icp.fit(idx, target)
+    for k in sorted({2, ndev}):
+        mtrans, mstat = icp.fit_multi(replicas[:k], target)
+        assert mstat.num_iteration == fstat.num_iteration and mstat.n_pairs == fstat.n_pairs
+        np.testing.assert_allclose(mtrans, ftrans, rtol=0, atol=1e-6)
+    rc, etrans, _, eit = orc.icp_fit(orc.Search(base, "kdtree"), target, orc.icp_params(1.0, f64_accumulate=True))
+    assert rc == orc.OK
+    np.testing.assert_allclose(mtrans, etrans, rtol=0, atol=1e-5)
+    for r in replicas[1:]:
+        r.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

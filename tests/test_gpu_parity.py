@@ -369,6 +369,23 @@ def test_icp_fast_mode_close_to_f64_oracle(pg, oracle, synth):
     np.testing.assert_allclose(trans, etrans, rtol=0, atol=1e-3)
 
 
+def test_icp_fast_mode_config1_within_1e5_of_reference_order(pg, oracle, synth):
+    """BASELINE config 1 (100k-point scan vs a 5 deg / 0.3 m perturbed copy): the fast mode (float64 tree sums) must
+    land within 1e-5 of the transform the reference's sequential float32 order produces (north_star: "final ICP
+    transforms within 1e-5 relative"; the transform's scale is 1, so the bound is applied to every entry)."""
+    base, target = synth.icp_pair(seed=1, n=100_000)
+    idx = pg.Index(base)
+    fast = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    strict = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0)))
+    ftrans, fstat = fast.fit(idx, target)
+    strans, sstat = strict.fit(idx, target)
+    rc, etrans, _, eit = oracle.icp_fit(oracle.Search(base, "kdtree"), target, oracle.icp_params(1.0))
+    assert rc == oracle.OK and sstat.num_iteration == eit
+    assert strans.tobytes() == etrans.tobytes()  # strict: the reference's bits
+    assert fstat.num_iteration == eit
+    np.testing.assert_allclose(ftrans, etrans, rtol=1e-5, atol=1e-5)
+
+
 def test_icp_fit_pairs_farm_matches_single(pg, synth):
     import torch
 
