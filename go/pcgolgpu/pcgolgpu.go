@@ -51,6 +51,14 @@ func statusError(s C.pcg_status) error {
 	return fmt.Errorf("pcgolgpu: status %d: %s", int(s), C.GoString(C.pcg_last_error()))
 }
 
+// pin keeps the calling goroutine on one OS thread until the returned function runs: pcg_last_error is
+// thread-local in C, and a goroutine may migrate between the failing call and the call that fetches its message.
+// Every method that may call statusError starts with `defer pin()()`.
+func pin() func() {
+	runtime.LockOSThread()
+	return runtime.UnlockOSThread
+}
+
 // flatten turns any Vec3RandomAccessor into (pointer, n, stride, xyz offsets).
 // Fast paths pass the caller's memory as is (no Go pointer is retained by C after the call):
 // pc.Vec3Slice is []mat.Vec3 = contiguous [3]float32 records.
@@ -81,7 +89,8 @@ type Index struct {
 	// MinDistSq mirrors KDTree.MinDistSq (kdtree.go:19-22): larger than zero makes Nearest (and the ICP
 	// correspondences searched through this index) the approximate search.
 	MinDistSq float32
-	shared    bool // a With() copy: the handle belongs to the original
+	shared    bool   // a With() copy: the handle belongs to the original
+	owner     *Index // ... which the copy keeps reachable: the original's finalizer frees the device index
 }
 
 // With is KDTree.With (kdtree.go:58-65): a shallow copy sharing the device index.
@@ -89,11 +98,17 @@ func (k *Index) With(minDistSq float32) *Index {
 	k2 := *k
 	k2.MinDistSq = minDistSq
 	k2.shared = true
+	k2.owner = k // kdtree.New(ra).With(x) drops the original: without this reference the GC would free k.h under k2
+	if k.owner != nil {
+		k2.owner = k.owner
+	}
 	return &k2
 }
 
 // DeletePoint is KDTree.DeletePoint (kdtree.go:322-332): the point stops matching any search.
 func (k *Index) DeletePoint(pID int) error {
+	defer runtime.KeepAlive(k) // the finalizer must not free k.h while C uses it
+	defer pin()()
 	id := C.int64_t(pID)
 	return statusError(C.pcg_index_delete_points(k.h, &id, 1))
 }
@@ -102,6 +117,7 @@ var _ storage.Search = (*Index)(nil)
 
 // NewIndex is the drop-in for kdtree.New (pc/storage/kdtree/kdtree.go:33).
 func NewIndex(ra pc.Vec3RandomAccessor, device int) (*Index, error) {
+	defer pin()()
 	p, n, stride, off, keep := flatten(ra)
 	idx := &Index{Vec3RandomAccessor: ra}
 	s := C.pcg_index_build(p, n, stride, &off[0], C.int32_t(device), &idx.h)
@@ -137,6 +153,8 @@ func (k *Index) Range(p mat.Vec3, maxRange float32) []storage.Neighbor {
 // NearestBatch answers every query in one call. storage.Neighbor{ID int; DistSq float32} has
 // the layout of C.pcg_neighbor on 64-bit targets, so `out` is written in place.
 func (k *Index) NearestBatch(q pc.Vec3RandomAccessor, maxRange float32, out []storage.Neighbor) {
+	defer runtime.KeepAlive(k) // the finalizer must not free k.h while C uses it
+	defer pin()()
 	p, n, stride, off, keep := flatten(q)
 	if n == 0 {
 		return
@@ -153,6 +171,8 @@ func (k *Index) NearestBatch(q pc.Vec3RandomAccessor, maxRange float32, out []st
 // RangeBatch returns CSR offsets (len(q)+1) and the concatenated neighbour lists, using the
 // two-call protocol so that the result lives in Go-allocated memory (count, then fill).
 func (k *Index) RangeBatch(q pc.Vec3RandomAccessor, maxRange float32) ([]int64, []storage.Neighbor) {
+	defer runtime.KeepAlive(k) // the finalizer must not free k.h while C uses it
+	defer pin()()
 	p, n, stride, off, keep := flatten(q)
 	offs := make([]int64, int(n)+1)
 	s := C.pcg_index_range_count(k.h, p, n, stride, &off[0], C.float(maxRange), (*C.int64_t)(unsafe.Pointer(&offs[0])))
@@ -215,6 +235,7 @@ func xyzOffsets(pp *pc.PointCloud) ([3]C.int64_t, error) {
 
 // Filter is voxelGrid.Filter (voxelgrid.go:35-134): same records, same order, same bits.
 func (f *voxelGrid) Filter(pp *pc.PointCloud) (*pc.PointCloud, error) {
+	defer pin()()
 	off, err := xyzOffsets(pp)
 	if err != nil {
 		return nil, err
@@ -243,7 +264,9 @@ func (f *voxelGrid) Filter(pp *pc.PointCloud) (*pc.PointCloud, error) {
 type NearestPointCorresponder struct{ MaxDist float32 }
 
 func (c *NearestPointCorresponder) Pairs(base storage.Search, target pc.Vec3RandomAccessor) []icp.PointToPointCorrespondence {
+	defer pin()()
 	idx := base.(*Index)
+	defer runtime.KeepAlive(idx)
 	p, n, stride, off, keep := flatten(target)
 	baseID := make([]int64, int(n)+1)
 	targetID := make([]int64, int(n)+1)
@@ -296,7 +319,9 @@ func evaluatedFromC(e *C.pcg_evaluated) icp.Evaluated {
 }
 
 func (e *PointToPointEvaluator) Evaluate(base storage.Search, target pc.Vec3RandomAccessor) (*icp.Evaluated, error) {
+	defer pin()()
 	idx := base.(*Index)
+	defer runtime.KeepAlive(idx)
 	p, n, stride, off, keep := flatten(target)
 	var ev C.pcg_evaluated
 	var np C.int64_t
@@ -325,7 +350,9 @@ type PointToPointICPGradient struct {
 }
 
 func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomAccessor) (mat.Mat4, icp.Stat, error) {
+	defer pin()()
 	idx := base.(*Index)
+	defer runtime.KeepAlive(idx)
 	p, n, stride, off, keep := flatten(target)
 	var prm C.pcg_icp_params
 	prm.max_dist = C.float(r.Evaluator.Corresponder.MaxDist)
@@ -350,6 +377,49 @@ func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomA
 	return trans, stat, statusError(s) // on ErrNotEnoughPairs: (trans so far, stat, err) like icp.go:51-53
 }
 
+// Replicate copies the built index to another GPU (NVLink peer copy, bit-identical; pcg_index_replicate).
+func (k *Index) Replicate(device int) (*Index, error) {
+	defer pin()()
+	defer runtime.KeepAlive(k)
+	r := &Index{Vec3RandomAccessor: k.Vec3RandomAccessor, MinDistSq: k.MinDistSq}
+	if err := statusError(C.pcg_index_replicate(k.h, C.int32_t(device), &r.h)); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(r, (*Index).Close)
+	return r, nil
+}
+
+// FitMulti is Fit with the target split over the GPUs that hold the replicas (bases[0] and its Replicate copies):
+// one process, no ranks - each device runs one persistent kernel and the ten partial sums of every iteration
+// travel as peer-memory stores over NVLink (pcg_icp_fit_multi).  Fast mode (float64 partial sums).
+func (r *PointToPointICPGradient) FitMulti(bases []*Index, target pc.Vec3RandomAccessor) (mat.Mat4, icp.Stat, error) {
+	defer pin()()
+	p, n, stride, off, keep := flatten(target)
+	hs := make([]*C.pcg_index, len(bases))
+	for i, b := range bases {
+		hs[i] = b.h
+	}
+	var prm C.pcg_icp_params
+	prm.max_dist = C.float(r.Evaluator.Corresponder.MaxDist)
+	prm.min_pairs = C.int32_t(r.Evaluator.MinPairs)
+	prm.mode = C.PCG_ICP_FAST
+	if f := r.UpdaterFactory; f != nil {
+		for i := 0; i < 6; i++ {
+			prm.weight[i] = C.float(f.Weight[i])
+			prm.threshold[i] = C.float(f.Threshold[i])
+		}
+		prm.max_iteration = C.int32_t(f.MaxIteration)
+	}
+	var trans mat.Mat4
+	var st C.pcg_icp_stat
+	// hs holds C pointers only (no Go pointers), so passing &hs[0] obeys the cgo pointer rules
+	s := C.pcg_icp_fit_multi(C.int32_t(len(hs)), &hs[0], p, n, stride, &off[0], &prm, (*C.float)(unsafe.Pointer(&trans[0])), &st)
+	runtime.KeepAlive(keep)
+	runtime.KeepAlive(bases)
+	stat := icp.Stat{Evaluated: evaluatedFromC(&st.evaluated), NumIteration: int(st.num_iteration)}
+	return trans, stat, statusError(s)
+}
+
 // RegionGrowing is the drop-in for regiongrowing.New / Segment (pc/segmentation/regiongrowing/regiongrowing.go:11-56):
 // every breadth-first level is one batched Range on the device.
 type RegionGrowing struct {
@@ -360,6 +430,7 @@ type RegionGrowing struct {
 // NewRegionGrowing takes the cloud the index was built from and the name of its uint32 property
 // (what pp.Uint32Iterator(field) would iterate).
 func NewRegionGrowing(search *Index, pp *pc.PointCloud, field string) (*RegionGrowing, error) {
+	defer pin()()
 	off, err := xyzOffsets(pp)
 	if err != nil {
 		return nil, err
@@ -400,6 +471,8 @@ func (r *RegionGrowing) Close() {
 
 // Segment is RegionGrowing.Segment (regiongrowing.go:23-56).
 func (r *RegionGrowing) Segment(p mat.Vec3, maxRange float32) []int {
+	defer runtime.KeepAlive(r)
+	defer pin()()
 	out := make([]int, r.n+1) // Go int == int64 on the 64-bit targets this library supports
 	var m C.int64_t
 	s := C.pcg_region_growing_segment(r.h, (*C.float)(unsafe.Pointer(&p[0])), C.float(maxRange),
@@ -416,6 +489,7 @@ type DeviceCloud struct{ h *C.pcg_cloud }
 
 // Unmarshal is pc.Unmarshal over a byte slice; ascii, binary and binary_compressed.
 func Unmarshal(pcd []byte, device int) (*DeviceCloud, error) {
+	defer pin()()
 	var p unsafe.Pointer
 	if len(pcd) > 0 {
 		p = unsafe.Pointer(&pcd[0])
@@ -430,6 +504,8 @@ func Unmarshal(pcd []byte, device int) (*DeviceCloud, error) {
 
 // Marshal is pc.Marshal ("DATA binary").
 func (c *DeviceCloud) Marshal() ([]byte, error) {
+	defer runtime.KeepAlive(c)
+	defer pin()()
 	var n C.int64_t
 	C.pcg_pcd_marshal(c.h, nil, 0, &n)
 	out := make([]byte, int(n))
@@ -448,6 +524,8 @@ func (c *DeviceCloud) Close() {
 
 // VoxelGrid is voxelGrid.Filter on the resident cloud.
 func (c *DeviceCloud) VoxelGrid(leaf mat.Vec3, chunk [3]int) (*DeviceCloud, error) {
+	defer runtime.KeepAlive(c)
+	defer pin()()
 	ck := [3]C.int64_t{C.int64_t(chunk[0]), C.int64_t(chunk[1]), C.int64_t(chunk[2])}
 	out := &DeviceCloud{}
 	if err := statusError(C.pcg_cloud_voxelgrid_filter(c.h, (*C.float)(unsafe.Pointer(&leaf[0])), &ck[0], &out.h)); err != nil {

@@ -553,8 +553,13 @@ pcg_status pcg_index_range_fill(pcg_index* idx, const void* q, int64_t nq, int64
                                 pcg_neighbor* out) {
   return guarded([&]() -> pcg_status {
     if (!idx || !offsets) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (nq < 0) throw StatusError{PCG_E_INVALID_ARG, "negative query count"};
+    // the CSR offsets come from the caller: they must be the monotone table pcg_index_range_count produced
+    if (offsets[0] != 0) throw StatusError{PCG_E_INVALID_ARG, "offsets[0] must be 0"};
+    for (int64_t i = 0; i < nq; i++)
+      if (offsets[i + 1] < offsets[i]) throw StatusError{PCG_E_INVALID_ARG, "offsets are not monotone"};
     const int64_t total = offsets[nq];
-    if (total < 0 || (total && !out)) throw StatusError{PCG_E_INVALID_ARG, "bad offsets / null output"};
+    if (total && !out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
     if (nq == 0 || total == 0) return PCG_OK;
     DeviceGuard g(idx->ix->device);
     cudaStream_t s = cudaStreamPerThread;
@@ -722,6 +727,7 @@ pcg_status pcg_icp_pairs_approx(pcg_index* base, const void* target, int64_t n, 
                                 int64_t* target_id, float* dist_sq, int64_t* n_pairs) {
   return guarded([&]() -> pcg_status {
     if (!base || !n_pairs) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    if (n > 0 && (!base_id || !target_id || !dist_sq)) throw StatusError{PCG_E_INVALID_ARG, "null output"};
     if (!(min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
     *n_pairs = 0;
     DeviceGuard g(base->ix->device);

@@ -231,6 +231,12 @@ struct Index {
   uint32_t* inv = nullptr;
   std::mutex mu;  // serialises DeletePoint calls (queries racing a delete are undefined, as in the reference)
   int64_t bytes = 0;
+  // recorded on the stream the index was built (or last modified) on: every consumer makes its own stream wait for
+  // it, so a build enqueued on one stream is ordered before queries enqueued on another
+  cudaEvent_t ready = nullptr;
+  void wait(cudaStream_t s) const {
+    if (ready) cudaStreamWaitEvent(s, ready, 0);
+  }
   IndexView view() const { return IndexView{pts, boxes, P, (uint32_t)n}; }
 };
 

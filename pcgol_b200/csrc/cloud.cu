@@ -256,6 +256,11 @@ Cloud* cloud_unmarshal(const uint8_t* pcd, int64_t len, int device, cudaStream_t
     return c;
   }
   if (fmt == kFmtAscii) {  // io.go:140-180
+    // every record takes at least one byte of text per F/U value (plus a separator): a POINTS count that the input
+    // cannot possibly hold would only make the reference allocate and zero a huge slice - refuse it instead of
+    // following it (a tiny file must not be able to demand a terabyte)
+    if (points * stride > (int64_t)64 * (len + 1024))
+      throw StatusError{PCG_E_TOO_LARGE, "ascii PCD: POINTS * record size is out of proportion to the input length"};
     std::vector<uint8_t> data((size_t)(points * stride), 0);
     int64_t off = 0;
     while (r.pos < r.n) {
@@ -429,6 +434,10 @@ static CloudView cloud_view(const Cloud& c) {
   if (!cloud_xyz_offsets(c.h, off)) throw StatusError{PCG_E_INVALID_FIELD, "invalid field name"};
   const int64_t stride = c.h.stride();
   check_view_args(c.d_data, c.points, stride, off);
+  // binary_compressed keeps len(Data) == nUncompressed (io.go:217), which a crafted header can make smaller than
+  // POINTS records: the reference would panic on the slice, here every consumer would read past the allocation
+  if (c.points * stride > c.bytes)
+    throw StatusError{PCG_E_REF_WOULD_PANIC, "slice bounds out of range (Data is shorter than POINTS records)"};
   return make_view(c.d_data, c.points, stride, off);
 }
 

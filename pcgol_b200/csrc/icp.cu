@@ -752,6 +752,7 @@ static void icp_enqueue_iterations(const Index& base, const CloudView& tgt, cons
 static void icp_prepare(const Index& base, const CloudView& tgt, const pcg_icp_params& prm, bool evaluate_only,
                         IcpWork& w, cudaStream_t stream) {
   const bool hess = (prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON;
+  base.wait(stream);  // the index may have been built on another stream
   w.nblocks = std::max(1, div_up(tgt.n, term_threads(prm.mode, hess)));
   if (tgt.n >= kMinQueriesToReorder && base.n > 0) {
     // the target moves by a small rigid transform per iteration: the order of the raw target stays coherent
@@ -904,6 +905,7 @@ void icp_fit_pairs_device(int32_t count, const void* const* d_base, const int64_
 // One shard's contribution to a single large ICP (see pcg_icp_partial_dev).
 void icp_partial_device(const Index& base, const CloudView& tgt, float max_dist, const float trans[16], bool first,
                         const uint32_t* d_order, double* d_partial16, cudaStream_t stream) {
+  base.wait(stream);
   IcpWork w;
   pcg_icp_params prm;
   std::memset(&prm, 0, sizeof(prm));
@@ -1333,6 +1335,7 @@ __global__ void __launch_bounds__(128)
 
 void icp_pairs_device(const Index& base, const CloudView& tgt, float max_dist, float min_dist_sq, int32_t* d_ids,
                       float* d_dsq, cudaStream_t stream) {
+  base.wait(stream);
   if (tgt.n == 0) return;
   if (min_dist_sq > 0.f)  // threshold capped at maxDist^2: see nearest_device
     PCG_LAUNCH(icp_pairs_kernel<true>, div_up(tgt.n, 128), 128, 0, stream, base.view(), tgt, max_dist * max_dist,

@@ -589,6 +589,8 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
     }
     PCG_LAUNCH(leaf_boxes_kernel, div_up(P, 256), 256, 0, stream, ix->pts, ix->boxes, ix->leaves, P);
     if (P >= 512) PCG_LAUNCH(top_boxes_kernel, 1, 1024, 0, stream, ix->boxes, P);
+    PCG_CUDA(cudaEventCreateWithFlags(&ix->ready, cudaEventDisableTiming));
+    PCG_CUDA(cudaEventRecord(ix->ready, stream));
   } catch (...) {
     index_free(ix);
     throw;
@@ -628,6 +630,8 @@ Index* index_replicate(const Index& src, int device) {
       ix->bytes += src.n * (int64_t)sizeof(uint32_t);
     }
     PCG_CUDA(cudaDeviceSynchronize());
+    PCG_CUDA(cudaEventCreateWithFlags(&ix->ready, cudaEventDisableTiming));
+    PCG_CUDA(cudaEventRecord(ix->ready, cudaStreamPerThread));
   } catch (...) {
     if (prev >= 0) cudaSetDevice(prev);
     index_free(ix);
@@ -646,6 +650,7 @@ void index_free(Index* ix) {
   if (ix->boxes) cudaFree(ix->boxes);
   if (ix->bbox) cudaFree(ix->bbox);
   if (ix->inv) cudaFree(ix->inv);
+  if (ix->ready) cudaEventDestroy(ix->ready);
   if (prev >= 0) cudaSetDevice(prev);
   delete ix;
 }
@@ -676,6 +681,7 @@ __global__ void __launch_bounds__(256)
 void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream) {
   if (n == 0 || ix.n == 0) return;
   std::lock_guard<std::mutex> lk(ix.mu);
+  ix.wait(stream);
   if (!ix.inv) {
     PCG_CUDA(cudaMallocAsync((void**)&ix.inv, (size_t)ix.n * sizeof(uint32_t), stream));
     ix.bytes += ix.n * (int64_t)sizeof(uint32_t);
@@ -683,6 +689,7 @@ void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cuda
     PCG_LAUNCH(inverse_slots_kernel, div_up(padded, 256), 256, 0, stream, ix.pts, padded, ix.inv);
   }
   PCG_LAUNCH(delete_points_kernel, div_up(n, 256), 256, 0, stream, ix.pts, ix.inv, d_ids, n);
+  if (ix.ready) PCG_CUDA(cudaEventRecord(ix.ready, stream));  // later queries on other streams see the tombstones
 }
 
 // For owners that know the stream the index was last used on (the scan-pair farm): cudaFree synchronises
@@ -693,6 +700,7 @@ void index_free_async(Index* ix, cudaStream_t stream) {
   if (ix->boxes) cudaFreeAsync(ix->boxes, stream);
   if (ix->bbox) cudaFreeAsync(ix->bbox, stream);
   if (ix->inv) cudaFreeAsync(ix->inv, stream);
+  if (ix->ready) cudaEventDestroy(ix->ready);
   delete ix;
 }
 
@@ -825,6 +833,7 @@ __global__ void __launch_bounds__(kNnThreads)
 void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
                     float* d_dist_sq, pcg_neighbor* d_aos, cudaStream_t stream) {
   if (q.n == 0) return;
+  ix.wait(stream);
   const float mrsq = max_range * max_range;  // kdtree.go:91
   DevBuf<uint32_t> perm;
   if (q.n >= kMinQueriesToReorder && ix.n > 0) {
@@ -858,14 +867,22 @@ __global__ void __launch_bounds__(128)
 
 __global__ void __launch_bounds__(128)
     range_fill_kernel(IndexView ix, CloudView q, float max_range_sq, const long long* __restrict__ offsets,
-                      unsigned long long* __restrict__ packed) {
+                      unsigned long long* __restrict__ packed, int* __restrict__ mismatch) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= q.n) return;
   float3 p = load_xyz(q, i);
+  // the offsets are the caller's (count pass): never write past the list's end, and report a list whose length
+  // differs from what this query finds (other queries / range than in the count pass, stale offsets)
   unsigned long long* dst = packed + offsets[i];
+  unsigned long long* const end = packed + offsets[i + 1];
+  bool over = false;
   range_traverse(ix, p.x, p.y, p.z, max_range_sq, [&](uint32_t id, float d) {
-    *dst++ = ((unsigned long long)__float_as_uint(d) << 32) | id;
+    if (dst < end)
+      *dst++ = ((unsigned long long)__float_as_uint(d) << 32) | id;
+    else
+      over = true;
   });
+  if (over || dst != end) atomicOr(mismatch, 1);
 }
 
 // exclusive scan uint32 counts -> int64 offsets (n+1 entries), decoupled look-back
@@ -1002,6 +1019,7 @@ void scan_counts(const uint32_t* counts, long long* offsets, uint32_t n, cudaStr
 void range_count_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
                         int64_t* total_out, cudaStream_t stream) {
   const uint32_t nq = (uint32_t)q.n;
+  ix.wait(stream);
   const float mrsq = max_range * max_range;  // kdtree.go:157
   offsets.alloc((size_t)nq + 1, stream);
   *total_out = 0;
@@ -1033,6 +1051,7 @@ void range_fill_device(const Index& ix, const CloudView& q, float max_range, con
                        int64_t total, pcg_neighbor* d_out, cudaStream_t stream) {
   const uint32_t nq = (uint32_t)q.n;
   if (nq == 0 || total == 0) return;
+  ix.wait(stream);
   const float mrsq = max_range * max_range;
   DevBuf<uint32_t> need(nq, stream);
   DevBuf<long long> scratch_off((size_t)nq + 1, stream);
@@ -1043,7 +1062,14 @@ void range_fill_device(const Index& ix, const CloudView& q, float max_range, con
   PCG_CUDA(cudaStreamSynchronize(stream));
   DevBuf<unsigned long long> packed((size_t)total, stream);
   DevBuf<unsigned long long> scratch((size_t)std::max<long long>(1, scratch_total), stream);
-  PCG_LAUNCH(range_fill_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, d_offsets, packed.p);
+  DevBuf<int> mismatch(1, stream);
+  PCG_CUDA(cudaMemsetAsync(mismatch.p, 0, sizeof(int), stream));
+  PCG_LAUNCH(range_fill_kernel, div_up(nq, 128), 128, 0, stream, ix.view(), q, mrsq, d_offsets, packed.p, mismatch.p);
+  int h_mismatch = 0;
+  PCG_CUDA(cudaMemcpyAsync(&h_mismatch, mismatch.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  if (h_mismatch)
+    throw StatusError{PCG_E_INVALID_ARG, "range_fill: the offsets do not match these queries / this range (count pass differs)"};
   PCG_LAUNCH(range_sort_kernel, nq, kSortThreads, 0, stream, d_offsets, packed.p, scratch.p, scratch_off.p);
   PCG_LAUNCH(range_unpack_kernel, div_up(total, 256), 256, 0, stream, packed.p, d_out, (long long)total);
   PCG_CUDA(cudaStreamSynchronize(stream));

@@ -89,6 +89,7 @@ __global__ void rg_widen_kernel(const uint32_t* __restrict__ in, long long n, lo
 
 RegionGrowing* region_growing_new_device(const Index& search, const CloudView& v, int64_t label_off,
                                          cudaStream_t stream) {
+  search.wait(stream);
   RegionGrowing* rg = new RegionGrowing();
   rg->search = &search;
   rg->device = search.device;

@@ -136,3 +136,58 @@ def test_replay_model_selftest(tmp_path):
         rows = [ln for ln in out.splitlines() if "| exact" in ln or "MISMATCH" in ln]
         assert len(rows) == 9 and all("| exact" in ln for ln in rows), out
         assert "MODEL ERROR" not in out
+
+
+def _strip_go(src: str) -> str:
+    """Go source without comments, string, rune and raw-string literals (enough for a structural check)."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        c = src[i]
+        if src.startswith("//", i):
+            i = src.find("\n", i) if src.find("\n", i) >= 0 else n
+        elif src.startswith("/*", i):
+            i = src.find("*/", i) + 2
+        elif c == '"':
+            i += 1
+            while src[i] != '"':
+                i += 2 if src[i] == "\\" else 1
+            i += 1
+        elif c == "`":
+            i = src.find("`", i + 1) + 1
+        elif c == "'":
+            i += 1
+            while src[i] != "'":
+                i += 2 if src[i] == "\\" else 1
+            i += 1
+        else:
+            out.append(c)
+            i += 1
+    return "".join(out)
+
+
+def test_go_shim_is_structurally_sound_and_binds_declared_symbols():
+    """No Go toolchain in this image (go version: not found), so the cgo shim cannot be compiled here.  This is the
+    check that can run: balanced delimiters outside literals, every C.pcg_* / C.PCG_* it names exists in the header,
+    every method that can report an error pins its OS thread (pcg_last_error is thread-local), and the With() copy
+    keeps its owner alive."""
+    path = os.path.join(ROOT, "go", "pcgolgpu", "pcgolgpu.go")
+    raw = open(path).read()
+    # the cgo preamble is a comment block right above `import "C"`: it must include the product header
+    assert '#include "pcgol_b200.h"' in raw and 'import "C"' in raw
+    code = _strip_go(raw)
+    for a, b in ("()", "[]", "{}"):
+        depth = 0
+        for ch in code:
+            depth += ch == a
+            depth -= ch == b
+            assert depth >= 0, f"unbalanced {a}{b}"
+        assert depth == 0, f"unbalanced {a}{b}"
+    header = open(os.path.join(ROOT, "include", "pcgol_b200.h")).read()
+    for sym in sorted(set(re.findall(r"\bC\.(pcg_[a-z0-9_]+|PCG_[A-Z0-9_]+)\b", code))):
+        assert re.search(r"\b%s\b" % sym, header), f"go shim binds {sym}, which include/pcgol_b200.h does not declare"
+    # every function body that calls statusError (directly) runs pinned to its OS thread
+    for m in re.finditer(r"\nfunc [^\n]*\{\n(.*?)\n\}\n", raw, flags=re.S):
+        body = m.group(1)
+        if "statusError(" in body and not m.group(0).startswith("\nfunc statusError"):
+            assert "defer pin()()" in body, m.group(0).splitlines()[1]
+    assert "k2.owner = k" in raw and "runtime.KeepAlive(k)" in raw
