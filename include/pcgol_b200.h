@@ -263,6 +263,33 @@ pcg_status pcg_voxelgrid_chunk_histogram_dev(const void* d_data, int64_t n, int6
 pcg_status pcg_voxelgrid_filter_chunks_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                            const float leaf[3], const int64_t chunk[3], int64_t cid_lo, int64_t cid_hi,
                                            int32_t device, void* d_out, int64_t* n_out, void* stream);
+/* The same Filter with the POINTS sharded: every rank holds a contiguous slice of the cloud (slice r before slice
+ * r+1 in point order) and nothing is replicated.  Steps, each a call below with a collective of the caller in between:
+ *   pcg_minmax_packed_dev        the slice's six MinMaxVec3 accumulators, 64-bit words that a signed MIN (first three)
+ *                                / MAX (last three) all-reduce combines; the low 32 bits are the global index of the
+ *                                winning point (max: its complement), so the first occurrence wins across ranks
+ *                                (minmax.go:17-22) and the owner of the winner reads the exact value, zero sign included
+ *   ..._chunk_histogram_mm_dev   points per chunk id of the slice under the bounds mm6 = {min xyz, max xyz} of the
+ *                                whole cloud; summed over ranks it balances the chunk ranges
+ *   ..._owner_order_dev          cuts[r] = first chunk id of rank r (cuts[0] = 0): d_perm = the slice's points ordered
+ *                                by owner (stable), counts[r] = points for rank r -> all-to-all of whole records
+ *   ..._filter_chunks_mm_dev     the owner filters the records it received (sources in rank order = global point
+ *                                order, which the stable sort keeps) under the same bounds
+ * Outputs concatenated in rank order are the reference's output (voxelgrid.go:102-133). */
+pcg_status pcg_minmax_packed_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                 int32_t device, int64_t index_base, int64_t* d_out6, void* stream);
+pcg_status pcg_voxelgrid_chunk_histogram_mm_dev(const void* d_data, int64_t n, int64_t stride,
+                                                const int64_t xyz_off[3], const float leaf[3], const int64_t chunk[3],
+                                                const float mm6[6], int32_t device, int64_t sample_step, int64_t* hist,
+                                                int64_t cap, int64_t* n_chunks, void* stream);
+pcg_status pcg_voxelgrid_owner_order_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                         const float leaf[3], const int64_t chunk[3], const float mm6[6],
+                                         const int64_t* cuts, int32_t world, int32_t device, uint32_t* d_perm,
+                                         int64_t* counts, void* stream);
+pcg_status pcg_voxelgrid_filter_chunks_mm_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                              const float leaf[3], const int64_t chunk[3], const float mm6[6],
+                                              int64_t cid_lo, int64_t cid_hi, int32_t device, void* d_out,
+                                              int64_t* n_out, void* stream);
 /* MinMaxVec3 (pc/minmax.go:9-26) — first step of the filter, exposed for sharded runs. */
 pcg_status pcg_minmax_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3], int32_t device,
                           float mn[3], float mx[3], void* stream);

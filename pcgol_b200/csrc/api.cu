@@ -64,11 +64,16 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
                                    int64_t* n_out, cudaStream_t stream);
 void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t stream);
 extern std::atomic<int> g_vg_path;
+void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream);
+void voxelgrid_owner_order_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], const float* mm6,
+                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts,
+                                  cudaStream_t stream);
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
-                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream);
+                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream,
+                                         const float* mm6 = nullptr);
 pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                           int64_t cid_lo, int64_t cid_hi, uint8_t* d_out, int64_t* n_out,
-                                          cudaStream_t stream);
+                                          cudaStream_t stream, const float* mm6 = nullptr);
 void nearest_device(const Index& ix, const CloudView& q, float max_range, float min_dist_sq, int32_t* d_ids,
                     float* d_dist_sq, pcg_neighbor* d_aos, cudaStream_t stream);
 void range_device(const Index& ix, const CloudView& q, float max_range, DevBuf<long long>& offsets,
@@ -701,6 +706,71 @@ pcg_status pcg_voxelgrid_filter_chunks_dev(const void* d_data, int64_t n, int64_
     DeviceGuard g(device);
     return voxelgrid_filter_chunks_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, cid_lo, cid_hi,
                                           (uint8_t*)d_out, n_out, (cudaStream_t)stream);
+  });
+}
+
+// ---- point-sharded Filter: the same steps with the bounds of the WHOLE cloud supplied by the caller ----
+pcg_status pcg_minmax_packed_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                 int32_t device, int64_t index_base, int64_t* d_out6, void* stream) {
+  return guarded([&]() -> pcg_status {
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    if (!d_out6 || index_base < 0 || index_base + n >= ((int64_t)1 << 31))
+      throw StatusError{PCG_E_INVALID_ARG, "null output / global point index out of range"};
+    DeviceGuard g(device);
+    minmax_packed_device(make_view(d_data, n, stride, xyz_off), (uint32_t)index_base, (long long*)d_out6,
+                         (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_voxelgrid_chunk_histogram_mm_dev(const void* d_data, int64_t n, int64_t stride,
+                                                const int64_t xyz_off[3], const float leaf[3], const int64_t chunk[3],
+                                                const float mm6[6], int32_t device, int64_t sample_step, int64_t* hist,
+                                                int64_t cap, int64_t* n_chunks, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!n_chunks || !mm6) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *n_chunks = 0;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    DeviceGuard g(device);
+    *n_chunks = voxelgrid_chunk_histogram_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, sample_step, hist,
+                                                 cap, (cudaStream_t)stream, mm6);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_voxelgrid_owner_order_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                         const float leaf[3], const int64_t chunk[3], const float mm6[6],
+                                         const int64_t* cuts, int32_t world, int32_t device, uint32_t* d_perm,
+                                         int64_t* counts, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!mm6 || !cuts || !counts || (n && !d_perm)) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    DeviceGuard g(device);
+    voxelgrid_owner_order_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, mm6, cuts, world, d_perm, counts,
+                                 (cudaStream_t)stream);
+    return PCG_OK;
+  });
+}
+
+pcg_status pcg_voxelgrid_filter_chunks_mm_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
+                                              const float leaf[3], const int64_t chunk[3], const float mm6[6],
+                                              int64_t cid_lo, int64_t cid_hi, int32_t device, void* d_out,
+                                              int64_t* n_out, void* stream) {
+  return guarded([&]() -> pcg_status {
+    if (!n_out || !mm6) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
+    *n_out = 0;
+    check_device(device);
+    check_view_args(d_data, n, stride, xyz_off);
+    check_vg_args(leaf, chunk);
+    if (n && !d_out) throw StatusError{PCG_E_INVALID_ARG, "null output"};
+    DeviceGuard g(device);
+    return voxelgrid_filter_chunks_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, cid_lo, cid_hi,
+                                          (uint8_t*)d_out, n_out, (cudaStream_t)stream, mm6);
   });
 }
 

@@ -19,7 +19,8 @@ namespace pcg {
 
 std::atomic<int> g_vg_path{0};
 
-__global__ void __launch_bounds__(256) minmax_kernel(CloudView v, unsigned long long* __restrict__ out6) {
+__global__ void __launch_bounds__(256)
+    minmax_kernel(CloudView v, uint32_t index_base, unsigned long long* __restrict__ out6) {
   __shared__ unsigned long long s_red[8][6];
   unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(256) minmax_kernel(CloudView v, unsigned long 
     for (int k = 0; k < 3; k++) {
       if (c[k] != c[k]) continue;  // NaN never wins a comparison in the reference
       unsigned long long o = (unsigned long long)ordered_bits(c[k]) << 32;
-      unsigned long long a = o | (uint32_t)i, b = o | (0xffffffffu - (uint32_t)i);
+      unsigned long long a = o | (index_base + (uint32_t)i), b = o | (0xffffffffu - (index_base + (uint32_t)i));
       mn[k] = a < mn[k] ? a : mn[k];
       mx[k] = b > mx[k] ? b : mx[k];
     }
@@ -97,7 +98,7 @@ void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t st
   }
   PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
   int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-  PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, acc.p);
+  PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, 0u, acc.p);
   PCG_LAUNCH(minmax_finalize_kernel, 1, 32, 0, stream, v, acc.p, res.p);
   float* h = (float*)pinned_scratch();
   PCG_CUDA(cudaMemcpyAsync(h, res.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -137,6 +138,31 @@ __global__ void __launch_bounds__(256)
   if (bad) atomicOr(flags, bad);
   __syncthreads();
   rsort::hist_flush(s_hist, hist, passes);
+}
+
+// MinMaxVec3 of one slice of a cloud that is split over several GPUs: the six accumulators themselves, so that the
+// caller can reduce them across ranks.  d_out6[0..2] = min over the slice of (ordered value bits << 32 | global
+// index), d_out6[3..5] = max of (ordered value bits << 32 | ~global index), both with the top bit flipped so that
+// SIGNED 64-bit MIN / MAX (what NCCL offers) orders them; NaN coordinates take no part (minmax.go:17-22); a slice
+// without candidates leaves the neutral element.  The first occurrence of the extreme value wins, across ranks too.
+__global__ void minmax_signed_order_kernel(const unsigned long long* __restrict__ acc, long long* __restrict__ out6) {
+  const int k = threadIdx.x;
+  if (k < 6) out6[k] = (long long)(acc[k] ^ 0x8000000000000000ull);
+}
+void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream) {
+  DevBuf<unsigned long long> acc(6, stream);
+  unsigned long long* init = (unsigned long long*)(pinned_scratch() + 64);
+  for (int k = 0; k < 3; k++) {
+    init[k] = ~0ull;
+    init[3 + k] = 0ull;
+  }
+  PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  if (v.n > 0) {
+    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
+    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, acc.p);
+  }
+  PCG_LAUNCH(minmax_signed_order_kernel, 1, 32, 0, stream, acc.p, d_out6);
+  PCG_CUDA(cudaStreamSynchronize(stream));  // the pinned init words are reused by the next call of this thread
 }
 
 // ---- segmented centroid + record gather ----------------------------------------------
@@ -1222,10 +1248,17 @@ __global__ void __launch_bounds__(256)
 }
 
 static void vg_params_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], VgParams* P,
-                             int* total_bits, cudaStream_t stream) {
-  if (v.n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
+                             int* total_bits, cudaStream_t stream, const float* mm6 = nullptr) {
   float vmin[3], vmax[3];
-  minmax_device(v, vmin, vmax, stream);
+  if (mm6) {  // the bounds of the WHOLE cloud, reduced over the ranks by the caller (this rank holds a slice)
+    for (int k = 0; k < 3; k++) {
+      vmin[k] = mm6[k];
+      vmax[k] = mm6[3 + k];
+    }
+  } else {
+    if (v.n == 0) throw StatusError{PCG_E_NO_POINT, "no point"};
+    minmax_device(v, vmin, vmax, stream);
+  }
   const long long chunk_ll[3] = {(long long)chunk[0], (long long)chunk[1], (long long)chunk[2]};
   const pcg_status prc = vg_make_params(vmin, vmax, leaf, chunk_ll, P, total_bits);
   if (prc != PCG_OK) throw StatusError{prc, vg_status_message(prc)};
@@ -1242,11 +1275,12 @@ static int64_t range_ids(const VgParams& P) {
 
 // Points per id, for balancing the ranges over the ranks.
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
-                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream) {
+                                         int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream,
+                                         const float* mm6) {
   if (sample_step < 1) throw StatusError{PCG_E_INVALID_ARG, "sample_step < 1"};
   VgParams P;
   int total_bits = 0;
-  vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
+  vg_params_device(v, leaf, chunk, &P, &total_bits, stream, mm6);
   if (P.n_chunks > ((int64_t)1 << 26)) throw StatusError{PCG_E_TOO_LARGE, "more than 2^26 chunks"};
   const int64_t ids = range_ids(P);
   const int shift = range_shift(P);
@@ -1256,8 +1290,9 @@ int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3]
   PCG_CUDA(cudaMemsetAsync(hist.p, 0, hist.bytes(), stream));
   PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
   const int64_t runs = div_up(div_up(v.n, (int64_t)32), sample_step);
-  PCG_LAUNCH(chunk_hist_kernel, (unsigned)div_up(runs * 32, (int64_t)256), 256, 0, stream, v, P, shift,
-             (unsigned long long)ids, sample_step, hist.p, d_flags.p);
+  if (runs > 0)
+    PCG_LAUNCH(chunk_hist_kernel, (unsigned)div_up(runs * 32, (int64_t)256), 256, 0, stream, v, P, shift,
+               (unsigned long long)ids, sample_step, hist.p, d_flags.p);
   std::vector<unsigned int> h((size_t)ids);
   int h_flags = 0;
   PCG_CUDA(cudaMemcpyAsync(h.data(), hist.p, hist.bytes(), cudaMemcpyDeviceToHost, stream));
@@ -1308,14 +1343,85 @@ static void run_range_reduce(const CloudView& v, const VgParams& P, int total_bi
              counter, status.p, d_n_out);
 }
 
+// Point-sharded Filter, exchange plan: every rank holds a slice of the cloud; the chunk ids [cuts[r], cuts[r+1]) belong
+// to rank r.  Writes the stable order of this slice's points by owner (d_perm[n]: first the points of rank 0's chunks
+// in index order, then rank 1's, ...) and counts[r] = points owned by rank r - what an all-to-all of the records needs.
+struct OwnerCuts {
+  unsigned long long cut[9];  // cut[r] = first id of rank r, r = 1 .. world-1 (entries past world are never reached)
+  int world;
+};
+__global__ void __launch_bounds__(256)
+    owner_key_kernel(CloudView v, VgParams P, int shift, OwnerCuts oc, uint32_t* __restrict__ owner,
+                     uint32_t* __restrict__ hist, int* __restrict__ flags) {
+  __shared__ uint32_t s_hist[rsort::kRadix];
+  rsort::hist_zero(s_hist, 1);
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rounds = (v.n + stride - 1) / stride;
+  int bad = 0;
+  const KeyConsts C(P);
+  for (int64_t r = 0; r < rounds; r++) {
+    const int64_t i = r * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < v.n;
+    uint32_t o = 0;
+    if (valid) {
+      const unsigned long long id = voxel_key_of(P, C, load_xyz(v, i), &bad) >> shift;
+      for (int q = 1; q < oc.world; q++) o += id >= oc.cut[q] ? 1u : 0u;
+      owner[i] = o;
+    }
+    rsort::hist_add_key(s_hist, o, valid, 0, 1);
+  }
+  if (bad) atomicOr(flags, bad);
+  __syncthreads();
+  rsort::hist_flush(s_hist, hist, 1);
+}
+
+void voxelgrid_owner_order_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], const float* mm6,
+                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts,
+                                  cudaStream_t stream) {
+  if (world < 1 || world > 8) throw StatusError{PCG_E_INVALID_ARG, "1 to 8 ranks"};
+  for (int r = 0; r < world; r++) counts[r] = 0;
+  VgParams P;
+  int total_bits = 0;
+  vg_params_device(v, leaf, chunk, &P, &total_bits, stream, mm6);
+  if (v.n == 0) return;
+  OwnerCuts oc;
+  std::memset(&oc, 0, sizeof(oc));
+  oc.world = world;
+  for (int r = 1; r < world; r++) {
+    if (cuts[r] < cuts[r - 1]) throw StatusError{PCG_E_INVALID_ARG, "chunk cuts are not monotone"};
+    oc.cut[r] = (unsigned long long)cuts[r];
+  }
+  const uint32_t n = (uint32_t)v.n;
+  DevBuf<uint32_t> k0(n, stream), k1(n, stream), v0(n, stream);
+  DevBuf<int> d_flags(1, stream);
+  PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
+  rsort::Sorter<uint32_t> sorter;
+  sorter.prepare(n, 0, 8, stream);
+  const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(n, 256));
+  PCG_LAUNCH(owner_key_kernel, blocks, 256, 0, stream, v, P, range_shift(P), oc, k0.p, sorter.hist(), d_flags.p);
+  uint32_t* kk[2] = {k0.p, k1.p};
+  uint32_t* vv[2] = {v0.p, d_perm};  // one pass: the payload ends on side 1
+  int res = 0;
+  sorter.run(kk, vv, /*identity_vals=*/true, /*keep_keys=*/false, stream, &res);
+  uint32_t h[8];
+  int h_flags = 0;
+  PCG_CUDA(cudaMemcpyAsync(h, sorter.hist(), sizeof(h), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaMemcpyAsync(&h_flags, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  PCG_CUDA(cudaStreamSynchronize(stream));
+  vg_throw_on_flags(h_flags);
+  for (int r = 0; r < world; r++) counts[r] = (int64_t)h[r];
+}
+
 // Filter restricted to the chunks [cid_lo, cid_hi). Synchronises `stream`.
 pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                           int64_t cid_lo, int64_t cid_hi, uint8_t* d_out, int64_t* n_out,
-                                          cudaStream_t stream) {
+                                          cudaStream_t stream, const float* mm6) {
   *n_out = 0;
   VgParams P;
   int total_bits = 0;
-  vg_params_device(v, leaf, chunk, &P, &total_bits, stream);
+  vg_params_device(v, leaf, chunk, &P, &total_bits, stream, mm6);
+  if (v.n == 0) return PCG_OK;  // a rank that owns no point of the cloud
   if (cid_lo < 0 || cid_hi < cid_lo) throw StatusError{PCG_E_INVALID_ARG, "bad chunk range"};
   DevBuf<long long> d_n(1, stream);
   DevBuf<int> d_flags(1, stream);

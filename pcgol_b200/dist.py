@@ -86,6 +86,144 @@ def sharded_voxelgrid(d_ptr: int, n: int, leaf, chunk, rank: int, world: int, d_
     return n_out.value, counts, (lo, hi)
 
 
+# ---- one large VoxelGrid with the POINTS sharded (all-to-all by chunk owner) -------------------------
+def ordered_bits(x: np.ndarray) -> np.ndarray:
+    """Order-preserving uint32 image of float32 values with -0 == +0 (the comparison Go's MinMaxVec3 makes)."""
+    x = np.where(x == 0, np.float32(0), x.astype(np.float32))
+    b = x.view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+
+
+class GpuVgShard:
+    """This rank's slice of the cloud on its GPU (a torch uint8 tensor of n * stride bytes) + the C-ABI steps."""
+
+    def __init__(self, records, n: int, stride: int, off, leaf, chunk, device: int, stream: int = 0):
+        self.rec, self.n, self.stride, self.off = records, n, stride, tuple(off)
+        self.leaf = (C.c_float * 3)(*[float(x) for x in leaf])
+        self.chunk = (C.c_int64 * 3)(*[int(x) for x in chunk])
+        self.offs = (C.c_int64 * 3)(*off)
+        self.device, self.stream = device, stream
+
+    def minmax_packed(self, index_base: int):
+        import torch
+        acc = torch.empty(6, dtype=torch.int64, device=self.rec.device)
+        _lib.check(_lib.lib.pcg_minmax_packed_dev(self.rec.data_ptr(), self.n, self.stride, self.offs, self.device,
+                                                 index_base, acc.data_ptr(), self.stream))
+        return acc
+
+    def coord_bits(self, local_idx: int, k: int) -> int:
+        import torch
+        b = self.rec[local_idx * self.stride + self.off[k]: local_idx * self.stride + self.off[k] + 4]
+        return int(b.cpu().numpy().view(np.int32)[0])
+
+    def histogram(self, mm6: np.ndarray, sample_step: int) -> np.ndarray:
+        n_chunks = C.c_int64(0)
+        hist = np.zeros(1 << 16, np.int64)
+        for _ in range(2):
+            _lib.check(_lib.lib.pcg_voxelgrid_chunk_histogram_mm_dev(
+                self.rec.data_ptr(), self.n, self.stride, self.offs, self.leaf, self.chunk, mm6.ctypes.data, self.device,
+                sample_step, hist.ctypes.data, len(hist), C.byref(n_chunks), self.stream))
+            if n_chunks.value <= len(hist):
+                break
+            hist = np.zeros(n_chunks.value, np.int64)
+        return hist[: n_chunks.value]
+
+    def owner_order(self, mm6: np.ndarray, cuts: np.ndarray):
+        import torch
+        world = len(cuts) - 1
+        perm = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.rec.device)
+        counts = np.zeros(world, np.int64)
+        _lib.check(_lib.lib.pcg_voxelgrid_owner_order_dev(
+            self.rec.data_ptr(), self.n, self.stride, self.offs, self.leaf, self.chunk, mm6.ctypes.data,
+            cuts.ctypes.data, world, self.device, perm.data_ptr(), counts.ctypes.data, self.stream))
+        return perm[: self.n], counts
+
+    def gather(self, perm):
+        return self.rec[: self.n * self.stride].view(self.n, self.stride)[perm.long()].reshape(-1)
+
+    def filter(self, recv, n_recv: int, mm6: np.ndarray, lo: int, hi: int, out):
+        n_out = C.c_int64(0)
+        _lib.check(_lib.lib.pcg_voxelgrid_filter_chunks_mm_dev(
+            recv.data_ptr(), n_recv, self.stride, self.offs, self.leaf, self.chunk, mm6.ctypes.data, lo, hi, self.device,
+            out.data_ptr() if out is not None else None, C.byref(n_out), self.stream))
+        return n_out.value
+
+
+def sharded_voxelgrid_points(shard, index_base: int, rank: int, world: int, out=None, group=None,
+                             sample_step: Optional[int] = None, n_total: Optional[int] = None):
+    """voxelGrid.Filter of ONE cloud whose points are split over the ranks (rank r holds the contiguous slice that
+    starts at global index `index_base`; nothing is replicated).  `shard` supplies the local steps (GpuVgShard on a
+    GPU; the CPU tests pass a numpy stand-in).  Collectives: MIN/MAX all-reduce of the six min/max accumulators,
+    SUM all-reduce of six coordinate words and of the chunk histogram, one all-to-all of the records by chunk owner,
+    all-gather of the output counts.  Returns (n_out_local, counts_of_all_ranks, (cid_lo, cid_hi), recv_records);
+    the ranks' outputs concatenated in rank order are the reference's output (voxelgrid.go:102-133)."""
+    import torch
+    import torch.distributed as dist
+
+    collective = world > 1 and dist.is_available() and dist.is_initialized()
+    # 1. MinMaxVec3 of the whole cloud: first occurrence of the extreme value wins across ranks
+    acc = shard.minmax_packed(index_base)
+    if collective:
+        lo3, hi3 = acc[:3].clone(), acc[3:].clone()
+        dist.all_reduce(lo3, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi3, op=dist.ReduceOp.MAX, group=group)
+        acc = torch.cat([lo3, hi3])
+    words = (acc.cpu().numpy().astype(np.int64).view(np.uint64) ^ np.uint64(1 << 63))
+    winners = [int(w & np.uint64(0xffffffff)) for w in words[:3]] + \
+              [0xffffffff - int(w & np.uint64(0xffffffff)) for w in words[3:]]
+    bits = np.zeros(9, np.int64)  # [0..5] value bits of the winners (from their owners), [6..8] point 0 (from rank 0)
+    for k in range(6):
+        if index_base <= winners[k] < index_base + shard.n:
+            bits[k] = shard.coord_bits(winners[k] - index_base, k % 3)
+    if index_base == 0 and shard.n > 0:
+        for c in range(3):
+            bits[6 + c] = shard.coord_bits(0, c)
+    if collective:
+        t = torch.from_numpy(bits).to(acc.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        bits = t.cpu().numpy()
+    mm6 = bits[:6].astype(np.int32).view(np.float32).copy()
+    first = bits[6:9].astype(np.int32).view(np.float32)
+    for c in range(3):  # a NaN at point 0 is never replaced (minmax.go:13,17-22)
+        if first[c] != first[c]:
+            mm6[c] = mm6[3 + c] = first[c]
+    # 2. chunk ranges balanced by points
+    total = n_total if n_total is not None else shard.n * world
+    step = int(sample_step) if sample_step else (16 if total >= (1 << 22) else 1)
+    hist = shard.histogram(mm6, step)
+    if collective:
+        t = torch.from_numpy(hist.copy()).to(acc.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        hist = t.cpu().numpy()
+    ranges = chunk_ranges(hist, world)
+    cuts = np.array([r[0] for r in ranges] + [len(hist)], np.int64)
+    lo, hi = ranges[rank]
+    # 3. records to their chunk's owner (whole records: the filter keeps the first member's fields)
+    perm, counts = shard.owner_order(mm6, cuts)
+    send = shard.gather(perm)
+    if collective:
+        cin = torch.from_numpy(counts.copy()).to(acc.device)
+        cout = torch.empty_like(cin)
+        dist.all_to_all_single(cout, cin, group=group)
+        recv_counts = cout.cpu().numpy()
+        recv = torch.empty(int(recv_counts.sum()) * shard.stride, dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=[int(c) * shard.stride for c in recv_counts],
+                               input_split_sizes=[int(c) * shard.stride for c in counts], group=group)
+    else:
+        recv_counts = counts
+        recv = send
+    n_recv = int(recv_counts.sum())
+    # 4. the owner filters what it received: sources arrive in rank order = global point order
+    n_out = shard.filter(recv, n_recv, mm6, lo, hi, out)
+    all_counts = [n_out]
+    if collective:
+        t = torch.tensor([n_out], dtype=torch.int64, device=acc.device)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t, group=group)
+        all_counts = [int(g.item()) for g in gathered]
+    return n_out, all_counts, (lo, hi), recv
+
+
 def sharded_icp_fit(partial_fn: Callable[[np.ndarray, bool], "object"], params: _lib.IcpParams,
                     group=None, all_reduce: Optional[Callable] = None):
     """PointToPointICPGradient.Fit (icp.go:23-67) over a target split across ranks.

@@ -140,3 +140,115 @@ def test_chunk_ranges_partition_the_chunk_table():
             if hist.sum() > 0:  # no rank exceeds its share by more than the largest chunk
                 assert max(pts) <= hist.sum() / world + hist.max()
     assert pdist.chunk_ranges([0, 0, 0], 2) == [(0, 0), (0, 3)] or pdist.chunk_ranges([0, 0, 0], 2)[-1][1] == 3
+
+
+# ---- point-sharded VoxelGrid: the plan (bounds, ranges, exchange) on CPU ranks -------------------------------------
+class _NumpyVgShard:
+    """CPU stand-in for dist.GpuVgShard: the same steps in numpy float32 (Go's arithmetic: every op rounded)."""
+
+    def __init__(self, xyz, leaf, chunk):
+        import torch
+        self.torch = torch
+        self.xyz = np.ascontiguousarray(xyz, np.float32)
+        self.n, self.stride = len(xyz), 12
+        self.leaf = np.float32(leaf)
+        self.chunk = chunk
+
+    def minmax_packed(self, index_base):
+        from pcgol_b200.dist import ordered_bits
+        out = np.empty(6, np.uint64)
+        idx = (np.arange(self.n) + index_base).astype(np.uint64)
+        for k in range(3):
+            col = self.xyz[:, k]
+            ok = col == col
+            o = ordered_bits(col[ok]).astype(np.uint64) << np.uint64(32)
+            out[k] = (o | idx[ok]).min() if ok.any() else np.uint64(0xffffffffffffffff)
+            out[3 + k] = (o | (np.uint64(0xffffffff) - idx[ok])).max() if ok.any() else np.uint64(0)
+        return self.torch.from_numpy((out ^ np.uint64(1 << 63)).view(np.int64).copy())
+
+    def coord_bits(self, local_idx, k):
+        return int(self.xyz[local_idx, k:k + 1].view(np.int32)[0])
+
+    def _cids(self, mm6):
+        vmin, vmax = mm6[:3], mm6[3:]
+        size = (vmax - vmin).astype(np.float32)
+        cs = np.minimum((self.leaf * np.float32(self.chunk)).astype(np.float32), (size + self.leaf).astype(np.float32))
+        ncx, ncy, _ = ((size / cs).astype(np.float32).astype(np.int64) + 1)
+        c = ((self.xyz - vmin).astype(np.float32) / cs).astype(np.float32).astype(np.int64)
+        return (c[:, 2] * ncy + c[:, 1]) * ncx + c[:, 0], int(np.prod((size / cs).astype(np.float32).astype(np.int64) + 1))
+
+    def histogram(self, mm6, sample_step):
+        cid, n_chunks = self._cids(mm6)
+        return np.bincount(cid, minlength=n_chunks).astype(np.int64)
+
+    def owner_order(self, mm6, cuts):
+        cid, _ = self._cids(mm6)
+        owner = np.searchsorted(cuts[1:-1], cid, side="right")
+        perm = np.argsort(owner, kind="stable")
+        return self.torch.from_numpy(perm.astype(np.int32)), np.bincount(owner, minlength=len(cuts) - 1).astype(np.int64)
+
+    def gather(self, perm):
+        return self.torch.from_numpy(self.xyz[perm.numpy()].reshape(-1).view(np.uint8).copy())
+
+    def filter(self, recv, n_recv, mm6, lo, hi, out):
+        self.received = recv.numpy().view(np.float32).reshape(-1, 3).copy()
+        self.mm6 = mm6.copy()
+        return n_recv  # the plan is what this test checks; the filter itself is covered on the GPU
+
+
+def _vg_cloud():
+    rng = np.random.default_rng(7)
+    xyz = (rng.random((9001, 3)) * np.array([6.0, 5.0, 1.5]) - np.array([1.0, 2.0, 0.25])).astype(np.float32)
+    xyz[100, 1] = xyz[:, 1].min()        # the extreme value twice: the first occurrence is what counts
+    xyz[7000, 0] = xyz[:, 0].max()       # ... and once in each rank's slice
+    xyz[20, 0] = xyz[:, 0].max()
+    xyz[:, 2] = np.abs(xyz[:, 2])
+    xyz[5000, 2] = np.float32(-0.0)      # the minimum is a zero: -0 first (slice 1), +0 later - the sign must survive
+    xyz[8000, 2] = np.float32(0.0)
+    return xyz
+
+
+def _vg_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from pcgol_b200.dist import shard_bounds, sharded_voxelgrid_points
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        xyz = _vg_cloud()
+        lo, hi = shard_bounds(len(xyz), rank, world)
+        shard = _NumpyVgShard(xyz[lo:hi], 0.1, 8)
+        n_out, counts, (clo, chi), _ = sharded_voxelgrid_points(shard, lo, rank, world, n_total=len(xyz))
+        q.put((rank, shard.mm6.tobytes(), clo, chi, shard.received.tobytes(), counts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_point_sharded_voxelgrid_plan_world2_gloo(oracle):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_vg_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=240) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    xyz = _vg_cloud()
+    # the reduced bounds are MinMaxVec3 of the whole cloud, bit for bit (first occurrence across ranks, zero sign)
+    mn, mx = oracle.minmax(xyz.view(np.uint8).reshape(-1), 12, (0, 4, 8))
+    for r in res:
+        assert r[1] == np.concatenate([mn, mx]).astype(np.float32).tobytes()
+    # contiguous chunk ranges; every rank received exactly the points of its chunks, in global point order
+    assert res[0][2] == 0 and res[0][3] == res[1][2]
+    whole = _NumpyVgShard(xyz, 0.1, 8)
+    cid, n_chunks = whole._cids(np.frombuffer(res[0][1], np.float32))
+    assert res[1][3] == n_chunks
+    for r in res:
+        mine = xyz[(cid >= r[2]) & (cid < r[3])]
+        assert r[4] == mine.tobytes()
+    assert res[0][5] == res[1][5] and sum(res[0][5]) == len(xyz)

@@ -135,11 +135,20 @@ def _worker(rank, world, port, q):
                                                d_vg.data_ptr(), device=rank)
         vg_bytes = d_vg[: m * 12].cpu().numpy().tobytes()
         assert counts[rank] == m and len(counts) == world
+        # the same Filter with the POINTS sharded: every rank holds a slice, records travel to their chunk's owner
+        data, stride, off = synth.with_fields(scan, extra_u32=1)  # xyz + label: whole records must travel
+        slo, shi = pdist.shard_bounds(len(scan), rank, world)
+        d_slice = torch.from_numpy(data[slo * stride: shi * stride].copy()).cuda()
+        d_pv = torch.empty(len(scan) * stride, dtype=torch.uint8, device="cuda")
+        shard = pdist.GpuVgShard(d_slice, shi - slo, stride, off, (0.1, 0.1, 0.1), (32, 32, 32), rank)
+        pm, pcounts, _, _ = pdist.sharded_voxelgrid_points(shard, slo, rank, world, out=d_pv, n_total=len(scan))
+        pv_bytes = d_pv[: pm * stride].cpu().numpy().tobytes()
+        assert pcounts[rank] == pm
         # query sharding: disjoint slices of the same queries, index replicated, no collective
         q_all = synth.nn_queries(base, 50000, seed=5)
         qlo, qhi = pdist.shard_bounds(len(q_all), rank, world)
         ids, dsq = idx.nearest_batch(q_all[qlo:qhi], 1.0)
-        q.put((rank, status, trans.tobytes(), iters, qlo, ids.tobytes(), dsq.tobytes(), vg_bytes, counts))
+        q.put((rank, status, trans.tobytes(), iters, qlo, ids.tobytes(), dsq.tobytes(), vg_bytes, counts, pv_bytes, pcounts))
     finally:
         dist.destroy_process_group()
 
@@ -181,3 +190,30 @@ def test_sharded_icp_and_queries_world2_nccl():
     full = pg.VoxelGrid((0.1, 0.1, 0.1), (32, 32, 32)).filter(pg.PointCloud.from_xyz(scan))
     assert b"".join(r[7] for r in res) == full.data[: full.points * 12].tobytes()
     assert res[0][8] == res[1][8] and sum(res[0][8]) == full.points
+    # point-sharded Filter of the labelled cloud: rank outputs in rank order == the single-GPU Filter == the oracle
+    from oracle import oracle as orc
+    data, stride, off = synth.with_fields(scan, extra_u32=1)
+    rc, exp = orc.voxelgrid_filter(data, stride, off, (0.1, 0.1, 0.1), (32, 32, 32), mode="sparse")
+    assert rc == orc.OK and b"".join(r[9] for r in res) == exp.tobytes()
+    assert res[0][10] == res[1][10] and sum(res[0][10]) * stride == len(exp)
+
+
+def test_point_sharded_voxelgrid_single_rank_equals_filter():
+    """World 1: the sharded driver with explicit bounds must reproduce the plain Filter (no collective involved)."""
+    import torch
+
+    import pcgol_b200 as pg
+    from pcgol_b200 import dist as pdist, synth
+
+    scan = synth.lidar_scan(4, n_az=900)
+    for chunk in ((32, 32, 32), (0, 0, 0)):
+        data, stride, off = synth.with_fields(scan, extra_u32=1)
+        d = torch.from_numpy(data.copy()).cuda()
+        out = torch.empty(len(data), dtype=torch.uint8, device="cuda")
+        shard = pdist.GpuVgShard(d, len(scan), stride, off, (0.1, 0.1, 0.1), chunk, 0)
+        m, counts, _, _ = pdist.sharded_voxelgrid_points(shard, 0, 0, 1, out=out, n_total=len(scan))
+        hdr = pg.PointCloudHeader(fields=["x", "y", "z", "label"], size=[4] * 4, type=["F", "F", "F", "U"],
+                                  count=[1] * 4, width=len(scan))
+        full = pg.VoxelGrid((0.1, 0.1, 0.1), chunk).filter(pg.PointCloud(hdr, data))
+        assert m == full.points and counts == [m]
+        assert out[: m * stride].cpu().numpy().tobytes() == full.data[: m * stride].tobytes()
