@@ -6,9 +6,11 @@ Primary line (BASELINE.json configs[1]): VoxelGrid downsample of a 1M-point synt
 A "step" is one Filter pass over one cloud.  `value` is measured with the cloud resident
 in HBM (pcg_voxelgrid_filter_dev); `e2e` goes through the host-buffer C-ABI call
 (pcg_voxelgrid_filter) with pinned host input/output, copies inside the timed region.
-The same JSON line carries, under "extra", the other two metrics of the path at N=1:
-batched Nearest (configs[2]: 10M queries vs a 1M-point target, maxRange 1 m) and
-point-to-point ICP (configs[0]: 100k-point scan vs a 5 deg / 0.3 m perturbed copy).
+The same JSON line carries compact top-level objects for the other workloads of BASELINE.json - "nn" (configs[2]:
+10M queries vs a 1M-point target, maxRange 1 m), "icp" (configs[0]: 100k-point scan vs a 5 deg / 0.3 m perturbed
+copy), "c4_farm" (configs[3]: scan pairs dealt to the GPUs), "c5" (configs[4]: the 50M-point map - VoxelGrid with the
+points sharded, query-sharded Range, one ICP sharded over NCCL and over NVLink peer memory) and, for N > 1, "parity"
+(sharded results against the single-GPU ones) - and their full detail under "extra".
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extra]
 
@@ -39,6 +41,8 @@ N_AZ_1M = 15625
 ROTATE = 16  # distinct device copies of the input cycled between steps: 16 x 12 MB > 126 MB L2
 CACHE = os.environ.get("PCGOL_BENCH_CACHE", "/tmp/pcgol_b200_cache")
 WORKLOAD = "voxelgrid 1M-pt synthetic 64-beam scan, leaf 0.05 m, xyz f32 stride 12, ChunkSize{128,128,128}"
+CONFIG = {"workload": WORKLOAD, "points_per_cloud": 1_000_000}  # identical in both arms
+MIN_TIMED_S = 0.1  # the timed region is stretched to at least this long (more steps than asked, the real count reported)
 
 
 _REAL_STDOUT = None
@@ -54,8 +58,21 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def _synth():
+    """The synthetic-cloud generator (numpy only) loaded as a stand-alone module: the reference arm must not import
+    the product package (importing pcgol_b200 maps libpcgol_b200.so)."""
+    import importlib.util
+
+    if "_pcgol_synth" not in sys.modules:
+        spec = importlib.util.spec_from_file_location("_pcgol_synth", os.path.join(ROOT, "pcgol_b200", "synth.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_pcgol_synth"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["_pcgol_synth"]
+
+
 def cached_scan(seed: int, n_az: int) -> np.ndarray:
-    from pcgol_b200 import synth
+    synth = _synth()
 
     os.makedirs(CACHE, exist_ok=True)
     path = os.path.join(CACHE, f"scan_{seed}_{n_az}.npy")
@@ -163,8 +180,13 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, int(psutil.virtual_memory().available * 0.5 // (200 << 20))))
     scan = cached_scan(2, N_AZ_1M)
-    for _ in range(min(args.warmup, 1)):
+    t_w = time.perf_counter()
+    warm = 0
+    for _ in range(args.warmup):
         cpu_voxelgrid(scan, threads, 1)
+        warm += 1
+        if time.perf_counter() - t_w > 30:  # bounded
+            break
     times = []
     for _ in range(args.steps):
         _, dt = cpu_voxelgrid(scan, threads, 1)
@@ -176,9 +198,9 @@ def run_reference(args):
     value = threads * steps * len(scan) / total / 1e6
     line = {
         "impl": "reference", "metric": "VoxelGrid Mpts/s", "value": value, "unit": "Mpts/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "points_per_step": threads * len(scan)},
+        "config": dict(CONFIG), "clouds_per_step": threads,
         "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": threads, "kind": "port",
                          "sample": f"{threads} threads x one full 1M-pt Filter per step (C++ restatement of "
                                    "voxelgrid.go:35-187, dense voxel array; not Go: no Go toolchain in the image)"},
@@ -289,8 +311,12 @@ def bench_voxelgrid(pg, torch, dist, rank, args, peak):
         sampler.start()
     for i in range(args.warmup):
         step(i)
+    # K steps of ~0.1 ms would be a 2 ms region: run as many steps as make it >= MIN_TIMED_S (the same count on every
+    # rank) and report the count actually timed
+    est_ms = timed_region(dist, torch, step, 8) / 8
+    steps = max(args.steps, int(np.ceil(MIN_TIMED_S * 1e3 / max(est_ms, 1e-3))))
     l0 = pg.kernel_launch_count()
-    ms = timed_region(dist, torch, step, args.steps)
+    ms = timed_region(dist, torch, step, steps)
     launches = pg.kernel_launch_count() - l0
     # the timed region lasts a few ms (K steps of ~0.2 ms): keep the same kernels running for
     # ~0.5 s more so that the 100 ms nvidia-smi sampler sees the clocks under this load
@@ -330,7 +356,7 @@ def bench_voxelgrid(pg, torch, dist, rank, args, peak):
         calls = [make_caller() for _ in range(callers)]
         # at least 24 calls per caller: the region is bracketed by Python barriers whose wake-up latency (tenths of a
         # millisecond) must stay small against the calls it times
-        per = max(24, args.steps // callers)
+        per = max(24, args.steps // callers, int(MIN_TIMED_S * 1e3 / 0.25 / callers) + 1)  # region >= MIN_TIMED_S
         ready = threading.Barrier(callers + 1)
         start = threading.Barrier(callers + 1)
         stop = threading.Barrier(callers + 1)
@@ -381,11 +407,12 @@ def bench_voxelgrid(pg, torch, dist, rank, args, peak):
     }
     report = profile_kernels(pg, torch, step, args.steps)
     roof, shares = dominant(report, algo, peak)
-    step_s = ms / args.steps / 1e3
+    step_s = ms / steps / 1e3
     pipeline_bytes = 12 * n + 12 * m  # N*stride read + M*stride written
     res = {
-        "value": world * n * args.steps / (ms / 1e3) / 1e6,
-        "ms_per_step": ms / args.steps,
+        "value": world * n * steps / (ms / 1e3) / 1e6,
+        "ms_per_step": ms / steps,
+        "steps": steps,
         "e2e": {"value": world * n * e2e_steps / (e2e_ms / 1e3) / 1e6, "unit": "Mpts/s",
                 "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": 12 * m, "ms_per_step": e2e_ms / e2e_steps,
                 "concurrent_callers": E2E_CALLERS, "steps": e2e_steps,
@@ -533,30 +560,34 @@ def bench_icp(pg, torch, dist, rank, args, peak):
             "modes": out, "_check": (base, target)}
 
 
-def bench_icp_farm(pg, torch, dist, rank, args, peak, pairs_per_gpu=64, distinct=4):
-    """BASELINE config 4: independent 64-beam scan pairs (~120k pts each, pose perturbed by <= 5 deg / 0.3 m),
-    dealt to the ranks; per GPU pcg_icp_fit_pairs_dev builds one index per pair and overlaps the fits on streams.
-    `distinct` scan pairs are generated (ray casting on the host is slow) and cycled."""
-    from pcgol_b200 import synth
+def distinct_pairs(count: int, rank: int):
+    """BASELINE config 4 stand-in: `count` DISTINCT scan pairs per GPU.  Ray casting a scan on the host takes about a
+    second, so four scenes are cast (cached) and every pair is its own rigid copy of one of them with its own
+    millimetre jitter (no two pairs share a point) seen from its own pose perturbed by <= 5 deg / 0.3 m."""
+    synth = _synth()
+    scenes = [cached_scan(100 + k, 1875) for k in range(4)]
+    out = []
+    for k in range(count):
+        rng = np.random.default_rng(1_000_000 + 1000 * rank + k)
+        scan = scenes[k % 4]
+        centre = scan.mean(axis=0)
+        base = synth.rigid(scan, float(rng.uniform(-180, 180)), rng.uniform(-2, 2, 3) * np.array([1, 1, 0.05]), centre)
+        base = (base + rng.normal(0.0, 0.002, base.shape)).astype(np.float32)
+        v = rng.normal(size=2)
+        v = v / np.linalg.norm(v) * rng.uniform(0, 0.3)
+        target = synth.rigid(base, float(rng.uniform(-5, 5)), (v[0], v[1], float(rng.uniform(-0.05, 0.05))), centre)
+        out.append((np.ascontiguousarray(base), np.ascontiguousarray(target)))
+    return out
 
+
+def bench_icp_farm(pg, torch, dist, rank, args, peak, pairs_per_gpu=128):
+    """BASELINE config 4: independent 64-beam scan pairs (~120k pts each, pose perturbed by <= 5 deg / 0.3 m), dealt
+    to the ranks; per GPU pcg_icp_fit_pairs_dev builds one index per pair and overlaps the fits on streams."""
     dev = torch.device("cuda")
     device = torch.cuda.current_device()
     stream = torch.cuda.current_stream().cuda_stream
-    host = []
-    for k in range(distinct):
-        key = f"pair_{k}"  # the same pairs on every rank: equal units for weak scaling
-        path = os.path.join(CACHE, key + ".npz")
-        if os.path.exists(path):
-            z = np.load(path)
-            host.append((z["b"], z["t"]))
-        else:
-            b, t = synth.scan_pair(k)
-            os.makedirs(CACHE, exist_ok=True)
-            np.savez(path + f".{os.getpid()}.tmp.npz", b=b, t=t)
-            os.replace(path + f".{os.getpid()}.tmp.npz", path)
-            host.append((b, t))
-    d = [(torch.from_numpy(b).to(dev), torch.from_numpy(t).to(dev)) for b, t in host]
-    sel = [d[i % distinct] for i in range(pairs_per_gpu)]
+    host = distinct_pairs(pairs_per_gpu, rank)
+    sel = [(torch.from_numpy(b).to(dev), torch.from_numpy(t).to(dev)) for b, t in host]
     out = {}
     # strict / fast: the reference's gradient-descent updater (bit-exact / float64 sums).  gauss_newton: NOT the
     # reference's algorithm (normal equations solved per iteration, SURVEY §8f N4) - reported beside it, never as it.
@@ -577,152 +608,237 @@ def bench_icp_farm(pg, torch, dist, rank, args, peak, pairs_per_gpu=64, distinct
         out[mode_name] = {"value": args.gpus * pairs_per_gpu * 2 / (ms / 1e3), "ms_per_pair": ms / 2 / pairs_per_gpu,
                           "iterations_mean": float(np.mean(iters)), "failed": int((status != 0).sum())}
     return {"metric": "ICP scan pairs/s (index build + Fit)", "unit": "pairs/s", "scaling": "weak",
-            "config": {"workload": f"{pairs_per_gpu} scan pairs per GPU ({distinct} distinct, ~120k pts each), "
-                                   "index built per pair, <= 20 iterations"},
+            "config": {"workload": f"{pairs_per_gpu} distinct scan pairs per GPU (~120k pts each; 4 ray-cast scenes, "
+                                   "every pair its own rigid copy + jitter + pose perturbation), index built per pair, "
+                                   "<= 20 iterations"},
             "modes": out}
 
 
-def bench_config5(pg, torch, dist, rank, args, peak):
-    """BASELINE config 5 on one GPU (opt-in, --config5): 50M-point map, VoxelGrid (multi-kernel path, HBM-sized
-    working set) and batched Range (1M queries, r = 0.2 m) against the 50M-point index."""
-    from pcgol_b200 import synth
+_GLOO = [None]
 
+
+def host_barrier(dist):
+    """Barrier that waits on the HOST (gloo): while rank 0 drives every GPU from one process (the peer-memory ICP) or
+    measures a single-GPU reference, the other ranks must not sit in an NCCL barrier - that is a kernel spinning on
+    their GPU."""
+    if dist is None:
+        return
+    import torch
+    torch.cuda.synchronize()
+    dist.barrier(group=_GLOO[0]) if _GLOO[0] is not None else dist.barrier()
+
+
+def _fnv(buf: bytes) -> str:
+    import hashlib
+    return hashlib.blake2b(buf, digest_size=8).hexdigest()
+
+
+def bench_config5(pg, torch, dist, rank, args, peak):
+    """BASELINE config 5 on the job's GPUs: a 50M-point map.
+      voxelgrid  ONE Filter.  N = 1: the multi-kernel pipeline.  N > 1: the POINTS are sharded (every rank holds a
+                 slice), min/max and the chunk histogram are all-reduced, whole records travel to their chunk's owner
+                 in one all-to-all (NCCL over NVLink) and every owner filters its chunks (strong scaling)
+      range      1M queries, r = 0.2 m, against the 50M-point index replicated on every GPU, queries sharded
+      icp        ONE Fit of a 1M-point scan against the DOWNSAMPLED map, target sharded, base index replicated:
+                 (a) one process per GPU, 16 float64 all-reduced by NCCL each iteration, loop resident on the device;
+                 (b) one process (rank 0) driving all GPUs: persistent kernel per device, the sums exchanged as
+                     NVLink peer-memory stores inside the kernels (pcg_icp_fit_multi_dev)
+    Parity (N > 1): hashes of the sharded outputs against the single-GPU ones, computed in this run."""
+    from pcgol_b200 import dist as pdist
+
+    synth = _synth()
+    world = args.gpus
     big = synth.tiled_map(10, 5)
     n = len(big)
     dev = torch.device("cuda")
     device = torch.cuda.current_device()
     stream = torch.cuda.current_stream().cuda_stream
-    d_in = torch.from_numpy(big).to(dev)
-    d_out = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+    out, parity = {}, {}
+
+    # ---- VoxelGrid of the whole map
     vg = pg.VoxelGrid(LEAF, CHUNK, device=device)
-    m_box = [0]
+    if world == 1:
+        d_in = torch.from_numpy(big).to(dev)
+        d_out = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+        m_box = [0]
 
-    def step(i):
-        m_box[0] = vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr(), stream)
+        def step(i):
+            m_box[0] = vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr(), stream)
 
-    step(0)
-    step(1)
-    ms = timed_region(dist, torch, step, 5)
-    report = profile_kernels(pg, torch, step, 3)
-    m = m_box[0]
-    kb = 8
-    algo = {"minmax_kernel": 12 * n, "(voxel_key_kernel<K>)": 12 * n + kb * n, "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n,
-            "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m}
-    roof, shares = dominant(report, algo, peak)
+        step(0)
+        step(1)
+        ms = timed_region(dist, torch, step, 5)
+        report = profile_kernels(pg, torch, step, 3)
+        m = m_box[0]
+        kb = 8
+        algo = {"minmax_kernel": 12 * n, "(voxel_key_kernel<K>)": 12 * n + kb * n,
+                "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n, "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m}
+        roof, shares = dominant(report, algo, peak)
+        down = d_out[: m * 12].clone()  # the downsampled map: base of the ICP below
+        del d_in, d_out
+        vgo = {"roofline": roof, "kernels": shares, "sharding": "single GPU"}
+    else:
+        lo, hi = pdist.shard_bounds(n, rank, world)
+        d_slice = torch.from_numpy(np.ascontiguousarray(big[lo:hi]).view(np.uint8).reshape(-1)).to(dev)
+        shard = pdist.GpuVgShard(d_slice, hi - lo, 12, (0, 4, 8), LEAF, CHUNK, device, stream)
+        box = [None]
+
+        def step(i):
+            box[0] = pdist.sharded_voxelgrid_points(shard, lo, rank, world, out=None, n_total=n)
+
+        step(0)
+        step(1)
+        ms = timed_region(dist, torch, step, 5)
+        laps = {}
+        for _ in range(3):  # separate pass: wall time per step of the pipeline (a device sync after every step)
+            pdist.sharded_voxelgrid_points(shard, lo, rank, world, out=None, n_total=n, timings=laps)
+        laps = {k: round(v / 3, 3) for k, v in laps.items() if not k.startswith("_") and k != "start"}
+        m_local, counts, (clo, chi), recv, d_out = box[0]
+        n_recv = len(recv) // 12
+        m = int(sum(counts))
+        # all ranks' records -> every rank (the downsampled map is the ICP base, and rank 0 hashes it)
+        sizes = [c * 12 for c in counts]
+        padded = torch.zeros(max(sizes), dtype=torch.uint8, device=dev)
+        padded[: m_local * 12] = d_out[: m_local * 12]
+        gathered = [torch.empty(max(sizes), dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, padded)
+        down = torch.cat([g[:sz] for g, sz in zip(gathered, sizes)])
+        del gathered, padded
+        vgo = {"sharding": "points: all-reduce of min/max + chunk histogram, all-to-all of records by chunk owner (NCCL)",
+               "counts_per_rank": counts, "rank0_chunk_range": [int(clo), int(chi)], "records_received_rank0": int(n_recv),
+               "rank0_ms_per_stage": laps}
+        if rank == 0:  # the same Filter on one GPU, for the parity hash and the speed-up
+            d_full = torch.from_numpy(big).to(dev)
+            d_fo = torch.empty(n * 12, dtype=torch.uint8, device=dev)
+            mf = vg.filter_dev(d_full.data_ptr(), n, 12, (0, 4, 8), d_fo.data_ptr(), stream)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                vg.filter_dev(d_full.data_ptr(), n, 12, (0, 4, 8), d_fo.data_ptr(), stream)
+            b.record()
+            torch.cuda.synchronize()
+            vgo["single_gpu_ms_per_step"] = a.elapsed_time(b) / 3
+            parity["voxelgrid_sharded_equals_single_gpu"] = bool(
+                mf == m and _fnv(d_fo[: mf * 12].cpu().numpy().tobytes()) == _fnv(down.cpu().numpy().tobytes()))
+            del d_full, d_fo
+        host_barrier(dist)
     step_s = ms / 5 / 1e3
-    out = {"voxelgrid": {"points": n, "voxels_out": int(m), "value_mpts": n / step_s / 1e6, "ms_per_step": ms / 5,
-                         "roofline": roof, "kernels": shares,
-                         "pipeline_roofline": {"algorithmic_bytes_per_step": 12 * n + 12 * m,
-                                               "achieved": (12 * n + 12 * m) / step_s / 1e9, "peak": peak[0],
-                                               "frac": (12 * n + 12 * m) / step_s / 1e9 / peak[0]}}}
+    vgo.update({"points": n, "voxels_out": int(m), "value_mpts": n / step_s / 1e6, "ms_per_step": ms / 5,
+                "scaling": "strong",
+                "pipeline_roofline": {"algorithmic_bytes_per_step": 12 * n + 12 * m,
+                                      "achieved": (12 * n + 12 * m) / step_s / 1e9, "peak": peak[0] * world,
+                                      "peak_note": "measured HBM copy bandwidth x GPUs",
+                                      "frac": (12 * n + 12 * m) / step_s / 1e9 / (peak[0] * world)}})
+    out["voxelgrid"] = vgo
+
+    # ---- Range: 1M queries, r = 0.2 m, index over the 50M-point map replicated, queries sharded
+    d_map = torch.from_numpy(big).to(dev)
     t0 = time.perf_counter()
-    idx = pg.Index.from_device(d_in.data_ptr(), n, device=device, stream=stream)
+    idx = pg.Index.from_device(d_map.data_ptr(), n, device=device, stream=stream)
     torch.cuda.synchronize()
     out["index_build_ms"] = 1e3 * (time.perf_counter() - t0)
     out["index_bytes"] = idx.device_bytes()
     rng = np.random.default_rng(5)
     sel = rng.choice(n, 1_000_000, replace=False)
     q = (big[sel] + rng.normal(0, 0.05, (len(sel), 3))).astype(np.float32)
-    t0 = time.perf_counter()
-    off, ids, dsq = idx.range_batch(q, 0.2)
-    dt = time.perf_counter() - t0
-    out["range"] = {"queries": len(q), "neighbours": int(off[-1]), "queries_per_s_e2e": len(q) / dt,
-                    "neighbours_per_s_e2e": int(off[-1]) / dt, "radius": 0.2}
-    d_q = torch.from_numpy(q).to(dev)
-    d_ids = torch.empty(len(q), dtype=torch.int32, device=dev)
-    d_d = torch.empty(len(q), dtype=torch.float32, device=dev)
-
-    def nstep(i):
-        idx.nearest_dev(d_q.data_ptr(), len(q), 1.0, d_ids.data_ptr(), d_d.data_ptr(), stream)
-
-    nstep(0)
-    ms = timed_region(dist, torch, nstep, 5)
-    out["nearest"] = {"queries": len(q), "value": len(q) * 5 / (ms / 1e3), "ms_per_step": ms / 5}
-    return out
-
-
-def bench_voxelgrid_sharded(pg, torch, dist, rank, args, peak):
-    """BASELINE config 5 (VoxelGrid part) over the job's GPUs: ONE 50M-point Filter, the cloud replicated, every rank
-    filtering a balanced range of chunk ids (dist.sharded_voxelgrid); strong scaling, the step includes the chunk
-    histogram, its read-back and the all-gather of the counts."""
-    from pcgol_b200 import dist as pdist, synth
-
-    big = synth.tiled_map(10, 5)
-    n = len(big)
-    dev = torch.device("cuda")
-    device = torch.cuda.current_device()
-    stream = torch.cuda.current_stream().cuda_stream
-    world = dist.get_world_size() if dist is not None else 1
-    d_in = torch.from_numpy(big).to(dev)
-    d_out = torch.empty(n * 12, dtype=torch.uint8, device=dev)
-    box = [None]
-
-    def step(i):
-        box[0] = pdist.sharded_voxelgrid(d_in.data_ptr(), n, LEAF, CHUNK, rank, world, d_out.data_ptr(), device=device,
-                                         stream=stream)
-
-    step(0)
-    step(1)
-    ms = timed_region(dist, torch, step, 5)
-    n_local, counts, (lo, hi) = box[0]
-    report = profile_kernels(pg, torch, step, 2) or {}
-    kernels = {k: round(v["total_ms"] / 2, 4) for k, v in report.items()}
-    vg = pg.VoxelGrid(LEAF, CHUNK, device=device)
-    full = [0]
-
-    def whole(i):
-        full[0] = vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr(), stream)
-
-    whole(0)
-    ms1 = timed_region(dist, torch, whole, 5)
-    return {"points": n, "world": world, "ms_per_step": ms / 5, "value_mpts": n / (ms / 5 / 1e3) / 1e6,
-            "counts_per_rank": counts, "voxels_out": int(sum(counts)), "rank0_chunk_range": [int(lo), int(hi)],
-            "unsharded_ms_per_step": ms1 / 5, "unsharded_voxels_out": int(full[0]), "scaling": "strong",
-            "rank0_kernel_ms_per_step": kernels}
-
-
-def bench_icp_sharded(pg, torch, dist, rank, args, peak):
-    """BASELINE config 5 (ICP part): ONE alignment of a 1M-pt scan against a 1M-pt base, target sharded over the
-    ranks, base index replicated, 16 float64 sums all-reduced over NCCL each iteration."""
-    from pcgol_b200 import dist as pdist, synth
-
-    world = args.gpus
-    scan = cached_scan(2, N_AZ_1M)
-    sensor = np.array([0.0, 0.0, synth.SENSOR_Z], np.float32) + (scan.min(axis=0) * 0)
-    target = synth.rigid(scan, 2.0, (0.1, 0.1, 0.05), scan.mean(axis=0))
-    lo, hi = pdist.shard_bounds(len(target), rank, world)
-    dev = torch.device("cuda")
-    device = torch.cuda.current_device()
-    stream = torch.cuda.current_stream().cuda_stream
-    d_b = torch.from_numpy(scan).to(dev)
-    d_t = torch.from_numpy(np.ascontiguousarray(target[lo:hi])).to(dev)
-    idx = pg.Index.from_device(d_b.data_ptr(), len(scan), device=device, stream=stream)
-    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
-    p = icp.params()
-    partial = pdist.make_gpu_partial(idx, d_t.data_ptr(), hi - lo, 1.0, stream)
+    qlo, qhi = pdist.shard_bounds(len(q), rank, world)
     res = {}
 
-    def step(i):  # loop resident on the device: partial -> NCCL all-reduce -> finish, no host round trip per iteration
-        res["r"] = pdist.sharded_icp_fit_device(idx, d_t.data_ptr(), hi - lo, p, stream=stream)
+    def rstep(i):
+        res["r"] = idx.range_batch(q[qlo:qhi], 0.2)
 
-    def step_host(i):  # the host-driven loop (pcg_icp_partial_dev + pcg_icp_finish), kept for comparison
-        res["h"] = pdist.sharded_icp_fit(partial, p)
+    rstep(0)
+    rms = wall_region(dist, torch, rstep, 2)
+    off_, ids_, dsq_ = res["r"]
+    tot = torch.tensor([int(off_[-1])], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot)
+    out["range"] = {"queries": len(q), "neighbours": int(tot.item()), "radius": 0.2, "ms_per_step": rms / 2,
+                    "queries_per_s": len(q) * 2 / (rms / 1e3), "neighbours_per_s": int(tot.item()) * 2 / (rms / 1e3),
+                    "scaling": "strong", "timer": "host wall clock around pcg_index_range_count + _fill on host buffers "
+                                                  "(variable-length result: two-call protocol), max over ranks"}
+    if world > 1:
+        h = torch.tensor([int(_fnv(off_.tobytes() + ids_.tobytes() + dsq_.tobytes()), 16) >> 1], dtype=torch.int64, device=dev)
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        if rank == 0:
+            ok = True
+            for r in range(world):
+                a, b = pdist.shard_bounds(len(q), r, world)
+                o2, i2, d2 = idx.range_batch(q[a:b], 0.2)
+                ok = ok and (int(_fnv(o2.tobytes() + i2.tobytes() + d2.tobytes()), 16) >> 1) == int(hs[r].item())
+            parity["range_sharded_equals_single_gpu"] = bool(ok)
+        host_barrier(dist)
+    idx.close()
+    del d_map
 
-    step(0)
-    step_host(0)
-    steps = 3
-    ms = timed_region(dist, torch, step, steps)
-    ms_host = timed_region(dist, torch, step_host, steps)
-    status, trans, stat = res["r"]
-    same = bool(np.array_equal(trans, res["h"][1]))
-    return {"metric": "sharded ICP alignments/s", "unit": "alignments/s",
-            "config": {"workload": "one ICP Fit of a 1M-pt scan (2 deg / 0.15 m perturbed) vs the 1M-pt scan; target "
-                                   "split across ranks, index replicated, per-iteration all-reduce of 16 f64 (NCCL), "
-                                   "loop resident on the device"},
-            "value": steps / (ms / 1e3), "ms_per_alignment": ms / steps, "iterations": int(stat.num_iteration),
-            "host_driven_loop": {"value": steps / (ms_host / 1e3), "ms_per_alignment": ms_host / steps,
-                                 "same_transform": same},
-            "scaling": "strong", "status": int(status), "trans": [float(x) for x in trans]}
+    # ---- one ICP: 1M-point scan against the downsampled map
+    base_n = len(down) // 12
+    scan = cached_scan(2, N_AZ_1M)
+    target = synth.rigid(scan, 2.0, (0.1, 0.1, 0.05), scan.mean(axis=0))
+    tlo, thi = pdist.shard_bounds(len(target), rank, world)
+    d_t = torch.from_numpy(np.ascontiguousarray(target[tlo:thi])).to(dev)
+    bidx = pg.Index.from_device(down.data_ptr(), base_n, device=device, stream=stream)
+    icp = pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST))
+    p = icp.params()
+    fit = {}
+
+    def istep(i):  # NCCL: partial -> all-reduce -> finish, loop resident on the device
+        fit["nccl"] = pdist.sharded_icp_fit_device(bidx, d_t.data_ptr(), thi - tlo, p, stream=stream)
+
+    istep(0)
+    ims = timed_region(dist, torch, istep, 3)
+    status, trans, stat = fit["nccl"]
+    io = {"base_points": int(base_n), "target_points": len(target), "iterations": int(stat.num_iteration),
+          "status": int(status), "scaling": "strong",
+          "nccl": {"value": 3 / (ims / 1e3), "ms_per_alignment": ims / 3,
+                   "collective": "ncclAllReduce of 16 float64 per iteration (torch.distributed), loop resident on the device"}}
+    # (b) one process, all GPUs: rank 0 drives every device, the others wait
+    if dist is not None:
+        host_barrier(dist)
+    if rank == 0:
+        devices = list(range(world))
+        replicas = [bidx] + [bidx.replicate(d) for d in devices[1:]]
+        slices = []
+        for r, d in enumerate(devices):
+            a, b = pdist.shard_bounds(len(target), r, world)
+            slices.append(torch.from_numpy(np.ascontiguousarray(target[a:b])).to(torch.device("cuda", d)))
+        torch.cuda.set_device(device)
+
+        def mstep(i):
+            fit["peer"] = icp.fit_multi_dev(replicas, [t.data_ptr() for t in slices], [len(t) for t in slices])
+
+        mstep(0)
+        t0 = time.perf_counter()
+        for i in range(3):
+            mstep(i)
+        pms = 1e3 * (time.perf_counter() - t0)
+        ptrans, pstat = fit["peer"]
+        io["peer"] = {"value": 3 / (pms / 1e3), "ms_per_alignment": pms / 3, "iterations": int(pstat.num_iteration),
+                      "collective": "none: ten float64 stored into every peer's exchange buffer over NVLink inside one "
+                                    "persistent cooperative kernel per device (pcg_icp_fit_multi_dev), one host process",
+                      "timer": "host wall clock around the synchronous call (it launches and joins all devices)"}
+        # single-GPU fast Fit of the same problem + the float64 oracle: the sharded transforms must agree
+        d_full = torch.from_numpy(target).to(dev)
+        strans, sstat = icp.fit_dev(bidx, d_full.data_ptr(), len(target), stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            icp.fit_dev(bidx, d_full.data_ptr(), len(target), stream)
+        b.record()
+        torch.cuda.synchronize()
+        io["single_gpu"] = {"value": 3 / (a.elapsed_time(b) / 1e3), "ms_per_alignment": a.elapsed_time(b) / 3}
+        parity["icp_nccl_vs_single_gpu_max_abs"] = float(np.abs(trans - strans).max())
+        parity["icp_peer_vs_single_gpu_max_abs"] = float(np.abs(ptrans - strans).max())
+        parity["icp_iterations_equal"] = bool(stat.num_iteration == sstat.num_iteration == pstat.num_iteration)
+        for r in replicas[1:]:
+            r.close()
+    if dist is not None:
+        host_barrier(dist)
+    out["icp"] = io
+    bidx.close()
+    return out, parity
 
 
 def cpu_extras(nn, icp, threads_all):
@@ -766,6 +882,10 @@ def cpu_extras(nn, icp, threads_all):
     return out
 
 
+def _r(x, nd=4):
+    return None if x is None else float(np.round(x, nd)) if abs(x) < 1e6 else float(np.round(x))
+
+
 def run_ours(args):
     import torch
 
@@ -783,26 +903,34 @@ def run_ours(args):
 
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
+        _GLOO[0] = dist.new_group(backend="gloo")  # host-side barriers (see host_barrier)
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}; using WORLD_SIZE")
         args.gpus = world
     peak = measured_peak()
     if args.only:
-        r = {"nn": bench_nn, "icp": bench_icp, "farm": bench_icp_farm, "vgshard": bench_voxelgrid_sharded}[args.only](pg, torch, dist, rank, args, peak)
+        fn = {"nn": bench_nn, "icp": bench_icp, "farm": bench_icp_farm, "c5": bench_config5}[args.only]
+        r = fn(pg, torch, dist, rank, args, peak)
+        if args.only == "c5":
+            r = {"c5": r[0], "parity": r[1]}
+            r["c5"].pop("_icp_check", None)
         r.pop("_check", None)
         if rank == 0:
             emit({"profiling_aid": args.only, **r})
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     vg = bench_voxelgrid(pg, torch, dist, rank, args, peak)
     scan = vg.pop("scan")
-    extra = {}
-    nn = icp = icp_sh = icp_farm = None
+    nn = icp = icp_farm = c5 = None
+    parity = {}
     if not args.no_extra:
         nn = bench_nn(pg, torch, dist, rank, args, peak)
         icp = bench_icp(pg, torch, dist, rank, args, peak)
-        icp_sh = bench_icp_sharded(pg, torch, dist, rank, args, peak)
         icp_farm = bench_icp_farm(pg, torch, dist, rank, args, peak)
-    cfg5 = bench_config5(pg, torch, dist, rank, args, peak) if args.config5 else None
+        torch.cuda.empty_cache()
+        c5, parity = bench_config5(pg, torch, dist, rank, args, peak)
     line = None
     if rank == 0:
         cores = os.cpu_count() or 1
@@ -812,21 +940,55 @@ def run_ours(args):
         cpu = {"value": v1, "unit": "Mpts/s", "cores": 1, "kind": "port",
                "sample": f"{reps} full 1M-pt Filter calls ({dt1:.1f} s), C++ restatement of voxelgrid.go:35-187 "
                          "(dense voxel array per chunk), not Go: no Go toolchain in the image"}
+        extra = {}
+        compact = {}
         if not args.no_extra:
             cpu_extras(nn, icp, cores)
-            extra = {"nn": nn, "icp": icp, "icp_sharded": icp_sh, "icp_farm": icp_farm}
-        if cfg5 is not None:
-            extra["config5_50m"] = cfg5
+            c5.pop("_icp_check", None)
+            extra = {"nn": nn, "icp": icp, "icp_farm": icp_farm, "config5_50m": c5}
+            f, st = icp["modes"]["fast"], icp["modes"]["strict"]
+            compact = {
+                "nn": {"metric": "NN queries/s", "value": _r(nn["value"]), "unit": "queries/s",
+                       "ms_per_step": _r(nn["ms_per_step"]), "e2e_value": _r(nn["e2e"]["value"]),
+                       "kernel": nn["roofline"]["kernel"], "kernel_us": _r(nn["roofline"]["avg_launch_us"], 1),
+                       "roofline_frac": _r(nn["roofline"]["frac"], 5),
+                       "cpu_1core": _r(nn["cpu_baseline"]["value"]), "cpu_all_cores": _r(nn["cpu_baseline"]["all_cores"]["value"]),
+                       "cpu_cores": cores, "parity_id_mismatches": nn["parity_sample"]["id_mismatches"],
+                       "parity_dist_bit_mismatches": nn["parity_sample"]["dist_sq_bit_mismatches"]},
+                "icp": {"metric": "ICP alignments/s", "unit": "alignments/s",
+                        "strict_value": _r(st["value"]), "strict_e2e": _r(st["e2e"]["value"]),
+                        "fast_value": _r(f["value"]), "fast_e2e": _r(f["e2e"]["value"]),
+                        "fast_kernel_us": _r(f["roofline"]["avg_launch_us"], 1), "fast_roofline_frac": _r(f["roofline"]["frac"], 5),
+                        "strict_roofline_frac": _r(st["roofline"]["frac"], 6), "cpu_1core": _r(icp["cpu_baseline"]["value"]),
+                        "strict_bit_exact": icp["parity"]["strict_trans_bit_exact"],
+                        "fast_max_abs_diff_vs_reference_order": icp["parity"]["fast_max_abs_diff_vs_reference_order"]},
+                "c4_farm": {"metric": "ICP scan pairs/s", "pairs_per_gpu": 128, "distinct_pairs": 128 * world,
+                            "strict_value": _r(icp_farm["modes"]["strict"]["value"]),
+                            "fast_value": _r(icp_farm["modes"]["fast"]["value"]),
+                            "failed": icp_farm["modes"]["fast"]["failed"] + icp_farm["modes"]["strict"]["failed"]},
+                "c5": {"voxelgrid_50m_mpts": _r(c5["voxelgrid"]["value_mpts"]), "voxelgrid_50m_ms": _r(c5["voxelgrid"]["ms_per_step"]),
+                       "voxelgrid_50m_pipeline_frac": _r(c5["voxelgrid"]["pipeline_roofline"]["frac"], 5),
+                       "voxelgrid_single_gpu_ms": _r(c5["voxelgrid"].get("single_gpu_ms_per_step")),
+                       "range_neighbours_per_s": _r(c5["range"]["neighbours_per_s"]), "range_queries_per_s": _r(c5["range"]["queries_per_s"]),
+                       "icp_nccl_alignments_per_s": _r(c5["icp"]["nccl"]["value"]),
+                       "icp_peer_alignments_per_s": _r(c5["icp"]["peer"]["value"]),
+                       "icp_single_gpu_alignments_per_s": _r(c5["icp"]["single_gpu"]["value"]),
+                       "icp_iterations": c5["icp"]["iterations"], "scaling": "strong"},
+                "parity": parity,
+            }
         line = {
             "metric": "VoxelGrid Mpts/s", "value": vg["value"], "unit": "Mpts/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": vg["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points_per_gpu_per_step": 1_000_000, "voxels_out": vg["voxels_out"],
-                       "l2": f"input rotates over {ROTATE} distinct device copies (192 MB > 126 MB L2)",
-                       "sharding": "one independent cloud per GPU per step, no data-path collective"},
+            "steps": vg["steps"], "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": vg["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CONFIG),
             "e2e": vg["e2e"], "gpu_launches": vg["gpu_launches"], "clocks": vg["clocks"], "roofline": vg["roofline"],
-            "pipeline_roofline": vg["pipeline_roofline"], "kernels": vg["kernels"], "cpu_baseline": cpu,
-            "host_cores": cores, "extra": extra,
+            "pipeline_roofline": vg["pipeline_roofline"], "cpu_baseline": cpu, "host_cores": cores,
+            **compact,
+            "config_detail": {"voxels_out": vg["voxels_out"],
+                              "l2": f"input rotates over {ROTATE} distinct device copies (192 MB > 126 MB L2)",
+                              "sharding": "one independent cloud per GPU per step, no data-path collective",
+                              "timed_region": f"{vg['steps']} steps (>= {MIN_TIMED_S} s), {args.steps} requested"},
+            "kernels": vg["kernels"], "extra": extra,
         }
     else:
         if nn is not None:
@@ -853,8 +1015,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="primary VoxelGrid line only")
-    ap.add_argument("--config5", action="store_true", help="add the 50M-point map workload (slow; not in the default run)")
-    ap.add_argument("--only", default=None, choices=["nn", "icp", "farm", "vgshard"],
+    ap.add_argument("--only", default=None, choices=["nn", "icp", "farm", "c5"],
                     help="profiling aid: run just this extra workload and print its object (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

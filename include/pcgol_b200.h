@@ -265,16 +265,20 @@ pcg_status pcg_voxelgrid_filter_chunks_dev(const void* d_data, int64_t n, int64_
                                            int32_t device, void* d_out, int64_t* n_out, void* stream);
 /* The same Filter with the POINTS sharded: every rank holds a contiguous slice of the cloud (slice r before slice
  * r+1 in point order) and nothing is replicated.  Steps, each a call below with a collective of the caller in between:
- *   pcg_minmax_packed_dev        the slice's six MinMaxVec3 accumulators, 64-bit words that a signed MIN (first three)
- *                                / MAX (last three) all-reduce combines; the low 32 bits are the global index of the
- *                                winning point (max: its complement), so the first occurrence wins across ranks
- *                                (minmax.go:17-22) and the owner of the winner reads the exact value, zero sign included
+ *   pcg_minmax_packed_dev        the slice's six MinMaxVec3 accumulators as 64-bit words that ONE signed MIN
+ *                                all-reduce combines (the maxima are stored negated): order-preserving value bits,
+ *                                then the global index of the point (first occurrence wins across ranks,
+ *                                minmax.go:17-22), then the sign of a zero; a NaN at global point 0 (which the
+ *                                reference never replaces, minmax.go:13) is a marker word.  pcgol_b200/dist.py
+ *                                (decode_minmax_words) turns the reduced words into the six floats (< 2^30 points)
  *   ..._chunk_histogram_mm_dev   points per chunk id of the slice under the bounds mm6 = {min xyz, max xyz} of the
  *                                whole cloud; summed over ranks it balances the chunk ranges
  *   ..._owner_order_dev          cuts[r] = first chunk id of rank r (cuts[0] = 0): d_perm = the slice's points ordered
- *                                by owner (stable), counts[r] = points for rank r -> all-to-all of whole records
+ *                                by owner (stable), counts[r] = points for rank r, d_send (optional, n * stride
+ *                                bytes) = the whole records in that order -> all-to-all
  *   ..._filter_chunks_mm_dev     the owner filters the records it received (sources in rank order = global point
- *                                order, which the stable sort keeps) under the same bounds
+ *                                order, which the stable sort keeps) under the same bounds; d_data must hold exactly
+ *                                the points of its chunks [cid_lo, cid_hi) - nothing is selected any more
  * Outputs concatenated in rank order are the reference's output (voxelgrid.go:102-133). */
 pcg_status pcg_minmax_packed_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                  int32_t device, int64_t index_base, int64_t* d_out6, void* stream);
@@ -285,7 +289,7 @@ pcg_status pcg_voxelgrid_chunk_histogram_mm_dev(const void* d_data, int64_t n, i
 pcg_status pcg_voxelgrid_owner_order_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                          const float leaf[3], const int64_t chunk[3], const float mm6[6],
                                          const int64_t* cuts, int32_t world, int32_t device, uint32_t* d_perm,
-                                         int64_t* counts, void* stream);
+                                         int64_t* counts, void* d_send, void* stream);
 pcg_status pcg_voxelgrid_filter_chunks_mm_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                               const float leaf[3], const int64_t chunk[3], const float mm6[6],
                                               int64_t cid_lo, int64_t cid_hi, int32_t device, void* d_out,
@@ -414,9 +418,10 @@ pcg_status pcg_query_order_dev(pcg_index* idx, const void* d_q, int64_t n, int64
 /* ---- multi-GPU from ONE process (the Go shim has no ranks): the device list is the list of index replicas.
  * pcg_index_replicate copies a built index to another device (NVLink peer copy; the replica is bit-identical).
  * pcg_icp_fit_multi* = PointToPointICPGradient.Fit (icp.go:23-67) with the target split over the replicas' devices:
- * one persistent cooperative kernel per device runs the whole loop; per iteration every device stores its ten float64
- * partial sums into every peer's exchange buffer over NVLink (peer-mapped memory, no library collective, no kernel
- * launch, no host round trip), waits on flags and applies the identical update.  Fast mode, gradient-descent
+ * every device runs the fast loop on its slice, one kernel per iteration; the last CTA of that kernel stores the
+ * device's ten float64 partial sums into every peer's exchange buffer over NVLink (peer-mapped memory), waits on flags,
+ * adds the slots in device order and applies the identical update - no library collective, no extra kernel and no
+ * host round trip per iteration; the host enqueues all iterations and joins once.  Fast mode, gradient-descent
  * updater, exact nearest neighbour (min_dist_sq == 0).  The transform equals the single-GPU fast Fit up to the
  * rounding of the float64 sums.  n_dev == 1 is allowed (no exchange).  _dev: d_targets[r] (n_targets[r] records) is
  * device memory on the device of bases[r]; the host variant cuts `target` into contiguous slices itself. */

@@ -160,7 +160,7 @@ _sigs = {
     "pcg_icp_partial_dev": (_i32, [_vp, _vp, _i64, _i64, _vp, _f, _vp, _i32, _vp, _vp, _vp]),
     "pcg_minmax_packed_dev": (_i32, [_vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp]),
     "pcg_voxelgrid_chunk_histogram_mm_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, C.POINTER(_i64), _vp]),
-    "pcg_voxelgrid_owner_order_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "pcg_voxelgrid_owner_order_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pcg_voxelgrid_filter_chunks_mm_dev": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, C.POINTER(_i64), _vp]),
     "pcg_index_replicate": (_i32, [_vp, _i32, C.POINTER(_vp)]),
     "pcg_icp_fit_multi": (_i32, [_i32, _vp, _vp, _i64, _i64, _vp, C.POINTER(IcpParams), _vp, C.POINTER(IcpStat)]),

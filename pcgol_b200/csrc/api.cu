@@ -66,7 +66,7 @@ void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t st
 extern std::atomic<int> g_vg_path;
 void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream);
 void voxelgrid_owner_order_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], const float* mm6,
-                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts,
+                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts, uint8_t* d_send,
                                   cudaStream_t stream);
 int64_t voxelgrid_chunk_histogram_device(const CloudView& v, const float leaf[3], const int64_t chunk[3],
                                          int64_t sample_step, int64_t* hist_out, int64_t cap, cudaStream_t stream,
@@ -715,7 +715,7 @@ pcg_status pcg_minmax_packed_dev(const void* d_data, int64_t n, int64_t stride, 
   return guarded([&]() -> pcg_status {
     check_device(device);
     check_view_args(d_data, n, stride, xyz_off);
-    if (!d_out6 || index_base < 0 || index_base + n >= ((int64_t)1 << 31))
+    if (!d_out6 || index_base < 0 || index_base + n >= ((int64_t)1 << 30))
       throw StatusError{PCG_E_INVALID_ARG, "null output / global point index out of range"};
     DeviceGuard g(device);
     minmax_packed_device(make_view(d_data, n, stride, xyz_off), (uint32_t)index_base, (long long*)d_out6,
@@ -744,7 +744,7 @@ pcg_status pcg_voxelgrid_chunk_histogram_mm_dev(const void* d_data, int64_t n, i
 pcg_status pcg_voxelgrid_owner_order_dev(const void* d_data, int64_t n, int64_t stride, const int64_t xyz_off[3],
                                          const float leaf[3], const int64_t chunk[3], const float mm6[6],
                                          const int64_t* cuts, int32_t world, int32_t device, uint32_t* d_perm,
-                                         int64_t* counts, void* stream) {
+                                         int64_t* counts, void* d_send, void* stream) {
   return guarded([&]() -> pcg_status {
     if (!mm6 || !cuts || !counts || (n && !d_perm)) throw StatusError{PCG_E_INVALID_ARG, "null argument"};
     check_device(device);
@@ -752,7 +752,7 @@ pcg_status pcg_voxelgrid_owner_order_dev(const void* d_data, int64_t n, int64_t 
     check_vg_args(leaf, chunk);
     DeviceGuard g(device);
     voxelgrid_owner_order_device(make_view(d_data, n, stride, xyz_off), leaf, chunk, mm6, cuts, world, d_perm, counts,
-                                 (cudaStream_t)stream);
+                                 (uint8_t*)d_send, (cudaStream_t)stream);
     return PCG_OK;
   });
 }

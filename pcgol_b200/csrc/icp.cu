@@ -16,9 +16,8 @@
 //   tail               evaluator.go:156-186 + gradientDescentUpdater.Update (updater.go:44-71)
 //                      run on the device, so the loop never returns to the host; once `done`
 //                      is set the remaining launches fall through.
-#include <cooperative_groups.h>
-
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 #include <vector>
 
@@ -59,9 +58,21 @@ inline int term_threads(int mode, bool hess) {
 constexpr int kTerms = 9;  // Value, SumW, G0..G5, R
 constexpr int kHTerms = 9; // sum p (3) + second moments of p (6): the Gauss-Newton Hessian
 
+// One large ICP over several GPUs driven by ONE process: exchange of the iteration's sums over NVLink peer memory,
+// done by the last CTA of the terms kernel (see icp_last_block).  n_dev <= 1: no exchange.
+constexpr int kMaxPeers = 8;
+constexpr int kXchg = 10;  // Value, SumW, G0..5, R, nPairs
+struct PeerCtx {
+  int n_dev, rank;
+  unsigned int seq_base;           // exchanges completed by earlier Fits on these buffers (flags only grow)
+  double* slots[kMaxPeers];        // device d's buffer [2][kMaxPeers][kXchg], addressable from this device
+  unsigned int* flags[kMaxPeers];  // device d's flags [kMaxPeers]: last exchange the source has published
+};
+
 __device__ __forceinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
                                                const double* __restrict__ hpartials, int nblocks, bool do_main,
-                                               bool do_hess, float* s_sum, int* s_last);
+                                               bool do_hess, float* s_sum, double* s_tot, int* s_last,
+                                               const PeerCtx& pc);
 
 // Block-wide float64 sum of K per-thread values -> out[blockIdx.x * K + k] (fixed order).
 template <int K, int THREADS>
@@ -94,12 +105,14 @@ template <int MODE, bool APPROX, bool HESS, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     icp_terms_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, uint32_t* __restrict__ warm,
                      float max_dist_sq, float min_dist_sq, IcpState* __restrict__ st, float* __restrict__ terms,
-                     int64_t n_pad, double* __restrict__ partials, double* __restrict__ hpartials, int finalize) {
+                     int64_t n_pad, double* __restrict__ partials, double* __restrict__ hpartials, int finalize,
+                     PeerCtx pc) {
   if (st->done) return;
   __shared__ float s_m[16];
   __shared__ int s_first;
   __shared__ int s_last;
   __shared__ float s_sum[kTerms];
+  __shared__ double s_tot[kXchg];
   __shared__ double s_red[THREADS / 32][kTerms];
   const int tid = threadIdx.x;
   if (tid < 16) s_m[tid] = st->trans.m[tid];
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(THREADS)
   if (HESS) block_sum_f64<kHTerms, THREADS>(ht, s_red, hpartials);
   if (MODE == PCG_ICP_FAST) block_sum_f64<kTerms, THREADS>(t, s_red, partials);
   if (finalize && (MODE == PCG_ICP_FAST || HESS))
-    icp_last_block(st, partials, hpartials, (int)gridDim.x, MODE == PCG_ICP_FAST, HESS, s_sum, &s_last);
+    icp_last_block(st, partials, hpartials, (int)gridDim.x, MODE == PCG_ICP_FAST, HESS, s_sum, s_tot, &s_last, pc);
 }
 
 constexpr int kFinishThreads = 32 * kTerms;
@@ -238,7 +251,8 @@ __device__ __forceinline__ void icp_finalize(IcpState* __restrict__ st, const fl
 // Evaluate sums (FAST mode) followed by the tail; do_hess: the nine moments of the normal equations.
 __device__ __forceinline__ void icp_last_block(IcpState* __restrict__ st, const double* __restrict__ partials,
                                                const double* __restrict__ hpartials, int nblocks, bool do_main,
-                                               bool do_hess, float* s_sum, int* s_last) {
+                                               bool do_hess, float* s_sum, double* s_tot, int* s_last,
+                                               const PeerCtx& pc) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   __threadfence();
   if (tid == 0) {
@@ -263,9 +277,47 @@ __device__ __forceinline__ void icp_last_block(IcpState* __restrict__ st, const 
       for (int b = lane; b < nblocks; b += 32) s += __ldcg(&partials[(int64_t)b * kTerms + k]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) s_sum[k] = (float)s;
+      if (lane == 0) s_tot[k] = s;
     }
   }
+  __syncthreads();
+  if (do_main && pc.n_dev > 1) {
+    // ---- exchange over NVLink peer memory: this device's ten sums are STORED into slot [parity][rank] of every
+    // device's buffer (plain stores to peer-mapped addresses), fenced, then its flag is raised on every device;
+    // it then waits until every device's flag shows this exchange and adds the slots in device order - the same
+    // order everywhere, so all devices apply the identical update without a broadcast.  Slots are double-buffered by
+    // iteration parity: nobody can be more than one exchange ahead of the slowest device.
+    const unsigned int it = (unsigned int)st->num_iteration;
+    const unsigned int seq = pc.seq_base + it + 1u;
+    const int parity = (int)(it & 1u);
+    if (tid == 0) s_tot[9] = (double)st->pair_counter;
+    __syncthreads();
+    for (int idx = tid; idx < pc.n_dev * kXchg; idx += (int)blockDim.x) {
+      const int d = idx / kXchg, k = idx % kXchg;
+      volatile double* dst = pc.slots[d] + ((size_t)parity * kMaxPeers + pc.rank) * kXchg + k;
+      *dst = s_tot[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pc.n_dev) {
+      volatile unsigned int* f = pc.flags[tid] + pc.rank;
+      *f = seq;
+      volatile unsigned int* mine = pc.flags[pc.rank] + tid;
+      while ((int)(*mine - seq) < 0) {  // flags only grow (wrap-safe comparison)
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < kXchg) {
+      double s = 0.0;
+      const volatile double* src = pc.slots[pc.rank] + (size_t)parity * kMaxPeers * kXchg;
+      for (int d = 0; d < pc.n_dev; d++) s += src[(size_t)d * kXchg + tid];
+      s_tot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) st->pair_counter = (unsigned int)(long long)s_tot[9];  // icp_finalize takes the pair count from here
+  }
+  if (do_main && tid < kTerms) s_sum[tid] = (float)s_tot[tid];
   __syncthreads();
   if (tid == 0) {
     st->ticket = 0;
@@ -708,14 +760,17 @@ static void check_icp_params(const pcg_icp_params& prm) {
 template <int MODE>
 static void launch_terms(const Index& base, const CloudView& tgt, const uint32_t* perm, uint32_t* warm, float mdsq,
                          float min_dist_sq, bool hess, IcpState* st, float* terms, int64_t n_pad, double* partials, double* hpartials,
-                         int nblocks, int finalize, cudaStream_t stream) {
+                         int nblocks, int finalize, cudaStream_t stream, const PeerCtx* peer = nullptr) {
+  PeerCtx pc;
+  std::memset(&pc, 0, sizeof(pc));
+  if (peer) pc = *peer;
   const char* name = MODE == PCG_ICP_STRICT ? "(icp_terms_kernel<PCG_ICP_STRICT>)" : "(icp_terms_kernel<PCG_ICP_FAST>)";
   const bool approx = min_dist_sq > 0.f;
   min_dist_sq = fminf(min_dist_sq, mdsq);  // only a real hit can end a search early: see nearest_device
   // nblocks was sized with term_threads(MODE, hess): strict without the Hessian moments walks in 32-thread blocks
 #define PCG_TERMS(A, H, T)                                                                                         \
   PCG_LAUNCH_NAMED(name, (icp_terms_kernel<MODE, A, H, T>), nblocks, T, 0, stream, base.view(), tgt, perm, warm,    \
-                   mdsq, min_dist_sq, st, terms, n_pad, partials, hpartials, finalize)
+                   mdsq, min_dist_sq, st, terms, n_pad, partials, hpartials, finalize, pc)
   constexpr int kT = MODE == PCG_ICP_STRICT ? kTermThreadsStrict : kTermThreadsReduce;
   if (approx && hess)
     PCG_TERMS(true, true, kTermThreadsReduce);
@@ -977,170 +1032,38 @@ pcg_status icp_shard_result(IcpShard& sh, float trans[16], pcg_icp_stat* stat, i
   return (pcg_status)h.status;
 }
 
-// ---- one large ICP over several GPUs of one process: persistent kernel + NVLink peer exchange ---------------------
+// ---- one large ICP over several GPUs of one process: NVLink peer exchange inside the iteration kernel ---------------
 // The same sharding as above (target split, base index replicated) for a caller that owns all devices from ONE process
-// (the Go shim: icp.Fit has no notion of ranks).  One cooperative kernel per device runs the whole Fit:
-//   per iteration   every thread walks its target points (grid-stride; the visit slot of a thread is the same in every
-//                   iteration, so the warm start of the walk is the slot's previous match), float64 partial sums,
-//                   block sums -> partials[block] -> grid.sync
-//                   block 0 folds the partials in block order, STORES the ten sums into slot [parity][rank] of EVERY
-//                   device's exchange buffer (peer-mapped memory: plain stores that travel over NVLink), fences, raises
-//                   its flag on every device; then waits until the flags of all devices show this iteration, adds the
-//                   slots in device order - the same order on every device, so all of them apply the identical update
-//                   without a broadcast - and runs the tail of Evaluate + Update (icp_finalize) -> grid.sync
-// No host round trip, no kernel launch and no library collective inside the loop: the exchange is ten stores + one
-// flag per peer and a spin on local memory.  Slots are double-buffered by iteration parity: a device can only be one
-// exchange ahead of the slowest one (it needs everybody's flag to proceed).
-namespace cg = cooperative_groups;
-constexpr int kMaxPeers = 8;
-constexpr int kXchg = 10;  // Value, SumW, G0..5, R, nPairs
-struct PeerCtx {
-  int n_dev, rank;
-  double* slots[kMaxPeers];        // device d's buffer [2][kMaxPeers][kXchg], addressable from this device
-  unsigned int* flags[kMaxPeers];  // device d's flags [kMaxPeers]: last exchange the source has published
-};
-
-constexpr int kMultiThreads = 256;
-__global__ void __launch_bounds__(kMultiThreads)
-    icp_multi_kernel(IndexView base, CloudView tgt, const uint32_t* __restrict__ perm, uint32_t* __restrict__ warm,
-                     float max_dist_sq, IcpState* __restrict__ st, double* __restrict__ partials, PeerCtx pc,
-                     int max_iterations) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ float s_m[16];
-  __shared__ int s_first, s_done;
-  __shared__ double s_red[kMultiThreads / 32][kXchg];
-  __shared__ double s_tot[kXchg];
-  __shared__ float s_sum[kTerms];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t stride = (int64_t)gridDim.x * kMultiThreads;
-  for (int it = 0; it < max_iterations; it++) {
-    if (tid == 0) {
-      s_done = __ldcg(&st->done);
-      s_first = __ldcg(&st->num_iteration) == 0;
-    }
-    if (tid < 16) s_m[tid] = __ldcg(&st->trans.m[tid]);
-    __syncthreads();
-    if (s_done) break;  // the same on every block and every device
-    double acc[kXchg];
-#pragma unroll
-    for (int k = 0; k < kXchg; k++) acc[k] = 0.0;
-    for (int64_t slot = (int64_t)blockIdx.x * kMultiThreads + tid; slot < tgt.n; slot += stride) {
-      const int64_t i = perm ? (int64_t)perm[slot] : slot;
-      const float3 p = load_xyz(tgt, i);
-      float x0 = p.x, y0 = p.y, z0 = p.z;
-      if (!s_first) im::m4transform(s_m, p.x, p.y, p.z, &x0, &y0, &z0);  // icp.go:27-30,62-64
-      uint64_t best = nn_init(max_dist_sq);
-      const uint64_t init = best;
-      uint32_t pos = 0;
-      const uint32_t w0 = warm[slot];
-      if (w0 != 0xffffffffu) {  // warm start: see icp_terms_kernel
-        const float4 c = __ldg(base.pts + w0);
-        const float d = dist_sq_ref(c.x, c.y, c.z, x0, y0, z0);
-        const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
-        if (packed < best) {
-          best = packed;
-          pos = w0;
-        }
-      }
-      nn_traverse4<false>(base, x0, y0, z0, best, pos, 0.f);
-      if (best != init) {  // correspondence.go:27-29, evaluator.go:130-144 with w = 1
-        warm[slot] = pos;
-        const float4 pb = __ldg(base.pts + pos);
-        const float x1 = pb.x, y1 = pb.y, z1 = pb.z;
-        acc[0] += (double)__uint_as_float((uint32_t)(best >> 32));
-        acc[1] += 1.0;
-        acc[2] += (double)im::sub(x0, x1);
-        acc[3] += (double)im::sub(y0, y1);
-        acc[4] += (double)im::sub(z0, z1);
-        acc[5] += (double)im::sub(im::mul(z0, y1), im::mul(y0, z1));
-        acc[6] += (double)im::sub(im::mul(x0, z1), im::mul(z0, x1));
-        acc[7] += (double)im::sub(im::mul(y0, x1), im::mul(x0, y1));
-        acc[8] += (double)im::add(im::add(im::mul(x0, x0), im::mul(y0, y0)), im::mul(z0, z0));
-        acc[9] += 1.0;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kXchg; k++) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < kXchg; k++) s_red[warp][k] = acc[k];
-    }
-    __syncthreads();
-    if (tid < kXchg) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < kMultiThreads / 32; w++) s += s_red[w][tid];
-      partials[(int64_t)blockIdx.x * kXchg + tid] = s;
-    }
-    __threadfence();
-    grid.sync();
-    if (blockIdx.x == 0) {
-      const unsigned int seq = (unsigned int)it + 1u;
-      const int parity = it & 1;
-      // fold the blocks' partials (fixed order)
-      for (int k = warp; k < kXchg; k += kMultiThreads / 32) {
-        double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&partials[(int64_t)b * kXchg + k]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (lane == 0) s_tot[k] = s;
-      }
-      __syncthreads();
-      if (pc.n_dev > 1) {
-        // publish to every device (its own buffer included), then the flag
-        for (int idx = tid; idx < pc.n_dev * kXchg; idx += kMultiThreads) {
-          const int d = idx / kXchg, k = idx % kXchg;
-          volatile double* dst = pc.slots[d] + ((size_t)parity * kMaxPeers + pc.rank) * kXchg + k;
-          *dst = s_tot[k];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < pc.n_dev) {
-          volatile unsigned int* f = pc.flags[tid] + pc.rank;
-          *f = seq;
-        }
-        // wait for everybody's sums of this iteration (flags only grow)
-        if (tid < pc.n_dev) {
-          volatile unsigned int* f = pc.flags[pc.rank] + tid;
-          while (*f < seq) {
-          }
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < kXchg) {
-          double s = 0.0;
-          const volatile double* src = pc.slots[pc.rank] + (size_t)parity * kMaxPeers * kXchg;
-          for (int d = 0; d < pc.n_dev; d++) s += src[(size_t)d * kXchg + tid];  // device order: identical everywhere
-          s_tot[tid] = s;
-        }
-        __syncthreads();
-      }
-      if (tid < kTerms) s_sum[tid] = (float)s_tot[tid];
-      __syncthreads();
-      if (tid == 0) {
-        st->pair_counter = (unsigned int)(long long)s_tot[9];  // icp_finalize takes the pair count from here
-        icp_finalize(st, s_sum);
-        __threadfence();
-      }
-    }
-    grid.sync();
-  }
-}
-
-struct MultiDev {
-  int device = -1;
+// (the Go shim: icp.Fit has no notion of ranks).  Every device runs the single-GPU fast loop on its slice - one
+// icp_terms_kernel per iteration - and the last CTA of that kernel exchanges the ten sums with the other devices over
+// peer-mapped memory before it runs the tail of Evaluate + Update (icp_last_block): no library collective, no extra
+// kernel and no host round trip per iteration.  The host enqueues MaxIteration kernels per device (finished ones fall
+// through) and joins once.  Exchange buffers, flags and streams are created once per device and reused.
+struct PeerResources {
   cudaStream_t stream = nullptr;
-  const Index* base = nullptr;
-  CloudView tgt;
-  IcpWork w;
-  DevBuf<double> partials;
-  double* slots = nullptr;        // cudaMalloc: peer access follows the device, not the memory pool
+  double* slots = nullptr;        // cudaMalloc (not the stream-ordered pool): peer access follows the device
   unsigned int* flags = nullptr;
-  int grid = 0;
 };
+static std::mutex g_peer_mu;           // one multi-GPU Fit at a time: the exchange buffers are per device
+static PeerResources g_peer[64];
+static unsigned int g_peer_seq = 0;    // exchanges ever enqueued (the flags only grow)
+static uint64_t g_peer_enabled = 0;    // bit (a * 8 + b) for small ordinals: peer access a -> b already enabled
+
+static PeerResources& peer_resources(int device) {
+  if (device < 0 || device >= 64) throw StatusError{PCG_E_INVALID_ARG, "device ordinal out of range"};
+  PeerResources& r = g_peer[device];
+  if (!r.stream) {
+    PCG_CUDA(cudaSetDevice(device));
+    ensure_pool(device);
+    PCG_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+    PCG_CUDA(cudaMalloc((void**)&r.slots, sizeof(double) * 2 * kMaxPeers * kXchg));
+    PCG_CUDA(cudaMalloc((void**)&r.flags, sizeof(unsigned int) * kMaxPeers));
+    PCG_CUDA(cudaMemset(r.slots, 0, sizeof(double) * 2 * kMaxPeers * kXchg));
+    PCG_CUDA(cudaMemset(r.flags, 0, sizeof(unsigned int) * kMaxPeers));
+    PCG_CUDA(cudaDeviceSynchronize());
+  }
+  return r;
+}
 
 // PointToPointICPGradient.Fit with the target sharded over the devices of bases[] (one replica of the base index
 // per device), one host thread, no library collective.  d_targets[r] (n_targets[r] records) lives on the device of
@@ -1155,111 +1078,88 @@ pcg_status icp_fit_multi_device(int n_dev, const Index* const* bases, const void
   if (prm.updater != PCG_UPDATER_GRADIENT_DESCENT || (prm.mode & PCG_ICP_WITH_HESSIAN) || prm.min_dist_sq > 0.f)
     throw StatusError{PCG_E_INVALID_ARG, "the multi-GPU loop is the exact-NN gradient-descent Fit (nine Evaluate sums)"};
   prm.mode = PCG_ICP_FAST;  // a sequential float32 sum has one order: it cannot be sharded
+  for (int r = 0; r < n_dev; r++) {
+    for (int q = 0; q < r; q++)
+      if (bases[q]->device == bases[r]->device) throw StatusError{PCG_E_INVALID_ARG, "one index per device"};
+    if (bases[r]->n != bases[0]->n) throw StatusError{PCG_E_INVALID_ARG, "the base replicas differ"};
+    check_view_args(d_targets[r], n_targets[r], stride, xyz_off);
+  }
+  std::lock_guard<std::mutex> lk(g_peer_mu);
   int prev = -1;
   cudaGetDevice(&prev);
-  std::vector<MultiDev> devs((size_t)n_dev);
-  auto cleanup = [&]() {
-    for (auto& d : devs) {
-      if (d.device < 0) continue;
-      cudaSetDevice(d.device);
-      if (d.stream) cudaStreamSynchronize(d.stream);
-      d.w = IcpWork();
-      d.partials.release();
-      if (d.slots) cudaFree(d.slots);
-      if (d.flags) cudaFree(d.flags);
-      if (d.stream) cudaStreamDestroy(d.stream);
+  struct Dev {
+    IcpWork w;
+    CloudView tgt;
+  };
+  std::vector<Dev> devs((size_t)n_dev);
+  auto restore = [&]() {
+    for (int r = 0; r < n_dev; r++) {  // the stream-ordered workspace must not outlive its stream's work
+      cudaSetDevice(bases[r]->device);
+      if (g_peer[bases[r]->device].stream) cudaStreamSynchronize(g_peer[bases[r]->device].stream);
+      devs[(size_t)r].w = IcpWork();
     }
     if (prev >= 0) cudaSetDevice(prev);
   };
   try {
-    for (int r = 0; r < n_dev; r++) {
-      for (int q = 0; q < r; q++)
-        if (bases[q]->device == bases[r]->device) throw StatusError{PCG_E_INVALID_ARG, "one index per device"};
-      if (bases[r]->n != bases[0]->n) throw StatusError{PCG_E_INVALID_ARG, "the base replicas differ"};
-    }
-    // peer access between every pair (NVLink / NVSwitch)
+    // peer access between every pair (NVLink / NVSwitch), enabled once
     for (int r = 0; r < n_dev && n_dev > 1; r++) {
-      PCG_CUDA(cudaSetDevice(bases[r]->device));
+      const int a = bases[r]->device;
       for (int q = 0; q < n_dev; q++) {
+        const int b = bases[q]->device;
         if (q == r) continue;
+        const bool small = a < 8 && b < 8;
+        if (small && (g_peer_enabled >> (a * 8 + b)) & 1ull) continue;
+        PCG_CUDA(cudaSetDevice(a));
         int can = 0;
-        PCG_CUDA(cudaDeviceCanAccessPeer(&can, bases[r]->device, bases[q]->device));
+        PCG_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
         if (!can) throw StatusError{PCG_E_INVALID_ARG, "devices without peer access"};
-        const cudaError_t e = cudaDeviceEnablePeerAccess(bases[q]->device, 0);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PCG_CUDA(e);
         cudaGetLastError();
+        if (small) g_peer_enabled |= 1ull << (a * 8 + b);
       }
     }
+    PeerCtx pc;
+    std::memset(&pc, 0, sizeof(pc));
+    pc.n_dev = n_dev;
+    pc.seq_base = g_peer_seq;
     for (int r = 0; r < n_dev; r++) {
-      MultiDev& d = devs[(size_t)r];
-      d.device = bases[r]->device;
-      d.base = bases[r];
-      PCG_CUDA(cudaSetDevice(d.device));
-      ensure_pool(d.device);
-      PCG_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-      check_view_args(d_targets[r], n_targets[r], stride, xyz_off);
-      d.tgt = make_view(d_targets[r], n_targets[r], stride, xyz_off);
-      icp_prepare(*d.base, d.tgt, prm, false, d.w, d.stream);
-      if (d.tgt.n == 0) {  // icp_prepare allocates the warm-start table only for a non-empty slice
-        d.w.warm.alloc(1, d.stream);
-      }
-      int per_sm = 0;
-      PCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_multi_kernel, kMultiThreads, 0));
-      int sms = 0;
-      PCG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device));
-      d.grid = std::max(1, std::min(per_sm * sms, std::max(1, div_up(d.tgt.n, kMultiThreads))));
-      d.partials.alloc((size_t)d.grid * kXchg, d.stream);
-      PCG_CUDA(cudaMalloc((void**)&d.slots, sizeof(double) * 2 * kMaxPeers * kXchg));
-      PCG_CUDA(cudaMalloc((void**)&d.flags, sizeof(unsigned int) * kMaxPeers));
-      PCG_CUDA(cudaMemsetAsync(d.flags, 0, sizeof(unsigned int) * kMaxPeers, d.stream));
-      PCG_CUDA(cudaMemsetAsync(d.slots, 0, sizeof(double) * 2 * kMaxPeers * kXchg, d.stream));
-    }
-    // every buffer must be zeroed before any device starts publishing into it
-    for (auto& d : devs) {
-      PCG_CUDA(cudaSetDevice(d.device));
-      PCG_CUDA(cudaStreamSynchronize(d.stream));
+      PeerResources& pr = peer_resources(bases[r]->device);
+      pc.slots[r] = pr.slots;
+      pc.flags[r] = pr.flags;
     }
     const int max_it = im::make_updater(prm).max_iteration;
-    const float mdsq = prm.max_dist * prm.max_dist;  // kdtree.go:91
+    g_peer_seq += (unsigned int)max_it;
     for (int r = 0; r < n_dev; r++) {
-      MultiDev& d = devs[(size_t)r];
-      PCG_CUDA(cudaSetDevice(d.device));
-      PeerCtx pc;
-      std::memset(&pc, 0, sizeof(pc));
-      pc.n_dev = n_dev;
-      pc.rank = r;
-      for (int q = 0; q < n_dev; q++) {
-        pc.slots[q] = devs[(size_t)q].slots;
-        pc.flags[q] = devs[(size_t)q].flags;
+      Dev& d = devs[(size_t)r];
+      PCG_CUDA(cudaSetDevice(bases[r]->device));
+      d.tgt = make_view(d_targets[r], n_targets[r], stride, xyz_off);
+      icp_prepare(*bases[r], d.tgt, prm, false, d.w, g_peer[bases[r]->device].stream);
+    }
+    const float mdsq = prm.max_dist * prm.max_dist;  // kdtree.go:91
+    // iteration-major: every device gets iteration k before anyone gets k + 1 (a device spins on its peers' flags)
+    for (int it = 0; it < max_it; it++) {
+      for (int r = 0; r < n_dev; r++) {
+        Dev& d = devs[(size_t)r];
+        PCG_CUDA(cudaSetDevice(bases[r]->device));
+        pc.rank = r;
+        launch_terms<PCG_ICP_FAST>(*bases[r], d.tgt, d.w.perm.p, d.w.warm.p, mdsq, 0.f, false, d.w.st.p, d.w.terms.p,
+                                   d.w.n_pad, d.w.partials.p, d.w.hpartials.p, d.w.nblocks, 1,
+                                   g_peer[bases[r]->device].stream, &pc);
       }
-      IndexView bv = d.base->view();
-      CloudView tv = d.tgt;
-      const uint32_t* perm = d.w.perm.p;
-      uint32_t* warm = d.w.warm.p;
-      float md = mdsq;
-      IcpState* stp = d.w.st.p;
-      double* parts = d.partials.p;
-      int mi = max_it;
-      void* params[] = {&bv, &tv, &perm, &warm, &md, &stp, &parts, &pc, &mi};
-      const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
-      if (prof) prof_begin("icp_multi_kernel", d.stream);
-      PCG_CUDA(cudaLaunchCooperativeKernel((const void*)icp_multi_kernel, dim3((unsigned)d.grid), dim3(kMultiThreads),
-                                           params, 0, d.stream));
-      if (prof) prof_end(d.stream);
-      g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     IcpState h;
-    PCG_CUDA(cudaSetDevice(devs[0].device));
-    PCG_CUDA(cudaMemcpyAsync(&h, devs[0].w.st.p, sizeof(h), cudaMemcpyDeviceToHost, devs[0].stream));
-    for (auto& d : devs) {
-      PCG_CUDA(cudaSetDevice(d.device));
-      PCG_CUDA(cudaStreamSynchronize(d.stream));
+    PCG_CUDA(cudaSetDevice(bases[0]->device));
+    PCG_CUDA(cudaMemcpyAsync(&h, devs[0].w.st.p, sizeof(h), cudaMemcpyDeviceToHost, g_peer[bases[0]->device].stream));
+    for (int r = 0; r < n_dev; r++) {
+      PCG_CUDA(cudaSetDevice(bases[r]->device));
+      PCG_CUDA(cudaStreamSynchronize(g_peer[bases[r]->device].stream));
     }
     state_to_outputs(h, trans, stat);
-    cleanup();
+    restore();
     return (pcg_status)h.status;
   } catch (...) {
-    cleanup();
+    restore();
     throw;
   }
 }

@@ -20,7 +20,7 @@ namespace pcg {
 std::atomic<int> g_vg_path{0};
 
 __global__ void __launch_bounds__(256)
-    minmax_kernel(CloudView v, uint32_t index_base, unsigned long long* __restrict__ out6) {
+    minmax_kernel(CloudView v, uint32_t index_base, int zero_sign, unsigned long long* __restrict__ out6) {
   __shared__ unsigned long long s_red[8][6];
   unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -31,7 +31,15 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < 3; k++) {
       if (c[k] != c[k]) continue;  // NaN never wins a comparison in the reference
       unsigned long long o = (unsigned long long)ordered_bits(c[k]) << 32;
-      unsigned long long a = o | (index_base + (uint32_t)i), b = o | (0xffffffffu - (index_base + (uint32_t)i));
+      unsigned long long a, b;
+      if (zero_sign) {  // sharded runs: bit 0 carries the sign of a zero (the value bits treat -0 as +0), index above it
+        const uint32_t g = index_base + (uint32_t)i, nz = __float_as_uint(c[k]) == 0x80000000u ? 1u : 0u;
+        a = o | ((g << 1) | nz);
+        b = o | (((0x7fffffffu - g) << 1) | nz);
+      } else {
+        a = o | (uint32_t)i;
+        b = o | (0xffffffffu - (uint32_t)i);
+      }
       mn[k] = a < mn[k] ? a : mn[k];
       mx[k] = b > mx[k] ? b : mx[k];
     }
@@ -98,7 +106,7 @@ void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t st
   }
   PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
   int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-  PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, 0u, acc.p);
+  PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, 0u, 0, acc.p);
   PCG_LAUNCH(minmax_finalize_kernel, 1, 32, 0, stream, v, acc.p, res.p);
   float* h = (float*)pinned_scratch();
   PCG_CUDA(cudaMemcpyAsync(h, res.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -140,29 +148,38 @@ __global__ void __launch_bounds__(256)
   rsort::hist_flush(s_hist, hist, passes);
 }
 
-// MinMaxVec3 of one slice of a cloud that is split over several GPUs: the six accumulators themselves, so that the
-// caller can reduce them across ranks.  d_out6[0..2] = min over the slice of (ordered value bits << 32 | global
-// index), d_out6[3..5] = max of (ordered value bits << 32 | ~global index), both with the top bit flipped so that
-// SIGNED 64-bit MIN / MAX (what NCCL offers) orders them; NaN coordinates take no part (minmax.go:17-22); a slice
-// without candidates leaves the neutral element.  The first occurrence of the extreme value wins, across ranks too.
-__global__ void minmax_signed_order_kernel(const unsigned long long* __restrict__ acc, long long* __restrict__ out6) {
+// MinMaxVec3 of one slice of a cloud that is split over several GPUs: six 64-bit words that ONE signed MIN all-reduce
+// (what NCCL offers) combines across ranks.  Word k = (ordered value bits << 32 | global index << 1 | sign of a zero)
+// for the minima; the maxima use the complemented index and are stored bitwise-negated, so MIN reduces them too; the
+// top bit is flipped for the signed order.  The first occurrence of the extreme value wins, across ranks as well; NaN
+// coordinates take no part (minmax.go:17-22) - except at global point 0, where the reference keeps the NaN for ever
+// (minmax.go:13): the slice that starts at index 0 then publishes a marker no real value can produce.
+__global__ void minmax_shard_init_kernel(unsigned long long* __restrict__ acc) {
   const int k = threadIdx.x;
-  if (k < 6) out6[k] = (long long)(acc[k] ^ 0x8000000000000000ull);
+  if (k < 6) acc[k] = k < 3 ? ~0ull : 0ull;
+}
+__global__ void minmax_shard_words_kernel(CloudView v, int first_slice, const unsigned long long* __restrict__ acc,
+                                          long long* __restrict__ out6) {
+  const int k = threadIdx.x;
+  if (k >= 6) return;
+  unsigned long long w = acc[k];
+  if (first_slice && v.n > 0) {
+    const float3 p0 = load_xyz(v, 0);
+    const int c = k % 3;
+    const float first = c == 0 ? p0.x : (c == 1 ? p0.y : p0.z);
+    if (first != first) w = k < 3 ? 0ull : ~0ull;  // beats every candidate of every rank
+  }
+  if (k >= 3) w = ~w;
+  out6[k] = (long long)(w ^ 0x8000000000000000ull);
 }
 void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream) {
   DevBuf<unsigned long long> acc(6, stream);
-  unsigned long long* init = (unsigned long long*)(pinned_scratch() + 64);
-  for (int k = 0; k < 3; k++) {
-    init[k] = ~0ull;
-    init[3 + k] = 0ull;
-  }
-  PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  PCG_LAUNCH(minmax_shard_init_kernel, 1, 32, 0, stream, acc.p);
   if (v.n > 0) {
     const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, acc.p);
+    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, 1, acc.p);
   }
-  PCG_LAUNCH(minmax_signed_order_kernel, 1, 32, 0, stream, acc.p, d_out6);
-  PCG_CUDA(cudaStreamSynchronize(stream));  // the pinned init words are reused by the next call of this thread
+  PCG_LAUNCH(minmax_shard_words_kernel, 1, 32, 0, stream, v, index_base == 0 ? 1 : 0, acc.p, d_out6);
 }
 
 // ---- segmented centroid + record gather ----------------------------------------------
@@ -1376,8 +1393,26 @@ __global__ void __launch_bounds__(256)
   rsort::hist_flush(s_hist, hist, 1);
 }
 
+// records (whole, `stride` bytes each) in the order of perm: 4-byte words when everything is aligned, else bytes
+__global__ void __launch_bounds__(256)
+    gather_records_kernel(const uint8_t* __restrict__ src, const uint32_t* __restrict__ perm, uint32_t n, uint32_t stride,
+                          int words, uint8_t* __restrict__ dst) {
+  if (words > 0) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)n * (uint32_t)words;
+    if (t >= total) return;
+    const uint32_t r = (uint32_t)(t / (uint32_t)words), w = (uint32_t)(t % (uint32_t)words);
+    reinterpret_cast<uint32_t*>(dst)[t] = __ldg(reinterpret_cast<const uint32_t*>(src + (uint64_t)perm[r] * stride) + w);
+  } else {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)n * stride) return;
+    const uint32_t r = (uint32_t)(t / stride), b = (uint32_t)(t % stride);
+    dst[t] = src[(uint64_t)perm[r] * stride + b];
+  }
+}
+
 void voxelgrid_owner_order_device(const CloudView& v, const float leaf[3], const int64_t chunk[3], const float* mm6,
-                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts,
+                                  const int64_t* cuts, int world, uint32_t* d_perm, int64_t* counts, uint8_t* d_send,
                                   cudaStream_t stream) {
   if (world < 1 || world > 8) throw StatusError{PCG_E_INVALID_ARG, "1 to 8 ranks"};
   for (int r = 0; r < world; r++) counts[r] = 0;
@@ -1404,6 +1439,13 @@ void voxelgrid_owner_order_device(const CloudView& v, const float leaf[3], const
   uint32_t* vv[2] = {v0.p, d_perm};  // one pass: the payload ends on side 1
   int res = 0;
   sorter.run(kk, vv, /*identity_vals=*/true, /*keep_keys=*/false, stream, &res);
+  if (d_send) {
+    const bool aligned = (v.stride & 3) == 0 && (((uintptr_t)v.data | (uintptr_t)d_send) & 3) == 0;
+    const int words = aligned ? (int)(v.stride >> 2) : 0;
+    const uint64_t work = aligned ? (uint64_t)n * (uint64_t)words : (uint64_t)n * (uint64_t)v.stride;
+    PCG_LAUNCH(gather_records_kernel, (unsigned)((work + 255) / 256), 256, 0, stream, v.data, d_perm, n, (uint32_t)v.stride,
+               words, d_send);
+  }
   uint32_t h[8];
   int h_flags = 0;
   PCG_CUDA(cudaMemcpyAsync(h, sorter.hist(), sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -1427,7 +1469,14 @@ pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3
   DevBuf<int> d_flags(1, stream);
   PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
   PCG_CUDA(cudaMemsetAsync(d_n.p, 0, sizeof(long long), stream));
-  if (total_bits <= 32)
+  if (mm6) {
+    // point-sharded Filter: the caller sent this rank exactly the points of its chunks (owner_order + all-to-all), so
+    // there is nothing to select - the plain pipeline under the global bounds
+    if (total_bits <= 32)
+      run_sorted_reduce<uint32_t>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
+    else
+      run_sorted_reduce<unsigned long long>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
+  } else if (total_bits <= 32)
     run_range_reduce<uint32_t>(v, P, total_bits, (unsigned long long)cid_lo, (unsigned long long)cid_hi, d_out, d_n.p,
                                d_flags.p, stream);
   else

@@ -94,6 +94,23 @@ def ordered_bits(x: np.ndarray) -> np.ndarray:
     return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
 
 
+def decode_minmax_words(words) -> np.ndarray:
+    """The six floats {min xyz, max xyz} from the all-reduced (signed MIN) words of pcg_minmax_packed_dev."""
+    w = np.asarray(words, np.int64).view(np.uint64) ^ np.uint64(1 << 63)
+    w[3:] = ~w[3:]
+    out = np.empty(6, np.uint32)
+    for k in range(6):
+        ob, low = int(w[k] >> np.uint64(32)), int(w[k] & np.uint64(0xffffffff))
+        if (k < 3 and int(w[k]) == 0) or (k >= 3 and int(w[k]) == 0xffffffffffffffff):
+            out[k] = 0x7fc00000  # a NaN at global point 0 stays (minmax.go:13); which NaN does not matter downstream
+            continue
+        bits = (ob & 0x7fffffff) if ob & 0x80000000 else (~ob & 0xffffffff)
+        if bits == 0 and (low & 1):
+            bits = 0x80000000  # the winning zero was a -0
+        out[k] = bits
+    return out.view(np.float32).copy()
+
+
 class GpuVgShard:
     """This rank's slice of the cloud on its GPU (a torch uint8 tensor of n * stride bytes) + the C-ABI steps."""
 
@@ -111,11 +128,6 @@ class GpuVgShard:
                                                  index_base, acc.data_ptr(), self.stream))
         return acc
 
-    def coord_bits(self, local_idx: int, k: int) -> int:
-        import torch
-        b = self.rec[local_idx * self.stride + self.off[k]: local_idx * self.stride + self.off[k] + 4]
-        return int(b.cpu().numpy().view(np.int32)[0])
-
     def histogram(self, mm6: np.ndarray, sample_step: int) -> np.ndarray:
         n_chunks = C.c_int64(0)
         hist = np.zeros(1 << 16, np.int64)
@@ -132,14 +144,16 @@ class GpuVgShard:
         import torch
         world = len(cuts) - 1
         perm = torch.empty(max(self.n, 1), dtype=torch.int32, device=self.rec.device)
+        self._send = torch.empty(max(self.n, 1) * self.stride, dtype=torch.uint8, device=self.rec.device)
         counts = np.zeros(world, np.int64)
         _lib.check(_lib.lib.pcg_voxelgrid_owner_order_dev(
             self.rec.data_ptr(), self.n, self.stride, self.offs, self.leaf, self.chunk, mm6.ctypes.data,
-            cuts.ctypes.data, world, self.device, perm.data_ptr(), counts.ctypes.data, self.stream))
+            cuts.ctypes.data, world, self.device, perm.data_ptr(), counts.ctypes.data, self._send.data_ptr(),
+            self.stream))
         return perm[: self.n], counts
 
     def gather(self, perm):
-        return self.rec[: self.n * self.stride].view(self.n, self.stride)[perm.long()].reshape(-1)
+        return self._send[: self.n * self.stride]  # written by owner_order (the library gathers whole records)
 
     def filter(self, recv, n_recv: int, mm6: np.ndarray, lo: int, hi: int, out):
         n_out = C.c_int64(0)
@@ -150,43 +164,35 @@ class GpuVgShard:
 
 
 def sharded_voxelgrid_points(shard, index_base: int, rank: int, world: int, out=None, group=None,
-                             sample_step: Optional[int] = None, n_total: Optional[int] = None):
+                             sample_step: Optional[int] = None, n_total: Optional[int] = None, timings=None):
     """voxelGrid.Filter of ONE cloud whose points are split over the ranks (rank r holds the contiguous slice that
     starts at global index `index_base`; nothing is replicated).  `shard` supplies the local steps (GpuVgShard on a
-    GPU; the CPU tests pass a numpy stand-in).  Collectives: MIN/MAX all-reduce of the six min/max accumulators,
-    SUM all-reduce of six coordinate words and of the chunk histogram, one all-to-all of the records by chunk owner,
-    all-gather of the output counts.  Returns (n_out_local, counts_of_all_ranks, (cid_lo, cid_hi), recv_records);
+    GPU; the CPU tests pass a numpy stand-in).  Collectives: one MIN all-reduce of the six min/max words,
+    a SUM all-reduce of the chunk histogram, one all-to-all of the records by chunk owner,
+    all-gather of the output counts.  Returns (n_out_local, counts_of_all_ranks, (cid_lo, cid_hi), recv_records, out)
+    where `out` (allocated here when None is passed) holds this rank's n_out_local output records;
     the ranks' outputs concatenated in rank order are the reference's output (voxelgrid.go:102-133)."""
     import torch
     import torch.distributed as dist
 
     collective = world > 1 and dist.is_available() and dist.is_initialized()
-    # 1. MinMaxVec3 of the whole cloud: first occurrence of the extreme value wins across ranks
+
+    def lap(name):  # tuning aid: wall time per step when a dict is passed (adds a device sync per step)
+        if timings is not None:
+            import time
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + 1e3 * (now - timings.get("_t", now))
+            timings["_t"] = now
+
+    lap("start")
+    # 1. MinMaxVec3 of the whole cloud: first occurrence of the extreme value wins across ranks (one all-reduce)
     acc = shard.minmax_packed(index_base)
     if collective:
-        lo3, hi3 = acc[:3].clone(), acc[3:].clone()
-        dist.all_reduce(lo3, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(hi3, op=dist.ReduceOp.MAX, group=group)
-        acc = torch.cat([lo3, hi3])
-    words = (acc.cpu().numpy().astype(np.int64).view(np.uint64) ^ np.uint64(1 << 63))
-    winners = [int(w & np.uint64(0xffffffff)) for w in words[:3]] + \
-              [0xffffffff - int(w & np.uint64(0xffffffff)) for w in words[3:]]
-    bits = np.zeros(9, np.int64)  # [0..5] value bits of the winners (from their owners), [6..8] point 0 (from rank 0)
-    for k in range(6):
-        if index_base <= winners[k] < index_base + shard.n:
-            bits[k] = shard.coord_bits(winners[k] - index_base, k % 3)
-    if index_base == 0 and shard.n > 0:
-        for c in range(3):
-            bits[6 + c] = shard.coord_bits(0, c)
-    if collective:
-        t = torch.from_numpy(bits).to(acc.device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        bits = t.cpu().numpy()
-    mm6 = bits[:6].astype(np.int32).view(np.float32).copy()
-    first = bits[6:9].astype(np.int32).view(np.float32)
-    for c in range(3):  # a NaN at point 0 is never replaced (minmax.go:13,17-22)
-        if first[c] != first[c]:
-            mm6[c] = mm6[3 + c] = first[c]
+        dist.all_reduce(acc, op=dist.ReduceOp.MIN, group=group)
+    mm6 = decode_minmax_words(acc.cpu().numpy())
+    lap("minmax")
     # 2. chunk ranges balanced by points
     total = n_total if n_total is not None else shard.n * world
     step = int(sample_step) if sample_step else (16 if total >= (1 << 22) else 1)
@@ -198,9 +204,11 @@ def sharded_voxelgrid_points(shard, index_base: int, rank: int, world: int, out=
     ranges = chunk_ranges(hist, world)
     cuts = np.array([r[0] for r in ranges] + [len(hist)], np.int64)
     lo, hi = ranges[rank]
+    lap("histogram")
     # 3. records to their chunk's owner (whole records: the filter keeps the first member's fields)
     perm, counts = shard.owner_order(mm6, cuts)
     send = shard.gather(perm)
+    lap("owner_order")
     if collective:
         cin = torch.from_numpy(counts.copy()).to(acc.device)
         cout = torch.empty_like(cin)
@@ -213,15 +221,20 @@ def sharded_voxelgrid_points(shard, index_base: int, rank: int, world: int, out=
         recv_counts = counts
         recv = send
     n_recv = int(recv_counts.sum())
+    lap("all_to_all")
     # 4. the owner filters what it received: sources arrive in rank order = global point order
+    if out is None:  # a rank's chunks may hold more points than its slice: sized after the exchange
+        out = torch.empty(max(1, n_recv) * shard.stride, dtype=torch.uint8, device=recv.device)
     n_out = shard.filter(recv, n_recv, mm6, lo, hi, out)
+    lap("filter")
     all_counts = [n_out]
     if collective:
         t = torch.tensor([n_out], dtype=torch.int64, device=acc.device)
         gathered = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(gathered, t, group=group)
         all_counts = [int(g.item()) for g in gathered]
-    return n_out, all_counts, (lo, hi), recv
+    lap("counts")
+    return n_out, all_counts, (lo, hi), recv, out
 
 
 def sharded_icp_fit(partial_fn: Callable[[np.ndarray, bool], "object"], params: _lib.IcpParams,

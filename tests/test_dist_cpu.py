@@ -155,19 +155,22 @@ class _NumpyVgShard:
         self.chunk = chunk
 
     def minmax_packed(self, index_base):
+        # the packing of pcg_minmax_packed_dev, restated: value bits | global index << 1 | sign of a zero; maxima
+        # complemented so that one signed MIN all-reduce serves all six words
         from pcgol_b200.dist import ordered_bits
         out = np.empty(6, np.uint64)
-        idx = (np.arange(self.n) + index_base).astype(np.uint64)
+        g = (np.arange(self.n) + index_base).astype(np.uint64)
         for k in range(3):
             col = self.xyz[:, k]
             ok = col == col
             o = ordered_bits(col[ok]).astype(np.uint64) << np.uint64(32)
-            out[k] = (o | idx[ok]).min() if ok.any() else np.uint64(0xffffffffffffffff)
-            out[3 + k] = (o | (np.uint64(0xffffffff) - idx[ok])).max() if ok.any() else np.uint64(0)
+            nz = (col[ok].view(np.uint32) == np.uint32(0x80000000)).astype(np.uint64)
+            out[k] = (o | (g[ok] << np.uint64(1)) | nz).min() if ok.any() else np.uint64(0xffffffffffffffff)
+            mx = (o | ((np.uint64(0x7fffffff) - g[ok]) << np.uint64(1)) | nz).max() if ok.any() else np.uint64(0)
+            if index_base == 0 and self.n and not ok[0]:
+                out[k], mx = np.uint64(0), np.uint64(0xffffffffffffffff)
+            out[3 + k] = ~mx
         return self.torch.from_numpy((out ^ np.uint64(1 << 63)).view(np.int64).copy())
-
-    def coord_bits(self, local_idx, k):
-        return int(self.xyz[local_idx, k:k + 1].view(np.int32)[0])
 
     def _cids(self, mm6):
         vmin, vmax = mm6[:3], mm6[3:]
@@ -220,7 +223,7 @@ def _vg_worker(rank, world, port, q):
         xyz = _vg_cloud()
         lo, hi = shard_bounds(len(xyz), rank, world)
         shard = _NumpyVgShard(xyz[lo:hi], 0.1, 8)
-        n_out, counts, (clo, chi), _ = sharded_voxelgrid_points(shard, lo, rank, world, n_total=len(xyz))
+        n_out, counts, (clo, chi), _, _ = sharded_voxelgrid_points(shard, lo, rank, world, n_total=len(xyz))
         q.put((rank, shard.mm6.tobytes(), clo, chi, shard.received.tobytes(), counts))
     finally:
         dist.destroy_process_group()
@@ -252,3 +255,22 @@ def test_point_sharded_voxelgrid_plan_world2_gloo(oracle):
         mine = xyz[(cid >= r[2]) & (cid < r[3])]
         assert r[4] == mine.tobytes()
     assert res[0][5] == res[1][5] and sum(res[0][5]) == len(xyz)
+
+
+def test_minmax_words_decode_nan_at_point_zero_and_zero_sign():
+    """The reduced words carry everything MinMaxVec3 needs: a NaN at global point 0 is kept (minmax.go:13), other NaNs
+    never win, and the sign of a winning zero is the first occurrence's."""
+    from pcgol_b200.dist import decode_minmax_words
+
+    xyz = np.array([[np.nan, 1.0, 0.0], [2.0, np.nan, -0.0], [-3.0, 5.0, 0.5], [4.0, -2.0, 0.0]], np.float32)
+    words = _NumpyVgShard(xyz, 0.1, 8).minmax_packed(0).numpy()
+    mm = decode_minmax_words(words)
+    assert np.isnan(mm[0]) and np.isnan(mm[3])                 # x: point 0 is NaN -> stays NaN
+    assert mm[1] == -2.0 and mm[4] == 5.0                       # y: the NaN of point 1 takes no part
+    assert mm[2] == 0.0 and not np.signbit(mm[2])               # z min: +0 of point 0 comes first
+    assert mm[5] == 0.5
+    # the same points as two slices whose second starts the zero run with -0: reduced with MIN like the all-reduce
+    a = _NumpyVgShard(xyz[2:3], 0.1, 8).minmax_packed(0).numpy()
+    b = _NumpyVgShard(xyz[1:2], 0.1, 8).minmax_packed(1).numpy()
+    mm = decode_minmax_words(np.minimum(a, b))
+    assert mm[2] == 0.0 and np.signbit(mm[2]) and mm[5] == 0.5  # z: min is the -0 of global point 1

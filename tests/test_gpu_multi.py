@@ -141,7 +141,7 @@ def _worker(rank, world, port, q):
         d_slice = torch.from_numpy(data[slo * stride: shi * stride].copy()).cuda()
         d_pv = torch.empty(len(scan) * stride, dtype=torch.uint8, device="cuda")
         shard = pdist.GpuVgShard(d_slice, shi - slo, stride, off, (0.1, 0.1, 0.1), (32, 32, 32), rank)
-        pm, pcounts, _, _ = pdist.sharded_voxelgrid_points(shard, slo, rank, world, out=d_pv, n_total=len(scan))
+        pm, pcounts, _, _, _ = pdist.sharded_voxelgrid_points(shard, slo, rank, world, out=d_pv, n_total=len(scan))
         pv_bytes = d_pv[: pm * stride].cpu().numpy().tobytes()
         assert pcounts[rank] == pm
         # query sharding: disjoint slices of the same queries, index replicated, no collective
@@ -211,7 +211,7 @@ def test_point_sharded_voxelgrid_single_rank_equals_filter():
         d = torch.from_numpy(data.copy()).cuda()
         out = torch.empty(len(data), dtype=torch.uint8, device="cuda")
         shard = pdist.GpuVgShard(d, len(scan), stride, off, (0.1, 0.1, 0.1), chunk, 0)
-        m, counts, _, _ = pdist.sharded_voxelgrid_points(shard, 0, 0, 1, out=out, n_total=len(scan))
+        m, counts, _, _, _ = pdist.sharded_voxelgrid_points(shard, 0, 0, 1, out=out, n_total=len(scan))
         hdr = pg.PointCloudHeader(fields=["x", "y", "z", "label"], size=[4] * 4, type=["F", "F", "F", "U"],
                                   count=[1] * 4, width=len(scan))
         full = pg.VoxelGrid((0.1, 0.1, 0.1), chunk).filter(pg.PointCloud(hdr, data))
