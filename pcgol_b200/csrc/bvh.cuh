@@ -168,6 +168,114 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
   }
 }
 
+// Warp-packet form of nn_traverse4 for DENSE query batches: the 32 lanes of a warp hold 32 neighbouring queries (the
+// visit list is Hilbert-ordered) and walk the tree TOGETHER - a node is entered when ANY lane still needs it, every lane
+// then tests the node's four children (or the leaf's eight points) against its own query.  Control flow is uniform, so
+// all 32 lanes stay active where the per-lane walk diverges (about 11 of 32 active on config 3); the price is that a
+// lane also steps through nodes only its neighbours need, which pays off exactly when the lanes' search balls overlap
+// (many more queries than points).  Exactness is that of the per-lane walk: every lane compares its own exact box
+// and point distances; the shared decisions only ever ADD nodes (a child is entered if any lane's box distance is
+// within that lane's bound; a deferred child is dropped only if its smallest box distance over the warp exceeds
+// every lane's bound).  `stack` = kMaxStack + 8 words of shared memory owned by the warp.
+template <bool APPROX = false>
+__device__ __forceinline__ void nn_traverse_packet(const IndexView& ix, float qx, float qy, float qz, bool active,
+                                                   uint64_t& best, uint32_t& best_pos, unsigned long long* stack,
+                                                   float min_dist_sq = 0.f) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const float inf = __int_as_float(0x7f800000);
+  active = active && ix.n != 0 && qx == qx && qy == qy && qz == qz;
+  float bestd = __uint_as_float((uint32_t)(best >> 32));
+  if (APPROX && active && bestd < min_dist_sq) active = false;
+  const uint32_t lane = threadIdx.x & 31;
+  int sp = 0;
+  {
+    const float d = active ? box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz) : inf;
+    if (__ballot_sync(kFull, active && d <= bestd) == 0) return;
+  }
+  const uint32_t P = ix.P;
+  uint32_t node = 1;
+  if (P > 1 && (__ffs(P) - 1) & 1) {  // odd depth: one binary step first (see nn_traverse4)
+    const float4* cb = ix.boxes + 4;
+    const float d0 = active ? box_dist_sq(__ldg(cb), __ldg(cb + 1), qx, qy, qz) : inf;
+    const float d1 = active ? box_dist_sq(__ldg(cb + 2), __ldg(cb + 3), qx, qy, qz) : inf;
+    const uint32_t m0 = __reduce_min_sync(kFull, __float_as_uint(d0)), m1 = __reduce_min_sync(kFull, __float_as_uint(d1));
+    const bool w0 = __ballot_sync(kFull, d0 <= bestd) != 0, w1 = __ballot_sync(kFull, d1 <= bestd) != 0;
+    if (!w0 && !w1) return;
+    const bool first0 = w0 && (!w1 || m0 <= m1);
+    if (w0 && w1 && lane == 0) stack[0] = ((unsigned long long)(first0 ? m1 : m0) << 32) | (first0 ? 3u : 2u);
+    if (w0 && w1) sp = 1;
+    node = first0 ? 2u : 3u;
+  }
+  for (;;) {
+    while (node < P) {
+      const float4* cb = ix.boxes + 8 * (size_t)node;  // boxes of nodes 4*node .. 4*node+3
+      uint32_t key[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float d = active ? box_dist_sq(__ldg(cb + 2 * j), __ldg(cb + 2 * j + 1), qx, qy, qz) : inf;
+        const uint32_t m = __reduce_min_sync(kFull, __float_as_uint(d));  // d >= 0: the bits order like the values
+        const bool want = __ballot_sync(kFull, d <= bestd) != 0;
+        key[j] = want ? ((m & ~3u) | (uint32_t)j) : 0xffffffffu;
+      }
+#define PCG_CSWAP(a, b)                 \
+  {                                     \
+    const uint32_t lo_ = min(a, b);     \
+    b = max(a, b);                      \
+    a = lo_;                            \
+  }
+      PCG_CSWAP(key[0], key[1]);
+      PCG_CSWAP(key[2], key[3]);
+      PCG_CSWAP(key[0], key[2]);
+      PCG_CSWAP(key[1], key[3]);
+      PCG_CSWAP(key[1], key[2]);
+#undef PCG_CSWAP
+      if (key[0] == 0xffffffffu) {
+        node = 0;
+        break;
+      }
+#pragma unroll
+      for (int j = 3; j >= 1; j--) {  // farthest first: the nearest of them is popped first
+        if (key[j] != 0xffffffffu) {
+          if (lane == 0) stack[sp] = ((unsigned long long)(key[j] & ~3u) << 32) | (4 * node + (key[j] & 3u));
+          sp++;
+        }
+      }
+      node = 4 * node + (key[0] & 3u);
+    }
+    if (node) {
+      const uint32_t base = (node - P) * kLeaf;
+      const float4* lp = ix.pts + base;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < kLeaf; j++) {
+          const float4 p = __ldg(lp + j);
+          const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
+          const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
+          if (packed < best) {
+            best = packed;
+            best_pos = base + j;
+          }
+        }
+        bestd = __uint_as_float((uint32_t)(best >> 32));
+        if (APPROX && bestd < min_dist_sq) active = false;
+      }
+    }
+    __syncwarp();  // lane 0's pushes are visible to the warp
+    // the largest bound any lane still holds: a deferred child whose smallest box distance exceeds it is dead
+    const uint32_t wmax = __reduce_max_sync(kFull, active ? __float_as_uint(bestd) : 0u);
+    if (__ballot_sync(kFull, active) == 0) return;
+    node = 0;
+    while (sp > 0) {
+      const unsigned long long e = stack[--sp];
+      if ((uint32_t)(e >> 32) <= wmax) {
+        node = (uint32_t)e;
+        break;
+      }
+    }
+    if (!node) break;
+  }
+}
+
 // Visits every point with DistSq < max_range_sq (strict, kdtree.go:167,179) and calls
 // f(original index, DistSq).
 template <typename F>

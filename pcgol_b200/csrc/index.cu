@@ -785,23 +785,30 @@ void query_order_device(const Index& ix, const CloudView& q, uint32_t* d_perm, c
 // its next one: its distance is a valid upper bound to start the next walk with (it is one of the candidates the
 // search would see anyway, so the (DistSq, ID) arg-min is unchanged) and prunes most of the backtracking.
 constexpr int kNnThreads = 128;
-template <bool APPROX>
+template <bool APPROX, bool PACKET>
 __global__ void __launch_bounds__(kNnThreads)
     nearest_kernel(IndexView ix, CloudView q, const uint32_t* __restrict__ perm, int per_thread, float max_range_sq,
                    float min_dist_sq, int32_t* __restrict__ ids, float* __restrict__ dist_sq,
                    pcg_neighbor* __restrict__ aos) {
+  __shared__ unsigned long long s_stack[PACKET ? kNnThreads / 32 : 1][PACKET ? kMaxStack + 8 : 1];
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t first = (t >> 5) * 32 * per_thread + (t & 31);
   const uint64_t init = nn_init(max_range_sq);
   uint32_t warm = 0xffffffffu;
   for (int k = 0; k < per_thread; k++) {
     const int64_t slot = first + (int64_t)k * 32;
-    if (slot >= q.n) return;
-    const int64_t i = perm ? (int64_t)perm[slot] : slot;
-    const float3 p = load_xyz(q, i);
+    if (PACKET) {
+      // the warp walks together: lanes past the end of the list stay in the loop as passengers
+      if (first - (t & 31) + (int64_t)k * 32 >= q.n) return;  // warp-uniform
+    } else if (slot >= q.n) {
+      return;
+    }
+    const bool live = slot < q.n;
+    const int64_t i = live ? (perm ? (int64_t)perm[slot] : slot) : 0;
+    const float3 p = live ? load_xyz(q, i) : make_float3(0.f, 0.f, 0.f);
     uint64_t best = init;
     uint32_t pos = 0;
-    if (warm != 0xffffffffu) {
+    if (live && warm != 0xffffffffu) {
       const float4 c = __ldg(ix.pts + warm);
       const float d = dist_sq_ref(c.x, c.y, c.z, p.x, p.y, p.z);
       const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
@@ -810,8 +817,13 @@ __global__ void __launch_bounds__(kNnThreads)
         pos = warm;
       }
     }
-    if (!(APPROX && best != init && __uint_as_float((uint32_t)(best >> 32)) < min_dist_sq))
+    if (PACKET) {
+      nn_traverse_packet<APPROX>(ix, p.x, p.y, p.z, live, best, pos, s_stack[threadIdx.x >> 5], min_dist_sq);
+      __syncwarp();
+    } else if (!(APPROX && best != init && __uint_as_float((uint32_t)(best >> 32)) < min_dist_sq)) {
       nn_traverse4<APPROX>(ix, p.x, p.y, p.z, best, pos, min_dist_sq);
+    }
+    if (!live) continue;
     const bool hit = best != init;
     if (hit) warm = pos;
     const int32_t id = hit ? (int32_t)(uint32_t)best : -1;
@@ -842,16 +854,29 @@ void nearest_device(const Index& ix, const CloudView& q, float max_range, float 
   }
   // queries per thread: as many as still leave every SM a few thousand threads
   const int per_thread = !perm.p ? 1 : (q.n >= (int64_t)kNumSMs * 2048 * 8 ? 8 : (q.n >= (int64_t)kNumSMs * 2048 * 2 ? 4 : 2));
-  const int blocks = div_up(div_up(q.n, per_thread), kNnThreads);
+  // blocks cover whole warps of `per_thread` runs of 32 queries
+  const int64_t warps = div_up(q.n, 32 * (int64_t)per_thread);
+  const int blocks = div_up(warps * 32, kNnThreads);
+  // dense batches (several ordered queries per indexed point): neighbouring queries need the same nodes, the warp
+  // walks the tree as a packet; sparse ones: one walk per lane
+  const bool packet = perm.p != nullptr && q.n >= 2 * ix.n;
   if (min_dist_sq > 0.f) {  // KDTree.MinDistSq > 0: approximate search (kdtree.go:19-22)
     // a miss keeps DistSq == maxRange^2: capping the threshold there means only a real hit can end the search
     // early (the reference's early miss for maxRange^2 < MinDistSq, kdtree.go:100-106, is not reproduced)
-    PCG_LAUNCH(nearest_kernel<true>, blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq,
-               fminf(min_dist_sq, mrsq), d_ids, d_dist_sq, d_aos);
+    if (packet)
+      PCG_LAUNCH((nearest_kernel<true, true>), blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq,
+                 fminf(min_dist_sq, mrsq), d_ids, d_dist_sq, d_aos);
+    else
+      PCG_LAUNCH((nearest_kernel<true, false>), blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq,
+                 fminf(min_dist_sq, mrsq), d_ids, d_dist_sq, d_aos);
     return;
   }
-  PCG_LAUNCH(nearest_kernel<false>, blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq, 0.f, d_ids,
-             d_dist_sq, d_aos);
+  if (packet)
+    PCG_LAUNCH((nearest_kernel<false, true>), blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq, 0.f,
+               d_ids, d_dist_sq, d_aos);
+  else
+    PCG_LAUNCH((nearest_kernel<false, false>), blocks, kNnThreads, 0, stream, ix.view(), q, perm.p, per_thread, mrsq, 0.f,
+               d_ids, d_dist_sq, d_aos);
 }
 
 // ---- KDTree.Range, batched (kdtree.go:148-197) -----------------------------------------

@@ -77,6 +77,167 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- MinMaxVec3 as a bulk-async pipeline (sm_100a data movement) -----------------------------------------------
+// The scan above issues three 4-byte loads per point and is latency-bound (36 % of the HBM copy rate on the 50M-point
+// map).  Here the records travel global -> shared memory as 1-D bulk copies (cp.async.bulk, the TMA engine without a
+// tensor map; UBLKCP in SASS) into a ring of kMmStages tiles, each completion counted in bytes on an mbarrier; one
+// thread keeps the ring full while all 256 threads reduce the tile that has landed.  Any record layout with 4-byte
+// aligned x/y/z works: a tile is a contiguous run of whole records.
+constexpr int kMmThreads = 256;
+constexpr int kMmTilePoints = 1024;
+constexpr int kMmStages = 4;
+constexpr int kMmMaxStride = 32;  // bytes per record the shared-memory ring is sized for
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kMmThreads)
+    minmax_bulk_kernel(CloudView v, uint32_t index_base, int zero_sign, unsigned long long* __restrict__ out6) {
+  extern __shared__ __align__(128) unsigned char mm_dyn[];
+  __shared__ __align__(8) uint64_t full[kMmStages];
+  __shared__ unsigned long long s_red[kMmThreads / 32][6];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t stride = (uint32_t)v.stride;
+  const uint32_t tile_bytes = kMmTilePoints * stride;
+  const uint32_t n = (uint32_t)v.n;
+  const uint32_t full_tiles = n / kMmTilePoints;
+  unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
+  auto take = [&](float c, int k, uint32_t i) {
+    if (c != c) return;  // NaN never wins a comparison in the reference
+    const unsigned long long o = (unsigned long long)ordered_bits(c) << 32;
+    unsigned long long a, b;
+    if (zero_sign) {
+      const uint32_t g = index_base + i, nz = __float_as_uint(c) == 0x80000000u ? 1u : 0u;
+      a = o | ((g << 1) | nz);
+      b = o | (((0x7fffffffu - g) << 1) | nz);
+    } else {
+      a = o | i;
+      b = o | (0xffffffffu - i);
+    }
+    mn[k] = a < mn[k] ? a : mn[k];
+    mx[k] = b > mx[k] ? b : mx[k];
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kMmStages; s++) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the ring is primed with the first kMmStages of them
+  const uint32_t my_tiles = full_tiles > blockIdx.x ? (full_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (uint32_t j = 0; j < my_tiles && j < (uint32_t)kMmStages; j++) {
+      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)j * gridDim.x;
+      mbar_expect_tx(&full[j], tile_bytes);
+      bulk_g2s(mm_dyn + (size_t)j * tile_bytes, v.data + t * tile_bytes, tile_bytes, &full[j]);
+    }
+  }
+  for (uint32_t j = 0; j < my_tiles; j++) {
+    const uint32_t s = j % kMmStages, parity = (j / kMmStages) & 1u;
+    mbar_wait(&full[s], parity);
+    const unsigned char* tile = mm_dyn + (size_t)s * tile_bytes;
+    const uint32_t first = (blockIdx.x + j * gridDim.x) * kMmTilePoints;
+#pragma unroll
+    for (int q = 0; q < kMmTilePoints / kMmThreads; q++) {
+      const uint32_t p = q * kMmThreads + tid;
+      const unsigned char* r = tile + (size_t)p * stride;
+      take(*reinterpret_cast<const float*>(r + v.off[0]), 0, first + p);
+      take(*reinterpret_cast<const float*>(r + v.off[1]), 1, first + p);
+      take(*reinterpret_cast<const float*>(r + v.off[2]), 2, first + p);
+    }
+    __syncthreads();  // everybody has read the slot: it can be refilled
+    if (tid == 0 && j + kMmStages < my_tiles) {
+      const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)(j + kMmStages) * gridDim.x;
+      mbar_expect_tx(&full[s], tile_bytes);
+      bulk_g2s(mm_dyn + (size_t)s * tile_bytes, v.data + t * tile_bytes, tile_bytes, &full[s]);
+    }
+  }
+  // the points after the last whole tile: plain loads, first CTA
+  if (blockIdx.x == 0) {
+    for (uint32_t i = full_tiles * kMmTilePoints + tid; i < n; i += kMmThreads) {
+      const float3 p = load_xyz(v, i);
+      take(p.x, 0, i);
+      take(p.y, 1, i);
+      take(p.z, 2, i);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const unsigned long long a = shfl_xor_u64(mn[k], d), b = shfl_xor_u64(mx[k], d);
+      mn[k] = a < mn[k] ? a : mn[k];
+      mx[k] = b > mx[k] ? b : mx[k];
+    }
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      s_red[tid >> 5][k] = mn[k];
+      s_red[tid >> 5][3 + k] = mx[k];
+    }
+  }
+  __syncthreads();
+  if (tid < 6) {
+    unsigned long long r = s_red[0][tid];
+    for (int w = 1; w < kMmThreads / 32; w++) {
+      const unsigned long long o = s_red[w][tid];
+      r = tid < 3 ? (o < r ? o : r) : (o > r ? o : r);
+    }
+    if (tid < 3) {
+      if (r != ~0ull) atomicMin(&out6[tid], r);
+    } else {
+      if (r != 0ull) atomicMax(&out6[tid], r);
+    }
+  }
+}
+
+// Launches the bulk-async scan when the layout allows it (4-byte aligned fields, records of up to 32 bytes, 16-byte
+// aligned base), else the plain one.  acc: [3] minima initialised to ~0, [3] maxima initialised to 0.
+static void launch_minmax(const CloudView& v, uint32_t index_base, int zero_sign, unsigned long long* acc,
+                          cudaStream_t stream) {
+  if (v.n <= 0) return;
+  const bool bulk = v.aligned && v.stride <= kMmMaxStride && (((uintptr_t)v.data) & 15) == 0 && v.n >= 64 * kMmTilePoints;
+  if (bulk) {
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    PCG_CUDA(cudaGetDevice(&dev));
+    const size_t smem = (size_t)kMmStages * kMmTilePoints * (size_t)v.stride;
+    if (!(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
+      PCG_CUDA(cudaFuncSetAttribute(minmax_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kMmStages * kMmTilePoints * kMmMaxStride));
+      configured.fetch_or(1ull << dev, std::memory_order_relaxed);
+    }
+    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 2, v.n / kMmTilePoints);
+    PCG_LAUNCH(minmax_bulk_kernel, blocks, kMmThreads, smem, stream, v, index_base, zero_sign, acc);
+  } else {
+    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
+    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, zero_sign, acc);
+  }
+}
+
 __global__ void minmax_finalize_kernel(CloudView v, const unsigned long long* __restrict__ in6,
                                        float* __restrict__ out6) {
   int k = threadIdx.x;
@@ -105,8 +266,7 @@ void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t st
     init[3 + k] = 0ull;
   }
   PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-  int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-  PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, 0u, 0, acc.p);
+  launch_minmax(v, 0u, 0, acc.p, stream);
   PCG_LAUNCH(minmax_finalize_kernel, 1, 32, 0, stream, v, acc.p, res.p);
   float* h = (float*)pinned_scratch();
   PCG_CUDA(cudaMemcpyAsync(h, res.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -175,10 +335,7 @@ __global__ void minmax_shard_words_kernel(CloudView v, int first_slice, const un
 void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream) {
   DevBuf<unsigned long long> acc(6, stream);
   PCG_LAUNCH(minmax_shard_init_kernel, 1, 32, 0, stream, acc.p);
-  if (v.n > 0) {
-    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, 1, acc.p);
-  }
+  launch_minmax(v, index_base, 1, acc.p, stream);
   PCG_LAUNCH(minmax_shard_words_kernel, 1, 32, 0, stream, v, index_base == 0 ? 1 : 0, acc.p, d_out6);
 }
 

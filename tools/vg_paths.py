@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import pcgol_b200 as pg  # noqa: E402
 from pcgol_b200 import _lib, synth  # noqa: E402
 
-NAMES = {1: "lsd", 2: "fused", 3: "partition"}
+NAMES = {0: "auto", 1: "lsd"}
 
 
 def run_dev(vg, d_in, n, stride, off, d_out):
@@ -22,7 +22,7 @@ def run_dev(vg, d_in, n, stride, off, d_out):
     return m, d_out[: m * stride].cpu().numpy().tobytes()
 
 
-def compare(name, data, stride, off, leaf, chunk, paths=(1, 2, 3), oracle=True):
+def compare(name, data, stride, off, leaf, chunk, paths=(1, 0), oracle=True):
     n = len(data) // stride
     d_in = torch.from_numpy(np.frombuffer(data, np.uint8).copy()).cuda()
     d_out = torch.empty(max(1, n * stride), dtype=torch.uint8, device="cuda")
@@ -30,8 +30,6 @@ def compare(name, data, stride, off, leaf, chunk, paths=(1, 2, 3), oracle=True):
     ref = None
     res = {}
     for p in paths:
-        if p == 2 and n > 1_200_000:
-            continue
         _lib.set_vg_path(p)
         try:
             m, b = run_dev(vg, d_in, n, stride, off, d_out)
@@ -55,8 +53,6 @@ def timing(name, xyz, leaf, chunk, paths, reps=10):
     d_out = torch.empty(n * 12, dtype=torch.uint8, device="cuda")
     vg = pg.VoxelGrid(leaf, chunk)
     for p in paths:
-        if p == 2 and n > 1_200_000:
-            continue
         _lib.set_vg_path(p)
         for _ in range(3):
             vg.filter_dev(d_in.data_ptr(), n, 12, (0, 4, 8), d_out.data_ptr())
@@ -103,13 +99,13 @@ def main():
     if not a.no_compare:
         compare("scan 1M xyz chunk 128", scan1m.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), oracle=False)
         compare("scan 1M xyz leaf 1mm (u64 keys)", scan1m.tobytes(), 12, (0, 4, 8), (0.001, 0.001, 0.001), (128, 128, 128),
-                paths=(1, 3), oracle=False)
-    timing("1M", scan1m, leaf, (128, 128, 128), (2, 1, 3))
+                paths=(1, 0), oracle=False)
+    timing("1M", scan1m, leaf, (128, 128, 128), (0, 1))
     if a.big:
         big = synth.tiled_map(a.big[0], a.big[1])
         if not a.no_compare:
-            compare(f"map {len(big)}", big.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), paths=(1, 3), oracle=False)
-        timing(f"map{len(big) // 1000000}M", big, leaf, (128, 128, 128), (1, 3), reps=5)
+            compare(f"map {len(big)}", big.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), paths=(1, 0), oracle=False)
+        timing(f"map{len(big) // 1000000}M", big, leaf, (128, 128, 128), (1,), reps=5)
 
 
 if __name__ == "__main__":
