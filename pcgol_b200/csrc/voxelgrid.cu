@@ -230,7 +230,7 @@ static void launch_minmax(const CloudView& v, uint32_t index_base, int zero_sign
                                     kMmStages * kMmTilePoints * kMmMaxStride));
       configured.fetch_or(1ull << dev, std::memory_order_relaxed);
     }
-    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 2, v.n / kMmTilePoints);
+    const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, v.n / kMmTilePoints);
     PCG_LAUNCH(minmax_bulk_kernel, blocks, kMmThreads, smem, stream, v, index_base, zero_sign, acc);
   } else {
     const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
@@ -626,6 +626,13 @@ constexpr int kParts = kThreads / (rsort::kRadix / 4);  // groups of 64 threads 
 constexpr int kIptSmall = 2048 / kThreads;         // tile of 2048 points (clouds up to 148 * 2048)
 constexpr int kIptLarge = 8192 / kThreads;         // tile of 8192 points
 
+template <int IPT>
+__host__ __device__ constexpr size_t dyn_smem_bytes() {
+  // max(sort staging 12 B, reduce staging (8 + 12) B with one pad slot per IPT positions) per position,
+  // + 2 B per position for the compacted list of voxel heads
+  return (size_t)(kThreads * IPT + kThreads) * 20 + (size_t)kThreads * IPT * 2;
+}
+
 struct Work {
   unsigned long long* acc;  // [6]: ~min / max packed (value bits, index), reduced with atomicMax; zero-initialised
   uint32_t* counts;         // [tiles][256]
@@ -678,6 +685,8 @@ struct Smem {
   uint32_t prefix;
   __align__(16) uint32_t part[kParts][2][rsort::kRadix];  // [part][total|prefix][digit]
   float mm[6];
+  __align__(8) uint64_t tile_bar;  // bulk copy of the tile's records into shared memory (phase 0)
+  int tile_in_smem;
   // the tile's last voxel when it runs on into the next tile(s): finished by warp 0 with parallel loads
   struct {
     unsigned long long key, rank;
@@ -718,7 +727,15 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       const uint32_t pos = warp_base + i * 32 + lane;
       unsigned long long k = ~0ull;
       if (pos < n) {
-        const float3 pt = load_xyz(v, pos);
+        float3 pt;
+        if (sm.tile_in_smem) {
+          const unsigned char* r = dyn + dyn_smem_bytes<IPT>() - (size_t)kTile * (size_t)v.stride +
+                                   (size_t)(pos - tile_base) * (size_t)v.stride;
+          pt = make_float3(*reinterpret_cast<const float*>(r + v.off[0]), *reinterpret_cast<const float*>(r + v.off[1]),
+                           *reinterpret_cast<const float*>(r + v.off[2]));
+        } else {
+          pt = load_xyz(v, pos);
+        }
         w.xyz4[pos] = make_float4(pt.x, pt.y, pt.z, 0.f);
         if (!voxel_key_fast(C, pt, &k)) {
           general = true;
@@ -1108,12 +1125,37 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
   }
 #endif
   PCG_VG_STAMP();  // start
+  // The tile's records arrive in shared memory as ONE bulk copy (cp.async.bulk, completion counted on an mbarrier):
+  // min/max and the key arithmetic then read them from there instead of issuing three 4-byte global loads per point
+  // twice.  The tile sits at the END of the dynamic buffer (the key parking area of phase 1 uses its start).  Needs
+  // whole tiles of 4-byte aligned records that fit beside the parking area; otherwise the plain loads.
+  const uint32_t tile_bytes = (uint32_t)kTile * (uint32_t)v.stride;
+  unsigned char* s_tile = dyn + dyn_smem_bytes<IPT>() - tile_bytes;
+  if (tid == 0) {
+    const bool ok = v.aligned && (((uintptr_t)v.data) & 15) == 0 && tile_base + (uint32_t)kTile <= n &&
+                    (size_t)tile_bytes + (size_t)kTile * 8 <= dyn_smem_bytes<IPT>();
+    sm.tile_in_smem = ok ? 1 : 0;
+    if (ok) {
+      mbar_init(&sm.tile_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&sm.tile_bar, tile_bytes);
+      bulk_g2s(s_tile, v.data + (size_t)tile_base * (size_t)v.stride, tile_bytes, &sm.tile_bar);
+    }
+  }
+  __syncthreads();
+  const bool tile_in_smem = sm.tile_in_smem != 0;
+  if (tile_in_smem) mbar_wait(&sm.tile_bar, 0);
+  auto tile_xyz = [&](uint32_t local) {
+    const unsigned char* r = s_tile + (size_t)local * (size_t)v.stride;
+    return make_float3(*reinterpret_cast<const float*>(r + v.off[0]), *reinterpret_cast<const float*>(r + v.off[1]),
+                       *reinterpret_cast<const float*>(r + v.off[2]));
+  };
   // ---- phase 0: MinMaxVec3 (pc/minmax.go:9-26), first occurrence wins (see minmax_kernel)
   unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
   for (int i = 0; i < IPT; i++) {
     const uint32_t pos = tile_base + i * kThreads + tid;
     if (pos < n) {
-      const float3 p = load_xyz(v, pos);
+      const float3 p = tile_in_smem ? tile_xyz(i * kThreads + tid) : load_xyz(v, pos);
       const float c[3] = {p.x, p.y, p.z};
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -1186,13 +1228,6 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
     run<uint32_t, IPT>(v, w, out, sm, dyn, grid);
   else
     run<unsigned long long, IPT>(v, w, out, sm, dyn, grid);
-}
-
-template <int IPT>
-constexpr size_t dyn_smem_bytes() {
-  // max(sort staging 12 B, reduce staging (8 + 12) B with one pad slot per IPT positions) per position,
-  // + 2 B per position for the compacted list of voxel heads
-  return (size_t)(kThreads * IPT + kThreads) * 20 + (size_t)kThreads * IPT * 2;
 }
 
 }  // namespace fused
