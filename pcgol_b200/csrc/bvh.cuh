@@ -42,9 +42,13 @@ struct IndexView {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float box_dist_sq(const float4 lo, const float4 hi, float qx, float qy, float qz) {
-  float ex = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.0f);
-  float ey = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.0f);
-  float ez = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.0f);
+  // per axis: the query minus its clamp into [lo, hi] (exact selection), ONE rounded subtraction - the same rounded
+  // operation the reference applies to (point - query), and |q - clamp(q)| <= |q - p| for every p in the box, so by
+  // monotonicity of the rounding the bound never exceeds the reference distance of a point inside.  An empty box
+  // (lo = +inf, hi = -inf) clamps to -inf: distance +inf.
+  const float ex = __fsub_rn(qx, fminf(fmaxf(qx, lo.x), hi.x));
+  const float ey = __fsub_rn(qy, fminf(fmaxf(qy, lo.y), hi.y));
+  const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo.z), hi.z));
   return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
 }
 
