@@ -295,11 +295,23 @@ const (
 	WithHessian Mode = C.PCG_ICP_WITH_HESSIAN // OR-ed in: Evaluate also fills Evaluated.Hessian
 )
 
-// PointToPointEvaluator implements icp.Evaluator (evaluator.go:32-36,69-189) with the default weight function.
+// WeightFn selects one of the parametric weight functions the device can evaluate (pcg_weight_fn): the reference's
+// EvaluateWeightFn (evaluator.go:19-23,72) is a closure, which cannot cross the boundary.
+type WeightFn int32
+
+const (
+	WeightConstant  WeightFn = C.PCG_WEIGHT_CONSTANT  // DefaultEvaluateWeightFn: w = 1
+	WeightTruncated WeightFn = C.PCG_WEIGHT_TRUNCATED // w = dsq < WeightParam ? 1 : 0
+	WeightHuber     WeightFn = C.PCG_WEIGHT_HUBER     // w = dsq <= WeightParam ? 1 : sqrt(WeightParam/dsq)
+)
+
+// PointToPointEvaluator implements icp.Evaluator (evaluator.go:32-36,69-189).
 type PointToPointEvaluator struct {
 	Corresponder *NearestPointCorresponder
 	MinPairs     int
 	Mode         Mode
+	WeightFn     WeightFn // zero value = the reference's default weight function
+	WeightParam  float32  // a squared distance (threshold / Huber k^2)
 }
 
 func (PointToPointEvaluator) HasGradient() bool  { return true }
@@ -330,6 +342,8 @@ func (e *PointToPointEvaluator) Evaluate(base storage.Search, target pc.Vec3Rand
 	prm.min_pairs = C.int32_t(e.MinPairs)
 	prm.mode = C.int32_t(e.Mode)
 	prm.min_dist_sq = C.float(idx.MinDistSq)
+	prm.weight_fn = C.int32_t(e.WeightFn)
+	prm.weight_param = C.float(e.WeightParam)
 	s := C.pcg_icp_evaluate_params(idx.h, p, n, stride, &off[0], &prm, &ev, &np)
 	runtime.KeepAlive(keep)
 	if err := statusError(s); err != nil {
@@ -359,6 +373,8 @@ func (r *PointToPointICPGradient) Fit(base storage.Search, target pc.Vec3RandomA
 	prm.min_pairs = C.int32_t(r.Evaluator.MinPairs)
 	prm.mode = C.int32_t(r.Evaluator.Mode)
 	prm.min_dist_sq = C.float(idx.MinDistSq)
+	prm.weight_fn = C.int32_t(r.Evaluator.WeightFn)
+	prm.weight_param = C.float(r.Evaluator.WeightParam)
 	if r.GaussNewton {
 		prm.updater = C.PCG_UPDATER_GAUSS_NEWTON
 	}
@@ -403,6 +419,8 @@ func (r *PointToPointICPGradient) FitMulti(bases []*Index, target pc.Vec3RandomA
 	prm.max_dist = C.float(r.Evaluator.Corresponder.MaxDist)
 	prm.min_pairs = C.int32_t(r.Evaluator.MinPairs)
 	prm.mode = C.PCG_ICP_FAST
+	prm.weight_fn = C.int32_t(r.Evaluator.WeightFn)
+	prm.weight_param = C.float(r.Evaluator.WeightParam)
 	if f := r.UpdaterFactory; f != nil {
 		for i := 0; i < 6; i++ {
 			prm.weight[i] = C.float(f.Weight[i])

@@ -40,7 +40,7 @@ extern "C" {
 
 /* 2: pcg_icp_params gained min_dist_sq + updater (appended); DeletePoint, MinDistSq search, Hessian,
  *    region growing and PCD entry points added. */
-#define PCGOL_B200_ABI_VERSION 2
+#define PCGOL_B200_ABI_VERSION 3
 
 typedef int32_t pcg_status;
 enum {
@@ -333,7 +333,19 @@ typedef struct pcg_icp_params {
   float min_dist_sq;     /* KDTree.MinDistSq of the base search (kdtree.go:19-22); 0 = exact.  The reference's own
                           * ICP test and benchmark set 0.01 (icp_test.go:58,118-120). */
   int32_t updater;       /* PCG_UPDATER_GRADIENT_DESCENT | PCG_UPDATER_GAUSS_NEWTON */
+  /* ABI 3 */
+  int32_t weight_fn;     /* PointToPointEvaluator.WeightFn (evaluator.go:19-23,72), see pcg_weight_fn; 0 = default */
+  float weight_param;    /* threshold of PCG_WEIGHT_TRUNCATED / k^2 of PCG_WEIGHT_HUBER (a squared distance) */
 } pcg_icp_params;
+
+/* EvaluateWeightFn is a Go closure in the reference (evaluator.go:19); a closure cannot run on the device, so the ABI
+ * offers the family real callers use, evaluated per pair in float32 with every operation rounded:
+ *   PCG_WEIGHT_CONSTANT   w = 1                                 DefaultEvaluateWeightFn (evaluator.go:21-23)
+ *   PCG_WEIGHT_TRUNCATED  w = dsq < param ? 1 : 0               hard rejection of far pairs (they still count as pairs)
+ *   PCG_WEIGHT_HUBER      w = dsq <= param ? 1 : sqrt(param / dsq)   Huber weight with k^2 = param
+ * The weight multiplies every term exactly as evaluator.go:130-144 does (Value += w*dsq, SumW += w, G += w*...).
+ * The Hessian extension (PCG_ICP_WITH_HESSIAN / Gauss-Newton) needs PCG_WEIGHT_CONSTANT. */
+typedef enum pcg_weight_fn { PCG_WEIGHT_CONSTANT = 0, PCG_WEIGHT_TRUNCATED = 1, PCG_WEIGHT_HUBER = 2 } pcg_weight_fn;
 
 /* icp.Evaluated (evaluator.go:25-30).  The reference never writes Hessian (HasHessian() == false,
  * evaluator.go:76): it is zero unless PCG_ICP_WITH_HESSIAN / PCG_UPDATER_GAUSS_NEWTON is selected.

@@ -263,6 +263,9 @@ struct PointToPointEvaluator {  // evaluator.go:69-189
   NearestPointCorresponder Corresponder;
   int MinPairs = 0;
   int Mode = PCG_ICP_STRICT;  // | PCG_ICP_WITH_HESSIAN to fill Evaluated.Hessian
+  // PointToPointEvaluator.WeightFn (evaluator.go:19-23,72) is a closure in the reference; here one of pcg_weight_fn
+  int WeightFn = PCG_WEIGHT_CONSTANT;
+  float WeightParam = 0.f;
   bool HasGradient() const { return true; }
   bool HasHessian() const { return (Mode & PCG_ICP_WITH_HESSIAN) != 0; }  // false like evaluator.go:76 by default
   Evaluated Evaluate(const storage::Index& base, const pc::View& target) const {
@@ -274,6 +277,8 @@ struct PointToPointEvaluator {  // evaluator.go:69-189
     p.min_pairs = MinPairs;
     p.mode = Mode;
     p.min_dist_sq = base.MinDistSq;
+    p.weight_fn = WeightFn;
+    p.weight_param = WeightParam;
     pcg_status s = pcg_icp_evaluate_params(base.handle(), target.data, target.n, target.stride, target.off.data(), &p,
                                            &ev, &np);
     if (s == PCG_E_NOT_ENOUGH_PAIRS) throw ErrNotEnoughPairs();
@@ -309,6 +314,8 @@ struct PointToPointICPGradient {  // icp.go:18-67
     p.mode = Evaluator.Mode;
     p.updater = UpdaterFactory.Kind;
     p.min_dist_sq = base.MinDistSq;
+    p.weight_fn = Evaluator.WeightFn;
+    p.weight_param = Evaluator.WeightParam;
     mat::Mat4 trans{};
     pcg_icp_stat st;
     pcg_status s = pcg_icp_fit(base.handle(), target.data, target.n, target.stride, target.off.data(), &p,

@@ -69,6 +69,9 @@ def lib():
         _lib.orc_icp_evaluate.restype = C.c_int32
         _lib.orc_icp_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]
+        _lib.orc_icp_evaluate_w.restype = C.c_int32
+        _lib.orc_icp_evaluate_w.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_float, C.c_void_p, C.c_void_p]
         _lib.orc_icp_update.restype = C.c_int32
         _lib.orc_icp_update.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         _lib.orc_icp_fit.restype = C.c_int32
@@ -109,10 +112,13 @@ class IcpParams(C.Structure):
         ("threshold", C.c_float * 6),
         ("max_iteration", C.c_int32),
         ("f64_accumulate", C.c_int32),
+        ("weight_fn", C.c_int32),     # EvaluateWeightFn family: 0 constant (default), 1 truncated, 2 Huber
+        ("weight_param", C.c_float),
     ]
 
 
-def icp_params(max_dist, min_pairs=0, weight=None, threshold=None, max_iteration=0, f64_accumulate=False) -> IcpParams:
+def icp_params(max_dist, min_pairs=0, weight=None, threshold=None, max_iteration=0, f64_accumulate=False,
+               weight_fn=0, weight_param=0.0) -> IcpParams:
     p = IcpParams()
     p.max_dist = max_dist
     p.min_pairs = min_pairs
@@ -121,6 +127,8 @@ def icp_params(max_dist, min_pairs=0, weight=None, threshold=None, max_iteration
         p.threshold[k] = 0.0 if threshold is None else threshold[k]
     p.max_iteration = max_iteration
     p.f64_accumulate = 1 if f64_accumulate else 0
+    p.weight_fn = weight_fn
+    p.weight_param = weight_param
     return p
 
 
@@ -225,13 +233,14 @@ def icp_pairs(base: Search, target, max_dist: float):
     return b[:n].copy(), ti[:n].copy(), d[:n].copy()
 
 
-def icp_evaluate(base: Search, target, max_dist: float, min_pairs: int = 0, f64_accumulate: bool = False):
+def icp_evaluate(base: Search, target, max_dist: float, min_pairs: int = 0, f64_accumulate: bool = False,
+                 weight_fn: int = 0, weight_param: float = 0.0):
     """Returns (status, ev8={Value, Gradient[6], DistRMS}, n_pairs)."""
     t = _f32(target).reshape(-1, 3)
     out = np.zeros(8, np.float32)
     npairs = C.c_int64(0)
-    rc = lib().orc_icp_evaluate(base._h, _p(t), len(t), max_dist, min_pairs, 1 if f64_accumulate else 0, _p(out),
-                                C.byref(npairs))
+    rc = lib().orc_icp_evaluate_w(base._h, _p(t), len(t), max_dist, min_pairs, 1 if f64_accumulate else 0,
+                                  weight_fn, weight_param, _p(out), C.byref(npairs))
     return rc, out, npairs.value
 
 

@@ -719,10 +719,25 @@ struct Evaluated {  // evaluator.go:25-30 (Hessian is never written by the refer
   float dist_rms;
 };
 
-// evaluator.go:91-189 with the default weight function (w = 1, evaluator.go:21-23)
+// EvaluateWeightFn (evaluator.go:19-23,72): a Go closure in the reference; here the parametric family the C ABI
+// offers (pcg_weight_fn), every operation a rounded float32 one.  0 = DefaultEvaluateWeightFn (w = 1).
+enum { ORC_WEIGHT_CONSTANT = 0, ORC_WEIGHT_TRUNCATED = 1, ORC_WEIGHT_HUBER = 2 };
+static float eval_weight(int fn, float param, float dsq) {
+  switch (fn) {
+    case ORC_WEIGHT_TRUNCATED: return dsq < param ? 1.0f : 0.0f;
+    case ORC_WEIGHT_HUBER: {
+      if (dsq <= param) return 1.0f;
+      float q = param / dsq;  // float32 division, then the correctly rounded float32 square root
+      return std::sqrt(q);
+    }
+    default: return 1.0f;
+  }
+}
+
+// evaluator.go:91-189; weight_fn = 0 is the default weight function (w = 1, evaluator.go:21-23)
 template <typename Acc>
 int icp_evaluate_t(const Search& base, const float* target, int64_t n, float max_dist, int min_pairs,
-                   Evaluated* out, int64_t* n_pairs) {
+                   Evaluated* out, int64_t* n_pairs, int weight_fn = 0, float weight_param = 0.f) {
   if (min_pairs == 0) min_pairs = 6;
   static thread_local std::vector<Pair> pairs;
   icp_pairs(base, target, n, max_dist, pairs);
@@ -733,7 +748,7 @@ int icp_evaluate_t(const Search& base, const float* target, int64_t n, float max
   for (const Pair& pr : pairs) {
     Vec3 pb = base.at(pr.base_id);
     Vec3 pt{{target[3 * pr.target_id], target[3 * pr.target_id + 1], target[3 * pr.target_id + 2]}};
-    float w = 1;
+    float w = eval_weight(weight_fn, weight_param, pr.dsq);  // evaluator.go:130
     value += w * pr.dsq;
     sum_weight += w;
     float x0 = pt[0], y0 = pt[1], z0 = pt[2];
@@ -789,6 +804,8 @@ struct IcpParams {
   float threshold[6];  // .Threshold, all-zero -> 0.01   updater.go:16,28-30
   int32_t max_iteration;  // .MaxIteration, 0 -> 20   updater.go:31-33
   int32_t f64_accumulate;  // oracle-only: accumulate the 9 sums in float64 (error budgeting)
+  int32_t weight_fn;       // EvaluateWeightFn family (evaluator.go:19-23): 0 constant, 1 truncated, 2 Huber
+  float weight_param;
 };
 
 struct IcpStat {  // stat.go:3-6
@@ -848,8 +865,10 @@ int icp_fit(const Search& base, const float* target, int64_t n, const IcpParams&
   for (;;) {
     Evaluated ev;
     int rc = prm.f64_accumulate
-                 ? icp_evaluate_t<double>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr)
-                 : icp_evaluate_t<float>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr);
+                 ? icp_evaluate_t<double>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr, prm.weight_fn,
+                                          prm.weight_param)
+                 : icp_evaluate_t<float>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr, prm.weight_fn,
+                                         prm.weight_param);
     stat->num_iteration++;
     if (rc != ORC_OK) {
       *trans_out = trans;
@@ -944,8 +963,10 @@ int icp_fit_gn(const Search& base, const float* target, int64_t n, const IcpPara
   for (;;) {
     Evaluated ev;
     int rc = prm.f64_accumulate
-                 ? icp_evaluate_t<double>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr)
-                 : icp_evaluate_t<float>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr);
+                 ? icp_evaluate_t<double>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr, prm.weight_fn,
+                                          prm.weight_param)
+                 : icp_evaluate_t<float>(base, tt.data(), n, prm.max_dist, prm.min_pairs, &ev, nullptr, prm.weight_fn,
+                                         prm.weight_param);
     stat->num_iteration++;
     if (rc != ORC_OK) {
       *trans_out = trans;
@@ -1170,6 +1191,22 @@ int64_t orc_icp_pairs(void* base, const float* target, int64_t n, float max_dist
 }
 
 // PointToPointEvaluator.Evaluate; out8 = {Value, Gradient[6], DistRMS}
+int32_t orc_icp_evaluate_w(void* base, const float* target, int64_t n, float max_dist, int32_t min_pairs,
+                           int32_t f64_accumulate, int32_t weight_fn, float weight_param, float* out8,
+                           int64_t* n_pairs) {
+  Evaluated ev{};
+  int rc = f64_accumulate ? icp_evaluate_t<double>(*static_cast<Search*>(base), target, n, max_dist, min_pairs, &ev,
+                                                   n_pairs, weight_fn, weight_param)
+                          : icp_evaluate_t<float>(*static_cast<Search*>(base), target, n, max_dist, min_pairs, &ev,
+                                                  n_pairs, weight_fn, weight_param);
+  if (rc == ORC_OK) {
+    out8[0] = ev.value;
+    for (int i = 0; i < 6; i++) out8[1 + i] = ev.gradient[i];
+    out8[7] = ev.dist_rms;
+  }
+  return rc;
+}
+
 int32_t orc_icp_evaluate(void* base, const float* target, int64_t n, float max_dist, int32_t min_pairs,
                          int32_t f64_accumulate, float* out8, int64_t* n_pairs) {
   Evaluated ev{};

@@ -45,6 +45,9 @@ class Neighbor(C.Structure):
     _fields_ = [("id", C.c_int64), ("dist_sq", C.c_float), ("pad_", C.c_uint32)]
 
 
+WEIGHT_CONSTANT, WEIGHT_TRUNCATED, WEIGHT_HUBER = 0, 1, 2
+
+
 class IcpParams(C.Structure):
     _fields_ = [
         ("max_dist", C.c_float),
@@ -55,6 +58,8 @@ class IcpParams(C.Structure):
         ("mode", C.c_int32),
         ("min_dist_sq", C.c_float),  # ABI 2: KDTree.MinDistSq of the base search (kdtree.go:19-22)
         ("updater", C.c_int32),      # ABI 2: UPDATER_GRADIENT_DESCENT | UPDATER_GAUSS_NEWTON
+        ("weight_fn", C.c_int32),    # ABI 3: EvaluateWeightFn family (evaluator.go:19-23): WEIGHT_CONSTANT | _TRUNCATED | _HUBER
+        ("weight_param", C.c_float),
     ]
 
 

@@ -42,7 +42,9 @@ struct IcpState {
   float sums[12];        // the nine accumulators of the current Evaluate (strict replay, one CTA each)
   // normal equations (never read unless want_hessian / Gauss-Newton)
   int32_t want_hessian;
-  int32_t pad_;
+  int32_t weight_fn;      // pcg_weight_fn (EvaluateWeightFn family, evaluator.go:19-23)
+  float weight_param;
+  float pad_;
   double hsum[9];        // sum x,y,z,xx,xy,xz,yy,yz,zz of the matched, transformed target points
   float hess[36];        // Evaluated.Hessian of the last Evaluate
 };
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(THREADS)
   const int tid = threadIdx.x;
   if (tid < 16) s_m[tid] = st->trans.m[tid];
   if (tid == 0) s_first = st->num_iteration == 0;
+  const int weight_fn = st->weight_fn;
+  const float weight_param = st->weight_param;
   __syncthreads();
   const int64_t slot = (int64_t)blockIdx.x * THREADS + tid;
   float t[kTerms];
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(THREADS)
       const float4 pb = __ldg(base.pts + pos);
       const float x1 = pb.x, y1 = pb.y, z1 = pb.z;
       const float dsq = __uint_as_float((uint32_t)(best >> 32));
-      // evaluator.go:130-144 with w = 1 (DefaultEvaluateWeightFn): w*v == v exactly
+      // evaluator.go:130-144; with w = 1 (DefaultEvaluateWeightFn) w*v == v exactly
       t[0] = dsq;
       t[1] = 1.f;
       t[2] = im::sub(x0, x1);
@@ -169,6 +173,17 @@ __global__ void __launch_bounds__(THREADS)
       t[6] = im::sub(im::mul(x0, z1), im::mul(z0, x1));
       t[7] = im::sub(im::mul(y0, x1), im::mul(x0, y1));
       t[8] = im::add(im::add(im::mul(x0, x0), im::mul(y0, y0)), im::mul(z0, z0));
+      if (weight_fn != PCG_WEIGHT_CONSTANT) {  // the parametric EvaluateWeightFn family (pcg_weight_fn)
+        float w;
+        if (weight_fn == PCG_WEIGHT_TRUNCATED)
+          w = dsq < weight_param ? 1.f : 0.f;
+        else
+          w = dsq <= weight_param ? 1.f : __fsqrt_rn(im::div(weight_param, dsq));
+        t[1] = w;
+#pragma unroll
+        for (int k = 0; k < kTerms; k++)
+          if (k != 1) t[k] = im::mul(w, t[k]);
+      }
       if (HESS) {
         ht[0] = x0;
         ht[1] = y0;
@@ -745,6 +760,8 @@ static IcpState make_state(const pcg_icp_params& prm, bool evaluate_only) {
   h.min_pairs = prm.min_pairs == 0 ? 6 : prm.min_pairs;  // evaluator.go:92-95
   h.evaluate_only = evaluate_only ? 1 : 0;
   h.want_hessian = ((prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON) ? 1 : 0;
+  h.weight_fn = prm.weight_fn;
+  h.weight_param = prm.weight_param;
   return h;
 }
 
@@ -754,6 +771,12 @@ static void check_icp_params(const pcg_icp_params& prm) {
   if (prm.updater != PCG_UPDATER_GRADIENT_DESCENT && prm.updater != PCG_UPDATER_GAUSS_NEWTON)
     throw StatusError{PCG_E_INVALID_ARG, "unknown ICP updater"};
   if (!(prm.min_dist_sq >= 0.f)) throw StatusError{PCG_E_INVALID_ARG, "MinDistSq must be >= 0"};
+  if (prm.weight_fn < PCG_WEIGHT_CONSTANT || prm.weight_fn > PCG_WEIGHT_HUBER)
+    throw StatusError{PCG_E_INVALID_ARG, "unknown weight function"};
+  if (prm.weight_fn != PCG_WEIGHT_CONSTANT && !(prm.weight_param > 0.f))
+    throw StatusError{PCG_E_INVALID_ARG, "the weight function's parameter (a squared distance) must be > 0"};
+  if (prm.weight_fn != PCG_WEIGHT_CONSTANT && ((prm.mode & PCG_ICP_WITH_HESSIAN) || prm.updater == PCG_UPDATER_GAUSS_NEWTON))
+    throw StatusError{PCG_E_INVALID_ARG, "the Hessian extension needs the constant weight function"};
 }
 
 // One launch of the fused correspondence + terms kernel for the (mode, MinDistSq, Hessian) combination.

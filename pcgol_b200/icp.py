@@ -70,11 +70,18 @@ class NearestPointCorresponder:
         return b[: m.value].copy(), t[: m.value].copy(), d[: m.value].copy()
 
 
+WEIGHT_CONSTANT, WEIGHT_TRUNCATED, WEIGHT_HUBER = _lib.WEIGHT_CONSTANT, _lib.WEIGHT_TRUNCATED, _lib.WEIGHT_HUBER
+
+
 @dataclass
 class PointToPointEvaluator:
     corresponder: NearestPointCorresponder
     min_pairs: int = 0
     mode: int = STRICT
+    #: PointToPointEvaluator.WeightFn (evaluator.go:19-23,72): a closure in Go, here one of the parametric family
+    #: WEIGHT_CONSTANT (the default, w = 1) | WEIGHT_TRUNCATED (w = dsq < param) | WEIGHT_HUBER (k^2 = param)
+    weight_fn: int = WEIGHT_CONSTANT
+    weight_param: float = 0.0
 
     def has_gradient(self) -> bool:
         return True
@@ -125,6 +132,8 @@ def _params(evaluator: PointToPointEvaluator, uf, base: Optional[Index] = None) 
     p.max_iteration = uf.max_iteration
     p.mode = evaluator.mode
     p.updater = uf.kind
+    p.weight_fn = evaluator.weight_fn
+    p.weight_param = evaluator.weight_param
     # the base search's own MinDistSq applies to the correspondences, as with a *kdtree.KDTree in the reference
     p.min_dist_sq = getattr(base, "min_dist_sq", 0.0) if base is not None else 0.0
     return p

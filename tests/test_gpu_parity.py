@@ -386,6 +386,49 @@ def test_icp_fast_mode_config1_within_1e5_of_reference_order(pg, oracle, synth):
     np.testing.assert_allclose(ftrans, etrans, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("fn,param", [("truncated", 0.04), ("huber", 0.01), ("huber", 0.25)])
+def test_icp_weight_function_family_bit_exact(pg, oracle, synth, fn, param):
+    """PointToPointEvaluator.WeightFn (evaluator.go:19-23,72) is a Go closure; the C ABI offers a parametric family.
+    The weight multiplies every term exactly as evaluator.go:130-144 does, so strict mode must reproduce the
+    sequential float32 restatement bit for bit: one Evaluate and a whole Fit."""
+    from pcgol_b200 import icp as picp
+
+    code = {"truncated": picp.WEIGHT_TRUNCATED, "huber": picp.WEIGHT_HUBER}[fn]
+    ocode = {"truncated": 1, "huber": 2}[fn]
+    base, target = synth.icp_pair(seed=5, n=20000, n_az=400)
+    idx = pg.Index(base)
+    e = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), weight_fn=code, weight_param=param)
+    ev = e.evaluate(idx, target)
+    search = oracle.Search(base, "kdtree")
+    rc, oev, _ = oracle.icp_evaluate(search, target, 1.0, 0, weight_fn=ocode, weight_param=param)
+    got = np.concatenate([[ev.value], ev.gradient, [ev.dist_rms]]).astype(f32)
+    assert rc == oracle.OK and got.tobytes() == oev.tobytes()
+    rc1, plain, _ = oracle.icp_evaluate(search, target, 1.0, 0)
+    assert plain.tobytes() != oev.tobytes()  # the weights do something on this pair
+    trans, stat = pg.PointToPointICPGradient(e).fit(idx, target)
+    rc, etrans, eev, eit = oracle.icp_fit(search, target, oracle.icp_params(1.0, weight_fn=ocode, weight_param=param))
+    assert rc == oracle.OK and stat.num_iteration == eit
+    assert trans.tobytes() == etrans.tobytes()
+    # fast mode: float64 tree sums of the same weighted terms
+    ef = pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), mode=pg.FAST, weight_fn=code, weight_param=param)
+    evf = ef.evaluate(idx, target)
+    rc, oev64, _ = oracle.icp_evaluate(search, target, 1.0, 0, f64_accumulate=True, weight_fn=ocode, weight_param=param)
+    gotf = np.concatenate([[evf.value], evf.gradient, [evf.dist_rms]]).astype(np.float64)
+    np.testing.assert_allclose(gotf, oev64.astype(np.float64), rtol=1e-6, atol=1e-7)
+
+
+def test_icp_weight_function_rejects_bad_combinations(pg, synth):
+    from pcgol_b200 import icp as picp
+
+    base, target = synth.icp_pair(seed=5, n=2000, n_az=200)
+    idx = pg.Index(base)
+    for kw in (dict(weight_fn=7, weight_param=1.0), dict(weight_fn=picp.WEIGHT_HUBER, weight_param=0.0),
+               dict(weight_fn=picp.WEIGHT_HUBER, weight_param=0.1, mode=pg.FAST | pg.WITH_HESSIAN)):
+        with pytest.raises(pg.PcgError) as ei:
+            pg.PointToPointICPGradient(pg.PointToPointEvaluator(pg.NearestPointCorresponder(1.0), **kw)).fit(idx, target)
+        assert ei.value.status == pg.E_INVALID_ARG
+
+
 def test_icp_fit_pairs_farm_matches_single(pg, synth):
     import torch
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(_lib.lib, s), f"libpcgol_b200.so does not export {s}"
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
-    assert _lib.lib.pcg_abi_version() == 2
+    assert _lib.lib.pcg_abi_version() == 3
 
 
 def test_neighbor_layout_matches_go():
