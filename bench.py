@@ -641,8 +641,8 @@ def bench_config5(pg, torch, dist, rank, args, peak):
       range      1M queries, r = 0.2 m, against the 50M-point index replicated on every GPU, queries sharded
       icp        ONE Fit of a 1M-point scan against the DOWNSAMPLED map, target sharded, base index replicated:
                  (a) one process per GPU, 16 float64 all-reduced by NCCL each iteration, loop resident on the device;
-                 (b) one process (rank 0) driving all GPUs: persistent kernel per device, the sums exchanged as
-                     NVLink peer-memory stores inside the kernels (pcg_icp_fit_multi_dev)
+                 (b) one process (rank 0) driving all GPUs: the sums exchanged as NVLink peer-memory stores by the
+                     last CTA of every iteration kernel (pcg_icp_fit_multi_dev)
     Parity (N > 1): hashes of the sharded outputs against the single-GPU ones, computed in this run."""
     from pcgol_b200 import dist as pdist
 
@@ -816,8 +816,8 @@ def bench_config5(pg, torch, dist, rank, args, peak):
         pms = 1e3 * (time.perf_counter() - t0)
         ptrans, pstat = fit["peer"]
         io["peer"] = {"value": 3 / (pms / 1e3), "ms_per_alignment": pms / 3, "iterations": int(pstat.num_iteration),
-                      "collective": "none: ten float64 stored into every peer's exchange buffer over NVLink inside one "
-                                    "persistent cooperative kernel per device (pcg_icp_fit_multi_dev), one host process",
+                      "collective": "none: the last CTA of every iteration kernel stores the device's ten float64 into every peer's "
+                                    "exchange buffer over NVLink and waits on flags (pcg_icp_fit_multi_dev), one host process",
                       "timer": "host wall clock around the synchronous call (it launches and joins all devices)"}
         # single-GPU fast Fit of the same problem + the float64 oracle: the sharded transforms must agree
         d_full = torch.from_numpy(target).to(dev)

@@ -18,6 +18,8 @@
 //                      is set the remaining launches fall through.
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <exception>
 #include <cstdlib>
 #include <vector>
 
@@ -1153,24 +1155,46 @@ pcg_status icp_fit_multi_device(int n_dev, const Index* const* bases, const void
     }
     const int max_it = im::make_updater(prm).max_iteration;
     g_peer_seq += (unsigned int)max_it;
-    for (int r = 0; r < n_dev; r++) {
-      Dev& d = devs[(size_t)r];
-      PCG_CUDA(cudaSetDevice(bases[r]->device));
-      d.tgt = make_view(d_targets[r], n_targets[r], stride, xyz_off);
-      icp_prepare(*bases[r], d.tgt, prm, false, d.w, g_peer[bases[r]->device].stream);
-    }
     const float mdsq = prm.max_dist * prm.max_dist;  // kdtree.go:91
-    // iteration-major: every device gets iteration k before anyone gets k + 1 (a device spins on its peers' flags)
-    for (int it = 0; it < max_it; it++) {
-      for (int r = 0; r < n_dev; r++) {
+    // One host thread per device prepares its slice (visit order, workspace) and enqueues all iterations: launching
+    // 8 x 20 kernels from a single thread costs more than the kernels run (a device spins on its peers' flags, so
+    // every device must get its kernels early).
+    std::vector<std::exception_ptr> errors((size_t)n_dev);
+    auto work = [&](int r) {
+      try {
         Dev& d = devs[(size_t)r];
         PCG_CUDA(cudaSetDevice(bases[r]->device));
-        pc.rank = r;
-        launch_terms<PCG_ICP_FAST>(*bases[r], d.tgt, d.w.perm.p, d.w.warm.p, mdsq, 0.f, false, d.w.st.p, d.w.terms.p,
-                                   d.w.n_pad, d.w.partials.p, d.w.hpartials.p, d.w.nblocks, 1,
-                                   g_peer[bases[r]->device].stream, &pc);
+        cudaStream_t stream = g_peer[bases[r]->device].stream;
+        d.tgt = make_view(d_targets[r], n_targets[r], stride, xyz_off);
+        icp_prepare(*bases[r], d.tgt, prm, false, d.w, stream);
+        PeerCtx mine = pc;
+        mine.rank = r;
+        for (int it = 0; it < max_it; it++)
+          launch_terms<PCG_ICP_FAST>(*bases[r], d.tgt, d.w.perm.p, d.w.warm.p, mdsq, 0.f, false, d.w.st.p, d.w.terms.p,
+                                     d.w.n_pad, d.w.partials.p, d.w.hpartials.p, d.w.nblocks, 1, stream, &mine);
+      } catch (...) {
+        errors[(size_t)r] = std::current_exception();
+      }
+    };
+    {
+      std::vector<std::thread> threads;
+      for (int r = 1; r < n_dev; r++) threads.emplace_back(work, r);
+      work(0);
+      for (auto& t : threads) t.join();
+    }
+    for (int r = 0; r < n_dev; r++) {
+      if (!errors[(size_t)r]) continue;
+      // A device that failed to enqueue its iterations would leave the others spinning on its flag for ever: raise
+      // that flag on every device from the host (the streams are non-blocking, a plain copy runs beside them); the
+      // sums they then read are meaningless, and so is the result - the call fails.
+      const unsigned int last = pc.seq_base + (unsigned int)max_it;
+      for (int q = 0; q < n_dev; q++) {
+        cudaSetDevice(bases[q]->device);
+        cudaMemcpy(pc.flags[q] + r, &last, sizeof(last), cudaMemcpyHostToDevice);
       }
     }
+    for (int r = 0; r < n_dev; r++)
+      if (errors[(size_t)r]) std::rethrow_exception(errors[(size_t)r]);
     IcpState h;
     PCG_CUDA(cudaSetDevice(bases[0]->device));
     PCG_CUDA(cudaMemcpyAsync(&h, devs[0].w.st.p, sizeof(h), cudaMemcpyDeviceToHost, g_peer[bases[0]->device].stream));
