@@ -14,132 +14,118 @@
 #include "icp_math.cuh"
 #include "radix_sort.cuh"
 #include "vg_common.cuh"
+#include "vg_packed.cuh"
 
 namespace pcg {
 
 std::atomic<int> g_vg_path{0};
 
+// ---- MinMaxVec3 (pc/minmax.go:9-26) ----------------------------------------------------------------------------------
+// Go keeps the FIRST occurrence of the extreme value (strict comparisons).  Equal floats have equal bits except for
+// the two zeros, so which occurrence wins only shows in the sign of a zero result.  The scan therefore keeps plain
+// float minima / maxima (FMNMX ignores NaN operands like the reference's comparisons do) plus, per axis, the first
+// index at which a zero occurs and that zero's sign - a handful of instructions per coordinate instead of a 64-bit
+// (value, index) compare-and-select.  A CTA publishes six words (ordered value bits << 32 | low), low = (global index
+// << 1 | sign) of the first zero when the extreme IS zero, else 0; 64-bit atomicMin / atomicMax combine them - over
+// CTAs, and over ranks for a sharded cloud (minmax_shard_words_kernel).
+struct MinMaxAcc {
+  float mn[3], mx[3];
+  uint32_t zc[3];  // (global index << 1 | sign bit) of the first zero seen, per axis
+  __device__ __forceinline__ MinMaxAcc() {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      mn[k] = __int_as_float(0x7f800000);
+      mx[k] = __int_as_float(0xff800000);
+      zc[k] = 0xffffffffu;
+    }
+  }
+  __device__ __forceinline__ void take(float c, int k, uint32_t g2) {  // g2 = global index << 1
+    mn[k] = fminf(mn[k], c);
+    mx[k] = fmaxf(mx[k], c);
+    if (c == 0.0f) zc[k] = min(zc[k], g2 | (__float_as_uint(c) >> 31));
+  }
+  // CTA-wide reduction and the six atomics.  s_f / s_z: [warps][6] and [warps][3] scratch.
+  __device__ __forceinline__ void publish(unsigned long long* __restrict__ out6, float (*s_f)[6], uint32_t (*s_z)[3],
+                                          int warps) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], d));
+        mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], d));
+        zc[k] = min(zc[k], __shfl_xor_sync(0xffffffffu, zc[k], d));
+      }
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        s_f[warp][k] = mn[k];
+        s_f[warp][3 + k] = mx[k];
+        s_z[warp][k] = zc[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      const int k = threadIdx.x, c = k % 3;
+      float r = s_f[0][k];
+      uint32_t z = s_z[0][c];
+      for (int w = 1; w < warps; w++) {
+        r = k < 3 ? fminf(r, s_f[w][k]) : fmaxf(r, s_f[w][k]);
+        z = min(z, s_z[w][c]);
+      }
+      if (z != 0xffffffffu || r != 0.0f) {  // (a zero extreme always comes with the index of a zero)
+        uint32_t low = 0;
+        if (r == 0.0f) low = k < 3 ? z : ((0x7fffffffu - (z >> 1)) << 1) | (z & 1u);
+        const unsigned long long w = ((unsigned long long)ordered_bits(r) << 32) | low;
+        if (k < 3)
+          atomicMin(&out6[k], w);
+        else
+          atomicMax(&out6[k], w);
+      }
+    }
+  }
+};
+
 __global__ void __launch_bounds__(256)
-    minmax_kernel(CloudView v, uint32_t index_base, int zero_sign, unsigned long long* __restrict__ out6) {
-  __shared__ unsigned long long s_red[8][6];
-  unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
+    minmax_kernel(CloudView v, uint32_t index_base, unsigned long long* __restrict__ out6) {
+  __shared__ float s_f[8][6];
+  __shared__ uint32_t s_z[8][3];
+  MinMaxAcc acc;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += stride) {
-    float3 p = load_xyz(v, i);
-    float c[3] = {p.x, p.y, p.z};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (c[k] != c[k]) continue;  // NaN never wins a comparison in the reference
-      unsigned long long o = (unsigned long long)ordered_bits(c[k]) << 32;
-      unsigned long long a, b;
-      if (zero_sign) {  // sharded runs: bit 0 carries the sign of a zero (the value bits treat -0 as +0), index above it
-        const uint32_t g = index_base + (uint32_t)i, nz = __float_as_uint(c[k]) == 0x80000000u ? 1u : 0u;
-        a = o | ((g << 1) | nz);
-        b = o | (((0x7fffffffu - g) << 1) | nz);
-      } else {
-        a = o | (uint32_t)i;
-        b = o | (0xffffffffu - (uint32_t)i);
-      }
-      mn[k] = a < mn[k] ? a : mn[k];
-      mx[k] = b > mx[k] ? b : mx[k];
-    }
+    const float3 p = load_xyz(v, i);
+    const uint32_t g2 = (index_base + (uint32_t)i) << 1;
+    acc.take(p.x, 0, g2);
+    acc.take(p.y, 1, g2);
+    acc.take(p.z, 2, g2);
   }
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      unsigned long long a = shfl_xor_u64(mn[k], d), b = shfl_xor_u64(mx[k], d);
-      mn[k] = a < mn[k] ? a : mn[k];
-      mx[k] = b > mx[k] ? b : mx[k];
-    }
-  }
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      s_red[warp][k] = mn[k];
-      s_red[warp][3 + k] = mx[k];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 6) {  // one global atomic per CTA and component
-    const int k = threadIdx.x;
-    unsigned long long r = s_red[0][k];
-    for (int w = 1; w < 8; w++) {
-      unsigned long long o = s_red[w][k];
-      r = k < 3 ? (o < r ? o : r) : (o > r ? o : r);
-    }
-    if (k < 3) {
-      if (r != ~0ull) atomicMin(&out6[k], r);
-    } else {
-      if (r != 0ull) atomicMax(&out6[k], r);
-    }
-  }
+  acc.publish(out6, s_f, s_z, 8);
 }
 
 // ---- MinMaxVec3 as a bulk-async pipeline (sm_100a data movement) -----------------------------------------------
-// The scan above issues three 4-byte loads per point and is latency-bound (36 % of the HBM copy rate on the 50M-point
-// map).  Here the records travel global -> shared memory as 1-D bulk copies (cp.async.bulk, the TMA engine without a
-// tensor map; UBLKCP in SASS) into a ring of kMmStages tiles, each completion counted in bytes on an mbarrier; one
-// thread keeps the ring full while all 256 threads reduce the tile that has landed.  Any record layout with 4-byte
-// aligned x/y/z works: a tile is a contiguous run of whole records.
+// The scan above issues three 4-byte loads per point and is latency-bound.  Here the records travel global -> shared
+// memory as 1-D bulk copies (cp.async.bulk, the TMA engine without a tensor map; UBLKCP in SASS) into a ring of
+// kMmStages tiles, each completion counted in bytes on an mbarrier; one thread keeps the ring full while all 256
+// threads reduce the tile that has landed.  Any record layout with 4-byte aligned x/y/z works: a tile is a contiguous
+// run of whole records.
 constexpr int kMmThreads = 256;
 constexpr int kMmTilePoints = 1024;
 constexpr int kMmStages = 4;
 constexpr int kMmMaxStride = 32;  // bytes per record the shared-memory ring is sized for
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 __global__ void __launch_bounds__(kMmThreads)
-    minmax_bulk_kernel(CloudView v, uint32_t index_base, int zero_sign, unsigned long long* __restrict__ out6) {
+    minmax_bulk_kernel(CloudView v, uint32_t index_base, unsigned long long* __restrict__ out6) {
   extern __shared__ __align__(128) unsigned char mm_dyn[];
   __shared__ __align__(8) uint64_t full[kMmStages];
-  __shared__ unsigned long long s_red[kMmThreads / 32][6];
+  __shared__ float s_f[kMmThreads / 32][6];
+  __shared__ uint32_t s_z[kMmThreads / 32][3];
   const uint32_t tid = threadIdx.x;
   const uint32_t stride = (uint32_t)v.stride;
   const uint32_t tile_bytes = kMmTilePoints * stride;
   const uint32_t n = (uint32_t)v.n;
   const uint32_t full_tiles = n / kMmTilePoints;
-  unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
-  auto take = [&](float c, int k, uint32_t i) {
-    if (c != c) return;  // NaN never wins a comparison in the reference
-    const unsigned long long o = (unsigned long long)ordered_bits(c) << 32;
-    unsigned long long a, b;
-    if (zero_sign) {
-      const uint32_t g = index_base + i, nz = __float_as_uint(c) == 0x80000000u ? 1u : 0u;
-      a = o | ((g << 1) | nz);
-      b = o | (((0x7fffffffu - g) << 1) | nz);
-    } else {
-      a = o | i;
-      b = o | (0xffffffffu - i);
-    }
-    mn[k] = a < mn[k] ? a : mn[k];
-    mx[k] = b > mx[k] ? b : mx[k];
-  };
+  MinMaxAcc acc;
   if (tid == 0) {
     for (int s = 0; s < kMmStages; s++) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,14 +144,15 @@ __global__ void __launch_bounds__(kMmThreads)
     const uint32_t s = j % kMmStages, parity = (j / kMmStages) & 1u;
     mbar_wait(&full[s], parity);
     const unsigned char* tile = mm_dyn + (size_t)s * tile_bytes;
-    const uint32_t first = (blockIdx.x + j * gridDim.x) * kMmTilePoints;
+    const uint32_t first = index_base + (blockIdx.x + j * gridDim.x) * kMmTilePoints;
 #pragma unroll
     for (int q = 0; q < kMmTilePoints / kMmThreads; q++) {
       const uint32_t p = q * kMmThreads + tid;
       const unsigned char* r = tile + (size_t)p * stride;
-      take(*reinterpret_cast<const float*>(r + v.off[0]), 0, first + p);
-      take(*reinterpret_cast<const float*>(r + v.off[1]), 1, first + p);
-      take(*reinterpret_cast<const float*>(r + v.off[2]), 2, first + p);
+      const uint32_t g2 = (first + p) << 1;
+      acc.take(*reinterpret_cast<const float*>(r + v.off[0]), 0, g2);
+      acc.take(*reinterpret_cast<const float*>(r + v.off[1]), 1, g2);
+      acc.take(*reinterpret_cast<const float*>(r + v.off[2]), 2, g2);
     }
     __syncthreads();  // everybody has read the slot: it can be refilled
     if (tid == 0 && j + kMmStages < my_tiles) {
@@ -178,46 +165,18 @@ __global__ void __launch_bounds__(kMmThreads)
   if (blockIdx.x == 0) {
     for (uint32_t i = full_tiles * kMmTilePoints + tid; i < n; i += kMmThreads) {
       const float3 p = load_xyz(v, i);
-      take(p.x, 0, i);
-      take(p.y, 1, i);
-      take(p.z, 2, i);
+      const uint32_t g2 = (index_base + i) << 1;
+      acc.take(p.x, 0, g2);
+      acc.take(p.y, 1, g2);
+      acc.take(p.z, 2, g2);
     }
   }
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const unsigned long long a = shfl_xor_u64(mn[k], d), b = shfl_xor_u64(mx[k], d);
-      mn[k] = a < mn[k] ? a : mn[k];
-      mx[k] = b > mx[k] ? b : mx[k];
-    }
-  }
-  if ((tid & 31) == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      s_red[tid >> 5][k] = mn[k];
-      s_red[tid >> 5][3 + k] = mx[k];
-    }
-  }
-  __syncthreads();
-  if (tid < 6) {
-    unsigned long long r = s_red[0][tid];
-    for (int w = 1; w < kMmThreads / 32; w++) {
-      const unsigned long long o = s_red[w][tid];
-      r = tid < 3 ? (o < r ? o : r) : (o > r ? o : r);
-    }
-    if (tid < 3) {
-      if (r != ~0ull) atomicMin(&out6[tid], r);
-    } else {
-      if (r != 0ull) atomicMax(&out6[tid], r);
-    }
-  }
+  acc.publish(out6, s_f, s_z, kMmThreads / 32);
 }
 
 // Launches the bulk-async scan when the layout allows it (4-byte aligned fields, records of up to 32 bytes, 16-byte
 // aligned base), else the plain one.  acc: [3] minima initialised to ~0, [3] maxima initialised to 0.
-static void launch_minmax(const CloudView& v, uint32_t index_base, int zero_sign, unsigned long long* acc,
-                          cudaStream_t stream) {
+static void launch_minmax(const CloudView& v, uint32_t index_base, unsigned long long* acc, cudaStream_t stream) {
   if (v.n <= 0) return;
   const bool bulk = v.aligned && v.stride <= kMmMaxStride && (((uintptr_t)v.data) & 15) == 0 && v.n >= 64 * kMmTilePoints;
   if (bulk) {
@@ -231,10 +190,10 @@ static void launch_minmax(const CloudView& v, uint32_t index_base, int zero_sign
       configured.fetch_or(1ull << dev, std::memory_order_relaxed);
     }
     const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, v.n / kMmTilePoints);
-    PCG_LAUNCH(minmax_bulk_kernel, blocks, kMmThreads, smem, stream, v, index_base, zero_sign, acc);
+    PCG_LAUNCH(minmax_bulk_kernel, blocks, kMmThreads, smem, stream, v, index_base, acc);
   } else {
     const int blocks = (int)std::min<int64_t>((int64_t)kNumSMs * 4, div_up(v.n, 256));
-    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, zero_sign, acc);
+    PCG_LAUNCH(minmax_kernel, blocks, 256, 0, stream, v, index_base, acc);
   }
 }
 
@@ -249,10 +208,11 @@ __global__ void minmax_finalize_kernel(CloudView v, const unsigned long long* __
   if (first != first) {
     r = first;  // min/max start at point 0; a NaN there is never replaced (minmax.go:13,17-22)
   } else {
-    unsigned long long w = in6[k];
-    uint32_t idx = k < 3 ? (uint32_t)w : 0xffffffffu - (uint32_t)w;
-    float3 p = load_xyz(v, idx);
-    r = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+    const unsigned long long w = in6[k];
+    const uint32_t o = (uint32_t)(w >> 32);
+    uint32_t bits = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    if (bits == 0u && (w & 1ull)) bits = 0x80000000u;  // the first zero was a -0
+    r = __uint_as_float(bits);
   }
   out6[k] = r;
 }
@@ -266,7 +226,7 @@ void minmax_device(const CloudView& v, float mn[3], float mx[3], cudaStream_t st
     init[3 + k] = 0ull;
   }
   PCG_CUDA(cudaMemcpyAsync(acc.p, init, 6 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-  launch_minmax(v, 0u, 0, acc.p, stream);
+  launch_minmax(v, 0u, acc.p, stream);
   PCG_LAUNCH(minmax_finalize_kernel, 1, 32, 0, stream, v, acc.p, res.p);
   float* h = (float*)pinned_scratch();
   PCG_CUDA(cudaMemcpyAsync(h, res.p, 6 * sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -335,7 +295,7 @@ __global__ void minmax_shard_words_kernel(CloudView v, int first_slice, const un
 void minmax_packed_device(const CloudView& v, uint32_t index_base, long long* d_out6, cudaStream_t stream) {
   DevBuf<unsigned long long> acc(6, stream);
   PCG_LAUNCH(minmax_shard_init_kernel, 1, 32, 0, stream, acc.p);
-  launch_minmax(v, index_base, 1, acc.p, stream);
+  launch_minmax(v, index_base, acc.p, stream);
   PCG_LAUNCH(minmax_shard_words_kernel, 1, 32, 0, stream, v, index_base == 0 ? 1 : 0, acc.p, d_out6);
 }
 
@@ -575,6 +535,18 @@ static void run_sorted_reduce(const CloudView& v, const VgParams& P, int total_b
   uint32_t* counter = (uint32_t*)(status.p + tiles);
   PCG_LAUNCH((voxel_reduce_kernel<K>), tiles, kSegThreads, 0, stream, v, P, kk[res], vbuf[res], xyz4.p, d_out,
              counter, status.p, d_n_out);
+}
+
+// The multi-kernel pipeline for a whole cloud: packed 64-bit words (vg_packed.cuh) whenever key + index bits fit 64,
+// else (key, index) pairs.  Test hook g_vg_path == 2 forces the pairs.
+static void run_pipeline(const CloudView& v, const VgParams& P, int total_bits, uint8_t* d_out, long long* d_n_out,
+                         int* d_flags, cudaStream_t stream) {
+  if (g_vg_path.load(std::memory_order_relaxed) != 2 && vgp::fits(v.n, total_bits))
+    vgp::run(v, P, total_bits, d_out, d_n_out, d_flags, stream);
+  else if (total_bits <= 32)
+    run_sorted_reduce<uint32_t>(v, P, total_bits, d_out, d_n_out, d_flags, stream);
+  else
+    run_sorted_reduce<unsigned long long>(v, P, total_bits, d_out, d_n_out, d_flags, stream);
 }
 
 // ======================================================================================
@@ -1338,7 +1310,7 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
   // pipeline below.  g_vg_path is a test hook (pcg_debug_set_vg_path): 1 forces the multi-kernel pipeline so that the
   // parity tests cover it at every size.
   const int path = g_vg_path.load(std::memory_order_relaxed);
-  if (path != 1 && v.n <= fused_capacity(kFusedIptLarge)) {
+  if (path == 0 && v.n <= fused_capacity(kFusedIptLarge)) {
     try {
       return voxelgrid_filter_fused(v, leaf, chunk, d_out, n_out, stream);
     } catch (const CudaError& e) {
@@ -1360,10 +1332,7 @@ pcg_status voxelgrid_filter_device(const CloudView& v, const float leaf[3], cons
   DevBuf<int> d_flags(1, stream);
   PCG_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream));
   PCG_CUDA(cudaMemsetAsync(d_n.p, 0, sizeof(long long), stream));
-  if (total_bits <= 32)
-    run_sorted_reduce<uint32_t>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
-  else
-    run_sorted_reduce<unsigned long long>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
+  run_pipeline(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
   long long* ph_n = (long long*)pinned_scratch();
   int* ph_flags = (int*)(pinned_scratch() + 16);
   PCG_CUDA(cudaMemcpyAsync(ph_n, d_n.p, sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -1664,10 +1633,7 @@ pcg_status voxelgrid_filter_chunks_device(const CloudView& v, const float leaf[3
   if (mm6) {
     // point-sharded Filter: the caller sent this rank exactly the points of its chunks (owner_order + all-to-all), so
     // there is nothing to select - the plain pipeline under the global bounds
-    if (total_bits <= 32)
-      run_sorted_reduce<uint32_t>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
-    else
-      run_sorted_reduce<unsigned long long>(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
+    run_pipeline(v, P, total_bits, d_out, d_n.p, d_flags.p, stream);
   } else if (total_bits <= 32)
     run_range_reduce<uint32_t>(v, P, total_bits, (unsigned long long)cid_lo, (unsigned long long)cid_hi, d_out, d_n.p,
                                d_flags.p, stream);

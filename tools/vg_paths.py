@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import pcgol_b200 as pg  # noqa: E402
 from pcgol_b200 import _lib, synth  # noqa: E402
 
-NAMES = {0: "auto", 1: "lsd"}
+NAMES = {0: "auto", 1: "packed", 2: "pairs"}
 
 
 def run_dev(vg, d_in, n, stride, off, d_out):
@@ -22,7 +22,7 @@ def run_dev(vg, d_in, n, stride, off, d_out):
     return m, d_out[: m * stride].cpu().numpy().tobytes()
 
 
-def compare(name, data, stride, off, leaf, chunk, paths=(1, 0), oracle=True):
+def compare(name, data, stride, off, leaf, chunk, paths=(2, 1, 0), oracle=True):
     n = len(data) // stride
     d_in = torch.from_numpy(np.frombuffer(data, np.uint8).copy()).cuda()
     d_out = torch.empty(max(1, n * stride), dtype=torch.uint8, device="cuda")
@@ -99,13 +99,13 @@ def main():
     if not a.no_compare:
         compare("scan 1M xyz chunk 128", scan1m.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), oracle=False)
         compare("scan 1M xyz leaf 1mm (u64 keys)", scan1m.tobytes(), 12, (0, 4, 8), (0.001, 0.001, 0.001), (128, 128, 128),
-                paths=(1, 0), oracle=False)
-    timing("1M", scan1m, leaf, (128, 128, 128), (0, 1))
+                paths=(2, 1, 0), oracle=False)
+    timing("1M", scan1m, leaf, (128, 128, 128), (0, 1, 2))
     if a.big:
         big = synth.tiled_map(a.big[0], a.big[1])
         if not a.no_compare:
-            compare(f"map {len(big)}", big.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), paths=(1, 0), oracle=False)
-        timing(f"map{len(big) // 1000000}M", big, leaf, (128, 128, 128), (1,), reps=5)
+            compare(f"map {len(big)}", big.tobytes(), 12, (0, 4, 8), leaf, (128, 128, 128), paths=(2, 1), oracle=False)
+        timing(f"map{len(big) // 1000000}M", big, leaf, (128, 128, 128), (1, 2), reps=5)
 
 
 if __name__ == "__main__":
