@@ -51,6 +51,10 @@ constexpr int kRowBlock = 64;           // super-tiles per block of the base tab
 #define PCG_VGP_CTAS 3
 #endif
 constexpr int kCtasPerSm = PCG_VGP_CTAS;
+#ifndef PCG_VGP_SUPER
+#define PCG_VGP_SUPER 4
+#endif
+constexpr int kSuperTiles = PCG_VGP_SUPER;  // tiles per super-tile for large clouds
 
 inline int passes_for(int total_bits) { return total_bits <= 0 ? 1 : (total_bits + kBits - 1) / kBits; }
 
@@ -556,7 +560,7 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
   const int passes = passes_for(total_bits);
   const uint32_t tiles = (n + kTile - 1) / kTile;
   // super-tiles: as large as keeps every SM supplied with several CTAs, at most 4096 of them
-  uint32_t S = std::min<uint32_t>(8u, std::max<uint32_t>(1u, tiles / (kNumSMs * 4)));
+  uint32_t S = std::min<uint32_t>((uint32_t)kSuperTiles, std::max<uint32_t>(1u, tiles / (kNumSMs * 4)));
   while ((tiles + S - 1) / S > 4096u) S *= 2;
   const uint32_t supers = (tiles + S - 1) / S;
   const uint32_t rowblocks = (supers + kRowBlock - 1) / kRowBlock;

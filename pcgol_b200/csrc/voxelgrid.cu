@@ -45,8 +45,9 @@ struct MinMaxAcc {
     if (c == 0.0f) zc[k] = min(zc[k], g2 | (__float_as_uint(c) >> 31));
   }
   // CTA-wide reduction and the six atomics.  s_f / s_z: [warps][6] and [warps][3] scratch.
+  // complement_min: the minima are combined as atomicMax of the complemented word (zero-initialised accumulators).
   __device__ __forceinline__ void publish(unsigned long long* __restrict__ out6, float (*s_f)[6], uint32_t (*s_z)[3],
-                                          int warps) {
+                                          int warps, bool complement_min = false) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
 #pragma unroll
@@ -78,10 +79,12 @@ struct MinMaxAcc {
         uint32_t low = 0;
         if (r == 0.0f) low = k < 3 ? z : ((0x7fffffffu - (z >> 1)) << 1) | (z & 1u);
         const unsigned long long w = ((unsigned long long)ordered_bits(r) << 32) | low;
-        if (k < 3)
-          atomicMin(&out6[k], w);
-        else
+        if (k >= 3)
           atomicMax(&out6[k], w);
+        else if (complement_min)
+          atomicMax(&out6[k], ~w);
+        else
+          atomicMin(&out6[k], w);
       }
     }
   }
@@ -606,7 +609,7 @@ __host__ __device__ constexpr size_t dyn_smem_bytes() {
 }
 
 struct Work {
-  unsigned long long* acc;  // [6]: ~min / max packed (value bits, index), reduced with atomicMax; zero-initialised
+  unsigned long long* acc;  // [6]: ~min / max words of MinMaxAcc::publish, reduced with atomicMax; zero-initialised
   uint32_t* counts;         // [tiles][256]
   uint32_t* head_counts;    // [tiles]
   void* keys[2];            // n keys each (uint32 or uint64 depending on the bits needed)
@@ -650,7 +653,8 @@ struct Smem {
   uint32_t digit_start[rsort::kRadix];
   uint32_t global_base[rsort::kRadix];
   uint32_t scan[kWarps];
-  unsigned long long red[kWarps][6];
+  float red_f[kWarps][6];
+  uint32_t red_z[kWarps][3];
   VgParams P;
   int status;
   int total_bits;
@@ -1123,43 +1127,19 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
                        *reinterpret_cast<const float*>(r + v.off[2]));
   };
   // ---- phase 0: MinMaxVec3 (pc/minmax.go:9-26), first occurrence wins (see minmax_kernel)
-  unsigned long long mn[3] = {~0ull, ~0ull, ~0ull}, mx[3] = {0ull, 0ull, 0ull};
-  for (int i = 0; i < IPT; i++) {
-    const uint32_t pos = tile_base + i * kThreads + tid;
-    if (pos < n) {
-      const float3 p = tile_in_smem ? tile_xyz(i * kThreads + tid) : load_xyz(v, pos);
-      const float c[3] = {p.x, p.y, p.z};
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        if (c[k] != c[k]) continue;
-        const unsigned long long o = (unsigned long long)ordered_bits(c[k]) << 32;
-        const unsigned long long a = o | pos, b = o | (0xffffffffu - pos);
-        mn[k] = a < mn[k] ? a : mn[k];
-        mx[k] = b > mx[k] ? b : mx[k];
+  {
+    MinMaxAcc acc;
+#pragma unroll 4
+    for (int i = 0; i < IPT; i++) {
+      const uint32_t pos = tile_base + i * kThreads + tid;
+      if (pos < n) {
+        const float3 p = tile_in_smem ? tile_xyz(i * kThreads + tid) : load_xyz(v, pos);
+        acc.take(p.x, 0, pos << 1);
+        acc.take(p.y, 1, pos << 1);
+        acc.take(p.z, 2, pos << 1);
       }
     }
-  }
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const unsigned long long a = shfl_xor_u64(mn[k], d), b = shfl_xor_u64(mx[k], d);
-      mn[k] = a < mn[k] ? a : mn[k];
-      mx[k] = b > mx[k] ? b : mx[k];
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      sm.red[warp][k] = ~mn[k];  // min as max of the complement: one zero-initialised accumulator type
-      sm.red[warp][3 + k] = mx[k];
-    }
-  }
-  __syncthreads();
-  if (tid < 6) {
-    unsigned long long r = sm.red[0][tid];
-    for (int wv = 1; wv < kWarps; wv++) r = sm.red[wv][tid] > r ? sm.red[wv][tid] : r;
-    if (r != 0ull) atomicMax(&w.acc[tid], r);
+    acc.publish(w.acc, sm.red_f, sm.red_z, kWarps, /*complement_min=*/true);
   }
   PCG_VG_STAMP();  // minmax local
   grid.sync();
@@ -1172,9 +1152,10 @@ __global__ void __launch_bounds__(kThreads, 1) voxelgrid_fused_kernel(CloudView 
     if (first == first) {
       unsigned long long a = __ldcg(&w.acc[k]);
       if (k < 3) a = ~a;
-      const uint32_t idx = k < 3 ? (uint32_t)a : 0xffffffffu - (uint32_t)a;
-      const float3 p = load_xyz(v, idx);
-      r = c == 0 ? p.x : (c == 1 ? p.y : p.z);
+      const uint32_t o = (uint32_t)(a >> 32);
+      uint32_t bits = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+      if (bits == 0u && (a & 1ull)) bits = 0x80000000u;  // the first zero was a -0
+      r = __uint_as_float(bits);
     }
     sm.mm[k] = r;
   }
