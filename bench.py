@@ -273,6 +273,20 @@ def ncu_traffic(kernel_name):
     return None
 
 
+def vg_pipeline_algo(n, m, kb):
+    """Algorithmic bytes per launch of the kernels of the multi-kernel VoxelGrid pipelines:
+    the packed-word pipeline (vg_packed.cuh) and the (key, index) one it replaces for keys that do not pack."""
+    return {
+        "minmax_kernel": 12 * n, "minmax_bulk_kernel": 12 * n,
+        # packed words: 8-byte word per point, 16-byte aligned copy of the point
+        "vgp::key_kernel": 12 * n + 8 * n + 16 * n, "vgp::hist_kernel": 8 * n, "vgp::scatter_kernel": 16 * n,
+        "vgp::head_count_kernel": 8 * n, "vgp::reduce_kernel": 8 * n + 16 * n + 12 * m,
+        # (key, index) pairs
+        "(voxel_key_kernel<K>)": 12 * n + kb * n, "(histogram_kernel<K>)": kb * n,
+        "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n, "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m,
+    }
+
+
 def dominant(report, algo_bytes, peak):
     """Roofline object for the kernel with the largest share of the step."""
     if not report:
@@ -397,14 +411,8 @@ def bench_voxelgrid(pg, torch, dist, rank, args, peak):
     world = args.gpus
     # algorithmic bytes per launch of each kernel of the pipeline
     kb = 4  # (chunk id, voxel key) needs 29 bits for this config -> 32-bit sort keys
-    algo = {
-        "voxelgrid_fused_kernel<IPT>": 12 * n + 12 * m,  # the whole Filter is this one kernel: N*stride in, M*stride out
-        "minmax_kernel": 12 * n,
-        "(voxel_key_kernel<K>)": 12 * n + kb * n,
-        "(histogram_kernel<K>)": kb * n,
-        "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n,
-        "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m,
-    }
+    algo = vg_pipeline_algo(n, m, kb)
+    algo["voxelgrid_fused_kernel<IPT>"] = 12 * n + 12 * m  # the whole Filter is this one kernel: N*stride in, M*stride out
     report = profile_kernels(pg, torch, step, args.steps)
     roof, shares = dominant(report, algo, peak)
     step_s = ms / steps / 1e3
@@ -670,10 +678,7 @@ def bench_config5(pg, torch, dist, rank, args, peak):
         ms = timed_region(dist, torch, step, 5)
         report = profile_kernels(pg, torch, step, 3)
         m = m_box[0]
-        kb = 8
-        algo = {"minmax_kernel": 12 * n, "(voxel_key_kernel<K>)": 12 * n + kb * n,
-                "(onesweep_kernel<K, IPT>)": 2 * (kb + 4) * n, "(voxel_reduce_kernel<K>)": (kb + 4) * n + 12 * n + 12 * m}
-        roof, shares = dominant(report, algo, peak)
+        roof, shares = dominant(report, vg_pipeline_algo(n, m, 8), peak)
         down = d_out[: m * 12].clone()  # the downsampled map: base of the ICP below
         del d_in, d_out
         vgo = {"roofline": roof, "kernels": shares, "sharding": "single GPU"}

@@ -210,7 +210,8 @@ def profile_enable(on: bool) -> None:
 
 
 def set_vg_path(path: int) -> None:
-    """Test hook: 0 automatic, 1 always the multi-kernel LSD pipeline."""
+    """Test hook: 0 automatic, 1 always the multi-kernel pipeline (packed words when they fit), 2 always the
+    (key, index) pairs pipeline."""
     lib.pcg_debug_set_vg_path(int(path))
 
 

@@ -55,6 +55,10 @@ constexpr int kCtasPerSm = PCG_VGP_CTAS;
 #define PCG_VGP_SUPER 4
 #endif
 constexpr int kSuperTiles = PCG_VGP_SUPER;  // tiles per super-tile for large clouds
+#ifndef PCG_VGP_BUFS
+#define PCG_VGP_BUFS 2
+#endif
+constexpr int kBufs = PCG_VGP_BUFS;  // tile buffers per scatter CTA (2: the next tile is in flight while one is ranked)
 
 inline int passes_for(int total_bits) { return total_bits <= 0 ? 1 : (total_bits + kBits - 1) / kBits; }
 
@@ -113,15 +117,15 @@ __global__ void __launch_bounds__(kThreads)
   __syncthreads();
   const uint64_t begin = (uint64_t)blockIdx.x * tiles_per_super * kTile;
   const uint64_t end = min((uint64_t)n, begin + (uint64_t)tiles_per_super * kTile);
-  for (uint64_t t = begin; t < end; t += kTile) {
-    u64 w[kIpt];
+  for (uint64_t t = begin; t < end; t += 8 * kThreads) {  // eight independent loads per thread in flight
+    u64 w[8];
 #pragma unroll
-    for (int j = 0; j < kIpt; j++) {
+    for (int j = 0; j < 8; j++) {
       const uint64_t i = t + j * kThreads + threadIdx.x;
       w[j] = i < end ? __ldcs(in + i) : 0ull;
     }
 #pragma unroll
-    for (int j = 0; j < kIpt; j++) hist_add(s_hist, digit_of(w[j], shift), t + j * kThreads + threadIdx.x < end);
+    for (int j = 0; j < 8; j++) hist_add(s_hist, digit_of(w[j], shift), t + j * kThreads + threadIdx.x < end);
   }
   __syncthreads();
   uint32_t* row = H + (size_t)blockIdx.x * kRadix;
@@ -220,15 +224,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scatter_kernel(ScatterAr
 
   uint32_t* hist32 = reinterpret_cast<uint32_t*>(&s_warp_hist[0][0]);  // [kWarps][256] pairs of 16-bit counters
   for (uint32_t tile = first_tile, j = 0; tile < end_tile; tile++, j++) {
-    const int b = (int)(j & 1u);
+    const int b = kBufs == 2 ? (int)(j & 1u) : 0;
     // the other buffer is free (its staged words were written out before the barrier that ended the last iteration)
-    if (tid == 0 && tile + 1 < end_tile) fetch(tile + 1, b ^ 1);
+    if (kBufs == 2 && tid == 0 && tile + 1 < end_tile) fetch(tile + 1, b ^ 1);
     const uint32_t tile_base = tile * (uint32_t)kTile;
     const uint32_t tile_count = min((uint32_t)kTile, n - tile_base);
     u64* buf = reinterpret_cast<u64*>(vgp_dyn + (size_t)b * kTileBytes);
 #pragma unroll
     for (int q = 0; q < kWarps * kRadix / 2 / kThreads; q++) hist32[q * kThreads + tid] = 0;
-    mbar_wait(&s_bar[b], (j >> 1) & 1u);
+    mbar_wait(&s_bar[b], kBufs == 2 ? (j >> 1) & 1u : j & 1u);
     u64 keys[kIpt];
     const uint32_t wl = warp * (32u * kIpt) + lane;
 #pragma unroll
@@ -296,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scatter_kernel(ScatterAr
       A.out[s_delta[digit_of(k, shift)] + s] = k;
     }
     __syncthreads();  // the staged words are read: the buffer can take the tile after next
+    if (kBufs == 1 && tid == 0 && tile + 1 < end_tile) fetch(tile + 1, 0);
   }
 }
 
@@ -303,7 +308,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) scatter_kernel(ScatterAr
 // counts[t] = first words of a voxel among the sorted positions [1024 t, 1024 (t+1)); one warp per tile, a streaming
 // read.  Their exclusive scan is the output slot of every tile's first voxel.
 constexpr int kRedThreads = 256;
-constexpr int kRedItems = 4;
+#ifndef PCG_VGP_RED_ITEMS
+#define PCG_VGP_RED_ITEMS 4
+#endif
+constexpr int kRedItems = PCG_VGP_RED_ITEMS;
 constexpr int kRedTile = kRedThreads * kRedItems;
 
 __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
@@ -348,13 +356,18 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- segmented centroid + record emit over the sorted words ------------------------------------------------------------
-__global__ void __launch_bounds__(kRedThreads)
+#ifndef PCG_VGP_RED_CTAS
+#define PCG_VGP_RED_CTAS 6
+#endif
+__global__ void __launch_bounds__(kRedThreads, PCG_VGP_RED_CTAS)
     reduce_kernel(CloudView v, VgParams P, const u64* __restrict__ words, const float4* __restrict__ xyz4, uint32_t n,
                   int idx_bits, uint8_t* __restrict__ out, const long long* __restrict__ first_slot,
                   long long* __restrict__ n_out) {
-  __shared__ float s_pt[3][kRedTile];  // raw points of the tile's sorted slice
+  __shared__ float4 s_pt[kRedTile];  // raw points of the tile's sorted slice (one 16-byte access per member)
   __shared__ u64 s_key[kRedTile];
   __shared__ uint16_t s_src[kRedTile];  // position of the tile's r-th voxel head
+  __shared__ u64 s_after_key[32];       // the 32 positions after the tile
+  __shared__ float4 s_after_pt[32];
   __shared__ uint32_t s_scan[kRedThreads / 32];
   __shared__ struct {
     u64 key, rank;
@@ -376,6 +389,10 @@ __global__ void __launch_bounds__(kRedThreads)
 
   // Phase A (striped: coalesced word loads, independent gathers from the input records; the sweep in sorted order
   // keeps the gathers of neighbouring voxels in the L2)
+  // Loaded alongside (so that no dependent global load is left for later): the word before the tile (is the tile's
+  // first word a head?) and, by the last warp, the 32 words + points after the tile - the tile's last voxel usually
+  // ends among them.
+  u64 word_before = 0;
   {
     u64 ww[kRedItems];
 #pragma unroll
@@ -383,16 +400,22 @@ __global__ void __launch_bounds__(kRedThreads)
       const uint32_t l = j * kRedThreads + tid;
       ww[j] = l < tile_count ? words[tile_base + l] : 0ull;
     }
+    if (tid == 0 && tile_base > 0) word_before = words[tile_base - 1];
+    u64 wn = 0;
+    const uint32_t after = tile_base + tile_count + lane;
+    if (warp == kRedThreads / 32 - 1 && after < n) wn = words[after];
 #pragma unroll
     for (int j = 0; j < kRedItems; j++) {
       const uint32_t l = j * kRedThreads + tid;
       if (l < tile_count) {
         const float4 pt = __ldg(xyz4 + (ww[j] & idx_mask));
         s_key[l] = ww[j] >> idx_bits;
-        s_pt[0][l] = pt.x;
-        s_pt[1][l] = pt.y;
-        s_pt[2][l] = pt.z;
+        s_pt[l] = pt;
       }
+    }
+    if (warp == kRedThreads / 32 - 1) {
+      s_after_key[lane] = after < n ? wn >> idx_bits : ~0ull;
+      s_after_pt[lane] = after < n ? __ldg(xyz4 + (wn & idx_mask)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
@@ -403,7 +426,7 @@ __global__ void __launch_bounds__(kRedThreads)
   if (l0 > 0 && l0 - 1 < tile_count)
     prev = s_key[l0 - 1];
   else if (l0 == 0 && tile_base > 0)
-    prev = words[tile_base - 1] >> idx_bits;
+    prev = word_before >> idx_bits;
   uint32_t heads = 0, cnt = 0;
 #pragma unroll
   for (int j = 0; j < kRedItems; j++) {
@@ -479,25 +502,28 @@ __global__ void __launch_bounds__(kRedThreads)
         vc_cid = cid;
       }
     }
+    // the voxel's members are the positions up to the next head: the trip count is known, no key is compared
+    const uint32_t l_end = r + 1 < total ? (uint32_t)s_src[r + 1] : tile_count;
     a_l = l;
-    a_fx = s_pt[0][l];
-    a_fy = s_pt[1][l];
-    a_fz = s_pt[2][l];
     float sx = 0.f, sy = 0.f, sz = 0.f;
-    uint32_t num = 0;
-    uint32_t ll = l;
-    do {
-      sx = __fadd_rn(sx, __fsub_rn(s_pt[0][ll], vc[0]));
-      sy = __fadd_rn(sy, __fsub_rn(s_pt[1][ll], vc[1]));
-      sz = __fadd_rn(sz, __fsub_rn(s_pt[2][ll], vc[2]));
-      num++;
-      ll++;
-    } while (ll < tile_count && s_key[ll] == key);
+    {
+      const float4 p = s_pt[l];
+      a_fx = p.x;
+      a_fy = p.y;
+      a_fz = p.z;
+    }
+    for (uint32_t ll = l; ll < l_end; ll++) {
+      const float4 p = s_pt[ll];
+      sx = __fadd_rn(sx, __fsub_rn(p.x, vc[0]));
+      sy = __fadd_rn(sy, __fsub_rn(p.y, vc[1]));
+      sz = __fadd_rn(sz, __fsub_rn(p.z, vc[2]));
+    }
+    const uint32_t num = l_end - l;
     a_sx = sx;
     a_sy = sy;
     a_sz = sz;
     a_num = num;
-    if (ll == tile_count && tile_base + tile_count < n) {
+    if (l_end == tile_count && tile_base + tile_count < n) {
       s_cont.key = key;
       s_cont.rank = r;  // relative to the tile's first voxel
       s_cont.sx = sx;
@@ -527,16 +553,19 @@ __global__ void __launch_bounds__(kRedThreads)
     uint32_t num = s_cont.num;
     for (uint32_t g = tile_base + tile_count;; g += 32) {
       const uint32_t idx = g + lane;
+      const bool staged = g == tile_base + tile_count;  // the first window was loaded with the tile
       u64 w = 0;
       bool match = false;
-      if (idx < n) {
+      if (staged) {
+        match = s_after_key[lane] == key;
+      } else if (idx < n) {
         w = words[idx];
         match = (w >> idx_bits) == key;
       }
       const uint32_t m = __ballot_sync(0xffffffffu, match);
       const int run = m == 0xffffffffu ? 32 : __ffs(~m) - 1;  // members are consecutive: the leading matches
       float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-      if ((int)lane < run) pt = __ldg(xyz4 + (w & idx_mask));
+      if ((int)lane < run) pt = staged ? s_after_pt[lane] : __ldg(xyz4 + (w & idx_mask));
       for (int q = 0; q < run; q++) {  // the additions stay in list order (every lane carries the same sums)
         sx = __fadd_rn(sx, __fsub_rn(__shfl_sync(0xffffffffu, pt.x, q), c0));
         sy = __fadd_rn(sy, __fsub_rn(__shfl_sync(0xffffffffu, pt.y, q), c1));
@@ -582,7 +611,7 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
   int dev = 0;
   PCG_CUDA(cudaGetDevice(&dev));
   if (!(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
-    PCG_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kTileBytes));
+    PCG_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBufs * kTileBytes));
     configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   u64* buf[2] = {w0.p, w1.p};
@@ -599,7 +628,7 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
     a.n = n;
     a.tiles_per_super = S;
     a.shift = shift;
-    PCG_LAUNCH_NAMED("vgp::scatter_kernel", scatter_kernel, supers, kThreads, 2 * kTileBytes, stream, a);
+    PCG_LAUNCH_NAMED("vgp::scatter_kernel", scatter_kernel, supers, kThreads, kBufs * kTileBytes, stream, a);
     cur ^= 1;
   }
   PCG_LAUNCH_NAMED("vgp::head_count_kernel", head_count_kernel, (rtiles + 7) / 8, 256, 0, stream, buf[cur], n, idx_bits,

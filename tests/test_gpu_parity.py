@@ -84,6 +84,162 @@ def test_voxelgrid_random_vs_oracle(pg, oracle, chunk, layout):
     assert out[: len(exp)].tobytes() == exp.tobytes()
 
 
+def _filter_raw(buf, n, stride, off, leaf, chunk):
+    import ctypes as C
+
+    from pcgol_b200 import _lib
+    out = np.empty(max(1, n * stride), np.uint8)
+    n_out = C.c_int64(0)
+    flat = np.ascontiguousarray(buf).reshape(-1)
+    rc = _lib.lib.pcg_voxelgrid_filter(flat.ctypes.data, n, stride, (C.c_int64 * 3)(*off),
+                                       np.asarray(leaf, f32).ctypes.data, np.asarray(chunk, np.int64).ctypes.data, 0,
+                                       out.ctypes.data, C.byref(n_out))
+    assert rc == 0, _lib.last_error()
+    return out[: n_out.value * stride].tobytes()
+
+
+@pytest.mark.parametrize("path", [1, 2])  # 1: packed 64-bit words (vg_packed.cuh), 2: (key, index) pairs
+@pytest.mark.parametrize("chunk", [(0, 0, 0), (128, 128, 128), (7, 3, 5)])
+@pytest.mark.parametrize("layout", [(12, (0, 4, 8)), (20, (4, 8, 12)), (13, (1, 5, 9))])
+def test_voxelgrid_multikernel_pipelines_vs_oracle(pg, oracle, path, chunk, layout):
+    # the pipelines used above 1.2M points, forced at a size the oracle finishes in seconds; voxelgrid.go:35-187
+    from pcgol_b200 import _lib
+    stride, off = layout
+    rng = np.random.default_rng(hash((chunk, layout)) % (2**32))
+    n = 30000
+    buf = rng.integers(0, 255, size=(n, stride), dtype=np.uint8)
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([4.0, 3.0, 1.5], f32)).astype(f32)
+    xyz -= xyz.min(axis=0)
+    for k in range(3):
+        buf[:, off[k]:off[k] + 4] = xyz[:, k:k + 1].copy().view(np.uint8)
+    leaf = (0.1, 0.07, 0.13)
+    rc, exp = oracle.voxelgrid_filter(buf, stride, off, leaf, chunk, mode="dense")
+    assert rc == oracle.OK
+    _lib.set_vg_path(path)
+    try:
+        got = _filter_raw(buf, n, stride, off, leaf, chunk)
+    finally:
+        _lib.set_vg_path(0)
+    assert got == exp.tobytes()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 1023, 1024, 1025, 4095, 4096, 4097, 8193, 16384 + 3])
+def test_voxelgrid_packed_pipeline_tile_edges(pg, oracle, n):
+    # sizes around the tiles of the packed pipeline (4096-word sort tiles, 1024-position reduce tiles, odd counts for
+    # the 16-byte granule of the bulk copies); a dozen heavy voxels so that voxels straddle tile boundaries
+    from pcgol_b200 import _lib
+    rng = np.random.default_rng(n)
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([1.0, 0.6, 0.3], f32)).astype(f32)
+    heavy = rng.random(n) < 0.5
+    xyz[heavy] = (xyz[rng.integers(0, min(n, 12), size=int(heavy.sum()))] + rng.random((int(heavy.sum()), 3), dtype=f32) * f32(0.01)).astype(f32)
+    buf = xyz.view(np.uint8).reshape(-1)
+    leaf, chunk = (0.05, 0.05, 0.05), (8, 8, 8)
+    rc, exp = oracle.voxelgrid_filter(buf, 12, (0, 4, 8), leaf, chunk, mode="dense")
+    assert rc == oracle.OK
+    _lib.set_vg_path(1)
+    try:
+        got = _filter_raw(buf, n, 12, (0, 4, 8), leaf, chunk)
+    finally:
+        _lib.set_vg_path(0)
+    assert got == exp.tobytes()
+
+
+def test_minmax_first_zero_sign(pg, oracle):
+    # pc/minmax.go:9-26: strict comparisons keep the FIRST occurrence of the extreme value, visible in the sign of a
+    # zero; all three VoxelGrid paths (one cooperative kernel, packed words, pairs) must agree with the oracle
+    from pcgol_b200 import _lib
+    rng = np.random.default_rng(3)
+    for first_neg in (False, True):
+        xyz = (rng.random((70000, 3), dtype=f32) * f32(2.0)).astype(f32)
+        zeros = rng.choice(len(xyz), 40, replace=False)
+        xyz[zeros, 0] = f32(0.0)
+        xyz[zeros[::2], 0] = f32(-0.0)
+        xyz[:, 1] -= f32(2.5)  # all negative: the maximum side
+        xyz[zeros, 1] = f32(-0.0)
+        xyz[zeros[1::2], 1] = f32(0.0)
+        first = int(zeros.min())
+        xyz[first, 0] = f32(-0.0) if first_neg else f32(0.0)
+        xyz[first, 1] = f32(0.0) if first_neg else f32(-0.0)
+        buf = xyz.view(np.uint8).reshape(-1)
+        rc, exp = oracle.voxelgrid_filter(buf, 12, (0, 4, 8), (0.1, 0.1, 0.1), (16, 16, 16), mode="dense")
+        assert rc == oracle.OK
+        for path in (0, 1, 2):
+            _lib.set_vg_path(path)
+            try:
+                got = _filter_raw(buf, len(xyz), 12, (0, 4, 8), (0.1, 0.1, 0.1), (16, 16, 16))
+            finally:
+                _lib.set_vg_path(0)
+            assert got == exp.tobytes(), (first_neg, path)
+
+
+@pytest.mark.parametrize("n", [5000, 300000])  # plain scan / bulk-async scan (>= 64 tiles of 1024 points)
+def test_minmax_dev_first_occurrence_and_nan(pg, n):
+    # pc/minmax.go:9-26 directly: bit patterns of the six results, incl. the sign of a zero extreme (first occurrence),
+    # NaN coordinates skipped, a NaN at point 0 kept; and the two-slice combination of the sharded words
+    import ctypes as C
+
+    import torch
+
+    from pcgol_b200 import _lib
+    from pcgol_b200.dist import decode_minmax_words
+    rng = np.random.default_rng(n)
+
+    def go_minmax(a):  # the reference loop, bit for bit
+        mn, mx = a[0].copy(), a[0].copy()
+        for k in range(3):
+            col = a[:, k]
+            if np.isnan(col[0]):
+                continue
+            # strict comparisons: the first occurrence of the extreme value stays
+            vmin, vmax = np.nanmin(col), np.nanmax(col)
+            mn[k] = col[np.flatnonzero(col == vmin)[0]]
+            mx[k] = col[np.flatnonzero(col == vmax)[0]]
+        return mn, mx
+
+    def gpu_minmax(a):
+        d = torch.from_numpy(a.copy()).cuda()
+        mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+        rc = _lib.lib.pcg_minmax_dev(d.data_ptr(), len(a), 12, (C.c_int64 * 3)(0, 4, 8), 0, mn, mx, None)
+        assert rc == 0, _lib.last_error()
+        return np.array(list(mn), f32), np.array(list(mx), f32)
+
+    for case in range(4):
+        a = (rng.random((n, 3), dtype=f32) * f32(3.0)).astype(f32)
+        a[:, 1] -= f32(3.5)  # axis 1: all negative, its maximum is the zero planted below
+        z = np.sort(rng.choice(np.arange(1, n), 30, replace=False))
+        a[z, 0] = f32(0.0)
+        a[z, 1] = f32(-0.0)
+        a[z[0], 0] = f32(-0.0) if case & 1 else f32(0.0)   # the first zero decides the sign
+        a[z[0], 1] = f32(0.0) if case & 1 else f32(-0.0)
+        a[rng.choice(np.arange(1, n), 20, replace=False), 2] = np.nan
+        if case & 2:
+            a[0, 2] = np.nan  # never replaced (minmax.go:13)
+        emn, emx = go_minmax(a)
+        gmn, gmx = gpu_minmax(a)
+        assert gmn.view(np.uint32)[:2].tolist() == emn.view(np.uint32)[:2].tolist(), case
+        assert gmx.view(np.uint32)[:2].tolist() == emx.view(np.uint32)[:2].tolist(), case
+        if case & 2:
+            assert np.isnan(gmn[2]) and np.isnan(gmx[2])
+        else:
+            assert gmn.view(np.uint32)[2] == emn.view(np.uint32)[2] and gmx.view(np.uint32)[2] == emx.view(np.uint32)[2]
+        # sharded: two slices, the signed MIN of their words
+        cut = n // 3
+        words = []
+        for lo, hi in ((0, cut), (cut, n)):
+            d = torch.from_numpy(a[lo:hi].copy()).cuda()
+            w = torch.empty(6, dtype=torch.int64, device="cuda")
+            rc = _lib.lib.pcg_minmax_packed_dev(d.data_ptr(), hi - lo, 12, (C.c_int64 * 3)(0, 4, 8), 0, lo, w.data_ptr(), None)
+            assert rc == 0, _lib.last_error()
+            words.append(w.cpu().numpy())
+        mm6 = decode_minmax_words(np.minimum(words[0], words[1]))
+        exp6 = np.concatenate([emn, emx])
+        for k in range(6):
+            if np.isnan(exp6[k]):
+                assert np.isnan(mm6[k])
+            else:
+                assert mm6.view(np.uint32)[k] == exp6.view(np.uint32)[k], (case, k)
+
+
 def test_voxelgrid_negative_coordinates_chunked(pg, oracle):
     rng = np.random.default_rng(11)
     xyz = (rng.standard_normal((30000, 3)) * np.array([5.0, 3.0, 0.5])).astype(f32)
