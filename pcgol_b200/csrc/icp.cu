@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "bulk_async.cuh"
 #include "bvh.cuh"
 #include "icp_math.cuh"
 
@@ -424,6 +425,7 @@ constexpr int kReplayPerLane = kReplayChunk / 32;     // consecutive elements pe
 static_assert(kReplayChunk % 128 == 0 || kReplayChunk == 64 || kReplayChunk == 32, "chunk = whole float4 rows per warp");
 constexpr int kReplayThreads = 512;
 constexpr int kReplayBatch = 256;  // chunk summaries staged in shared memory per round of the walk
+constexpr int kReplayStage = 128;  // chunks whose elements can wait in shared memory per round (128 KB)
 
 // Summary of one chunk as the walk consumes it, in the float domain.  p = parity of the accumulator's integer
 // mantissa M (acc = M * ulp, 2^23 <= |M| < 2^24).  The chunk is one exact add iff acc lies in [lo_pos[p], hi_pos[p]]
@@ -571,7 +573,14 @@ __global__ void __launch_bounds__(256)
       rc.lo_neg[p] = neg_ok ? __fmul_rn((float)lo_neg, ulp) : inf;
       rc.hi_neg[p] = neg_ok ? __fmul_rn((float)hi_neg, ulp) : -inf;
     }
-    rc.pad_[0] = rc.pad_[1] = 0.f;
+    // Will the walk have to replay this chunk element by element?  The float64 guess failing the interval test (for
+    // either parity) predicts it (exactly, on every stream tried): the walk kernel then has the chunk's elements
+    // waiting in shared memory.  A wrong prediction only costs the on-demand load.
+    auto inside = [&](int p) {
+      return (guess >= rc.lo_pos[p] && guess <= rc.hi_pos[p]) || (guess >= rc.lo_neg[p] && guess <= rc.hi_neg[p]);
+    };
+    rc.pad_[0] = (inside(0) && inside(1)) ? 0.f : 1.f;
+    rc.pad_[1] = 0.f;
     chunks[w] = rc;
   }
 }
@@ -582,14 +591,24 @@ __global__ void __launch_bounds__(kReplayThreads)
     icp_replay_walk_kernel(IcpState* __restrict__ st, const float* __restrict__ terms, int64_t n, int64_t n_pad,
                            int64_t nchunks, const ReplayChunk* __restrict__ chunks_all) {
   if (st->done) return;
+  extern __shared__ __align__(128) float s_stage[];  // [kReplayStage][kReplayChunk]: elements of the chunks to replay
   __shared__ __align__(16) float s_x[kReplayChunk];
   __shared__ ReplayChunk s_chunks[kReplayBatch];
+  __shared__ short s_slot[kReplayBatch];  // staging slot of the batch's i-th chunk, -1: not staged
+  __shared__ int s_wcount[kReplayBatch / 32];
+  __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = blockIdx.x;
   const float* __restrict__ x = terms + (int64_t)k * n_pad;
   const ReplayChunk* __restrict__ chunks = chunks_all + (int64_t)k * nchunks;
+  const bool can_stage = ((reinterpret_cast<uintptr_t>(x)) & 15) == 0;  // bulk copies need 16-byte aligned rows
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   float acc = 0.f;
   unsigned int n_fast = 0, n_slow = 0;
+  uint32_t stage_phase = 0;
   const long long t_walk0 = clock64();
   for (int64_t c0 = 0; c0 < nchunks; c0 += kReplayBatch) {
     const int batch = (int)min((int64_t)kReplayBatch, nchunks - c0);
@@ -601,7 +620,45 @@ __global__ void __launch_bounds__(kReplayThreads)
       for (int i = tid; i < words; i += kReplayThreads) dst[i] = src[i];
     }
     __syncthreads();
+    // The chunks the walk is predicted to replay arrive as bulk-async copies (one 1 KB cp.async.bulk each, all in
+    // flight together, completion counted on an mbarrier) while the walk is still in its exact-add steps.
+    bool staged_any = false;
+    {
+      bool want = false;
+      if (tid < batch)
+        want = can_stage && s_chunks[tid].pad_[0] != 0.f && (c0 + tid + 1) * (int64_t)kReplayChunk <= n;
+      const unsigned m = __ballot_sync(0xffffffffu, want);
+      if (tid < kReplayBatch && lane == 0) s_wcount[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kReplayBatch / 32; w++) {
+        const int c = s_wcount[w];
+        before += w < warp ? c : 0;
+        total += c;
+      }
+      const int slot = before + __popc(m & ((1u << lane) - 1u));
+      const bool take = want && slot < kReplayStage;
+      if (tid < kReplayBatch) s_slot[tid] = take ? (short)slot : (short)-1;
+      const int nstaged = min(total, kReplayStage);
+      staged_any = nstaged > 0;
+      if (staged_any) {
+        if (tid == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slots were last read by ordinary loads
+          mbar_expect_tx(&s_bar, (uint32_t)nstaged * kReplayChunk * (uint32_t)sizeof(float));
+        }
+        __syncthreads();  // the expectation is posted before any copy can complete the phase
+        if (take)
+          bulk_g2s(s_stage + (size_t)slot * kReplayChunk, x + (c0 + tid) * (int64_t)kReplayChunk,
+                   kReplayChunk * (uint32_t)sizeof(float), &s_bar);
+      }
+      __syncthreads();  // s_slot is complete
+    }
     if (warp == 0) {
+      if (staged_any) {
+        mbar_wait(&s_bar, stage_phase & 1u);
+        stage_phase++;
+      }
       // one step of the integer path: exact add if the accumulator lies in the chunk's safe interval
       // (summaries travel as three 16-byte shared-memory loads into registers; selects, not indexed loads)
       struct Rc {
@@ -626,13 +683,16 @@ __global__ void __launch_bounds__(kReplayThreads)
       // the reference's own loop over one chunk (from shared memory)
       auto replay = [&](float a, int64_t chunk) {
         const int64_t base = chunk * kReplayChunk;
+        const int slot = s_slot[(int)(chunk - c0)];
+        if (slot < 0) {  // not predicted (or no room): load now
 #pragma unroll
-        for (int j = 0; j < kReplayChunk / 32; j++) {
-          const int64_t i = base + j * 32 + lane;
-          s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
+          for (int j = 0; j < kReplayChunk / 32; j++) {
+            const int64_t i = base + j * 32 + lane;
+            s_x[j * 32 + lane] = i < n ? x[i] : 0.f;
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        const float4* b4 = reinterpret_cast<const float4*>(s_x);
+        const float4* b4 = reinterpret_cast<const float4*>(slot < 0 ? s_x : s_stage + (size_t)slot * kReplayChunk);
 #pragma unroll 8
         for (int j = 0; j < kReplayChunk / 4; j++) {
           const float4 v = b4[j];
@@ -711,7 +771,15 @@ static void launch_exact_replay(IcpState* st, const float* terms, int64_t n, int
   const int blocks = div_up(nchunks * streams, 256 / 32);
   PCG_LAUNCH(icp_replay_sums_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums);
   PCG_LAUNCH(icp_replay_summaries_kernel, blocks, 256, 0, stream, st, terms, n, n_pad, nchunks, streams, sums, chunks);
-  PCG_LAUNCH(icp_replay_walk_kernel, streams, kReplayThreads, 0, stream, st, terms, n, n_pad, nchunks, chunks);
+  constexpr size_t kStageBytes = (size_t)kReplayStage * kReplayChunk * sizeof(float);
+  static std::atomic<uint64_t> configured{0};
+  int dev = 0;
+  PCG_CUDA(cudaGetDevice(&dev));
+  if (!(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
+    PCG_CUDA(cudaFuncSetAttribute(icp_replay_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytes));
+    configured.fetch_or(1ull << dev, std::memory_order_relaxed);
+  }
+  PCG_LAUNCH(icp_replay_walk_kernel, streams, kReplayThreads, kStageBytes, stream, st, terms, n, n_pad, nchunks, chunks);
 }
 
 // Sharded ICP: fold the per-CTA float64 partials into 16 doubles for the all-reduce.

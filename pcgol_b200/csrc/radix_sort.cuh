@@ -168,13 +168,10 @@ __global__ void __launch_bounds__(kThreads)
     int leader = __ffs(peers) - 1;
     uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     uint32_t pre = 0;
-    if (valid && (int)lane == leader) {
-      pre = s_warp_hist[warp][d];
-      s_warp_hist[warp][d] = pre + __popc(peers);
-    }
+    // atomics of one warp on one address execute in program order: no barrier between the rounds
+    if (valid && (int)lane == leader) pre = atomicAdd(&s_warp_hist[warp][d], (uint32_t)__popc(peers));
     pre = __shfl_sync(0xffffffffu, pre, leader);
     offs[i] = pre + rank;
-    __syncwarp();
   }
   __syncthreads();
 

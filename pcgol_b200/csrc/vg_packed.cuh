@@ -15,7 +15,7 @@
 //
 //   key_kernel      point -> word; counts the first pass's digit per super-tile in the same read
 //   hist_kernel     digit counts per super-tile for the later passes (one streaming read)
-//   colsum_kernel / base_kernel   table -> first output slot per (super-tile, digit)
+//   base_kernel     table -> first output slot per (super-tile, digit)
 //   scatter_kernel  one CTA per super-tile; its tiles arrive in shared memory as bulk-async copies (cp.async.bulk +
 //                   mbarrier, UBLKCP / SYNCS in SASS), the next one in flight while the current one is ranked (warp
 //                   match-any) and written out in runs through the buffer it arrived in
@@ -74,7 +74,7 @@ __device__ __forceinline__ void hist_add(uint32_t* s_hist, uint32_t d, bool vali
 // One CTA per tile of 4096 points; H0[super-tile][digit] += the tile's counts (zeroed by the host).
 __global__ void __launch_bounds__(kThreads)
     key_kernel(CloudView v, VgParams P, int idx_bits, uint32_t tiles_per_super, u64* __restrict__ words,
-               float4* __restrict__ xyz4, uint32_t* __restrict__ H0, int* __restrict__ flags) {
+               float4* __restrict__ xyz4, uint32_t* __restrict__ H0, uint32_t* __restrict__ T0, int* __restrict__ flags) {
   __shared__ uint32_t s_hist[kRadix];
   s_hist[threadIdx.x] = 0;
   s_hist[threadIdx.x + kThreads] = 0;
@@ -100,17 +100,23 @@ __global__ void __launch_bounds__(kThreads)
   }
   if (bad) atomicOr(flags, bad);
   __syncthreads();
-  uint32_t* row = H0 + (size_t)(blockIdx.x / tiles_per_super) * kRadix;
+  const uint32_t super = blockIdx.x / tiles_per_super;
+  uint32_t* row = H0 + (size_t)super * kRadix;
+  uint32_t* trow = T0 + (size_t)(super / kRowBlock) * kRadix;  // column sums over the row block (see base_kernel)
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const uint32_t c = s_hist[threadIdx.x + q * kThreads];
-    if (c) atomicAdd(&row[threadIdx.x + q * kThreads], c);
+    if (c) {
+      atomicAdd(&row[threadIdx.x + q * kThreads], c);
+      atomicAdd(&trow[threadIdx.x + q * kThreads], c);
+    }
   }
 }
 
 // ---- digit counts per super-tile (passes after the first) ------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-    hist_kernel(const u64* __restrict__ in, uint32_t n, int shift, uint32_t tiles_per_super, uint32_t* __restrict__ H) {
+    hist_kernel(const u64* __restrict__ in, uint32_t n, int shift, uint32_t tiles_per_super, uint32_t* __restrict__ H,
+                uint32_t* __restrict__ T) {
   __shared__ uint32_t s_hist[kRadix];
   s_hist[threadIdx.x] = 0;
   s_hist[threadIdx.x + kThreads] = 0;
@@ -129,55 +135,73 @@ __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
   uint32_t* row = H + (size_t)blockIdx.x * kRadix;
-  row[threadIdx.x] = s_hist[threadIdx.x];
-  row[threadIdx.x + kThreads] = s_hist[threadIdx.x + kThreads];
+  uint32_t* trow = T + (size_t)(blockIdx.x / kRowBlock) * kRadix;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const uint32_t c = s_hist[threadIdx.x + q * kThreads];
+    row[threadIdx.x + q * kThreads] = c;
+    if (c) atomicAdd(&trow[threadIdx.x + q * kThreads], c);
+  }
 }
 
 // ---- table -> first output slot of every (super-tile, digit) ----------------------------------------------------------
-// colsum: T[rb][d] = sum of H over the 64 super-tiles of row block rb.   base: B[s][d] = (slots of all smaller digits)
-// + (counts of digit d in the super-tiles before s).  512 threads: one per digit.
-__global__ void __launch_bounds__(kRadix)
-    colsum_kernel(const uint32_t* __restrict__ H, uint32_t supers, uint32_t* __restrict__ T) {
-  const uint32_t d = threadIdx.x, s0 = blockIdx.x * kRowBlock, s1 = min(supers, s0 + kRowBlock);
-  uint32_t sum = 0;
-#pragma unroll 8
-  for (uint32_t s = s0; s < s1; s++) sum += H[(size_t)s * kRadix + d];
-  T[(size_t)blockIdx.x * kRadix + d] = sum;
-}
-__global__ void __launch_bounds__(kRadix)
+// B[s][d] = (slots of all smaller digits) + (counts of digit d in the super-tiles before s).  T[rb][d] = the counts of
+// digit d over the 64 super-tiles of row block rb, accumulated by the kernels that count.
+// 1024 threads: two per digit, each half takes every other row block of T and 32 of the block's 64 rows.
+__global__ void __launch_bounds__(2 * kRadix)
     base_kernel(const uint32_t* __restrict__ H, const uint32_t* __restrict__ T, uint32_t supers, uint32_t rowblocks,
                 uint32_t* __restrict__ B) {
   __shared__ uint32_t s_warp[kRadix / 32];
-  const uint32_t d = threadIdx.x, lane = d & 31, warp = d >> 5;
+  __shared__ uint32_t s_tot[kRadix], s_pre[kRadix], s_half[kRadix];
+  const uint32_t d = threadIdx.x & (kRadix - 1), h = threadIdx.x >> kBits, lane = d & 31, warp = d >> 5;
   uint32_t tot = 0, pre = 0;
 #pragma unroll 8
-  for (uint32_t rb = 0; rb < rowblocks; rb++) {
+  for (uint32_t rb = h; rb < rowblocks; rb += 2) {
     const uint32_t t = T[(size_t)rb * kRadix + d];
     tot += t;
     pre += rb < blockIdx.x ? t : 0u;
   }
-  uint32_t incl = tot;  // exclusive scan of the digit totals over the 512 threads
+  // this half's 32 rows of the block, all loads in flight together
+  constexpr int kHalfRows = kRowBlock / 2;
+  const uint32_t s0 = blockIdx.x * kRowBlock + h * kHalfRows, s1 = min(supers, s0 + kHalfRows);
+  uint32_t hv[kHalfRows];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int q = 0; q < kHalfRows; q++) {
+    hv[q] = s0 + q < s1 ? H[(size_t)(s0 + q) * kRadix + d] : 0u;
+    mine += hv[q];
+  }
+  if (h == 1) {
+    s_tot[d] = tot;
+    s_pre[d] = pre;
+  } else {
+    s_half[d] = mine;
+  }
+  __syncthreads();
+  if (h == 0) {
+    tot += s_tot[d];
+    pre += s_pre[d];
+  }
+  uint32_t incl = tot;  // exclusive scan of the digit totals (first half's 512 threads)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= (uint32_t)o) incl += t;
   }
-  if (lane == 31) s_warp[warp] = incl;
+  if (h == 0 && lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  uint32_t wbase = 0;
+  if (h == 0) {
+    uint32_t wbase = 0;
 #pragma unroll
-  for (int w = 0; w < kRadix / 32; w++) wbase += w < (int)warp ? s_warp[w] : 0u;
-  uint32_t run = wbase + incl - tot + pre;
-  const uint32_t s0 = blockIdx.x * kRowBlock, s1 = min(supers, s0 + kRowBlock);
-  uint32_t h[8];
-  for (uint32_t s = s0; s < s1; s += 8) {
+    for (int w = 0; w < kRadix / 32; w++) wbase += w < (int)warp ? s_warp[w] : 0u;
+    s_tot[d] = wbase + incl - tot + pre;  // first slot of digit d in this row block
+  }
+  __syncthreads();
+  uint32_t run = s_tot[d] + (h == 1 ? s_half[d] : 0u);
 #pragma unroll
-    for (int q = 0; q < 8; q++) h[q] = s + q < s1 ? H[(size_t)(s + q) * kRadix + d] : 0u;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      if (s + q < s1) B[(size_t)(s + q) * kRadix + d] = run;
-      run += h[q];
-    }
+  for (int q = 0; q < kHalfRows; q++) {
+    if (s0 + q < s1) B[(size_t)(s0 + q) * kRadix + d] = run;
+    run += hv[q];
   }
 }
 
@@ -588,24 +612,32 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
   const int idx_bits = std::max(1, bits_for((long long)n));
   const int passes = passes_for(total_bits);
   const uint32_t tiles = (n + kTile - 1) / kTile;
-  // super-tiles: as large as keeps every SM supplied with several CTAs, at most 4096 of them
-  uint32_t S = std::min<uint32_t>((uint32_t)kSuperTiles, std::max<uint32_t>(1u, tiles / (kNumSMs * 4)));
+  // super-tiles: as large as leaves the scatter kernel at least six full waves of CTAs, at most 4096 of them
+  uint32_t S = std::min<uint32_t>((uint32_t)kSuperTiles, std::max<uint32_t>(1u, tiles / (kNumSMs * kCtasPerSm * 6)));
   while ((tiles + S - 1) / S > 4096u) S *= 2;
   const uint32_t supers = (tiles + S - 1) / S;
   const uint32_t rowblocks = (supers + kRowBlock - 1) / kRowBlock;
   const uint32_t rtiles = (n + kRedTile - 1) / kRedTile;
-  DevBuf<u64> w0((size_t)n + 2, stream), w1((size_t)n + 2, stream);
-  DevBuf<float4> xyz4(n, stream);
-  // [H: supers x 512 | B: supers x 512 | T: rowblocks x 512]
-  const size_t table = (size_t)supers * kRadix;
-  DevBuf<uint32_t> tab(2 * table + (size_t)rowblocks * kRadix, stream);
-  uint32_t* H = tab.p;
-  uint32_t* B = tab.p + table;
-  uint32_t* T = tab.p + 2 * table;
-  DevBuf<uint32_t> head_counts(rtiles, stream);
-  DevBuf<long long> first_slot((size_t)rtiles + 1, stream);
-  PCG_CUDA(cudaMemsetAsync(H, 0, table * sizeof(uint32_t), stream));
-  PCG_LAUNCH_NAMED("vgp::key_kernel", key_kernel, tiles, kThreads, 0, stream, v, P, idx_bits, S, w0.p, xyz4.p, H, d_flags);
+  // ONE allocation per call (a pool that served many small requests before hands out eight large ones slowly):
+  // [T: passes x rowblocks x 512 | H: supers x 512 | B: supers x 512 | head counts | first slots | words 0 | words 1 |
+  //  float4 points]; T and H (first pass) are accumulated, hence zeroed
+  const size_t table = (size_t)supers * kRadix, ttable = (size_t)rowblocks * kRadix;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t tab_bytes = up(((size_t)passes * ttable + 2 * table) * sizeof(uint32_t));
+  const size_t hc_bytes = up((size_t)rtiles * sizeof(uint32_t));
+  const size_t fs_bytes = up(((size_t)rtiles + 1) * sizeof(long long));
+  const size_t w_bytes = up(((size_t)n + 2) * sizeof(u64));
+  DevBuf<uint8_t> ws(tab_bytes + hc_bytes + fs_bytes + 2 * w_bytes + (size_t)n * sizeof(float4), stream);
+  uint32_t* T = reinterpret_cast<uint32_t*>(ws.p);
+  uint32_t* H = T + (size_t)passes * ttable;
+  uint32_t* B = H + table;
+  uint32_t* head_counts = reinterpret_cast<uint32_t*>(ws.p + tab_bytes);
+  long long* first_slot = reinterpret_cast<long long*>(ws.p + tab_bytes + hc_bytes);
+  u64* w0 = reinterpret_cast<u64*>(ws.p + tab_bytes + hc_bytes + fs_bytes);
+  u64* w1 = reinterpret_cast<u64*>(ws.p + tab_bytes + hc_bytes + fs_bytes + w_bytes);
+  float4* xyz4 = reinterpret_cast<float4*>(ws.p + tab_bytes + hc_bytes + fs_bytes + 2 * w_bytes);
+  PCG_CUDA(cudaMemsetAsync(T, 0, ((size_t)passes * ttable + table) * sizeof(uint32_t), stream));
+  PCG_LAUNCH_NAMED("vgp::key_kernel", key_kernel, tiles, kThreads, 0, stream, v, P, idx_bits, S, w0, xyz4, H, T, d_flags);
 
   static std::atomic<uint64_t> configured{0};
   int dev = 0;
@@ -614,13 +646,14 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
     PCG_CUDA(cudaFuncSetAttribute(scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBufs * kTileBytes));
     configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
-  u64* buf[2] = {w0.p, w1.p};
+  u64* buf[2] = {w0, w1};
   int cur = 0;
   for (int p = 0; p < passes; p++) {
     const int shift = idx_bits + p * kBits;
-    if (p > 0) PCG_LAUNCH_NAMED("vgp::hist_kernel", hist_kernel, supers, kThreads, 0, stream, buf[cur], n, shift, S, H);
-    PCG_LAUNCH_NAMED("vgp::colsum_kernel", colsum_kernel, rowblocks, kRadix, 0, stream, H, supers, T);
-    PCG_LAUNCH_NAMED("vgp::base_kernel", base_kernel, rowblocks, kRadix, 0, stream, H, T, supers, rowblocks, B);
+    uint32_t* Tp = T + (size_t)p * ttable;
+    if (p > 0)
+      PCG_LAUNCH_NAMED("vgp::hist_kernel", hist_kernel, supers, kThreads, 0, stream, buf[cur], n, shift, S, H, Tp);
+    PCG_LAUNCH_NAMED("vgp::base_kernel", base_kernel, rowblocks, 2 * kRadix, 0, stream, H, Tp, supers, rowblocks, B);
     ScatterArgs a;
     a.in = buf[cur];
     a.out = buf[cur ^ 1];
@@ -632,10 +665,10 @@ inline void run(const CloudView& v, const VgParams& P, int total_bits, uint8_t* 
     cur ^= 1;
   }
   PCG_LAUNCH_NAMED("vgp::head_count_kernel", head_count_kernel, (rtiles + 7) / 8, 256, 0, stream, buf[cur], n, idx_bits,
-                   head_counts.p);
-  scan_counts(head_counts.p, first_slot.p, rtiles, stream);
-  PCG_LAUNCH_NAMED("vgp::reduce_kernel", reduce_kernel, rtiles, kRedThreads, 0, stream, v, P, buf[cur], xyz4.p, n,
-                   idx_bits, d_out, first_slot.p, d_n_out);
+                   head_counts);
+  scan_counts(head_counts, first_slot, rtiles, stream);
+  PCG_LAUNCH_NAMED("vgp::reduce_kernel", reduce_kernel, rtiles, kRedThreads, 0, stream, v, P, buf[cur], xyz4, n,
+                   idx_bits, d_out, first_slot, d_n_out);
 }
 
 }  // namespace vgp

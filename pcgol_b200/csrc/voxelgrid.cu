@@ -765,13 +765,11 @@ __device__ __forceinline__ void run(const CloudView& v, const Work& w, uint8_t* 
       const int leader = __ffs(peers) - 1;
       const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
       uint32_t pre = 0;
-      if (valid && (int)lane == leader) {
-        pre = sm.warp_hist[warp][d];
-        sm.warp_hist[warp][d] = pre + __popc(peers);
-      }
+      // atomics of one warp on one address execute in program order: the returned counts need no barrier between
+      // the rounds, and the rounds overlap instead of waiting for a load-add-store each
+      if (valid && (int)lane == leader) pre = atomicAdd(&sm.warp_hist[warp][d], (uint32_t)__popc(peers));
       pre = __shfl_sync(0xffffffffu, pre, leader);
       offs[i] = pre + rank;
-      __syncwarp();
     }
     __syncthreads();
     uint32_t count = 0;
