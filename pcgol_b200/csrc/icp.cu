@@ -659,27 +659,6 @@ __global__ void __launch_bounds__(kReplayThreads)
         mbar_wait(&s_bar, stage_phase & 1u);
         stage_phase++;
       }
-      // one step of the integer path: exact add if the accumulator lies in the chunk's safe interval
-      // (summaries travel as three 16-byte shared-memory loads into registers; selects, not indexed loads)
-      struct Rc {
-        float4 a, b, c;  // {t0,t1,lp0,lp1} {hp0,hp1,ln0,ln1} {hn0,hn1,-,-}
-      };
-      auto load_rc = [&](int i) {
-        const float4* q = reinterpret_cast<const float4*>(&s_chunks[i]);
-        Rc r;
-        r.a = q[0];
-        r.b = q[1];
-        r.c = q[2];
-        return r;
-      };
-      auto step = [](float a, const Rc rc, bool* fast) {
-        const bool p = (__float_as_uint(a) & 1u) != 0;
-        const float t = p ? rc.a.y : rc.a.x;
-        const float lp = p ? rc.a.w : rc.a.z, hp = p ? rc.b.y : rc.b.x;
-        const float ln = p ? rc.b.w : rc.b.z, hn = p ? rc.c.y : rc.c.x;
-        *fast = (a >= lp && a <= hp) || (a >= ln && a <= hn);
-        return __fadd_rn(a, t);
-      };
       // the reference's own loop over one chunk (from shared memory)
       auto replay = [&](float a, int64_t chunk) {
         const int64_t base = chunk * kReplayChunk;
@@ -704,42 +683,66 @@ __global__ void __launch_bounds__(kReplayThreads)
         __syncwarp();
         return a;
       };
-      // Four chunks per round, speculatively: the data dependency between chunks is one select and one add; the
-      // interval tests run beside it and are looked at once per round.
-      int ci = 0;
-      for (; ci + 4 <= batch; ci += 4) {
-        const Rc r0 = load_rc(ci), r1 = load_rc(ci + 1), r2 = load_rc(ci + 2), r3 = load_rc(ci + 3);
-        bool f0, f1, f2, f3;
-        const float a1 = step(acc, r0, &f0);
-        const float a2 = step(a1, r1, &f1);
-        const float a3 = step(a2, r2, &f2);
-        const float a4 = step(a3, r3, &f3);
-        if (f0 && f1 && f2 && f3) {
-          acc = a4;
-          n_fast += 4;
-        } else {
-          for (int k = 0; k < 4; k++) {
-            bool f;
-            const float a = step(acc, load_rc(ci + k), &f);
-            if (f) {
-              acc = a;
+      // 32 chunks per round, one per lane.  The dependency between chunks is three instructions - parity of the
+      // accumulator, select the chunk's total for that parity, add - so that chain runs first (the totals come from
+      // shared memory, independent of the accumulator), every lane keeping the accumulator its own chunk starts from;
+      // the interval tests (ten comparisons per chunk) then run side by side, one chunk per lane.  The chain stops in
+      // front of every chunk the summaries kernel predicted to need a replay, so nothing is computed twice; a chunk
+      // that fails its test unpredicted is replayed from the accumulator it really starts with, and the chain resumes
+      // behind it.
+      for (int g0 = 0; g0 < batch; g0 += 32) {
+        const int cnt = min(32, batch - g0);
+        float t0 = 0.f, t1 = 0.f, lp0 = 0.f, lp1 = 0.f, hp0 = 0.f, hp1 = 0.f, ln0 = 0.f, ln1 = 0.f, hn0 = 0.f, hn1 = 0.f;
+        bool predicted = false;
+        if (lane < cnt) {
+          const float4* q = reinterpret_cast<const float4*>(&s_chunks[g0 + lane]);
+          const float4 qa = q[0], qb = q[1], qc = q[2];  // {t0,t1,lp0,lp1} {hp0,hp1,ln0,ln1} {hn0,hn1,flag,-}
+          t0 = qa.x, t1 = qa.y, lp0 = qa.z, lp1 = qa.w;
+          hp0 = qb.x, hp1 = qb.y, ln0 = qb.z, ln1 = qb.w;
+          hn0 = qc.x, hn1 = qc.y;
+          predicted = qc.z != 0.f;
+        }
+        auto passes = [&](float a) {  // this lane's chunk: one exact add from accumulator a?
+          const bool p = (__float_as_uint(a) & 1u) != 0;
+          const float lp = p ? lp1 : lp0, hp = p ? hp1 : hp0, ln = p ? ln1 : ln0, hn = p ? hn1 : hn0;
+          return (a >= lp && a <= hp) || (a >= ln && a <= hn);
+        };
+        const unsigned predmask = __ballot_sync(0xffffffffu, predicted);
+        int start = 0;
+        while (start < cnt) {
+          const unsigned ahead = predmask & (0xffffffffu << start);
+          const int stop = ahead ? __ffs(ahead) - 1 : cnt;  // first predicted replay at or behind start
+          float mine = 0.f;  // the accumulator this lane's chunk starts from
+          float a = acc;
+#pragma unroll 4
+          for (int j = start; j < stop; j++) {
+            const float2 t = *reinterpret_cast<const float2*>(&s_chunks[g0 + j]);
+            if ((int)lane == j) mine = a;
+            a = __fadd_rn(a, (__float_as_uint(a) & 1u) ? t.y : t.x);
+          }
+          const unsigned bad = __ballot_sync(0xffffffffu, (int)lane >= start && (int)lane < stop && !passes(mine));
+          if (bad != 0u) {  // not predicted: replay the first failing chunk from its true accumulator
+            const int f = __ffs(bad) - 1;
+            n_fast += (unsigned)(f - start);
+            acc = replay(__shfl_sync(0xffffffffu, mine, f), c0 + g0 + f);
+            n_slow++;
+            start = f + 1;
+            continue;
+          }
+          acc = a;
+          n_fast += (unsigned)(stop - start);
+          if (stop < cnt) {  // the predicted chunk, from the true accumulator (it may pass after all)
+            const bool ok = (__ballot_sync(0xffffffffu, passes(acc)) >> stop) & 1u;
+            if (ok) {
+              const float s0 = __shfl_sync(0xffffffffu, t0, stop), s1 = __shfl_sync(0xffffffffu, t1, stop);
+              acc = __fadd_rn(acc, (__float_as_uint(acc) & 1u) ? s1 : s0);
               n_fast++;
             } else {
-              acc = replay(acc, c0 + ci + k);
+              acc = replay(acc, c0 + g0 + stop);
               n_slow++;
             }
           }
-        }
-      }
-      for (; ci < batch; ci++) {
-        bool f;
-        const float a = step(acc, load_rc(ci), &f);
-        if (f) {
-          acc = a;
-          n_fast++;
-        } else {
-          acc = replay(acc, c0 + ci);
-          n_slow++;
+          start = stop + 1;
         }
       }
     }
