@@ -41,15 +41,56 @@ struct IndexView {
 };
 
 #ifdef __CUDACC__
+// Packed float32 pairs (sm_100a: FADD2 / FMUL2, one instruction for two IEEE round-to-nearest operations - the same
+// per-element results as the scalar instructions).  x and y travel as a pair (they sit in adjacent registers after a
+// 16-byte load), z stays scalar.
+#ifndef PCG_NO_F32X2
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// ((dx*dx + dy*dy) + dz*dz) with d = a - b: bit-identical to dist_sq_ref (mat/vec3.go:18-20,38-40)
+__device__ __forceinline__ float dist_sq_pair(float ax, float ay, float az, unsigned long long bxy, float bz) {
+  const unsigned long long d = f2_sub(f2_pack(ax, ay), bxy);
+  float sx, sy;
+  f2_unpack(f2_mul(d, d), sx, sy);
+  const float dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+}
+#endif
+
 __device__ __forceinline__ float box_dist_sq(const float4 lo, const float4 hi, float qx, float qy, float qz) {
   // per axis: the query minus its clamp into [lo, hi] (exact selection), ONE rounded subtraction - the same rounded
   // operation the reference applies to (point - query), and |q - clamp(q)| <= |q - p| for every p in the box, so by
   // monotonicity of the rounding the bound never exceeds the reference distance of a point inside.  An empty box
   // (lo = +inf, hi = -inf) clamps to -inf: distance +inf.
+#ifndef PCG_NO_F32X2
+  const unsigned long long e =
+      f2_sub(f2_pack(qx, qy), f2_pack(fminf(fmaxf(qx, lo.x), hi.x), fminf(fmaxf(qy, lo.y), hi.y)));
+  float sx, sy;
+  f2_unpack(f2_mul(e, e), sx, sy);
+  const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo.z), hi.z));
+  return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(ez, ez));
+#else
   const float ex = __fsub_rn(qx, fminf(fmaxf(qx, lo.x), hi.x));
   const float ey = __fsub_rn(qy, fminf(fmaxf(qy, lo.y), hi.y));
   const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo.z), hi.z));
   return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+#endif
 }
 
 __device__ __forceinline__ uint64_t nn_init(float max_range_sq) {
@@ -88,6 +129,9 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
   unsigned long long stack[kMaxStack + 8];
   int sp = 0;
   float bestd = __uint_as_float((uint32_t)(best >> 32));
+#ifndef PCG_NO_F32X2
+  const unsigned long long qxy = f2_pack(qx, qy);
+#endif
   {
     const float d = box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz);
     if (!(d <= bestd)) return;
@@ -150,7 +194,11 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
 #pragma unroll
       for (int j = 0; j < kLeaf; j++) {
         const float4 p = __ldg(lp + j);
+#ifndef PCG_NO_F32X2
+        const float d = dist_sq_pair(p.x, p.y, p.z, qxy, qz);
+#else
         const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
+#endif
         const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
         if (packed < best) {
           best = packed;
@@ -192,6 +240,9 @@ __device__ __forceinline__ void nn_traverse_packet(const IndexView& ix, float qx
   if (APPROX && active && bestd < min_dist_sq) active = false;
   const uint32_t lane = threadIdx.x & 31;
   int sp = 0;
+#ifndef PCG_NO_F32X2
+  const unsigned long long qxy = f2_pack(qx, qy);
+#endif
   {
     const float d = active ? box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz) : inf;
     if (__ballot_sync(kFull, active && d <= bestd) == 0) return;
@@ -253,7 +304,11 @@ __device__ __forceinline__ void nn_traverse_packet(const IndexView& ix, float qx
 #pragma unroll
         for (int j = 0; j < kLeaf; j++) {
           const float4 p = __ldg(lp + j);
+#ifndef PCG_NO_F32X2
+          const float d = dist_sq_pair(p.x, p.y, p.z, qxy, qz);
+#else
           const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
+#endif
           const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
           if (packed < best) {
             best = packed;
