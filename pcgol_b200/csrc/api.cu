@@ -391,7 +391,11 @@ pcg_status pcg_debug_index_slots(const pcg_index* idx, float* out, int64_t cap_s
     if (!out || idx->ix->n == 0) return PCG_OK;
     if (cap_slots < total) throw StatusError{PCG_E_INVALID_ARG, "buffer too small"};
     DeviceGuard g(idx->ix->device);
-    PCG_CUDA(cudaMemcpy(out, idx->ix->pts, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost));
+    // device layout: one line per leaf, x[8] y[8] z[8] id[8] (bvh.cuh); the hook reports slots as {x, y, z, id}
+    std::vector<float> raw((size_t)total * 4);
+    PCG_CUDA(cudaMemcpy(raw.data(), idx->ix->pts, raw.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < total; s++)
+      for (int c = 0; c < 4; c++) out[4 * s + c] = raw[(size_t)(s / kLeaf) * (4 * kLeaf) + (size_t)c * kLeaf + (size_t)(s % kLeaf)];
     return PCG_OK;
   });
 }

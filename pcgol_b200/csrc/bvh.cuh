@@ -3,13 +3,18 @@
 // iteration (icp.cu).
 //
 // Layout in HBM (all built on the GPU, see index.cu):
-//   pts   float4[leaves*kLeaf]  points in Morton order: x, y, z, original index (bits);
-//                               the tail is padded with (+inf,+inf,+inf, 0xffffffff)
-//   boxes float4[2*2*P]         implicit complete binary tree over the leaves, heap
-//                               indexed: node k has children 2k and 2k+1, root = 1,
-//                               leaf l is node P + l (P = leaves rounded up to 2^m).
-//                               Box of node k = {boxes[2k] = lo.xyz, boxes[2k+1] = hi.xyz};
-//                               both child boxes of a node are one aligned 64-byte line.
+//   pts   float4[leaves*kLeaf]  points in KD order, one 128-byte line per leaf of 8 points, coordinate-major INSIDE
+//                               the leaf: x[8] y[8] z[8] id[8] (original index bits); the tail is padded with
+//                               (+inf,+inf,+inf, 0xffffffff).  load_point() returns slot pos as {x, y, z, id}.
+//   boxes float4[2*2*P]         implicit complete binary tree over the leaves, heap indexed: node k has children 2k
+//                               and 2k+1, root = 1, leaf l is node P + l (P = leaves rounded up to 2^m).  The boxes
+//                               of the four nodes 4g .. 4g+3 (the children of a 4-ary step, two sibling pairs of the
+//                               binary tree) are one 128-byte line, coordinate-major: lo.x[4] lo.y[4] lo.z[4]
+//                               hi.x[4] hi.y[4] hi.z[4] (+ 8 floats of padding).  load_box() / store_box() address
+//                               a single node.
+// Coordinate-major lines put the same coordinate of two neighbouring boxes / points in adjacent registers after a
+// 16-byte load, which is what the packed float32 pair instructions of sm_100a (FADD2 / FMUL2) take: a box or point
+// test is 8 packed instructions per PAIR instead of 8 scalar ones per item.
 //
 // Exactness.  The reference distance is ((dx*dx + dy*dy) + dz*dz) in float32 with
 // d = point - query and every operation rounded (mat/vec3.go:18-20,38-40).  The box
@@ -42,56 +47,136 @@ struct IndexView {
 
 #ifdef __CUDACC__
 // Packed float32 pairs (sm_100a: FADD2 / FMUL2, one instruction for two IEEE round-to-nearest operations - the same
-// per-element results as the scalar instructions).  x and y travel as a pair (they sit in adjacent registers after a
-// 16-byte load), z stays scalar.
-#ifndef PCG_NO_F32X2
-__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
-  unsigned long long r;
+// per-element results as the scalar instructions).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float a, float b) {
+  f32x2 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
   return r;
 }
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& a, float& b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
 }
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+  f32x2 r;
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// ((dx*dx + dy*dy) + dz*dz) with d = a - b: bit-identical to dist_sq_ref (mat/vec3.go:18-20,38-40)
-__device__ __forceinline__ float dist_sq_pair(float ax, float ay, float az, unsigned long long bxy, float bz) {
-  const unsigned long long d = f2_sub(f2_pack(ax, ay), bxy);
-  float sx, sy;
-  f2_unpack(f2_mul(d, d), sx, sy);
-  const float dz = __fsub_rn(az, bz);
-  return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
+// ((x*x + y*y) + z*z) for both halves.  The squares are packed; the sums are scalar on purpose: ptxas contracts a packed
+// multiply feeding a packed add into FFMA2 (even with explicit .rn and -fmad=false), and the reference never fuses.
+__device__ __forceinline__ void sum_squares_x2(f32x2 x, f32x2 y, f32x2 z, float& a, float& b) {
+  float xa, xb, ya, yb, za, zb;
+  f2_unpack(f2_mul(x, x), xa, xb);
+  f2_unpack(f2_mul(y, y), ya, yb);
+  f2_unpack(f2_mul(z, z), za, zb);
+  a = __fadd_rn(__fadd_rn(xa, ya), za);
+  b = __fadd_rn(__fadd_rn(xb, yb), zb);
 }
-#endif
+// The query as three pairs {q, q}.
+struct Query2 {
+  f32x2 x, y, z;
+  __device__ __forceinline__ Query2(float qx, float qy, float qz)
+      : x(f2_pack(qx, qx)), y(f2_pack(qy, qy)), z(f2_pack(qz, qz)) {}
+};
+// ((dx*dx + dy*dy) + dz*dz), d = point - query, for TWO points: bit-identical to dist_sq_ref (mat/vec3.go:18-20,38-40)
+__device__ __forceinline__ void dist_sq_x2(float xa, float xb, float ya, float yb, float za, float zb, const Query2& q,
+                                           float& da, float& db) {
+  const f32x2 dx = f2_sub(f2_pack(xa, xb), q.x), dy = f2_sub(f2_pack(ya, yb), q.y), dz = f2_sub(f2_pack(za, zb), q.z);
+  sum_squares_x2(dx, dy, dz, da, db);
+}
 
-__device__ __forceinline__ float box_dist_sq(const float4 lo, const float4 hi, float qx, float qy, float qz) {
+__device__ __forceinline__ float box_dist_sq(const float lo[3], const float hi[3], float qx, float qy, float qz) {
   // per axis: the query minus its clamp into [lo, hi] (exact selection), ONE rounded subtraction - the same rounded
   // operation the reference applies to (point - query), and |q - clamp(q)| <= |q - p| for every p in the box, so by
   // monotonicity of the rounding the bound never exceeds the reference distance of a point inside.  An empty box
   // (lo = +inf, hi = -inf) clamps to -inf: distance +inf.
-#ifndef PCG_NO_F32X2
-  const unsigned long long e =
-      f2_sub(f2_pack(qx, qy), f2_pack(fminf(fmaxf(qx, lo.x), hi.x), fminf(fmaxf(qy, lo.y), hi.y)));
-  float sx, sy;
-  f2_unpack(f2_mul(e, e), sx, sy);
-  const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo.z), hi.z));
-  return __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(ez, ez));
-#else
-  const float ex = __fsub_rn(qx, fminf(fmaxf(qx, lo.x), hi.x));
-  const float ey = __fsub_rn(qy, fminf(fmaxf(qy, lo.y), hi.y));
-  const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo.z), hi.z));
+  const float ex = __fsub_rn(qx, fminf(fmaxf(qx, lo[0]), hi[0]));
+  const float ey = __fsub_rn(qy, fminf(fmaxf(qy, lo[1]), hi[1]));
+  const float ez = __fsub_rn(qz, fminf(fmaxf(qz, lo[2]), hi[2]));
   return __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
-#endif
 }
+// The same bound for two boxes at once (coordinates given per box a / b).
+__device__ __forceinline__ void box_dist_sq_x2(float lxa, float lxb, float lya, float lyb, float lza, float lzb, float hxa,
+                                               float hxb, float hya, float hyb, float hza, float hzb, float qx, float qy,
+                                               float qz, const Query2& q, float& da, float& db) {
+  const f32x2 ex = f2_sub(q.x, f2_pack(fminf(fmaxf(qx, lxa), hxa), fminf(fmaxf(qx, lxb), hxb)));
+  const f32x2 ey = f2_sub(q.y, f2_pack(fminf(fmaxf(qy, lya), hya), fminf(fmaxf(qy, lyb), hyb)));
+  const f32x2 ez = f2_sub(q.z, f2_pack(fminf(fmaxf(qz, lza), hza), fminf(fmaxf(qz, lzb), hzb)));
+  sum_squares_x2(ex, ey, ez, da, db);
+}
+
+// ---- addressing of the coordinate-major lines ---------------------------------------------------------------------
+static_assert(kLeaf == 8, "a leaf is one 128-byte line: x[8] y[8] z[8] id[8]");
+__device__ __forceinline__ float4 load_point(const float4* pts, uint32_t pos) {
+  const float* f = reinterpret_cast<const float*>(pts) + (size_t)(pos >> 3) * 32 + (pos & 7u);
+  return make_float4(__ldg(f), __ldg(f + 8), __ldg(f + 16), __ldg(f + 24));
+}
+__device__ __forceinline__ void store_point(float4* pts, uint32_t pos, float4 v) {
+  float* f = reinterpret_cast<float*>(pts) + (size_t)(pos >> 3) * 32 + (pos & 7u);
+  f[0] = v.x;
+  f[8] = v.y;
+  f[16] = v.z;
+  f[24] = v.w;
+}
+__device__ __forceinline__ void load_box(const float4* boxes, uint32_t node, float lo[3], float hi[3]) {
+  const float* f = reinterpret_cast<const float*>(boxes) + (size_t)(node >> 2) * 32 + (node & 3u);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    lo[k] = __ldg(f + 4 * k);
+    hi[k] = __ldg(f + 12 + 4 * k);
+  }
+}
+__device__ __forceinline__ void store_box(float4* boxes, uint32_t node, const float lo[3], const float hi[3]) {
+  float* f = reinterpret_cast<float*>(boxes) + (size_t)(node >> 2) * 32 + (node & 3u);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    f[4 * k] = lo[k];
+    f[12 + 4 * k] = hi[k];
+  }
+}
+// The four boxes of nodes 4g .. 4g+3 (six 16-byte loads) and their bounds for one query.
+struct BoxLine {
+  float4 lx, ly, lz, hx, hy, hz;
+  __device__ __forceinline__ BoxLine(const float4* boxes, uint32_t group) {
+    const float4* g = boxes + 8 * (size_t)group;
+    lx = __ldg(g), ly = __ldg(g + 1), lz = __ldg(g + 2), hx = __ldg(g + 3), hy = __ldg(g + 4), hz = __ldg(g + 5);
+  }
+  // nodes 4g and 4g+1 / 4g+2 and 4g+3
+  __device__ __forceinline__ void dist_low(float qx, float qy, float qz, const Query2& q, float& d0, float& d1) const {
+    box_dist_sq_x2(lx.x, lx.y, ly.x, ly.y, lz.x, lz.y, hx.x, hx.y, hy.x, hy.y, hz.x, hz.y, qx, qy, qz, q, d0, d1);
+  }
+  __device__ __forceinline__ void dist_high(float qx, float qy, float qz, const Query2& q, float& d2, float& d3) const {
+    box_dist_sq_x2(lx.z, lx.w, ly.z, ly.w, lz.z, lz.w, hx.z, hx.w, hy.z, hy.w, hz.z, hz.w, qx, qy, qz, q, d2, d3);
+  }
+};
+// The eight points of a leaf (eight 16-byte loads): squared distances to one query and the ids.
+struct LeafLine {
+  float4 xa, xb, ya, yb, za, zb, ia, ib;
+  __device__ __forceinline__ explicit LeafLine(const float4* lp) {
+    xa = __ldg(lp), xb = __ldg(lp + 1), ya = __ldg(lp + 2), yb = __ldg(lp + 3);
+    za = __ldg(lp + 4), zb = __ldg(lp + 5), ia = __ldg(lp + 6), ib = __ldg(lp + 7);
+  }
+  __device__ __forceinline__ void dist8(const Query2& q, float d[8]) const {
+    dist_sq_x2(xa.x, xa.y, ya.x, ya.y, za.x, za.y, q, d[0], d[1]);
+    dist_sq_x2(xa.z, xa.w, ya.z, ya.w, za.z, za.w, q, d[2], d[3]);
+    dist_sq_x2(xb.x, xb.y, yb.x, yb.y, zb.x, zb.y, q, d[4], d[5]);
+    dist_sq_x2(xb.z, xb.w, yb.z, yb.w, zb.z, zb.w, q, d[6], d[7]);
+  }
+  __device__ __forceinline__ void ids(uint32_t id[8]) const {
+    id[0] = __float_as_uint(ia.x), id[1] = __float_as_uint(ia.y), id[2] = __float_as_uint(ia.z), id[3] = __float_as_uint(ia.w);
+    id[4] = __float_as_uint(ib.x), id[5] = __float_as_uint(ib.y), id[6] = __float_as_uint(ib.z), id[7] = __float_as_uint(ib.w);
+  }
+};
 
 __device__ __forceinline__ uint64_t nn_init(float max_range_sq) {
   // strict "<" against maxRange^2 with ID -1: nothing packs below (bits, 0) at equal distance
@@ -129,36 +214,36 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
   unsigned long long stack[kMaxStack + 8];
   int sp = 0;
   float bestd = __uint_as_float((uint32_t)(best >> 32));
-#ifndef PCG_NO_F32X2
-  const unsigned long long qxy = f2_pack(qx, qy);
-#endif
-  {
-    const float d = box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz);
-    if (!(d <= bestd)) return;
-  }
+  const Query2 q2(qx, qy, qz);
   const uint32_t P = ix.P;
   uint32_t node = 1;
-  // leaves sit at depth log2(P); with an odd depth the first step is binary so that 4-ary steps land on them
-  if (P > 1 && (__ffs(P) - 1) & 1) {
-    const float4* cb = ix.boxes + 4;
-    const float d0 = box_dist_sq(__ldg(cb), __ldg(cb + 1), qx, qy, qz);
-    const float d1 = box_dist_sq(__ldg(cb + 2), __ldg(cb + 3), qx, qy, qz);
-    const bool first0 = d0 <= d1;
-    const float dn = first0 ? d0 : d1, df = first0 ? d1 : d0;
-    if (!(dn <= bestd)) return;
-    if (df <= bestd) stack[sp++] = ((unsigned long long)__float_as_uint(df) << 32) | (first0 ? 3u : 2u);
-    node = first0 ? 2u : 3u;
+  {
+    // nodes 0..3 share a line: the root's box and, for an odd depth, the first (binary) step so that the 4-ary
+    // steps land on the leaves
+    const BoxLine top(ix.boxes, 0);
+    float dx, d1, d2, d3;
+    top.dist_low(qx, qy, qz, q2, dx, d1);
+    if (!(d1 <= bestd)) return;
+    if (P > 1 && (__ffs(P) - 1) & 1) {
+      top.dist_high(qx, qy, qz, q2, d2, d3);
+      const bool first0 = d2 <= d3;
+      const float dn = first0 ? d2 : d3, df = first0 ? d3 : d2;
+      if (!(dn <= bestd)) return;
+      if (df <= bestd) stack[sp++] = ((unsigned long long)__float_as_uint(df) << 32) | (first0 ? 3u : 2u);
+      node = first0 ? 2u : 3u;
+    }
   }
   for (;;) {
     while (node < P) {
-      const float4* cb = ix.boxes + 8 * (size_t)node;  // boxes of nodes 4*node .. 4*node+3
+      const BoxLine cb(ix.boxes, node);  // boxes of nodes 4*node .. 4*node+3
       PCG_STAT(0);
+      float d[4];
+      cb.dist_low(qx, qy, qz, q2, d[0], d[1]);
+      cb.dist_high(qx, qy, qz, q2, d[2], d[3]);
       uint32_t key[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float d = box_dist_sq(__ldg(cb + 2 * j), __ldg(cb + 2 * j + 1), qx, qy, qz);
-        key[j] = (__float_as_uint(d) & ~3u) | (uint32_t)j;  // d >= 0 (or +inf / NaN pattern for empty boxes)
-      }
+      for (int j = 0; j < 4; j++)
+        key[j] = (__float_as_uint(d[j]) & ~3u) | (uint32_t)j;  // d >= 0 (or +inf / NaN pattern for empty boxes)
       // sorting network for 4 keys (ascending)
 #define PCG_CSWAP(a, b)                 \
   {                                     \
@@ -190,16 +275,14 @@ __device__ __forceinline__ void nn_traverse4(const IndexView& ix, float qx, floa
     if (node) {
       PCG_STAT(1);
       const uint32_t base = (node - P) * kLeaf;
-      const float4* lp = ix.pts + base;
+      const LeafLine leaf(ix.pts + base);
+      float d[8];
+      uint32_t id[8];
+      leaf.dist8(q2, d);
+      leaf.ids(id);
 #pragma unroll
       for (int j = 0; j < kLeaf; j++) {
-        const float4 p = __ldg(lp + j);
-#ifndef PCG_NO_F32X2
-        const float d = dist_sq_pair(p.x, p.y, p.z, qxy, qz);
-#else
-        const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
-#endif
-        const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
+        const uint64_t packed = ((uint64_t)__float_as_uint(d[j]) << 32) | (uint64_t)id[j];
         if (packed < best) {
           best = packed;
           best_pos = base + j;
@@ -240,36 +323,39 @@ __device__ __forceinline__ void nn_traverse_packet(const IndexView& ix, float qx
   if (APPROX && active && bestd < min_dist_sq) active = false;
   const uint32_t lane = threadIdx.x & 31;
   int sp = 0;
-#ifndef PCG_NO_F32X2
-  const unsigned long long qxy = f2_pack(qx, qy);
-#endif
-  {
-    const float d = active ? box_dist_sq(__ldg(ix.boxes + 2), __ldg(ix.boxes + 3), qx, qy, qz) : inf;
-    if (__ballot_sync(kFull, active && d <= bestd) == 0) return;
-  }
+  const Query2 q2(qx, qy, qz);
   const uint32_t P = ix.P;
   uint32_t node = 1;
-  if (P > 1 && (__ffs(P) - 1) & 1) {  // odd depth: one binary step first (see nn_traverse4)
-    const float4* cb = ix.boxes + 4;
-    const float d0 = active ? box_dist_sq(__ldg(cb), __ldg(cb + 1), qx, qy, qz) : inf;
-    const float d1 = active ? box_dist_sq(__ldg(cb + 2), __ldg(cb + 3), qx, qy, qz) : inf;
-    const uint32_t m0 = __reduce_min_sync(kFull, __float_as_uint(d0)), m1 = __reduce_min_sync(kFull, __float_as_uint(d1));
-    const bool w0 = __ballot_sync(kFull, d0 <= bestd) != 0, w1 = __ballot_sync(kFull, d1 <= bestd) != 0;
-    if (!w0 && !w1) return;
-    const bool first0 = w0 && (!w1 || m0 <= m1);
-    if (w0 && w1 && lane == 0) stack[0] = ((unsigned long long)(first0 ? m1 : m0) << 32) | (first0 ? 3u : 2u);
-    if (w0 && w1) sp = 1;
-    node = first0 ? 2u : 3u;
+  {
+    const BoxLine top(ix.boxes, 0);  // nodes 0..3: the root and, for an odd depth, the first (binary) step
+    float dx, dr, d0, d1;
+    top.dist_low(qx, qy, qz, q2, dx, dr);
+    if (!active) dr = inf;
+    if (__ballot_sync(kFull, active && dr <= bestd) == 0) return;
+    if (P > 1 && (__ffs(P) - 1) & 1) {
+      top.dist_high(qx, qy, qz, q2, d0, d1);
+      if (!active) d0 = d1 = inf;
+      const uint32_t m0 = __reduce_min_sync(kFull, __float_as_uint(d0)), m1 = __reduce_min_sync(kFull, __float_as_uint(d1));
+      const bool w0 = __ballot_sync(kFull, d0 <= bestd) != 0, w1 = __ballot_sync(kFull, d1 <= bestd) != 0;
+      if (!w0 && !w1) return;
+      const bool first0 = w0 && (!w1 || m0 <= m1);
+      if (w0 && w1 && lane == 0) stack[0] = ((unsigned long long)(first0 ? m1 : m0) << 32) | (first0 ? 3u : 2u);
+      if (w0 && w1) sp = 1;
+      node = first0 ? 2u : 3u;
+    }
   }
   for (;;) {
     while (node < P) {
-      const float4* cb = ix.boxes + 8 * (size_t)node;  // boxes of nodes 4*node .. 4*node+3
+      const BoxLine cb(ix.boxes, node);  // boxes of nodes 4*node .. 4*node+3
+      float d[4];
+      cb.dist_low(qx, qy, qz, q2, d[0], d[1]);
+      cb.dist_high(qx, qy, qz, q2, d[2], d[3]);
       uint32_t key[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const float d = active ? box_dist_sq(__ldg(cb + 2 * j), __ldg(cb + 2 * j + 1), qx, qy, qz) : inf;
-        const uint32_t m = __reduce_min_sync(kFull, __float_as_uint(d));  // d >= 0: the bits order like the values
-        const bool want = __ballot_sync(kFull, d <= bestd) != 0;
+        const float dj = active ? d[j] : inf;
+        const uint32_t m = __reduce_min_sync(kFull, __float_as_uint(dj));  // d >= 0: the bits order like the values
+        const bool want = __ballot_sync(kFull, dj <= bestd) != 0;
         key[j] = want ? ((m & ~3u) | (uint32_t)j) : 0xffffffffu;
       }
 #define PCG_CSWAP(a, b)                 \
@@ -299,17 +385,15 @@ __device__ __forceinline__ void nn_traverse_packet(const IndexView& ix, float qx
     }
     if (node) {
       const uint32_t base = (node - P) * kLeaf;
-      const float4* lp = ix.pts + base;
+      const LeafLine leaf(ix.pts + base);
       if (active) {
+        float d[8];
+        uint32_t id[8];
+        leaf.dist8(q2, d);
+        leaf.ids(id);
 #pragma unroll
         for (int j = 0; j < kLeaf; j++) {
-          const float4 p = __ldg(lp + j);
-#ifndef PCG_NO_F32X2
-          const float d = dist_sq_pair(p.x, p.y, p.z, qxy, qz);
-#else
-          const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
-#endif
-          const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(p.w);
+          const uint64_t packed = ((uint64_t)__float_as_uint(d[j]) << 32) | (uint64_t)id[j];
           if (packed < best) {
             best = packed;
             best_pos = base + j;
@@ -344,18 +428,28 @@ __device__ __forceinline__ void range_traverse(const IndexView& ix, float qx, fl
   if (qx != qx || qy != qy || qz != qz) return;
   uint32_t stack_node[kMaxStack];
   int sp = 0;
+  const Query2 q2(qx, qy, qz);
   {
-    float d = box_dist_sq(ix.boxes[2], ix.boxes[3], qx, qy, qz);
+    float lo[3], hi[3];
+    load_box(ix.boxes, 1, lo, hi);
+    const float d = box_dist_sq(lo, hi, qx, qy, qz);
     if (!(d < max_range_sq)) return;
   }
   const uint32_t P = ix.P;
   uint32_t node = 1;
   for (;;) {
     while (node < P) {
-      const float4* cb = ix.boxes + 4 * (size_t)node;
-      const float4 l0 = __ldg(cb), h0 = __ldg(cb + 1), l1 = __ldg(cb + 2), h1 = __ldg(cb + 3);
-      const bool in0 = box_dist_sq(l0, h0, qx, qy, qz) < max_range_sq;
-      const bool in1 = box_dist_sq(l1, h1, qx, qy, qz) < max_range_sq;
+      // the children 2*node, 2*node+1 are one half of the line of nodes 4g .. 4g+3
+      const float* g = reinterpret_cast<const float*>(ix.boxes) + (size_t)(node >> 1) * 32 + ((2 * node) & 3u);
+      float d0, d1;
+      {
+        const float2 lx = __ldg(reinterpret_cast<const float2*>(g)), ly = __ldg(reinterpret_cast<const float2*>(g + 4)),
+                     lz = __ldg(reinterpret_cast<const float2*>(g + 8)), hx = __ldg(reinterpret_cast<const float2*>(g + 12)),
+                     hy = __ldg(reinterpret_cast<const float2*>(g + 16)), hz = __ldg(reinterpret_cast<const float2*>(g + 20));
+        box_dist_sq_x2(lx.x, lx.y, ly.x, ly.y, lz.x, lz.y, hx.x, hx.y, hy.x, hy.y, hz.x, hz.y, qx, qy, qz, q2, d0, d1);
+      }
+      const bool in0 = d0 < max_range_sq;
+      const bool in1 = d1 < max_range_sq;
       if (in0 && in1) {
         stack_node[sp++] = 2 * node + 1;
         node = 2 * node;
@@ -369,13 +463,14 @@ __device__ __forceinline__ void range_traverse(const IndexView& ix, float qx, fl
       }
     }
     if (node) {
-      const float4* lp = ix.pts + (size_t)(node - P) * kLeaf;
+      const LeafLine leaf(ix.pts + (size_t)(node - P) * kLeaf);
+      float d[8];
+      uint32_t id[8];
+      leaf.dist8(q2, d);
+      leaf.ids(id);
 #pragma unroll
-      for (int j = 0; j < kLeaf; j++) {
-        const float4 p = __ldg(lp + j);
-        const float d = dist_sq_ref(p.x, p.y, p.z, qx, qy, qz);
-        if (d < max_range_sq) f(__float_as_uint(p.w), d);
-      }
+      for (int j = 0; j < kLeaf; j++)
+        if (d[j] < max_range_sq) f(id[j], d[j]);
     }
     if (sp == 0) break;
     node = stack_node[--sp];

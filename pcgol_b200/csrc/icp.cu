@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(THREADS)
     // and prunes almost all backtracking
     const uint32_t w0 = warm ? warm[slot] : 0xffffffffu;
     if (w0 != 0xffffffffu) {
-      const float4 c = __ldg(base.pts + w0);
+      const float4 c = load_point(base.pts, w0);
       const float d = dist_sq_ref(c.x, c.y, c.z, x0, y0, z0);
       const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
       if (packed < best) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(THREADS)
     if (warm && best != init) warm[slot] = pos;
     if (best != init) {  // correspondence.go:27-29
       matched = 1;
-      const float4 pb = __ldg(base.pts + pos);
+      const float4 pb = load_point(base.pts, pos);
       const float x1 = pb.x, y1 = pb.y, z1 = pb.z;
       const float dsq = __uint_as_float((uint32_t)(best >> 32));
       // evaluator.go:130-144; with w = 1 (DefaultEvaluateWeightFn) w*v == v exactly

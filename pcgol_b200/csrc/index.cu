@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256)
     const float inf = __int_as_float(0x7f800000);
     o = make_float4(inf, inf, inf, __uint_as_float(0xffffffffu));
   }
-  pts[i] = o;
+  store_point(pts, i, o);  // coordinate-major inside the leaf's line (bvh.cuh)
 }
 
 // Leaf boxes and the 8 levels above them, one CTA per 256 leaves.
@@ -140,10 +140,9 @@ __global__ void __launch_bounds__(256)
   const float inf = __int_as_float(0x7f800000);
   float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   if (leaf < leaves) {
-    const float4* lp = pts + (size_t)leaf * kLeaf;
 #pragma unroll
     for (int j = 0; j < kLeaf; j++) {
-      float4 p = lp[j];
+      const float4 p = load_point(pts, leaf * kLeaf + j);
       if (__float_as_uint(p.w) == 0xffffffffu) continue;  // padding
       // fminf/fmaxf drop NaN operands; +-inf coordinates stay out of the boxes as well
       if (isfinite(p.x)) { lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x); }
@@ -151,10 +150,7 @@ __global__ void __launch_bounds__(256)
       if (isfinite(p.z)) { lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z); }
     }
   }
-  if (leaf < P) {
-    boxes[2 * (size_t)(P + leaf)] = make_float4(lo[0], lo[1], lo[2], 0.f);
-    boxes[2 * (size_t)(P + leaf) + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
-  }
+  if (leaf < P) store_box(boxes, P + leaf, lo, hi);
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     s_lo[t][k] = lo[k];
@@ -184,9 +180,7 @@ __global__ void __launch_bounds__(256)
         s_lo[t][k] = l[k];
         s_hi[t][k] = u[k];
       }
-      uint32_t node = first + t;
-      boxes[2 * (size_t)node] = make_float4(l[0], l[1], l[2], 0.f);
-      boxes[2 * (size_t)node + 1] = make_float4(u[0], u[1], u[2], 0.f);
+      store_box(boxes, first + t, l, u);
     }
     __syncthreads();
   }
@@ -197,11 +191,16 @@ __global__ void __launch_bounds__(1024) top_boxes_kernel(float4* __restrict__ bo
   // level with `count` nodes starting at node id `count` (heap indexing), children already written
   for (uint32_t count = P >> 9; count >= 1; count >>= 1) {
     for (uint32_t j = threadIdx.x; j < count; j += blockDim.x) {
-      uint32_t node = count + j;
-      float4 l0 = boxes[2 * (size_t)(2 * node)], h0 = boxes[2 * (size_t)(2 * node) + 1];
-      float4 l1 = boxes[2 * (size_t)(2 * node + 1)], h1 = boxes[2 * (size_t)(2 * node + 1) + 1];
-      boxes[2 * (size_t)node] = make_float4(fminf(l0.x, l1.x), fminf(l0.y, l1.y), fminf(l0.z, l1.z), 0.f);
-      boxes[2 * (size_t)node + 1] = make_float4(fmaxf(h0.x, h1.x), fmaxf(h0.y, h1.y), fmaxf(h0.z, h1.z), 0.f);
+      const uint32_t node = count + j;
+      // plain loads: the children were written by this kernel (or the one before) - not through the read-only path
+      const float* c0 = reinterpret_cast<const float*>(boxes) + (size_t)((2 * node) >> 2) * 32 + ((2 * node) & 3u);
+      float lo[3], hi[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        lo[k] = fminf(c0[4 * k], c0[4 * k + 1]);
+        hi[k] = fmaxf(c0[12 + 4 * k], c0[12 + 4 * k + 1]);
+      }
+      store_box(boxes, node, lo, hi);
     }
     __syncthreads();
   }
@@ -572,7 +571,7 @@ Index* index_build_device(const CloudView& v, int device, cudaStream_t stream) {
   try {
     const size_t padded = (size_t)ix->leaves * kLeaf;
     const size_t pts_bytes = padded * sizeof(float4);
-    const size_t box_bytes = (size_t)4 * P * sizeof(float4);
+    const size_t box_bytes = (size_t)4 * std::max<uint32_t>(P, 2u) * sizeof(float4);  // whole lines of four nodes (bvh.cuh)
     PCG_CUDA(cudaMallocAsync((void**)&ix->pts, pts_bytes, stream));
     PCG_CUDA(cudaMallocAsync((void**)&ix->boxes, box_bytes, stream));
     ix->bytes = (int64_t)(pts_bytes + box_bytes);
@@ -616,7 +615,7 @@ Index* index_replicate(const Index& src, int device) {
     PCG_CUDA(cudaDeviceSynchronize());  // the source may still be building on some stream
     PCG_CUDA(cudaSetDevice(device));
     const size_t pts_bytes = (size_t)src.leaves * kLeaf * sizeof(float4);
-    const size_t box_bytes = (size_t)4 * src.P * sizeof(float4);
+    const size_t box_bytes = (size_t)4 * std::max<uint32_t>(src.P, 2u) * sizeof(float4);
     PCG_CUDA(cudaMalloc((void**)&ix->pts, pts_bytes));
     PCG_CUDA(cudaMalloc((void**)&ix->boxes, box_bytes));
     PCG_CUDA(cudaMalloc((void**)&ix->bbox, 8 * sizeof(uint32_t)));
@@ -660,7 +659,7 @@ __global__ void __launch_bounds__(256)
     inverse_slots_kernel(const float4* __restrict__ pts, uint32_t padded, uint32_t* __restrict__ inv) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= padded) return;
-  const uint32_t id = __float_as_uint(pts[i].w);
+  const uint32_t id = __float_as_uint(load_point(pts, i).w);
   if (id != 0xffffffffu) inv[id] = i;
 }
 
@@ -672,10 +671,10 @@ __global__ void __launch_bounds__(256)
   const uint32_t slot = inv[ids[i]];
   const float inf = __int_as_float(0x7f800000);
   // x,y,z only: the id in .w stays (deleting twice is a no-op, like the reference's second walk)
-  float* p = reinterpret_cast<float*>(pts + slot);
+  float* p = reinterpret_cast<float*>(pts) + (size_t)(slot >> 3) * 32 + (slot & 7u);  // x, y, z of the slot (bvh.cuh)
   p[0] = inf;
-  p[1] = inf;
-  p[2] = inf;
+  p[8] = inf;
+  p[16] = inf;
 }
 
 void index_delete_points_device(Index& ix, const int64_t* d_ids, int64_t n, cudaStream_t stream) {
@@ -809,7 +808,7 @@ __global__ void __launch_bounds__(kNnThreads)
     uint64_t best = init;
     uint32_t pos = 0;
     if (live && warm != 0xffffffffu) {
-      const float4 c = __ldg(ix.pts + warm);
+      const float4 c = load_point(ix.pts, warm);
       const float d = dist_sq_ref(c.x, c.y, c.z, p.x, p.y, p.z);
       const uint64_t packed = ((uint64_t)__float_as_uint(d) << 32) | (uint64_t)__float_as_uint(c.w);
       if (packed < best) {
