@@ -232,7 +232,7 @@ def sharded_voxelgrid_points(shard, index_base: int, rank: int, world: int, out=
         t = torch.tensor([n_out], dtype=torch.int64, device=acc.device)
         gathered = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(gathered, t, group=group)
-        all_counts = [int(g.item()) for g in gathered]
+        all_counts = [int(c) for c in torch.cat(gathered).cpu().tolist()]  # one device -> host copy, not one per rank
     lap("counts")
     return n_out, all_counts, (lo, hi), recv, out
 
