@@ -191,3 +191,33 @@ def test_go_shim_is_structurally_sound_and_binds_declared_symbols():
         if "statusError(" in body and not m.group(0).startswith("\nfunc statusError"):
             assert "defer pin()()" in body, m.group(0).splitlines()[1]
     assert "k2.owner = k" in raw and "runtime.KeepAlive(k)" in raw
+
+
+def test_sass_has_no_fused_packed_multiply_add_and_uses_bulk_async():
+    """Static check of the built library (cuobjdump works without a GPU).
+
+    * No FFMA2: the reference never fuses multiply-add, and ptxas contracts a packed float32 multiply that feeds a
+      packed add into FFMA2 even with explicit .rn and -fmad=false (one ulp off; it happened once, bvh.cuh keeps the
+      sums scalar because of it).  Scalar FFMA only appears inside division / square-root sequences.
+    * The kernels that move tiles use the bulk-async engine: UBLKCP (cp.async.bulk) + SYNCS (mbarrier)."""
+    import shutil
+    import subprocess
+
+    from pcgol_b200 import _lib
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "FFMA2" not in sass
+    assert sass.count("FADD2") > 100 and sass.count("FMUL2") > 100  # the packed pairs of the index walks are there
+    per_kernel, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            per_kernel[name] = ""
+        elif name:
+            per_kernel[name] += line + "\n"
+    for frag in ("voxelgrid_fused_kernel", "scatter_kernel", "minmax_bulk_kernel", "icp_replay_walk_kernel"):
+        hits = [k for k in per_kernel if frag in k]
+        assert hits, frag
+        for k in hits:
+            assert "UBLKCP" in per_kernel[k] and "SYNCS" in per_kernel[k], k
