@@ -23,3 +23,9 @@ for name, x in streams.items():
     for _ in range(5): pg._lib.lib.pcg_debug_sequential_sum_f32(x.ctypes.data, len(x), 0, 1, out)
     dt = (time.perf_counter() - t0) / 5
     print(f"{name:4s} sum {out[0]:.6g} fast {int(out[1])} slow {int(out[2])} walk cycles {int(out[3])} ({out[3]/1.965e3:.1f} us)  call {dt*1e3:.3f} ms  matched {m.mean():.3f}")
+# near convergence the gradient terms are zero-mean: the accumulator wanders through binades
+rng = np.random.default_rng(5)
+for name, x in {"conv_g": rng.normal(0, 0.02, 100_000).astype(f32), "conv_gw": (rng.normal(0, 0.02, 100_000) * rng.uniform(1, 30, 100_000)).astype(f32)}.items():
+    out = (C.c_float * 4)()
+    pg._lib.lib.pcg_debug_sequential_sum_f32(x.ctypes.data, len(x), 0, 1, out)
+    print(f"{name:7s} sum {out[0]:.6g} fast {int(out[1])} slow {int(out[2])} walk cycles {int(out[3])} ({out[3]/1.965e3:.1f} us)")
