@@ -69,3 +69,39 @@ def test_nearest_and_range_on_50m_map(big_map, oracle):
         eoff, erids, erdsq = kd.range(qs[:500], 0.2)
         assert np.array_equal(off, eoff)
         assert np.array_equal(rids, cand[erids]) and rdsq.tobytes() == erdsq.tobytes()
+
+
+@pytest.mark.parametrize("layout", [(20, (4, 8, 12)), (13, (1, 5, 9))])
+def test_voxelgrid_packed_words_equal_pairs_at_3m_records(layout, oracle):
+    """Above 1.2M points the Filter takes the packed-word pipeline (vg_packed.cuh: several super-tiles, four passes,
+    records with payload fields / unaligned records); the (key, index) pairs pipeline must give the same bytes, and
+    the sparse restatement of voxelgrid.go:35-187 agrees with both."""
+    import ctypes as C
+
+    from pcgol_b200 import _lib
+    stride, off = layout
+    n = 3_000_000
+    rng = np.random.default_rng(stride)
+    buf = rng.integers(0, 255, size=(n, stride), dtype=np.uint8)
+    xyz = (rng.random((n, 3), dtype=f32) * np.array([60.0, 40.0, 6.0], f32)).astype(f32)
+    xyz[: n // 3] = (xyz[: n // 3] * f32(0.05)).astype(f32)  # a dense corner: voxels with many members
+    for k in range(3):
+        buf[:, off[k]:off[k] + 4] = xyz[:, k:k + 1].copy().view(np.uint8)
+    flat = np.ascontiguousarray(buf).reshape(-1)
+    leaf, chunk = (0.05, 0.05, 0.05), (128, 128, 128)
+    outs = []
+    for path in (0, 2):
+        _lib.set_vg_path(path)
+        try:
+            out = np.empty(n * stride, np.uint8)
+            n_out = C.c_int64(0)
+            rc = _lib.lib.pcg_voxelgrid_filter(flat.ctypes.data, n, stride, (C.c_int64 * 3)(*off),
+                                               np.asarray(leaf, f32).ctypes.data, np.asarray(chunk, np.int64).ctypes.data,
+                                               0, out.ctypes.data, C.byref(n_out))
+            assert rc == 0, _lib.last_error()
+            outs.append(out[: n_out.value * stride].tobytes())
+        finally:
+            _lib.set_vg_path(0)
+    assert outs[0] == outs[1]
+    rc, exp = oracle.voxelgrid_filter(flat, stride, off, leaf, chunk, mode="sparse")
+    assert rc == oracle.OK and exp.tobytes() == outs[0]
