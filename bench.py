@@ -750,19 +750,30 @@ def bench_config5(pg, torch, dist, rank, args, peak):
     qlo, qhi = pdist.shard_bounds(len(q), rank, world)
     res = {}
 
+    # the two-call protocol with caller-owned PINNED buffers that are reused (allocated once, outside the timed region):
+    # count -> offsets, fill -> storage.Neighbor records; both copies back to the host are inside the timed region
+    qs = np.ascontiguousarray(q[qlo:qhi])
+    h_off = torch.zeros(len(qs) + 1, dtype=torch.int64).pin_memory()
+    idx.range_count_into(qs, 0.2, h_off.data_ptr())
+    h_nb = torch.empty(max(1, int(h_off[-1])) * 16, dtype=torch.uint8).pin_memory()
+
     def rstep(i):
-        res["r"] = idx.range_batch(q[qlo:qhi], 0.2)
+        idx.range_count_into(qs, 0.2, h_off.data_ptr())
+        idx.range_fill_into(qs, 0.2, h_off.data_ptr(), h_nb.data_ptr())
 
     rstep(0)
     rms = wall_region(dist, torch, rstep, 2)
-    off_, ids_, dsq_ = res["r"]
+    off_ = h_off.numpy()
+    nb_ = h_nb.numpy()[: int(off_[-1]) * 16].view(np.dtype([("id", "<i8"), ("dist_sq", "<f4"), ("pad", "<u4")]))
+    ids_, dsq_ = nb_["id"].copy(), nb_["dist_sq"].copy()
+    res["r"] = (off_, ids_, dsq_)
     tot = torch.tensor([int(off_[-1])], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(tot)
     out["range"] = {"queries": len(q), "neighbours": int(tot.item()), "radius": 0.2, "ms_per_step": rms / 2,
                     "queries_per_s": len(q) * 2 / (rms / 1e3), "neighbours_per_s": int(tot.item()) * 2 / (rms / 1e3),
-                    "scaling": "strong", "timer": "host wall clock around pcg_index_range_count + _fill on host buffers "
-                                                  "(variable-length result: two-call protocol), max over ranks"}
+                    "scaling": "strong", "timer": "host wall clock around pcg_index_range_count + _fill into reused pinned "
+                                                  "host buffers (variable-length result: two-call protocol), max over ranks"}
     if world > 1:
         h = torch.tensor([int(_fnv(off_.tobytes() + ids_.tobytes() + dsq_.tobytes()), 16) >> 1], dtype=torch.int64, device=dev)
         hs = [torch.zeros_like(h) for _ in range(world)]

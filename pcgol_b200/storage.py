@@ -148,6 +148,17 @@ class Index:
                                                 offs.ctypes.data, nb.ctypes.data))
         return offs, nb["id"][:total].copy(), nb["dist_sq"][:total].copy()
 
+    def range_count_into(self, queries, max_range: float, offsets_ptr: int) -> None:
+        """First call of the two-call protocol into a caller-owned (reusable, ideally pinned) int64[nq + 1] buffer."""
+        data, n, stride, off = as_vec3_buffer(queries)
+        _lib.check(_lib.lib.pcg_index_range_count(self._h, data.ctypes.data, n, stride, _off(off), max_range, offsets_ptr))
+
+    def range_fill_into(self, queries, max_range: float, offsets_ptr: int, neighbors_ptr: int) -> None:
+        """Second call: offsets[nq] storage.Neighbor records (16 bytes each) into a caller-owned buffer."""
+        data, n, stride, off = as_vec3_buffer(queries)
+        _lib.check(_lib.lib.pcg_index_range_fill(self._h, data.ctypes.data, n, stride, _off(off), max_range, offsets_ptr,
+                                                neighbors_ptr))
+
     def range_batch_owned(self, queries, max_range: float):
         """Same result through the one-call form (library-owned CSR, pcg_index_range)."""
         data, n, stride, off = as_vec3_buffer(queries)
